@@ -1,0 +1,10 @@
+"""smplk -- B200-native SMPL / SMPL-H body-model forward + backward (sm_100a CUDA behind a C ABI).
+
+Drop-in for the body-model path of bokchoy-mian/3D-human-body-reconstruction:
+  torch modules   SMPL, SMPLH            (models/smpl.py, models/smplh.py)
+  numpy twins     SMPLModel, SMPLHModel  (models/smpl_np.py, models/smplh_np.py)
+  rigged mesh     RecoverModel           (lib/model2video.py:12-130, lib/mesh2smpl_model.py:131-313)
+"""
+from . import synthetic  # noqa: F401
+
+__all__ = ["synthetic"]
