@@ -6,5 +6,15 @@ Drop-in for the body-model path of bokchoy-mian/3D-human-body-reconstruction:
   rigged mesh     RecoverModel           (lib/model2video.py:12-130, lib/mesh2smpl_model.py:131-313)
 """
 from . import synthetic  # noqa: F401
+from . import _lib  # noqa: F401
+from ._lib import DeviceModel, build, load  # noqa: F401
 
-__all__ = ["synthetic"]
+
+def __getattr__(name):  # torch-dependent modules load lazily
+    if name in ("SMPL", "SMPLH", "ModelOutput", "create", "body_model_apply", "load_model_file"):
+        from . import body_models
+        return getattr(body_models, name)
+    if name in ("SMPLModel", "SMPLHModel", "RecoverModel"):
+        from . import np_twins
+        return getattr(np_twins, name)
+    raise AttributeError(name)

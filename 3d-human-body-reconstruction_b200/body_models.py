@@ -1,0 +1,377 @@
+"""Drop-in torch modules for the reference's body models.
+
+    SMPLH  <-> models/smplh.py:13-39  (subclass of upstream smplx.SMPLH; created through
+               smplx.create(...) at lib/gen_smplh.py:75-90 and called at
+               lib/Gen_SMPLH/fitting.py:243-245)
+    SMPL   <-> models/smpl.py:11-37
+
+Same constructor keywords, same `forward` signature, same `ModelOutput` fields.  The math runs in
+libsmplk.so (hand-written sm_100a kernels behind the C ABI of include/smplk.h) through a
+`torch.autograd.Function`, so the modules are differentiable w.r.t. betas, global_orient,
+body_pose, hand poses (axis-angle or PCA) and transl.  torch only provides device memory, the
+current stream and the autograd glue.
+"""
+import ctypes
+import pickle
+from collections import namedtuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+ModelOutput = namedtuple("ModelOutput", ["vertices", "joints", "full_pose", "betas",
+                                         "global_orient", "body_pose", "expression",
+                                         "left_hand_pose", "right_hand_pose", "jaw_pose"])
+ModelOutput.__new__.__defaults__ = (None,) * len(ModelOutput._fields)
+
+
+def load_model_file(path):
+    """Model dict from a `.pkl` (official layout, latin1 pickles) or `.npz` file."""
+    if str(path).endswith(".npz"):
+        d = np.load(path, allow_pickle=True)
+        return {k: d[k] for k in d.files}
+    with open(path, "rb") as f:
+        return pickle.load(f, encoding="latin1")
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _prep(t, device):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("smplk needs CUDA tensors (no CPU path): got a tensor on %s" % t.device)
+    if t.dtype != torch.float32:
+        raise RuntimeError("smplk computes in float32: got %s" % t.dtype)
+    return t.contiguous()
+
+
+class _BodyModelFn(torch.autograd.Function):
+    """verts, joints, joints_regressed, full_pose = f(betas, pose, pca_l, pca_r, transl)."""
+
+    @staticmethod
+    def forward(ctx, dm, flags, want_regressed, betas, pose, pca_l, pca_r, transl):
+        B = pose.shape[0]
+        dev = pose.device
+        needs_grad = any(t is not None and t.requires_grad
+                         for t in (betas, pose, pca_l, pca_r, transl))
+        if needs_grad:
+            flags |= _lib.FLAG_SAVE_FOR_BACKWARD
+        betas_c, pose_c = _prep(betas, dev), _prep(pose, dev)
+        pl, pr, tr = _prep(pca_l, dev), _prep(pca_r, dev), _prep(transl, dev)
+        verts = torch.empty(B, dm.V, 3, device=dev, dtype=torch.float32)
+        joints = torch.empty(B, dm.J + dm.E, 3, device=dev, dtype=torch.float32)
+        jreg = (torch.empty(B, dm.R, 3, device=dev, dtype=torch.float32)
+                if (want_regressed and dm.R > 0) else None)
+        full_pose = torch.empty(B, 3 * dm.J, device=dev, dtype=torch.float32)
+        ws_bytes = dm.workspace_bytes(B, flags)
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        a = _lib.ForwardArgs()
+        a.batch, a.flags = B, flags
+        a.betas, a.betas_batch = _ptr(betas_c), (betas_c.shape[0] if betas_c is not None else 1)
+        a.pose, a.hand_pca_l, a.hand_pca_r, a.transl = _ptr(pose_c), _ptr(pl), _ptr(pr), _ptr(tr)
+        a.verts, a.joints, a.joints_regressed = _ptr(verts), _ptr(joints), _ptr(jreg)
+        a.full_pose = _ptr(full_pose)
+        a.workspace, a.workspace_bytes = _ptr(ws), ws_bytes
+        a.stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            dm.forward(a)
+        ctx.dm, ctx.flags = dm, flags
+        if needs_grad:
+            ctx.ws = ws
+            ctx.inputs = (betas_c, pose_c, pl, pr, tr)
+        ctx.mark_non_differentiable(full_pose)
+        if jreg is None:
+            jreg = torch.empty(0, device=dev)
+            ctx.mark_non_differentiable(jreg)
+        return verts, joints, jreg, full_pose
+
+    @staticmethod
+    def backward(ctx, d_verts, d_joints, d_jreg, d_full_pose):
+        dm = ctx.dm
+        betas, pose, pl, pr, tr = ctx.inputs
+        B = pose.shape[0]
+        dev = pose.device
+        need = ctx.needs_input_grad  # (dm, flags, want_reg, betas, pose, pca_l, pca_r, transl)
+
+        def grad_in(g):
+            if g is None:
+                return None
+            return g.contiguous().float()
+
+        d_verts, d_joints = grad_in(d_verts), grad_in(d_joints)
+        d_jreg = grad_in(d_jreg) if (d_jreg is not None and d_jreg.numel() > 0) else None
+        d_betas = torch.empty_like(betas) if (betas is not None and need[3]) else None
+        d_pose = torch.empty_like(pose) if need[4] else None
+        d_pl = torch.empty_like(pl) if (pl is not None and need[5]) else None
+        d_pr = torch.empty_like(pr) if (pr is not None and need[6]) else None
+        d_tr = torch.empty_like(tr) if (tr is not None and need[7]) else None
+        sc_bytes = dm.backward_scratch_bytes(B)
+        sc = torch.empty(sc_bytes, device=dev, dtype=torch.uint8)
+        a = _lib.BackwardArgs()
+        a.batch, a.flags = B, ctx.flags
+        a.betas, a.betas_batch = _ptr(betas), (betas.shape[0] if betas is not None else 1)
+        a.pose, a.hand_pca_l, a.hand_pca_r = _ptr(pose), _ptr(pl), _ptr(pr)
+        a.d_verts, a.d_joints, a.d_joints_regressed = _ptr(d_verts), _ptr(d_joints), _ptr(d_jreg)
+        a.d_betas, a.d_pose = _ptr(d_betas), _ptr(d_pose)
+        a.d_hand_pca_l, a.d_hand_pca_r, a.d_transl = _ptr(d_pl), _ptr(d_pr), _ptr(d_tr)
+        a.workspace, a.workspace_bytes = _ptr(ctx.ws), ctx.ws.numel()
+        a.scratch, a.scratch_bytes = _ptr(sc), sc_bytes
+        a.stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            dm.backward(a)
+        return None, None, None, d_betas, d_pose, d_pl, d_pr, d_tr
+
+
+def body_model_apply(dm, betas, pose, pca_l=None, pca_r=None, transl=None, add_pose_mean=False,
+                     want_regressed=False, flags=0):
+    """Functional entry point: (verts, joints_fk_plus_picks, joints_regressed|None, full_pose)."""
+    if add_pose_mean:
+        flags |= _lib.FLAG_ADD_POSE_MEAN
+    v, j, r, fp = _BodyModelFn.apply(dm, flags, want_regressed, betas, pose, pca_l, pca_r, transl)
+    return v, j, (r if r.numel() > 0 else None), fp
+
+
+class _BodyModelBase(nn.Module):
+    NUM_BODY_JOINTS = 23
+    NUM_HAND_JOINTS = 0
+    KIND = "smpl"
+
+    def __init__(self, model_path=None, model=None, joint_mapper=None, create_betas=True,
+                 betas=None, num_betas=None, create_global_orient=True, global_orient=None,
+                 create_body_pose=True, body_pose=None, create_transl=True, transl=None,
+                 dtype=torch.float32, batch_size=1, gender="neutral", J_regressor_extra=None,
+                 joint_map=None, vertex_ids=None, device=None, **kwargs):
+        super().__init__()
+        if dtype != torch.float32:
+            raise ValueError("smplk computes in float32 (got dtype %s)" % dtype)
+        if model is None:
+            if model_path is None:
+                raise ValueError("give `model` (dict) or `model_path`")
+            model = load_model_file(model_path)
+        self.batch_size = batch_size
+        self.gender = gender
+        self.dtype = dtype
+        self.joint_mapper = joint_mapper
+        self._model_dict = model
+        self._dm = {}
+        self._dm_kwargs = {}
+        self.faces = np.asarray(model["f"]).astype(np.int64)
+        self.register_buffer("faces_tensor", torch.from_numpy(self.faces.copy()))
+        self.register_buffer("v_template", torch.tensor(np.asarray(model["v_template"]), dtype=dtype))
+        W = model["weights"]
+        W = W.toarray() if hasattr(W, "toarray") else np.asarray(W)
+        self.register_buffer("lbs_weights", torch.tensor(W, dtype=dtype))
+        sd = np.asarray(model["shapedirs"])
+        self.num_betas = sd.shape[2] if num_betas is None else min(num_betas, sd.shape[2])
+        self.parents = _lib.parents_from_model(model)
+        self.num_joints = int(self.parents.shape[0])
+        if vertex_ids is None:
+            vertex_ids = model.get("extra_vertex_ids")
+        self.extra_vertex_ids = None if vertex_ids is None else np.asarray(vertex_ids, np.int32)
+        if J_regressor_extra is None:
+            J_regressor_extra = kwargs.pop("regressor_extra", None)
+        self._regressor_extra = None
+        if J_regressor_extra is not None:
+            self._regressor_extra = np.asarray(J_regressor_extra, np.float64)
+            self.register_buffer("J_regressor_extra", torch.tensor(self._regressor_extra, dtype=dtype))
+        self.joint_map = None if joint_map is None else torch.as_tensor(np.asarray(joint_map), dtype=torch.long)
+
+        def param(flag, value, shape, name):
+            if not flag:
+                return
+            if value is None:
+                t = torch.zeros(shape, dtype=dtype)
+            else:
+                t = torch.as_tensor(value, dtype=dtype).clone().reshape(shape)
+            self.register_parameter(name, nn.Parameter(t, requires_grad=True))
+
+        param(create_betas, betas, [batch_size, self.num_betas], "betas")
+        param(create_global_orient, global_orient, [batch_size, 3], "global_orient")
+        param(create_body_pose, body_pose, [batch_size, self.NUM_BODY_JOINTS * 3], "body_pose")
+        param(create_transl, transl, [batch_size, 3], "transl")
+        self._verts_cache = None
+        if device is not None:
+            self.to(device)
+
+    # ---- device-side packed model, one per GPU (lazy: built on first forward on that device)
+    def device_model(self, device):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        dm = self._dm.get(idx)
+        if dm is None:
+            dm = _lib.DeviceModel(self._model_dict, device=idx, num_betas=self.num_betas,
+                                  extra_vertex_ids=self.extra_vertex_ids,
+                                  regressor_posed=self._regressor_extra, **self._dm_kwargs)
+            self._dm[idx] = dm
+        return dm
+
+    @property
+    def verts_numpy(self):
+        """models/smplh.py:38 caches vertices[0] on the host every forward (a device sync);
+        here the copy happens only when the attribute is read."""
+        return None if self._verts_cache is None else self._verts_cache[0].detach().cpu().numpy()
+
+    @torch.no_grad()
+    def reset_params(self, **params_dict):
+        """upstream smplx reset_params (lib/Gen_SMPLH/fit_single_frame.py:283,361)."""
+        for name, p in self.named_parameters():
+            if name in params_dict:
+                p[:] = torch.as_tensor(params_dict[name], dtype=p.dtype, device=p.device).reshape(p.shape)
+            else:
+                p.fill_(0)
+
+    def _default(self, value, name, batch, cols, device):
+        if value is None:
+            value = getattr(self, name, None)
+        if value is None:
+            value = torch.zeros(batch, cols, dtype=torch.float32, device=device)
+        return value
+
+    @staticmethod
+    def _expand(t, B):
+        if t.shape[0] == B:
+            return t
+        if t.shape[0] == 1:
+            return t.expand(B, -1)
+        raise ValueError("batch mismatch: %d vs %d" % (t.shape[0], B))
+
+    def _finish(self, verts, joints, jreg, transl_used):
+        if self.joint_mapper is not None:
+            joints = self.joint_mapper(joints)
+        if jreg is not None:
+            joints = torch.cat([joints, jreg], dim=1)
+        if self.joint_map is not None:
+            joints = joints[:, self.joint_map.to(joints.device)]
+        return joints
+
+
+class SMPL(_BodyModelBase):
+    """24-joint SMPL; drop-in for models/smpl.py:11-37 (upstream smplx.SMPL + extra joints)."""
+    NUM_BODY_JOINTS = 23
+    KIND = "smpl"
+
+    def forward(self, betas=None, body_pose=None, global_orient=None, transl=None,
+                return_verts=True, return_full_pose=False, pose2rot=True, **kwargs):
+        if not pose2rot:
+            raise NotImplementedError("pose2rot=False (rotation-matrix input) is not supported")
+        dev = self.v_template.device
+        go = self._default(global_orient, "global_orient", self.batch_size, 3, dev)
+        bp = self._default(body_pose, "body_pose", self.batch_size, 69, dev)
+        be = self._default(betas, "betas", self.batch_size, self.num_betas, dev)
+        tr = transl if transl is not None else getattr(self, "transl", None)
+        B = max(go.shape[0], bp.shape[0], be.shape[0])
+        pose = torch.cat([self._expand(go, B), self._expand(bp, B)], dim=1)
+        if tr is not None:
+            tr = self._expand(tr, B)
+        dm = self.device_model(dev)
+        verts, joints, jreg, full_pose = body_model_apply(
+            dm, be, pose, transl=tr, want_regressed=self._regressor_extra is not None)
+        self._verts_cache = verts
+        joints = self._finish(verts, joints, jreg, tr)
+        if return_full_pose:  # differentiable view of the assembled pose (cheap torch glue)
+            full_pose = pose
+        return ModelOutput(vertices=verts if return_verts else None, joints=joints,
+                           full_pose=full_pose if return_full_pose else None, betas=be,
+                           global_orient=go, body_pose=bp)
+
+
+class SMPLH(_BodyModelBase):
+    """52-joint SMPL-H; drop-in for models/smplh.py:13-39 and for the object
+    `smplx.create(model_type='smplh', ...)` returns at lib/gen_smplh.py:90."""
+    NUM_BODY_JOINTS = 21
+    NUM_HAND_JOINTS = 15
+    KIND = "smplh"
+
+    def __init__(self, model_path=None, model=None, create_left_hand_pose=True,
+                 left_hand_pose=None, create_right_hand_pose=True, right_hand_pose=None,
+                 use_pca=True, num_pca_comps=6, flat_hand_mean=False, **kwargs):
+        dtype = kwargs.get("dtype", torch.float32)
+        batch_size = kwargs.get("batch_size", 1)
+        super().__init__(model_path=model_path, model=model, **kwargs)
+        self.use_pca = use_pca
+        self.num_pca_comps = num_pca_comps
+        self.flat_hand_mean = flat_hand_mean
+        m = self._model_dict
+        if self.num_joints != 52:
+            raise ValueError("SMPLH needs a 52-joint model (got %d joints)" % self.num_joints)
+        self._dm_kwargs = dict(num_pca_comps=num_pca_comps if use_pca else 0,
+                               flat_hand_mean=flat_hand_mean)
+        if use_pca:
+            self.register_buffer("left_hand_components", torch.tensor(
+                np.asarray(m["hands_componentsl"])[:num_pca_comps], dtype=dtype))
+            self.register_buffer("right_hand_components", torch.tensor(
+                np.asarray(m["hands_componentsr"])[:num_pca_comps], dtype=dtype))
+        ml = np.zeros(45) if flat_hand_mean else np.asarray(m["hands_meanl"], np.float64)
+        mr = np.zeros(45) if flat_hand_mean else np.asarray(m["hands_meanr"], np.float64)
+        self.register_buffer("left_hand_mean", torch.tensor(ml, dtype=dtype))
+        self.register_buffer("right_hand_mean", torch.tensor(mr, dtype=dtype))
+        self.register_buffer("pose_mean", torch.tensor(np.concatenate([np.zeros(66), ml, mr]), dtype=dtype))
+        hand_dim = num_pca_comps if use_pca else 45
+        for flag, val, name in ((create_left_hand_pose, left_hand_pose, "left_hand_pose"),
+                                (create_right_hand_pose, right_hand_pose, "right_hand_pose")):
+            if flag:
+                t = (torch.zeros(batch_size, hand_dim, dtype=dtype) if val is None
+                     else torch.as_tensor(val, dtype=dtype).clone().reshape(batch_size, hand_dim))
+                self.register_parameter(name, nn.Parameter(t, requires_grad=True))
+        dev = kwargs.get("device")
+        if dev is not None:
+            self.to(dev)
+
+    def forward(self, betas=None, global_orient=None, body_pose=None, left_hand_pose=None,
+                right_hand_pose=None, transl=None, return_verts=True, return_full_pose=False,
+                pose2rot=True, get_skin=True, **kwargs):
+        if not pose2rot:
+            raise NotImplementedError("pose2rot=False (rotation-matrix input) is not supported")
+        dev = self.v_template.device
+        hand_dim = self.num_pca_comps if self.use_pca else 45
+        go = self._default(global_orient, "global_orient", self.batch_size, 3, dev)
+        bp = self._default(body_pose, "body_pose", self.batch_size, 63, dev)
+        be = self._default(betas, "betas", self.batch_size, self.num_betas, dev)
+        lh = self._default(left_hand_pose, "left_hand_pose", self.batch_size, hand_dim, dev)
+        rh = self._default(right_hand_pose, "right_hand_pose", self.batch_size, hand_dim, dev)
+        tr = transl if transl is not None else getattr(self, "transl", None)
+        B = max(go.shape[0], bp.shape[0], be.shape[0], lh.shape[0], rh.shape[0])
+        go_e, bp_e = self._expand(go, B), self._expand(bp, B)
+        lh_e, rh_e = self._expand(lh, B), self._expand(rh, B)
+        if tr is not None:
+            tr = self._expand(tr, B)
+        dm = self.device_model(dev)
+        if self.use_pca:
+            pad = torch.zeros(B, 90, dtype=torch.float32, device=dev)
+            pose = torch.cat([go_e, bp_e, pad], dim=1)
+            pca_l, pca_r = lh_e, rh_e
+        else:
+            pose = torch.cat([go_e, bp_e, lh_e, rh_e], dim=1)
+            pca_l = pca_r = None
+        verts, joints, jreg, full_pose = body_model_apply(
+            dm, be, pose, pca_l=pca_l, pca_r=pca_r, transl=tr, add_pose_mean=True,
+            want_regressed=self._regressor_extra is not None)
+        self._verts_cache = verts
+        joints = self._finish(verts, joints, jreg, tr)
+        if return_full_pose:  # differentiable assembly (upstream: cat + PCA einsum + pose_mean)
+            if self.use_pca:
+                lh_aa = lh_e @ self.left_hand_components
+                rh_aa = rh_e @ self.right_hand_components
+            else:
+                lh_aa, rh_aa = lh_e, rh_e
+            full_pose = torch.cat([go_e, bp_e, lh_aa, rh_aa], dim=1) + self.pose_mean
+        return ModelOutput(vertices=verts if return_verts else None, joints=joints,
+                           full_pose=full_pose if return_full_pose else None, betas=be,
+                           global_orient=go, body_pose=bp, left_hand_pose=lh, right_hand_pose=rh)
+
+
+def create(model_path=None, model_type="smplh", **kwargs):
+    """Mirror of `smplx.create` as used at lib/gen_smplh.py:90."""
+    kwargs.pop("create_expression", None)
+    kwargs.pop("create_jaw_pose", None)
+    kwargs.pop("create_leye_pose", None)
+    kwargs.pop("create_reye_pose", None)
+    if model_type.lower() == "smpl":
+        return SMPL(model_path=model_path, **kwargs)
+    if model_type.lower() == "smplh":
+        return SMPLH(model_path=model_path, **kwargs)
+    raise ValueError("Unknown model type %s, exiting!" % model_type)

@@ -1,0 +1,419 @@
+// Backward (vector-Jacobian product) of the body-model forward -- replaces the autograd pass of
+// total_loss.backward() at lib/Gen_SMPLH/fitting.py:256 through upstream smplx lbs().
+//
+//   d_verts ----> skin_backward_kernel : d_v_posed = (sum_k w_k R_A[j_k])^T d_verts   (tf32 hi/lo)
+//           \---> dA_kernel            : dA[b,j] = sum_v w[v,j] d_verts[b,v] (x) [v_posed[b,v];1]
+//   d_v_posed --> blend GEMM (split-K) : d_feat = d_v_posed . [posedirs | shapedirs]
+//   dA, d_feat, d_joints --> pose_backward_kernel : chain / rest-joint / Rodrigues / PCA backward
+#pragma once
+#include "common.cuh"
+#include "pose_kernels.cuh"
+#include "ptx_sm100.cuh"
+#include "skinning.cuh"
+
+namespace smplk {
+
+// d_verts_eff[b, vid[e]] += d_joints[b, J+e];  d_verts_eff[b, col[n]] += val[n] d_jreg[b, r]
+__global__ void scatter_joint_grads_kernel(const ModelDev m, int B, const float* __restrict__ d_joints,
+                                           int joints_ld, const float* __restrict__ d_jreg,
+                                           float* __restrict__ dverts) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float* dvb = dverts + (size_t)b * m.V * 3;
+  if (d_joints != nullptr && i < m.E) {
+    const float* g = d_joints + (size_t)b * joints_ld + 3 * (m.J + i);
+    float* o = dvb + (size_t)m.extra_vids[i] * 3;
+    atomicAdd(o + 0, g[0]); atomicAdd(o + 1, g[1]); atomicAdd(o + 2, g[2]);
+  }
+  if (d_jreg != nullptr) {
+    const int nnz = m.reg_ptr[m.R];
+    for (int n = i; n < nnz; n += gridDim.x * blockDim.x) {
+      int r = 0;
+      while (n >= m.reg_ptr[r + 1]) ++r;
+      const float w = m.reg_val[n];
+      const float* g = d_jreg + ((size_t)b * m.R + r) * 3;
+      float* o = dvb + (size_t)m.reg_col[n] * 3;
+      atomicAdd(o + 0, w * g[0]); atomicAdd(o + 1, w * g[1]); atomicAdd(o + 2, w * g[2]);
+    }
+  }
+}
+
+struct SkinBwdArgs {
+  int B;
+  int bodies_per_block;
+  const float* dverts;   // (B,V,3)
+  const float* A;        // (B,J,12)
+  float* dvp_hi;         // (B,Npad) tf32-rounded d_v_posed
+  float* dvp_lo;         // (B,Npad) residual
+};
+
+template <bool kReg4>
+__global__ void __launch_bounds__(kSkinThreads)
+skin_backward_kernel(const ModelDev m, const SkinBwdArgs a) {
+  extern __shared__ __align__(16) float sb_smem[];
+  const int tid = threadIdx.x;
+  const int v0 = blockIdx.x * kSkinTileVerts;
+  const int nv = min(kSkinTileVerts, m.V - v0);
+  const int nfloat = nv * 3;
+  const int nstore = min(kSkinTileVerts * 3, m.Npad - v0 * 3);   // incl. zeroed K padding
+  float* t_in = sb_smem;                              // [3072] d_verts tile
+  float* t_hi = sb_smem + kSkinTileVerts * 3;         // [3072]
+  float* t_lo = sb_smem + 2 * kSkinTileVerts * 3;     // [3072]
+  float* As = sb_smem + 3 * kSkinTileVerts * 3;       // [J*12]
+  const int b0 = blockIdx.y * a.bodies_per_block;
+  const int b1 = min(a.B, b0 + a.bodies_per_block);
+
+  uint32_t idx4[kSkinVPT];
+  float4 w4[kSkinVPT];
+  if (kReg4) {
+#pragma unroll
+    for (int i = 0; i < kSkinVPT; ++i) {
+      const int v = v0 + tid + kSkinThreads * i;
+      idx4[i] = v < m.V ? m.skin_idx4[v] : 0u;
+      w4[i] = v < m.V ? m.skin_w4[v] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  for (int b = b0; b < b1; ++b) {
+    const float* src = a.dverts + (size_t)b * m.V * 3 + (size_t)v0 * 3;
+    for (int c = tid; c < kSkinTileVerts * 3; c += kSkinThreads) {
+      t_in[c] = c < nfloat ? __ldcs(src + c) : 0.f;
+      t_hi[c] = 0.f;
+      t_lo[c] = 0.f;
+    }
+    const float* asrc = a.A + (size_t)b * m.J * 12;
+    for (int c = tid; c < m.J * 12; c += kSkinThreads) As[c] = asrc[c];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kSkinVPT; ++i) {
+      const int lv = tid + kSkinThreads * i;
+      if (lv < nv) {
+        const float gx = t_in[3 * lv + 0], gy = t_in[3 * lv + 1], gz = t_in[3 * lv + 2];
+        float T[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) T[q] = 0.f;
+        if (kReg4) {
+          const float wk[4] = {w4[i].x, w4[i].y, w4[i].z, w4[i].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int j = (idx4[i] >> (8 * k)) & 0xff;
+            const float* Aj = As + j * 12;
+            const float w = wk[k];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              T[3 * r + 0] = fmaf(w, Aj[4 * r + 0], T[3 * r + 0]);
+              T[3 * r + 1] = fmaf(w, Aj[4 * r + 1], T[3 * r + 1]);
+              T[3 * r + 2] = fmaf(w, Aj[4 * r + 2], T[3 * r + 2]);
+            }
+          }
+        } else {
+          const int v = v0 + lv;
+          for (int k = 0; k < m.ell_k; ++k) {
+            const float w = m.ell_w[(size_t)k * m.V + v];
+            if (w != 0.f) {
+              const float* Aj = As + m.ell_idx[(size_t)k * m.V + v] * 12;
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                T[3 * r + 0] = fmaf(w, Aj[4 * r + 0], T[3 * r + 0]);
+                T[3 * r + 1] = fmaf(w, Aj[4 * r + 1], T[3 * r + 1]);
+                T[3 * r + 2] = fmaf(w, Aj[4 * r + 2], T[3 * r + 2]);
+              }
+            }
+          }
+        }
+        // d_v_posed = T_R^T g
+        const float ox = T[0] * gx + T[3] * gy + T[6] * gz;
+        const float oy = T[1] * gx + T[4] * gy + T[7] * gz;
+        const float oz = T[2] * gx + T[5] * gy + T[8] * gz;
+        const float hx = ptx::tf32_round(ox), hy = ptx::tf32_round(oy), hz = ptx::tf32_round(oz);
+        t_hi[3 * lv + 0] = hx; t_hi[3 * lv + 1] = hy; t_hi[3 * lv + 2] = hz;
+        t_lo[3 * lv + 0] = ox - hx; t_lo[3 * lv + 1] = oy - hy; t_lo[3 * lv + 2] = oz - hz;
+      }
+    }
+    __syncthreads();
+    float4* oh = reinterpret_cast<float4*>(a.dvp_hi + (size_t)b * m.Npad + (size_t)v0 * 3);
+    float4* ol = reinterpret_cast<float4*>(a.dvp_lo + (size_t)b * m.Npad + (size_t)v0 * 3);
+    for (int c = tid; c < (nstore >> 2); c += kSkinThreads) {
+      oh[c] = reinterpret_cast<const float4*>(t_hi)[c];
+      ol[c] = reinterpret_cast<const float4*>(t_lo)[c];
+    }
+    __syncthreads();
+  }
+}
+
+// dA[b,j] (3x4) = sum over the vertices bound to joint j of  w * g (x) [v_posed; 1];
+// also dtr[b] = sum_v g[b,v].  One block per body; warps walk the joint -> vertex (CSC) lists.
+struct DAArgs {
+  int B;
+  const float* dverts;    // (B,V,3)
+  const float* vsrc;      // v_posed rows or shared template
+  size_t vsrc_stride;
+  float* dA;              // (B,J,12)
+  float* dtr;             // (B,3)
+};
+
+constexpr int kDAThreads = 256;
+
+__global__ void __launch_bounds__(kDAThreads) dA_kernel(const ModelDev m, const DAArgs a) {
+  __shared__ float red[3][kDAThreads / 32];
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* g = a.dverts + (size_t)b * m.V * 3;
+  const float* vp = a.vsrc + (size_t)b * a.vsrc_stride;
+  for (int j = warp; j < m.J; j += kDAThreads / 32) {
+    float acc[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) acc[q] = 0.f;
+    for (int n = m.csc_ptr[j] + lane; n < m.csc_ptr[j + 1]; n += 32) {
+      const int v = m.csc_vert[n];
+      const float w = m.csc_w[n];
+      const float gx = w * g[3 * v + 0], gy = w * g[3 * v + 1], gz = w * g[3 * v + 2];
+      const float x = vp[3 * v + 0], y = vp[3 * v + 1], z = vp[3 * v + 2];
+      acc[0] = fmaf(gx, x, acc[0]); acc[1] = fmaf(gx, y, acc[1]); acc[2] = fmaf(gx, z, acc[2]); acc[3] += gx;
+      acc[4] = fmaf(gy, x, acc[4]); acc[5] = fmaf(gy, y, acc[5]); acc[6] = fmaf(gy, z, acc[6]); acc[7] += gy;
+      acc[8] = fmaf(gz, x, acc[8]); acc[9] = fmaf(gz, y, acc[9]); acc[10] = fmaf(gz, z, acc[10]); acc[11] += gz;
+    }
+#pragma unroll
+    for (int q = 0; q < 12; ++q) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    }
+    if (lane == 0) {
+      float* o = a.dA + ((size_t)b * m.J + j) * 12;
+#pragma unroll
+      for (int q = 0; q < 12; ++q) o[q] = acc[q];
+    }
+  }
+  // translation gradient: plain sum of the vertex gradients
+  float s[3] = {0.f, 0.f, 0.f};
+  for (int v = threadIdx.x; v < m.V; v += kDAThreads) {
+    s[0] += g[3 * v + 0]; s[1] += g[3 * v + 1]; s[2] += g[3 * v + 2];
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+    if (lane == 0) red[q][warp] = s[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int w = 0; w < kDAThreads / 32; ++w) t += red[threadIdx.x][w];
+    a.dtr[3 * b + threadIdx.x] = t;
+  }
+}
+
+// d r  from  dL/dR for R = rodrigues(r)  (same parametrisation as the forward).
+__device__ __forceinline__ void rodrigues_backward(const float* r, const float* dR, float* dr) {
+  const float ex = r[0] + 1e-8f, ey = r[1] + 1e-8f, ez = r[2] + 1e-8f;
+  const float a = sqrtf(ex * ex + ey * ey + ez * ez);
+  const float inv = 1.0f / a;
+  const float nx = r[0] * inv, ny = r[1] * inv, nz = r[2] * inv;
+  float s, c;
+  sincosf(a, &s, &c);
+  const float sh = sinf(0.5f * a);
+  const float omc = 2.0f * sh * sh;
+  const float tr = dR[0] + dR[4] + dR[8];
+  const float kx = dR[7] - dR[5], ky = dR[2] - dR[6], kz = dR[3] - dR[1];
+  const float gK = nx * kx + ny * ky + nz * kz;
+  const float sx = 2.f * dR[0] * nx + (dR[1] + dR[3]) * ny + (dR[2] + dR[6]) * nz;
+  const float sy = (dR[1] + dR[3]) * nx + 2.f * dR[4] * ny + (dR[5] + dR[7]) * nz;
+  const float sz = (dR[2] + dR[6]) * nx + (dR[5] + dR[7]) * ny + 2.f * dR[8] * nz;
+  const float nn = nx * nx + ny * ny + nz * nz;
+  const float gK2 = 0.5f * (sx * nx + sy * ny + sz * nz) - nn * tr;
+  const float dnx = s * kx + omc * (sx - 2.f * tr * nx);
+  const float dny = s * ky + omc * (sy - 2.f * tr * ny);
+  const float dnz = s * kz + omc * (sz - 2.f * tr * nz);
+  const float da = c * gK + s * gK2 - (dnx * r[0] + dny * r[1] + dnz * r[2]) * inv * inv;
+  dr[0] = dnx * inv + da * ex * inv;
+  dr[1] = dny * inv + da * ey * inv;
+  dr[2] = dnz * inv + da * ez * inv;
+}
+
+struct PoseBwdArgs {
+  int B;
+  const float* betas;
+  int betas_B;
+  const float* pose;
+  const float* pca_l;
+  const float* pca_r;
+  int add_mean;
+  const float* dA;           // (B,J,12)
+  const float* d_joints;     // (B,joints_ld) or null; first 3J entries = FK joints
+  int joints_ld;
+  const float* d_feat;       // [splits][split_stride] partial rows of Kpad floats, or null
+  int feat_splits;
+  size_t feat_split_stride;  // floats
+  const float* dtr_verts;    // (B,3) or null
+  float* d_betas;            // (betas_B,NB) or null (atomic accumulate when betas_B == 1)
+  float* d_pose;             // (B,3J) or null
+  float* d_pca_l;            // (B,C) or null
+  float* d_pca_r;
+  float* d_transl;           // (B,3) or null
+};
+
+template <int SLOTS>
+__global__ void __launch_bounds__(kPoseWarps * 32)
+pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
+  extern __shared__ float pb_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kPoseWarps + warp;
+  if (b >= a.B) return;
+  const int per_warp = m.J * 18;
+  float* dG = pb_smem + warp * per_warp;   // [J][12]
+  float* dJ = dG + m.J * 12;               // [J][3]
+  float* dfull = dJ + m.J * 3;             // [3J]
+  const float* betas_row = a.betas ? a.betas + (size_t)(a.betas_B == 1 ? 0 : b) * m.NB : nullptr;
+
+  float rv[SLOTS][3], R[SLOTS][9], Jr[SLOTS][3], Jrel[SLOTS][3], G[SLOTS][12];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int j = lane + 32 * s;
+    rv[s][0] = rv[s][1] = rv[s][2] = 0.f;
+    if (j < m.J) load_joint_pose(m, a.pose, a.pca_l, a.pca_r, a.add_mean, b, j, rv[s]);
+  }
+  pose_forward_core<SLOTS>(m, betas_row, rv, R, Jr, Jrel, G, lane);
+
+  // ---- seed: A_j = [G_R | G_t - G_R J_j], joints_fk = G_t
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int j = lane + 32 * s;
+    if (j < m.J) {
+      const float* g = a.dA + ((size_t)b * m.J + j) * 12;
+      float gt[3] = {g[3], g[7], g[11]};
+      float djr[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          dG[j * 12 + r * 4 + c] = g[r * 4 + c] - gt[r] * Jr[s][c];
+          djr[c] -= G[s][r * 4 + c] * gt[r];
+        }
+      }
+      if (a.d_joints) {
+        const float* gj = a.d_joints + (size_t)b * a.joints_ld + 3 * j;
+        gt[0] += gj[0]; gt[1] += gj[1]; gt[2] += gj[2];
+      }
+      dG[j * 12 + 3] = gt[0]; dG[j * 12 + 7] = gt[1]; dG[j * 12 + 11] = gt[2];
+      dJ[j * 3 + 0] = djr[0]; dJ[j * 3 + 1] = djr[1]; dJ[j * 3 + 2] = djr[2];
+    }
+  }
+  __syncwarp();
+
+  // ---- chain backward, deepest level first:  G_j = G_p [R_j | Jrel_j]
+  float dRl[SLOTS][9];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) dRl[s][i] = 0.f;
+  for (int d = m.max_depth; d >= 1; --d) {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const int j = lane + 32 * s;
+      const bool act = (j < m.J) && (m.depth[j] == d);
+      const int p = act ? m.parents[j] : 0;
+      float Pm[12];
+      fetch_parent<SLOTS>(G, p, Pm);
+      if (act) {
+        float dg[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) dg[i] = dG[j * 12 + i];
+        // G (world) of this joint is no longer needed by the forward; but children were handled
+        // already, so G[s] may still be fetched by nobody at shallower levels except as a parent
+        // of deeper joints -- keep it untouched.
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            dRl[s][r * 3 + c] = Pm[0 * 4 + r] * dg[0 * 4 + c] + Pm[1 * 4 + r] * dg[1 * 4 + c] +
+                                Pm[2 * 4 + r] * dg[2 * 4 + c];
+          const float djrel = Pm[0 * 4 + r] * dg[3] + Pm[1 * 4 + r] * dg[7] + Pm[2 * 4 + r] * dg[11];
+          dJ[j * 3 + r] += djrel;
+          atomicAdd(&dJ[p * 3 + r], -djrel);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float v = dg[i * 4 + 0] * R[s][k * 3 + 0] + dg[i * 4 + 1] * R[s][k * 3 + 1] +
+                            dg[i * 4 + 2] * R[s][k * 3 + 2] + dg[i * 4 + 3] * Jrel[s][k];
+            atomicAdd(&dG[p * 12 + i * 4 + k], v);
+          }
+          atomicAdd(&dG[p * 12 + i * 4 + 3], dg[i * 4 + 3]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {  // root: L_0 = [R_0 | J_0]
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dRl[0][r * 3 + c] = dG[r * 4 + c];
+      dJ[r] += dG[r * 4 + 3];
+    }
+  }
+  __syncwarp();
+
+  // ---- pose-feature gradient from the blend GEMM, Rodrigues backward
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int j = lane + 32 * s;
+    if (j < m.J) {
+      if (a.d_feat != nullptr && j >= 1) {
+        for (int sp = 0; sp < a.feat_splits; ++sp) {
+          const float* f = a.d_feat + (size_t)sp * a.feat_split_stride + (size_t)b * m.Kpad + 9 * (j - 1);
+#pragma unroll
+          for (int i = 0; i < 9; ++i) dRl[s][i] += f[i];
+        }
+      }
+      float dr[3];
+      rodrigues_backward(rv[s], dRl[s], dr);
+      dfull[3 * j + 0] = dr[0]; dfull[3 * j + 1] = dr[1]; dfull[3 * j + 2] = dr[2];
+    }
+  }
+  __syncwarp();
+
+  const int hand0 = m.J - 30;
+  if (a.d_pose) {
+    for (int i = lane; i < 3 * m.J; i += 32) {
+      const int j = i / 3;
+      const bool from_pca = (a.pca_l && j >= hand0 && j < hand0 + 15) || (a.pca_r && j >= hand0 + 15);
+      a.d_pose[(size_t)b * 3 * m.J + i] = from_pca ? 0.f : dfull[i];
+    }
+  }
+  if (a.d_pca_l && a.pca_l) {
+    for (int c = lane; c < m.C; c += 32) {
+      float acc = 0.f;
+      for (int i = 0; i < 45; ++i) acc = fmaf(m.comp_l[c * 45 + i], dfull[3 * hand0 + i], acc);
+      a.d_pca_l[(size_t)b * m.C + c] = acc;
+    }
+  }
+  if (a.d_pca_r && a.pca_r) {
+    for (int c = lane; c < m.C; c += 32) {
+      float acc = 0.f;
+      for (int i = 0; i < 45; ++i) acc = fmaf(m.comp_r[c * 45 + i], dfull[3 * (hand0 + 15) + i], acc);
+      a.d_pca_r[(size_t)b * m.C + c] = acc;
+    }
+  }
+  // ---- d_betas = J_shapedirs^T dJ + (blend GEMM columns P..P+NB)
+  if (a.d_betas) {
+    for (int i = lane; i < m.NB; i += 32) {
+      float acc = 0.f;
+      for (int q = 0; q < 3 * m.J; ++q) acc = fmaf(dJ[q], m.J_shapedirs[(size_t)q * m.NB + i], acc);
+      if (a.d_feat != nullptr)
+        for (int sp = 0; sp < a.feat_splits; ++sp)
+          acc += a.d_feat[(size_t)sp * a.feat_split_stride + (size_t)b * m.Kpad + m.P + i];
+      if (a.betas_B == 1) atomicAdd(&a.d_betas[i], acc);
+      else a.d_betas[(size_t)b * m.NB + i] = acc;
+    }
+  }
+  if (a.d_transl && lane < 3) {
+    float t = a.dtr_verts ? a.dtr_verts[3 * b + lane] : 0.f;
+    if (a.d_joints)
+      for (int j = 0; j < m.J; ++j) t += a.d_joints[(size_t)b * a.joints_ld + 3 * j + lane];
+    a.d_transl[3 * b + lane] = t;
+  }
+}
+
+}  // namespace smplk

@@ -1,0 +1,148 @@
+// Host orchestration of the backward pass (included by smplk_api.cu).
+
+struct BwdLayout {
+  int m_blocks, n_blocks, k_blocks, splits, kbps, mpad;
+  size_t off_dverts, off_dvp_hi, off_dvp_lo, off_dA, off_dtr, off_dfeat, total;
+};
+
+static BwdLayout bwd_layout(const smplk_model* mdl, int batch) {
+  const ModelDev& d = mdl->d;
+  BwdLayout L;
+  memset(&L, 0, sizeof(L));
+  L.m_blocks = (batch + kBlendBM - 1) / kBlendBM;
+  L.mpad = L.m_blocks * kBlendBM;
+  size_t off = 0;
+  L.off_dverts = off; off += align_up((size_t)batch * d.V * 3 * sizeof(float), 1024);
+  L.off_dA = off;     off += align_up((size_t)batch * d.J * 12 * sizeof(float), 1024);
+  L.off_dtr = off;    off += align_up((size_t)batch * 3 * sizeof(float), 1024);
+  if (!d.lbs_only) {
+    L.n_blocks = (d.Kpad + kBlendBN - 1) / kBlendBN;
+    L.k_blocks = d.Npad / kBlendBK;
+    int splits = std::max(1, mdl->num_sms / (L.m_blocks * L.n_blocks));
+    splits = std::min(splits, L.k_blocks);
+    L.kbps = (L.k_blocks + splits - 1) / splits;
+    L.splits = (L.k_blocks + L.kbps - 1) / L.kbps;
+    L.off_dvp_hi = off; off += align_up((size_t)batch * d.Npad * sizeof(float), 1024);
+    L.off_dvp_lo = off; off += align_up((size_t)batch * d.Npad * sizeof(float), 1024);
+    L.off_dfeat = off;  off += align_up((size_t)L.splits * L.mpad * d.Kpad * sizeof(float), 1024);
+  }
+  L.total = off;
+  return L;
+}
+
+extern "C" size_t smplk_backward_scratch_bytes(const smplk_model* model, int32_t batch) {
+  if (!model || batch < 1) return 0;
+  return bwd_layout(model, batch).total;
+}
+
+extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_args* a) {
+  if (!model || !a) return fail(SMPLK_E_ARG, "null argument");
+  const ModelDev& d = model->d;
+  if (a->batch < 1 || !a->pose) return fail(SMPLK_E_ARG, "batch and pose are required");
+  if (!(a->flags & SMPLK_FLAG_SAVE_FOR_BACKWARD))
+    return fail(SMPLK_E_ARG, "backward needs the workspace of a forward run with SMPLK_FLAG_SAVE_FOR_BACKWARD");
+  if (a->betas && a->betas_batch != 1 && a->betas_batch != a->batch)
+    return fail(SMPLK_E_SHAPE, "betas_batch must be 1 or batch");
+  const WsLayout w = ws_layout(d, a->batch, a->flags);
+  if (!a->workspace || a->workspace_bytes < w.total)
+    return fail(SMPLK_E_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total, a->workspace_bytes);
+  const BwdLayout L = bwd_layout(model, a->batch);
+  if (!a->scratch || a->scratch_bytes < L.total)
+    return fail(SMPLK_E_WORKSPACE, "scratch too small: need %zu bytes, got %zu", L.total, a->scratch_bytes);
+  if ((reinterpret_cast<uintptr_t>(a->scratch) & 255) || (reinterpret_cast<uintptr_t>(a->workspace) & 255))
+    return fail(SMPLK_E_WORKSPACE, "workspace and scratch must be 256-byte aligned");
+  CUDA_TRY(cudaSetDevice(model->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(a->stream);
+  const int B = a->batch;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
+  const float* A = reinterpret_cast<const float*>(ws + w.off_A);
+  const float* v_posed = reinterpret_cast<const float*>(ws + w.off_vposed);
+  uint8_t* sc = reinterpret_cast<uint8_t*>(a->scratch);
+  float* dverts_eff = reinterpret_cast<float*>(sc + L.off_dverts);
+  float* dA = reinterpret_cast<float*>(sc + L.off_dA);
+  float* dtr = reinterpret_cast<float*>(sc + L.off_dtr);
+  float* dvp_hi = reinterpret_cast<float*>(sc + L.off_dvp_hi);
+  float* dvp_lo = reinterpret_cast<float*>(sc + L.off_dvp_lo);
+  float* dfeat = reinterpret_cast<float*>(sc + L.off_dfeat);
+  const int joints_ld = 3 * (d.J + d.E);
+
+  // ---- effective vertex gradient (vertex picks and posed-vertex regressors fold into it)
+  const bool scatter = (a->d_joints && d.E > 0) || (a->d_joints_regressed && d.R > 0);
+  const float* dverts = a->d_verts;
+  if (scatter) {
+    const size_t bytes = (size_t)B * d.V * 3 * sizeof(float);
+    if (a->d_verts) CUDA_TRY(cudaMemcpyAsync(dverts_eff, a->d_verts, bytes, cudaMemcpyDeviceToDevice, st));
+    else CUDA_TRY(cudaMemsetAsync(dverts_eff, 0, bytes, st));
+    const int work = std::max(d.E, a->d_joints_regressed ? 1024 : 0);
+    dim3 grid((work + 127) / 128, B);
+    scatter_joint_grads_kernel<<<grid, 128, 0, st>>>(d, B, (d.E > 0) ? a->d_joints : nullptr, joints_ld,
+                                                     (d.R > 0) ? a->d_joints_regressed : nullptr,
+                                                     dverts_eff);
+    LAUNCH_CHECK("scatter_joint_grads_kernel");
+    dverts = dverts_eff;
+  }
+
+  const bool have_dv = dverts != nullptr;
+  if (have_dv) {
+    DAArgs da;
+    da.B = B; da.dverts = dverts;
+    da.vsrc = d.lbs_only ? d.bias : v_posed;
+    da.vsrc_stride = d.lbs_only ? 0 : (size_t)d.Npad;
+    da.dA = dA; da.dtr = dtr;
+    dA_kernel<<<B, kDAThreads, 0, st>>>(d, da);
+    LAUNCH_CHECK("dA_kernel");
+  } else {
+    CUDA_TRY(cudaMemsetAsync(dA, 0, (size_t)B * d.J * 12 * sizeof(float), st));
+    CUDA_TRY(cudaMemsetAsync(dtr, 0, (size_t)B * 3 * sizeof(float), st));
+  }
+
+  const bool blend_bwd = have_dv && !d.lbs_only && (a->d_pose || a->d_betas || a->d_hand_pca_l || a->d_hand_pca_r);
+  if (blend_bwd) {
+    if (!model->has_tma) return fail(SMPLK_E_DEVICE, "tcgen05 path unavailable");
+    SkinBwdArgs sb;
+    sb.B = B; sb.dverts = dverts; sb.A = A; sb.dvp_hi = dvp_hi; sb.dvp_lo = dvp_lo;
+    const int tiles = (d.V + kSkinTileVerts - 1) / kSkinTileVerts;
+    int bpb = 16;
+    while (bpb > 1 && (long)tiles * ((B + bpb - 1) / bpb) < 4L * 4 * model->num_sms) bpb >>= 1;
+    sb.bodies_per_block = bpb;
+    dim3 grid(tiles, (B + bpb - 1) / bpb);
+    const size_t smem = (size_t)(3 * kSkinTileVerts * 3 + d.J * 12) * sizeof(float);
+    if (d.ell_k <= 4) skin_backward_kernel<true><<<grid, kSkinThreads, smem, st>>>(d, sb);
+    else skin_backward_kernel<false><<<grid, kSkinThreads, smem, st>>>(d, sb);
+    LAUNCH_CHECK("skin_backward_kernel");
+
+    CUtensorMap tm_ahi, tm_alo, tm_out;
+    if (int r = make_tmap_2d(model, &tm_ahi, dvp_hi, d.Npad, B, kBlendBK, kBlendBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return r;
+    if (int r = make_tmap_2d(model, &tm_alo, dvp_lo, d.Npad, B, kBlendBK, kBlendBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return r;
+    if (int r = make_tmap_2d(model, &tm_out, dfeat, d.Kpad, (uint64_t)L.splits * L.mpad, kEpiCols, kBlendBM,
+                             CU_TENSOR_MAP_L2_PROMOTION_NONE)) return r;
+    BlendGemmArgs ga;
+    ga.num_m_blocks = L.m_blocks; ga.num_n_blocks = L.n_blocks; ga.num_k_blocks = L.k_blocks;
+    ga.num_splits = L.splits; ga.k_blocks_per_split = L.kbps; ga.out_rows_per_split = L.mpad;
+    ga.bias = nullptr;
+    const int tiles_g = L.m_blocks * L.n_blocks * L.splits;
+    blend_tcgen05_kernel<<<std::min(tiles_g, model->num_sms), kGemmThreads, kGemmSmemAlloc, st>>>(
+        tm_ahi, tm_alo, model->tmap_pdkn_hi, model->tmap_pdkn_lo, tm_out, ga);
+    LAUNCH_CHECK("blend_tcgen05_kernel(backward)");
+  }
+
+  PoseBwdArgs pb;
+  pb.B = B; pb.betas = a->betas; pb.betas_B = a->betas ? a->betas_batch : 1;
+  pb.pose = a->pose; pb.pca_l = a->hand_pca_l; pb.pca_r = a->hand_pca_r;
+  pb.add_mean = (a->flags & SMPLK_FLAG_ADD_POSE_MEAN) ? 1 : 0;
+  pb.dA = dA; pb.d_joints = a->d_joints; pb.joints_ld = joints_ld;
+  pb.d_feat = blend_bwd ? dfeat : nullptr;
+  pb.feat_splits = L.splits; pb.feat_split_stride = (size_t)L.mpad * d.Kpad;
+  pb.dtr_verts = dtr;
+  pb.d_betas = d.NB > 0 ? a->d_betas : nullptr;
+  pb.d_pose = a->d_pose; pb.d_pca_l = a->d_hand_pca_l; pb.d_pca_r = a->d_hand_pca_r;
+  pb.d_transl = a->d_transl;
+  if (pb.d_betas && pb.betas_B == 1)
+    CUDA_TRY(cudaMemsetAsync(a->d_betas, 0, (size_t)d.NB * sizeof(float), st));
+  const int blocks = (B + kPoseWarps - 1) / kPoseWarps;
+  const size_t smem = (size_t)kPoseWarps * d.J * 18 * sizeof(float);
+  if (d.J <= 32) pose_backward_kernel<1><<<blocks, kPoseWarps * 32, smem, st>>>(d, pb);
+  else pose_backward_kernel<2><<<blocks, kPoseWarps * 32, smem, st>>>(d, pb);
+  LAUNCH_CHECK("pose_backward_kernel");
+  return 0;
+}

@@ -1,0 +1,52 @@
+// Shared definitions: packed device-side model constants and small helpers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace smplk {
+
+constexpr int kMaxJoints = 64;     // two joints per lane in the warp-per-body kernels
+constexpr int kBlendBM = 128;      // bodies per blend-GEMM tile (UMMA M)
+constexpr int kBlendBN = 256;      // vertex coordinates per blend-GEMM tile (UMMA N)
+constexpr int kBlendBK = 32;       // tf32 elements per k-block = one 128-byte swizzle row
+constexpr int kSkinTileVerts = 1024;
+
+// Device pointers + sizes of one packed body model. Passed by value to kernels.
+struct ModelDev {
+  int V, J, NB, P;       // vertices, joints, betas, pose features 9(J-1)
+  int K, Kpad;           // K = P + NB blend-GEMM depth; Kpad = round_up(K, 32)
+  int N, Npad;           // N = 3V; Npad = round_up(N, 256)
+  int E, R, C;           // extra vertex picks, posed-vertex regressors, hand PCA comps
+  int max_depth;
+  int ell_k;             // LBS weights per vertex kept by the packer
+  int lbs_only;
+  const float* bias;          // [Npad] v_template flattened (zero padded)
+  const float* pd_nk_hi;      // [Npad][Kpad] tf32-rounded (posedirs|shapedirs)^T, K contiguous
+  const float* pd_nk_lo;      // [Npad][Kpad] residual  x - hi
+  const float* pd_kn;         // [Kpad][Npad] exact fp32, N contiguous
+  const float* pd_kn_hi;      // [Kpad][Npad] tf32-rounded (backward GEMM operand)
+  const float* pd_kn_lo;      // [Kpad][Npad] residual
+  const float* J_template;    // [J][3]
+  const float* J_shapedirs;   // [J][3][NB]
+  const int* parents;         // [J]
+  const int* depth;           // [J]
+  const uint32_t* skin_idx4;  // [V] four u8 joint ids (ell_k <= 4)
+  const float4* skin_w4;      // [V] four weights      (ell_k <= 4)
+  const int* ell_idx;         // [ell_k][V]
+  const float* ell_w;         // [ell_k][V]
+  const int* csc_ptr;         // [J+1] joint -> (vertex, weight) lists for the backward
+  const int* csc_vert;        // [nnz]
+  const float* csc_w;         // [nnz]
+  const float* comp_l;        // [C][45]
+  const float* comp_r;        // [C][45]
+  const float* pose_mean;     // [3J]
+  const int* extra_vids;      // [E]
+  const int* reg_ptr;         // [R+1] CSR of regressor_posed
+  const int* reg_col;         // [nnzR]
+  const float* reg_val;       // [nnzR]
+};
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace smplk

@@ -1,0 +1,655 @@
+// C ABI of the smplk library (see include/smplk.h): model packing, forward / backward
+// orchestration, error handling.  Host code only glues kernels together; all math on the hot
+// path runs in the CUDA kernels of pose_kernels.cuh, blend_gemm.cuh, skinning.cuh, backward.cuh.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/smplk.h"
+#include "backward.cuh"
+#include "blend_gemm.cuh"
+#include "common.cuh"
+#include "pose_kernels.cuh"
+#include "skinning.cuh"
+
+using namespace smplk;
+
+// ------------------------------------------------------------------------------------------
+// errors / bookkeeping
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail((int)e_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                             \
+  } while (0)
+
+#define LAUNCH_CHECK(name)                                                               \
+  do {                                                                                   \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                  \
+    cudaError_t e_ = cudaGetLastError();                                                 \
+    if (e_ != cudaSuccess)                                                               \
+      return fail((int)e_, "launch of %s failed: %s", name, cudaGetErrorString(e_));     \
+  } while (0)
+
+extern "C" const char* smplk_last_error_string(void) { return g_err; }
+extern "C" int smplk_version(void) { return SMPLK_VERSION; }
+extern "C" uint64_t smplk_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct smplk_model {
+  ModelDev d;
+  int device;
+  int num_sms;
+  int cc_major;
+  std::vector<void*> allocs;
+  EncodeTiledFn encode;
+  bool has_tma;
+  CUtensorMap tmap_pd_hi, tmap_pd_lo;      // forward: B operand rows = vertex coords
+  CUtensorMap tmap_pdkn_hi, tmap_pdkn_lo;  // backward: B operand rows = blend features
+  // host staging for smplk_forward_host
+  void* stage_dev;
+  size_t stage_bytes;
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static float tf32_rn_host(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;
+  u += 0xfffu + ((u >> 13) & 1u);
+  u &= ~0x1fffu;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
+template <typename T>
+static int upload(smplk_model* mdl, const std::vector<T>& h, const T** out) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(h.size() * sizeof(T), 16);
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  mdl->allocs.push_back(p);
+  if (!h.empty()) CUDA_TRY(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = reinterpret_cast<const T*>(p);
+  return 0;
+}
+
+static int make_tmap_2d(const smplk_model* mdl, CUtensorMap* map, const void* ptr, uint64_t inner,
+                        uint64_t outer, uint32_t box_inner, uint32_t box_outer,
+                        CUtensorMapL2promotion promo) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * sizeof(float)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = mdl->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SMPLK_E_DEVICE, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return 0;
+}
+
+extern "C" int smplk_model_destroy(smplk_model* model) {
+  if (!model) return 0;
+  cudaSetDevice(model->device);
+  for (void* p : model->allocs) cudaFree(p);
+  if (model->stage_dev) cudaFree(model->stage_dev);
+  delete model;
+  return 0;
+}
+
+static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
+  ModelDev& d = mdl->d;
+  const int V = desc->num_verts, J = desc->num_joints, NB = desc->num_betas;
+  const bool lbs_only = desc->posedirs == nullptr;
+  d.V = V; d.J = J; d.NB = lbs_only ? 0 : NB;
+  d.P = 9 * (J - 1);
+  d.K = lbs_only ? 0 : d.P + d.NB;
+  d.Kpad = lbs_only ? 0 : round_up(d.K, kBlendBK);
+  d.N = 3 * V;
+  d.Npad = round_up(d.N, kBlendBN);
+  d.E = desc->extra_vertex_ids ? desc->num_extra_verts : 0;
+  d.R = desc->regressor_posed ? desc->num_regressors : 0;
+  d.C = (desc->hand_comp_l && desc->hand_comp_r) ? desc->num_pca : 0;
+  d.lbs_only = lbs_only ? 1 : 0;
+
+  // ---- tree tables
+  std::vector<int> parents(J), depth(J, 0);
+  int max_depth = 0;
+  for (int j = 0; j < J; ++j) {
+    parents[j] = desc->parents[j];
+    if (j == 0) {
+      if (parents[0] >= 0) return fail(SMPLK_E_ARG, "parents[0] must be -1");
+    } else {
+      if (parents[j] < 0 || parents[j] >= j)
+        return fail(SMPLK_E_ARG, "parents[%d]=%d must satisfy 0 <= parent < joint", j, parents[j]);
+      depth[j] = depth[parents[j]] + 1;
+      max_depth = std::max(max_depth, depth[j]);
+    }
+  }
+  d.max_depth = max_depth;
+  if (int r = upload(mdl, parents, &d.parents)) return r;
+  if (int r = upload(mdl, depth, &d.depth)) return r;
+
+  // ---- template / bias
+  std::vector<float> bias(d.Npad, 0.f);
+  for (int n = 0; n < d.N; ++n) bias[n] = (float)desc->v_template[n];
+  if (int r = upload(mdl, bias, &d.bias)) return r;
+
+  // ---- rest joints: J = J_template + J_shapedirs . beta  (== J_regressor (v_template + S beta))
+  std::vector<float> Jt(J * 3, 0.f), Js((size_t)J * 3 * std::max(d.NB, 1), 0.f);
+  if (lbs_only) {
+    if (!desc->joints_fixed) return fail(SMPLK_E_ARG, "rigged-mesh model needs joints_fixed");
+    for (int i = 0; i < J * 3; ++i) Jt[i] = (float)desc->joints_fixed[i];
+  } else {
+    if (!desc->J_regressor || !desc->shapedirs)
+      return fail(SMPLK_E_ARG, "blendshape model needs J_regressor and shapedirs");
+    std::vector<double> acc(3 + 3 * NB);
+    for (int j = 0; j < J; ++j) {
+      std::fill(acc.begin(), acc.end(), 0.0);
+      const double* row = desc->J_regressor + (size_t)j * V;
+      for (int v = 0; v < V; ++v) {
+        const double w = row[v];
+        if (w == 0.0) continue;
+        for (int a = 0; a < 3; ++a) {
+          acc[a] += w * desc->v_template[3 * v + a];
+          const double* sd = desc->shapedirs + ((size_t)3 * v + a) * NB;
+          for (int i = 0; i < NB; ++i) acc[3 + a * NB + i] += w * sd[i];
+        }
+      }
+      for (int a = 0; a < 3; ++a) {
+        Jt[3 * j + a] = (float)acc[a];
+        for (int i = 0; i < NB; ++i) Js[((size_t)3 * j + a) * NB + i] = (float)acc[3 + a * NB + i];
+      }
+    }
+  }
+  if (int r = upload(mdl, Jt, &d.J_template)) return r;
+  if (int r = upload(mdl, Js, &d.J_shapedirs)) return r;
+
+  // ---- blend operand: PD[n][k] = posedirs | shapedirs, as tf32 hi/lo (N x K) and exact (K x N)
+  if (!lbs_only) {
+    const size_t nk = (size_t)d.Npad * d.Kpad;
+    std::vector<float> hi(nk, 0.f), lo(nk, 0.f), kn(nk, 0.f), knh(nk, 0.f), knl(nk, 0.f);
+    for (int n = 0; n < d.N; ++n) {
+      const double* pdrow = desc->posedirs + (size_t)n * d.P;
+      const double* sdrow = desc->shapedirs + (size_t)n * NB;
+      for (int k = 0; k < d.K; ++k) {
+        const float x = (float)(k < d.P ? pdrow[k] : sdrow[k - d.P]);
+        const float h = tf32_rn_host(x);
+        hi[(size_t)n * d.Kpad + k] = h;
+        lo[(size_t)n * d.Kpad + k] = x - h;
+        kn[(size_t)k * d.Npad + n] = x;
+        knh[(size_t)k * d.Npad + n] = h;
+        knl[(size_t)k * d.Npad + n] = x - h;
+      }
+    }
+    if (int r = upload(mdl, hi, &d.pd_nk_hi)) return r;
+    if (int r = upload(mdl, lo, &d.pd_nk_lo)) return r;
+    if (int r = upload(mdl, kn, &d.pd_kn)) return r;
+    if (int r = upload(mdl, knh, &d.pd_kn_hi)) return r;
+    if (int r = upload(mdl, knl, &d.pd_kn_lo)) return r;
+  } else {
+    d.pd_nk_hi = d.pd_nk_lo = d.pd_kn = d.pd_kn_hi = d.pd_kn_lo = nullptr;
+  }
+
+  // ---- LBS weights: ELL (k-major) + packed 4-wide form + CSC for the backward
+  {
+    int ell_k = 1;
+    std::vector<std::vector<std::pair<float, int>>> rows(V);
+    for (int v = 0; v < V; ++v) {
+      for (int j = 0; j < J; ++j) {
+        const float w = (float)desc->weights[(size_t)v * J + j];
+        if (w != 0.f) rows[v].push_back({w, j});
+      }
+      std::sort(rows[v].begin(), rows[v].end(),
+                [](const std::pair<float, int>& a, const std::pair<float, int>& b) {
+                  return a.first > b.first || (a.first == b.first && a.second < b.second);
+                });
+      ell_k = std::max<int>(ell_k, (int)rows[v].size());
+    }
+    d.ell_k = ell_k;
+    std::vector<int> eidx((size_t)ell_k * V, 0);
+    std::vector<float> ew((size_t)ell_k * V, 0.f);
+    std::vector<uint32_t> idx4(V, 0);
+    std::vector<float4> w4(V, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<int> cnt(J + 1, 0);
+    for (int v = 0; v < V; ++v) {
+      float wq[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t packed = 0;
+      for (size_t k = 0; k < rows[v].size(); ++k) {
+        eidx[k * V + v] = rows[v][k].second;
+        ew[k * V + v] = rows[v][k].first;
+        cnt[rows[v][k].second + 1]++;
+        if (k < 4) {
+          wq[k] = rows[v][k].first;
+          packed |= (uint32_t)rows[v][k].second << (8 * k);
+        }
+      }
+      idx4[v] = packed;
+      w4[v] = make_float4(wq[0], wq[1], wq[2], wq[3]);
+    }
+    for (int j = 0; j < J; ++j) cnt[j + 1] += cnt[j];
+    std::vector<int> cptr(cnt), cvert(cnt[J]);
+    std::vector<float> cw(cnt[J]);
+    std::vector<int> fillp(cnt.begin(), cnt.end() - 1);
+    for (int v = 0; v < V; ++v)
+      for (auto& e : rows[v]) {
+        const int pos = fillp[e.second]++;
+        cvert[pos] = v;
+        cw[pos] = e.first;
+      }
+    if (int r = upload(mdl, eidx, &d.ell_idx)) return r;
+    if (int r = upload(mdl, ew, &d.ell_w)) return r;
+    if (int r = upload(mdl, idx4, &d.skin_idx4)) return r;
+    if (int r = upload(mdl, w4, &d.skin_w4)) return r;
+    if (int r = upload(mdl, cptr, &d.csc_ptr)) return r;
+    if (int r = upload(mdl, cvert, &d.csc_vert)) return r;
+    if (int r = upload(mdl, cw, &d.csc_w)) return r;
+  }
+
+  // ---- hand PCA, pose mean
+  {
+    std::vector<float> cl, cr, pm;
+    if (d.C > 0) {
+      if (J < 31) return fail(SMPLK_E_SHAPE, "hand PCA needs a skeleton with 30 hand joints");
+      cl.resize((size_t)d.C * 45);
+      cr.resize((size_t)d.C * 45);
+      for (size_t i = 0; i < cl.size(); ++i) {
+        cl[i] = (float)desc->hand_comp_l[i];
+        cr[i] = (float)desc->hand_comp_r[i];
+      }
+    }
+    if (desc->pose_mean) {
+      pm.resize(3 * J);
+      for (int i = 0; i < 3 * J; ++i) pm[i] = (float)desc->pose_mean[i];
+    }
+    if (int r = upload(mdl, cl, &d.comp_l)) return r;
+    if (int r = upload(mdl, cr, &d.comp_r)) return r;
+    if (int r = upload(mdl, pm, &d.pose_mean)) return r;
+    if (!desc->pose_mean) d.pose_mean = nullptr;
+  }
+
+  // ---- vertex picks and posed-vertex regressors
+  {
+    std::vector<int> ev(d.E);
+    for (int e = 0; e < d.E; ++e) {
+      ev[e] = desc->extra_vertex_ids[e];
+      if (ev[e] < 0 || ev[e] >= V) return fail(SMPLK_E_ARG, "extra_vertex_ids[%d] out of range", e);
+    }
+    if (int r = upload(mdl, ev, &d.extra_vids)) return r;
+    std::vector<int> rptr(d.R + 1, 0), rcol;
+    std::vector<float> rval;
+    for (int r = 0; r < d.R; ++r) {
+      for (int v = 0; v < V; ++v) {
+        const double w = desc->regressor_posed[(size_t)r * V + v];
+        if (w != 0.0) {
+          rcol.push_back(v);
+          rval.push_back((float)w);
+        }
+      }
+      rptr[r + 1] = (int)rcol.size();
+    }
+    if (int r = upload(mdl, rptr, &d.reg_ptr)) return r;
+    if (int r = upload(mdl, rcol, &d.reg_col)) return r;
+    if (int r = upload(mdl, rval, &d.reg_val)) return r;
+  }
+
+  // ---- TMA descriptors of the constant GEMM operand
+  mdl->has_tma = false;
+  if (!lbs_only && mdl->cc_major == 10) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || fn == nullptr)
+      return fail(SMPLK_E_DEVICE, "cuTensorMapEncodeTiled not available from the driver");
+    mdl->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    if (int r = make_tmap_2d(mdl, &mdl->tmap_pd_hi, d.pd_nk_hi, d.Kpad, d.Npad, kBlendBK, kBlendBN,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return r;
+    if (int r = make_tmap_2d(mdl, &mdl->tmap_pd_lo, d.pd_nk_lo, d.Kpad, d.Npad, kBlendBK, kBlendBN,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return r;
+    if (int r = make_tmap_2d(mdl, &mdl->tmap_pdkn_hi, d.pd_kn_hi, d.Npad, d.Kpad, kBlendBK, kBlendBN,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return r;
+    if (int r = make_tmap_2d(mdl, &mdl->tmap_pdkn_lo, d.pd_kn_lo, d.Npad, d.Kpad, kBlendBK, kBlendBN,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return r;
+    CUDA_TRY(cudaFuncSetAttribute(blend_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kGemmSmemAlloc));
+    mdl->has_tma = true;
+  }
+  return 0;
+}
+
+extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smplk_model** out) {
+  if (!desc || !out) return fail(SMPLK_E_ARG, "null argument");
+  *out = nullptr;
+  if (desc->num_joints < 1 || desc->num_joints > kMaxJoints)
+    return fail(SMPLK_E_SHAPE, "num_joints=%d unsupported (1..%d)", desc->num_joints, kMaxJoints);
+  if (desc->num_verts < 1) return fail(SMPLK_E_SHAPE, "num_verts must be positive");
+  if (!desc->v_template || !desc->weights || !desc->parents)
+    return fail(SMPLK_E_ARG, "v_template, weights and parents are required");
+  if (desc->posedirs && (desc->num_betas < 0 || desc->num_betas > 300))
+    return fail(SMPLK_E_SHAPE, "num_betas=%d unsupported", desc->num_betas);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(SMPLK_E_DEVICE, "no CUDA device available (%s); smplk has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(SMPLK_E_DEVICE, "device %d out of range", device);
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  smplk_model* mdl = new (std::nothrow) smplk_model();
+  if (!mdl) return fail(SMPLK_E_ARG, "out of host memory");
+  memset(&mdl->d, 0, sizeof(mdl->d));
+  mdl->device = device;
+  mdl->num_sms = prop.multiProcessorCount;
+  mdl->cc_major = prop.major;
+  mdl->stage_dev = nullptr;
+  mdl->stage_bytes = 0;
+  mdl->encode = nullptr;
+  if (prop.major != 10) {
+    delete mdl;
+    return fail(SMPLK_E_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                device, prop.major, prop.minor);
+  }
+  int r = build_model(desc, mdl);
+  if (r != 0) {
+    smplk_model_destroy(mdl);
+    return r;
+  }
+  *out = mdl;
+  return 0;
+}
+
+extern "C" int smplk_model_get_info(const smplk_model* model, smplk_model_info* info) {
+  if (!model || !info) return fail(SMPLK_E_ARG, "null argument");
+  const ModelDev& d = model->d;
+  info->num_verts = d.V; info->num_joints = d.J; info->num_betas = d.NB;
+  info->num_pose_feats = d.P; info->num_extra_verts = d.E; info->num_regressors = d.R;
+  info->num_pca = d.C; info->max_weights_per_vertex = d.ell_k; info->lbs_only = d.lbs_only;
+  info->device = model->device; info->has_tcgen05_path = model->has_tma ? 1 : 0;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// workspace layout
+// ------------------------------------------------------------------------------------------
+constexpr int kDefaultChunk = 8192;
+
+struct WsLayout {
+  int chunk;
+  size_t off_fhi, off_flo, off_A, off_vposed, total;
+};
+
+static WsLayout ws_layout(const ModelDev& d, int batch, uint32_t flags) {
+  WsLayout w;
+  w.chunk = (flags & SMPLK_FLAG_SAVE_FOR_BACKWARD) ? batch : std::min(batch, kDefaultChunk);
+  if (w.chunk < 1) w.chunk = 1;
+  const size_t rows_pad = (size_t)round_up(w.chunk, kBlendBM);
+  size_t off = 0;
+  w.off_fhi = off; off += align_up(rows_pad * d.Kpad * sizeof(float), 1024);
+  w.off_flo = off; off += align_up(rows_pad * d.Kpad * sizeof(float), 1024);
+  w.off_A = off;   off += align_up((size_t)w.chunk * d.J * 12 * sizeof(float), 1024);
+  w.off_vposed = off;
+  if (!d.lbs_only) off += align_up((size_t)w.chunk * d.Npad * sizeof(float), 1024);
+  w.total = off;
+  return w;
+}
+
+extern "C" size_t smplk_workspace_bytes(const smplk_model* model, int32_t batch, uint32_t flags) {
+  if (!model || batch < 1) return 0;
+  return ws_layout(model->d, batch, flags).total;
+}
+
+extern "C" int smplk_workspace_layout(const smplk_model* model, int32_t batch, uint32_t flags,
+                                      size_t offsets[4], int32_t* chunk) {
+  if (!model || !offsets || batch < 1) return fail(SMPLK_E_ARG, "bad argument");
+  const WsLayout w = ws_layout(model->d, batch, flags);
+  offsets[0] = w.off_fhi; offsets[1] = w.off_flo; offsets[2] = w.off_A; offsets[3] = w.off_vposed;
+  if (chunk) *chunk = w.chunk;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+static int launch_pose_forward(const smplk_model* mdl, const PoseFwdArgs& pa, cudaStream_t st) {
+  const ModelDev& d = mdl->d;
+  const int blocks = (pa.B + kPoseWarps - 1) / kPoseWarps;
+  const size_t smem = (size_t)kPoseWarps * std::max(d.Kpad, 32) * sizeof(float);
+  if (d.J <= 32)
+    pose_forward_kernel<1><<<blocks, kPoseWarps * 32, smem, st>>>(d, pa);
+  else
+    pose_forward_kernel<2><<<blocks, kPoseWarps * 32, smem, st>>>(d, pa);
+  LAUNCH_CHECK("pose_forward_kernel");
+  return 0;
+}
+
+static int launch_blend(const smplk_model* mdl, int rows, float* F_hi, float* F_lo, float* v_posed,
+                        uint32_t flags, cudaStream_t st) {
+  const ModelDev& d = mdl->d;
+  bool use_tc = rows >= 32;
+  if (flags & SMPLK_FLAG_BLEND_SIMT) use_tc = false;
+  if (flags & SMPLK_FLAG_BLEND_TCGEN05) use_tc = true;
+  if (use_tc) {
+    if (!mdl->has_tma) return fail(SMPLK_E_DEVICE, "tcgen05 blend path unavailable on this device");
+    CUtensorMap tm_fhi, tm_flo, tm_out;
+    if (int r = make_tmap_2d(mdl, &tm_fhi, F_hi, d.Kpad, rows, kBlendBK, kBlendBM,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return r;
+    if (int r = make_tmap_2d(mdl, &tm_flo, F_lo, d.Kpad, rows, kBlendBK, kBlendBM,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return r;
+    if (int r = make_tmap_2d(mdl, &tm_out, v_posed, d.Npad, rows, kEpiCols, kBlendBM,
+                             CU_TENSOR_MAP_L2_PROMOTION_NONE)) return r;
+    BlendGemmArgs ga;
+    ga.num_m_blocks = (rows + kBlendBM - 1) / kBlendBM;
+    ga.num_n_blocks = d.Npad / kBlendBN;
+    ga.num_k_blocks = d.Kpad / kBlendBK;
+    ga.num_splits = 1;
+    ga.k_blocks_per_split = ga.num_k_blocks;
+    ga.out_rows_per_split = 0;
+    ga.bias = d.bias;
+    const int tiles = ga.num_m_blocks * ga.num_n_blocks;
+    const int grid = std::min(tiles, mdl->num_sms);
+    blend_tcgen05_kernel<<<grid, kGemmThreads, kGemmSmemAlloc, st>>>(
+        tm_fhi, tm_flo, mdl->tmap_pd_hi, mdl->tmap_pd_lo, tm_out, ga);
+    LAUNCH_CHECK("blend_tcgen05_kernel");
+  } else {
+    BlendSimtArgs sa;
+    sa.M = rows; sa.F_hi = F_hi; sa.F_lo = F_lo; sa.out = v_posed;
+    dim3 grid((d.Npad / 4 + kSimtThreads - 1) / kSimtThreads, (rows + kSimtBodies - 1) / kSimtBodies);
+    const size_t smem = (size_t)d.Kpad * kSimtBodies * sizeof(float);
+    blend_simt_kernel<<<grid, kSimtThreads, smem, st>>>(d, sa);
+    LAUNCH_CHECK("blend_simt_kernel");
+  }
+  return 0;
+}
+
+static int launch_skin(const smplk_model* mdl, int rows, const float* vsrc, size_t vstride,
+                       const float* A, const float* transl, float* out, cudaStream_t st) {
+  const ModelDev& d = mdl->d;
+  SkinArgs sa;
+  sa.B = rows;
+  const int tiles = (d.V + kSkinTileVerts - 1) / kSkinTileVerts;
+  // enough blocks for >= ~4 waves of 4 CTAs/SM, at most 16 bodies per block
+  int bpb = 16;
+  while (bpb > 1 && (long)tiles * ((rows + bpb - 1) / bpb) < 4L * 4 * mdl->num_sms) bpb >>= 1;
+  sa.bodies_per_block = bpb;
+  sa.vsrc = vsrc; sa.vsrc_stride = vstride; sa.A = A; sa.transl = transl; sa.out = out;
+  dim3 grid(tiles, (rows + bpb - 1) / bpb);
+  const size_t smem = (size_t)(2 * kSkinTileVerts * 3 + 2 * ((d.J * 12 + 3) & ~3)) * sizeof(float);
+  if (d.ell_k <= 4)
+    skin_kernel<true><<<grid, kSkinThreads, smem, st>>>(d, sa);
+  else
+    skin_kernel<false><<<grid, kSkinThreads, smem, st>>>(d, sa);
+  LAUNCH_CHECK("skin_kernel");
+  return 0;
+}
+
+extern "C" int smplk_forward(const smplk_model* model, const smplk_forward_args* a) {
+  if (!model || !a) return fail(SMPLK_E_ARG, "null argument");
+  const ModelDev& d = model->d;
+  if (a->batch < 1) return fail(SMPLK_E_ARG, "batch must be >= 1");
+  if (!a->pose) return fail(SMPLK_E_ARG, "pose is required");
+  if (a->betas && a->betas_batch != 1 && a->betas_batch != a->batch)
+    return fail(SMPLK_E_SHAPE, "betas_batch must be 1 or batch (got %d for batch %d)",
+                a->betas_batch, a->batch);
+  if ((a->hand_pca_l || a->hand_pca_r) && d.C == 0)
+    return fail(SMPLK_E_ARG, "hand PCA coefficients given but the model has no PCA components");
+  if ((a->joints && d.E > 0 && !a->verts) || (a->joints_regressed && !a->verts))
+    return fail(SMPLK_E_ARG, "vertex picks / regressed joints need the verts output buffer");
+  if (a->joints_regressed && d.R == 0)
+    return fail(SMPLK_E_ARG, "joints_regressed requested but the model has no regressor_posed");
+  const WsLayout w = ws_layout(d, a->batch, a->flags);
+  if (!a->workspace || a->workspace_bytes < w.total)
+    return fail(SMPLK_E_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
+                a->workspace_bytes);
+  if (reinterpret_cast<uintptr_t>(a->workspace) & 255)
+    return fail(SMPLK_E_WORKSPACE, "workspace must be 256-byte aligned");
+  int cur = -1;
+  CUDA_TRY(cudaGetDevice(&cur));
+  if (cur != model->device) CUDA_TRY(cudaSetDevice(model->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(a->stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
+  float* F_hi = reinterpret_cast<float*>(ws + w.off_fhi);
+  float* F_lo = reinterpret_cast<float*>(ws + w.off_flo);
+  float* A = reinterpret_cast<float*>(ws + w.off_A);
+  float* v_posed = reinterpret_cast<float*>(ws + w.off_vposed);
+  const int joints_ld = 3 * (d.J + d.E);
+
+  for (int c0 = 0; c0 < a->batch; c0 += w.chunk) {
+    const int rows = std::min(w.chunk, a->batch - c0);
+    PoseFwdArgs pa;
+    pa.B = rows;
+    pa.betas = a->betas ? (a->betas_batch == 1 ? a->betas : a->betas + (size_t)c0 * d.NB) : nullptr;
+    pa.betas_B = a->betas_batch == 1 ? 1 : rows;
+    pa.pose = a->pose + (size_t)c0 * 3 * d.J;
+    pa.pca_l = a->hand_pca_l ? a->hand_pca_l + (size_t)c0 * d.C : nullptr;
+    pa.pca_r = a->hand_pca_r ? a->hand_pca_r + (size_t)c0 * d.C : nullptr;
+    pa.add_mean = (a->flags & SMPLK_FLAG_ADD_POSE_MEAN) ? 1 : 0;
+    pa.transl = a->transl ? a->transl + (size_t)c0 * 3 : nullptr;
+    pa.F_hi = d.lbs_only ? nullptr : F_hi;
+    pa.F_lo = d.lbs_only ? nullptr : F_lo;
+    pa.A = A;
+    pa.joints = a->joints ? a->joints + (size_t)c0 * joints_ld : nullptr;
+    pa.joints_ld = joints_ld;
+    pa.full_pose = a->full_pose ? a->full_pose + (size_t)c0 * 3 * d.J : nullptr;
+    if (int r = launch_pose_forward(model, pa, st)) return r;
+    if (!d.lbs_only && (a->verts || (a->flags & SMPLK_FLAG_SAVE_FOR_BACKWARD))) {
+      if (int r = launch_blend(model, rows, F_hi, F_lo, v_posed, a->flags, st)) return r;
+    }
+    if (a->verts) {
+      float* vout = a->verts + (size_t)c0 * d.V * 3;
+      if (int r = launch_skin(model, rows, d.lbs_only ? d.bias : v_posed,
+                              d.lbs_only ? 0 : (size_t)d.Npad, A, pa.transl, vout, st)) return r;
+      if (a->joints && d.E > 0) {
+        const int n = rows * d.E;
+        gather_extra_joints_kernel<<<(n + 127) / 128, 128, 0, st>>>(d, rows, vout, pa.joints, joints_ld);
+        LAUNCH_CHECK("gather_extra_joints_kernel");
+      }
+      if (a->joints_regressed) {
+        const long nthreads = (long)rows * d.R * 32;
+        regress_joints_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(
+            d, rows, vout, a->joints_regressed + (size_t)c0 * d.R * 3);
+        LAUNCH_CHECK("regress_joints_kernel");
+      }
+    }
+  }
+  return 0;
+}
+
+extern "C" int smplk_regress_joints(const smplk_model* model, int32_t batch, const float* verts,
+                                    float* out, smplk_stream stream) {
+  if (!model || !verts || !out || batch < 1) return fail(SMPLK_E_ARG, "bad argument");
+  const ModelDev& d = model->d;
+  if (d.R == 0) return fail(SMPLK_E_ARG, "model has no regressor_posed");
+  CUDA_TRY(cudaSetDevice(model->device));
+  const long nthreads = (long)batch * d.R * 32;
+  regress_joints_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0,
+                          reinterpret_cast<cudaStream_t>(stream)>>>(d, batch, verts, out);
+  LAUNCH_CHECK("regress_joints_kernel");
+  return 0;
+}
+
+extern "C" int smplk_batch_rodrigues(int32_t n, const float* axis_angle, float* rotmats, int device,
+                                     smplk_stream stream) {
+  if (n < 1 || !axis_angle || !rotmats) return fail(SMPLK_E_ARG, "bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  rodrigues_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      n, axis_angle, rotmats);
+  LAUNCH_CHECK("rodrigues_kernel");
+  return 0;
+}
+
+extern "C" int smplk_forward_host(smplk_model* model, int32_t batch, uint32_t flags,
+                                  const float* betas, int32_t betas_batch, const float* pose,
+                                  const float* transl, float* verts, float* joints,
+                                  smplk_stream stream) {
+  if (!model || !pose || batch < 1) return fail(SMPLK_E_ARG, "bad argument");
+  const ModelDev& d = model->d;
+  CUDA_TRY(cudaSetDevice(model->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  flags &= ~SMPLK_FLAG_SAVE_FOR_BACKWARD;
+  const size_t ws_bytes = smplk_workspace_bytes(model, batch, flags);
+  const size_t nb_betas = betas ? align_up((size_t)betas_batch * d.NB * 4, 256) : 0;
+  const size_t nb_pose = align_up((size_t)batch * 3 * d.J * 4, 256);
+  const size_t nb_tr = transl ? align_up((size_t)batch * 12, 256) : 0;
+  const size_t nb_verts = align_up((size_t)batch * d.V * 12, 256);
+  const size_t nb_joints = joints ? align_up((size_t)batch * (d.J + d.E) * 12, 256) : 0;
+  const size_t total = align_up(ws_bytes, 256) + nb_betas + nb_pose + nb_tr + nb_verts + nb_joints;
+  if (total > model->stage_bytes) {
+    if (model->stage_dev) CUDA_TRY(cudaFree(model->stage_dev));
+    model->stage_dev = nullptr;
+    model->stage_bytes = 0;
+    CUDA_TRY(cudaMalloc(&model->stage_dev, total));
+    model->stage_bytes = total;
+  }
+  uint8_t* p = reinterpret_cast<uint8_t*>(model->stage_dev);
+  void* ws = p; p += align_up(ws_bytes, 256);
+  float* d_betas = betas ? reinterpret_cast<float*>(p) : nullptr; p += nb_betas;
+  float* d_pose = reinterpret_cast<float*>(p); p += nb_pose;
+  float* d_tr = transl ? reinterpret_cast<float*>(p) : nullptr; p += nb_tr;
+  float* d_verts = reinterpret_cast<float*>(p); p += nb_verts;
+  float* d_joints = joints ? reinterpret_cast<float*>(p) : nullptr;
+  if (betas) CUDA_TRY(cudaMemcpyAsync(d_betas, betas, (size_t)betas_batch * d.NB * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_pose, pose, (size_t)batch * 3 * d.J * 4, cudaMemcpyHostToDevice, st));
+  if (transl) CUDA_TRY(cudaMemcpyAsync(d_tr, transl, (size_t)batch * 12, cudaMemcpyHostToDevice, st));
+  smplk_forward_args fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.batch = batch; fa.flags = flags; fa.betas = d_betas; fa.betas_batch = betas ? betas_batch : 1;
+  fa.pose = d_pose; fa.transl = d_tr; fa.verts = d_verts; fa.joints = d_joints;
+  fa.workspace = ws; fa.workspace_bytes = ws_bytes; fa.stream = stream;
+  if (int r = smplk_forward(model, &fa)) return r;
+  if (verts) CUDA_TRY(cudaMemcpyAsync(verts, d_verts, (size_t)batch * d.V * 12, cudaMemcpyDeviceToHost, st));
+  if (joints) CUDA_TRY(cudaMemcpyAsync(joints, d_joints, (size_t)batch * (d.J + d.E) * 12, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+#include "backward_host.inl"

@@ -1,0 +1,180 @@
+/* smplk.h -- C ABI of the B200-native SMPL / SMPL-H body-model path.
+ *
+ * This is the drop-in boundary for the body-model forward/backward of
+ * bokchoy-mian/3D-human-body-reconstruction.  Every entry point cites the reference interface it
+ * replaces (paths relative to the reference repo).  Plain pointers and sizes only: no torch types,
+ * no C++ types.  All `float*` data arguments of forward/backward/skin/regress are DEVICE pointers
+ * on the model's device unless the function name ends in `_host`.
+ *
+ * Error convention: every function returns 0 on success, a negative SMPLK_E_* code for argument /
+ * shape / device errors, or a positive cudaError_t value for CUDA failures.  Nothing throws across
+ * the ABI; `smplk_last_error_string()` returns a per-thread description of the last failure.
+ *
+ * Threading / streams: work is launched on the caller-supplied stream (a cudaStream_t passed as
+ * void*), with no internal synchronisation and no hidden allocation in forward/backward; a model
+ * handle is bound to one device and immutable after creation (one handle per GPU for multi-GPU).
+ */
+#ifndef SMPLK_H_
+#define SMPLK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMPLK_VERSION 1
+
+#define SMPLK_OK 0
+#define SMPLK_E_ARG (-1)       /* null / inconsistent argument */
+#define SMPLK_E_SHAPE (-2)     /* unsupported shape (e.g. J > 64) */
+#define SMPLK_E_WORKSPACE (-3) /* workspace too small or misaligned */
+#define SMPLK_E_DEVICE (-4)    /* no CUDA device / wrong device / not sm_100 */
+#define SMPLK_E_UNSUPPORTED (-5)
+
+typedef struct smplk_model smplk_model;
+typedef void* smplk_stream; /* cudaStream_t */
+
+/* Host-side description of a body model; all arrays are HOST pointers, float64 as in the official
+ * pickles (reference loads them at models/smplh_np.py:8-17, models/smpl_np.py:124-133; upstream
+ * smplx registers the same tensors as buffers).  A rigged-mesh ("LBS only") model, the
+ * RecoverModel of lib/model2video.py:12-40 / lib/mesh2smpl_model.py:131-181, has no blendshapes
+ * and FIXED rest joints: set shapedirs = posedirs = J_regressor = NULL and give `joints_fixed`. */
+typedef struct {
+  int32_t num_verts;            /* V (6890 for SMPL/SMPL-H; arbitrary for a rigged mesh)          */
+  int32_t num_joints;           /* J (24 SMPL, 52 SMPL-H; <= 64)                                  */
+  int32_t num_betas;            /* NB (10 or 16; 0 for a rigged mesh)                             */
+  const double* v_template;     /* (V,3)                                                          */
+  const double* shapedirs;      /* (V,3,NB)  or NULL                                              */
+  const double* posedirs;       /* (V,3,9*(J-1)) pickle layout, or NULL                           */
+  const double* J_regressor;    /* (J,V) dense row-major, or NULL                                 */
+  const double* joints_fixed;   /* (J,3) rest joints for a rigged mesh, else NULL                 */
+  const double* weights;        /* (V,J) LBS weights                                              */
+  const int32_t* parents;       /* (J) parents[0] = -1, parents[i] < i                            */
+  int32_t num_pca;              /* hand PCA components C (0 = none); upstream smplx use_pca       */
+  const double* hand_comp_l;    /* (C,45) or NULL                                                 */
+  const double* hand_comp_r;    /* (C,45) or NULL                                                 */
+  const double* pose_mean;      /* (3J) added to the full pose (upstream `pose_mean`), or NULL    */
+  int32_t num_extra_verts;      /* E: VertexJointSelector vertex picks appended to the FK joints  */
+  const int32_t* extra_vertex_ids; /* (E) or NULL                                                 */
+  int32_t num_regressors;       /* number of rows R of `regressor_posed` (0 = none)               */
+  const double* regressor_posed;/* (R,V): joints regressed from POSED vertices, i.e. the
+                                   J_regressor_extra of models/smplh.py:22-29 and gen_J_3d of
+                                   models/smplh_np.py:116-117                                     */
+} smplk_model_desc;
+
+/* Replaces: SMPLHModel.__init__ (models/smplh_np.py:7-37), SMPLModel.__init__
+ * (models/smpl_np.py:123-156), RecoverModel.__init__ (lib/model2video.py:14-40) and the buffer
+ * registration of upstream smplx.SMPL/SMPLH.__init__ behind models/smplh.py:16-24.
+ * Packs the constants on `device`: posedirs|shapedirs as TF32 hi/lo operand pairs with their TMA
+ * descriptors, sparse LBS weights, J_template / J_shapedirs, tree depth tables. */
+int smplk_model_create(const smplk_model_desc* desc, int device, smplk_model** out);
+int smplk_model_destroy(smplk_model* model);
+
+/* Model facts a binding needs to size its buffers. */
+typedef struct {
+  int32_t num_verts, num_joints, num_betas, num_pose_feats; /* V, J, NB, P */
+  int32_t num_extra_verts, num_regressors, num_pca;
+  int32_t max_weights_per_vertex; /* ELL width chosen by the packer (<=4 takes the register path) */
+  int32_t lbs_only;               /* 1 for a rigged mesh                                          */
+  int32_t device;
+  int32_t has_tcgen05_path;       /* 1 when the TMA descriptors for the blend GEMM were built     */
+} smplk_model_info;
+int smplk_model_get_info(const smplk_model* model, smplk_model_info* info);
+
+#define SMPLK_FLAG_SAVE_FOR_BACKWARD 1u /* keep v_posed & transforms of ALL bodies in the workspace */
+#define SMPLK_FLAG_ADD_POSE_MEAN 2u     /* full_pose += pose_mean (flat_hand_mean=False upstream)   */
+#define SMPLK_FLAG_BLEND_SIMT 4u        /* force the exact-fp32 SIMT blend kernel (small batch / bring-up) */
+#define SMPLK_FLAG_BLEND_TCGEN05 8u     /* force the tcgen05 3xTF32 blend GEMM                       */
+
+/* Bytes of device workspace `smplk_forward` needs for `batch` bodies (256-byte aligned base). */
+size_t smplk_workspace_bytes(const smplk_model* model, int32_t batch, uint32_t flags);
+
+/* Diagnostic: byte offsets of the workspace segments {F_hi, F_lo, A, v_posed} and the chunk size
+ * (bodies processed per pass) for (batch, flags).  Used by the parity tests to read intermediates:
+ * A = per-joint 3x4 skinning transforms (B,J,12), v_posed rows of stride round_up(3V,256). */
+int smplk_workspace_layout(const smplk_model* model, int32_t batch, uint32_t flags,
+                           size_t offsets[4], int32_t* chunk);
+
+typedef struct {
+  int32_t batch;              /* B                                                                 */
+  uint32_t flags;             /* SMPLK_FLAG_*                                                      */
+  const float* betas;         /* (betas_batch, NB); NULL = zeros                                   */
+  int32_t betas_batch;        /* 1 (broadcast, upstream lbs batch_size = max(...)) or B            */
+  const float* pose;          /* (B, 3J) axis-angle: global_orient | body_pose | hands             */
+  const float* hand_pca_l;    /* (B, C) or NULL: if given, joints 22..36 = hand_pca_l @ comp_l     */
+  const float* hand_pca_r;    /* (B, C) or NULL: joints 37..51                                     */
+  const float* transl;        /* (B,3) or NULL                                                     */
+  float* verts;               /* out (B,V,3) or NULL                                               */
+  float* joints;              /* out (B, J+E, 3): FK joints then vertex picks, + transl; or NULL   */
+  float* joints_regressed;    /* out (B, R, 3): regressor_posed @ verts; or NULL                   */
+  float* full_pose;           /* out (B, 3J) assembled pose (PCA + mean applied); or NULL          */
+  void* workspace;
+  size_t workspace_bytes;
+  smplk_stream stream;
+} smplk_forward_args;
+
+/* Replaces, per batch of bodies: upstream smplx.SMPLH.forward / SMPL.forward + lbs() as called at
+ * models/smplh.py:26-31 and lib/Gen_SMPLH/fitting.py:243-245, and the numpy twins
+ * SMPLHModel.set_params/update/compute_R_G/do_skinning (models/smplh_np.py:39-86),
+ * SMPLModel (models/smpl_np.py:158-206), RecoverModel.set_params (lib/model2video.py:42-81). */
+int smplk_forward(const smplk_model* model, const smplk_forward_args* args);
+
+typedef struct {
+  int32_t batch;
+  uint32_t flags;             /* same flags as the forward that filled `workspace`                 */
+  const float* betas;         /* inputs of the forward (transforms are recomputed from them)       */
+  int32_t betas_batch;
+  const float* pose;
+  const float* hand_pca_l;
+  const float* hand_pca_r;
+  const float* d_verts;       /* in (B,V,3) dL/dverts or NULL                                      */
+  const float* d_joints;      /* in (B,J+E,3) dL/djoints or NULL                                   */
+  const float* d_joints_regressed; /* in (B,R,3) or NULL                                           */
+  float* d_betas;             /* out (betas_batch, NB) or NULL                                     */
+  float* d_pose;              /* out (B,3J) or NULL (w.r.t. the `pose` argument)                   */
+  float* d_hand_pca_l;        /* out (B,C) or NULL                                                 */
+  float* d_hand_pca_r;        /* out (B,C) or NULL                                                 */
+  float* d_transl;            /* out (B,3) or NULL                                                 */
+  void* workspace;            /* the forward's workspace (SMPLK_FLAG_SAVE_FOR_BACKWARD)            */
+  size_t workspace_bytes;
+  void* scratch;              /* smplk_backward_scratch_bytes() bytes                              */
+  size_t scratch_bytes;
+  smplk_stream stream;
+} smplk_backward_args;
+
+size_t smplk_backward_scratch_bytes(const smplk_model* model, int32_t batch);
+
+/* Replaces the autograd backward of the forward above (total_loss.backward() at
+ * lib/Gen_SMPLH/fitting.py:256): vector-Jacobian product w.r.t. betas, pose, hand PCA, transl. */
+int smplk_backward(const smplk_model* model, const smplk_backward_args* args);
+
+/* Replaces gen_J_3d (models/smplh_np.py:116-117, models/smpl_np.py:230-231,
+ * lib/mesh2smpl_model.py:112-113) and vertices2joints(J_regressor_extra, vertices) at
+ * models/smplh.py:29: out (B,R,3) = regressor_posed (R,V) @ verts (B,V,3). */
+int smplk_regress_joints(const smplk_model* model, int32_t batch, const float* verts, float* out,
+                         smplk_stream stream);
+
+/* Replaces utils/geometry.py:9-23 batch_rodrigues (axis-angle (n,3) -> rotation matrices (n,3,3)). */
+int smplk_batch_rodrigues(int32_t n, const float* axis_angle, float* rotmats, int device,
+                          smplk_stream stream);
+
+/* End-to-end call with HOST buffers (the reference's numpy API works on host arrays:
+ * set_params(pose, beta, trans) -> verts, models/smplh_np.py:39-47).  Copies inputs H2D,
+ * runs the forward on `stream`, copies verts/joints D2H and synchronises the stream.  Device
+ * staging buffers are owned by the model and grown on demand. */
+int smplk_forward_host(smplk_model* model, int32_t batch, uint32_t flags, const float* betas,
+                       int32_t betas_batch, const float* pose, const float* transl, float* verts,
+                       float* joints, smplk_stream stream);
+
+const char* smplk_last_error_string(void);
+int smplk_version(void);
+
+/* Number of kernels this library has launched since load (benchmark bookkeeping). */
+uint64_t smplk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMPLK_H_ */
