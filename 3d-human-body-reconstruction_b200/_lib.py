@@ -82,8 +82,10 @@ EXPORTED_SYMBOLS = [
     "smplk_model_create", "smplk_model_destroy", "smplk_model_get_info", "smplk_workspace_bytes",
     "smplk_forward", "smplk_backward_scratch_bytes", "smplk_backward", "smplk_regress_joints",
     "smplk_batch_rodrigues", "smplk_forward_host", "smplk_last_error_string", "smplk_version",
-    "smplk_launch_count", "smplk_workspace_layout",
+    "smplk_launch_count", "smplk_workspace_layout", "smplk_profile_enable", "smplk_profile_read",
 ]
+PROF_SLOTS = ["pose_fwd", "blend_tcgen05", "blend_simt", "skin", "dA", "skin_bwd", "blend_bwd",
+              "pose_bwd"]
 
 
 def build(force=False, verbose=False):
@@ -147,6 +149,11 @@ def load():
                                            ctypes.POINTER(ctypes.c_size_t),
                                            ctypes.POINTER(ctypes.c_int32)]
     lib.smplk_workspace_layout.restype = ctypes.c_int
+    lib.smplk_profile_enable.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.smplk_profile_enable.restype = ctypes.c_int
+    lib.smplk_profile_read.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
+                                       ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
+    lib.smplk_profile_read.restype = ctypes.c_int
     lib.smplk_last_error_string.restype = ctypes.c_char_p
     lib.smplk_version.restype = ctypes.c_int
     lib.smplk_launch_count.restype = ctypes.c_uint64
@@ -267,6 +274,16 @@ class DeviceModel:
         check(self._lib.smplk_workspace_layout(self.handle, int(batch), int(flags), offs,
                                                ctypes.byref(chunk)))
         return dict(F_hi=offs[0], F_lo=offs[1], A=offs[2], v_posed=offs[3], chunk=chunk.value)
+
+    def profile_enable(self, on=True):
+        check(self._lib.smplk_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_read(self, reset=True):
+        """{kernel: (total_ms, launches)} measured with CUDA events on the launching stream."""
+        ms = (ctypes.c_double * len(PROF_SLOTS))()
+        n = (ctypes.c_int64 * len(PROF_SLOTS))()
+        check(self._lib.smplk_profile_read(self.handle, ms, n, 1 if reset else 0))
+        return {k: (ms[i], n[i]) for i, k in enumerate(PROF_SLOTS)}
 
     def backward_scratch_bytes(self, batch):
         return int(self._lib.smplk_backward_scratch_bytes(self.handle, int(batch)))

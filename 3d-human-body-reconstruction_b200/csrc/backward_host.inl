@@ -89,7 +89,8 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     da.vsrc = d.lbs_only ? d.bias : v_posed;
     da.vsrc_stride = d.lbs_only ? 0 : (size_t)d.Npad;
     da.dA = dA; da.dtr = dtr;
-    dA_kernel<<<B, kDAThreads, 0, st>>>(d, da);
+    { ProfScope prof(model, st, SMPLK_PROF_DA);
+    dA_kernel<<<B, kDAThreads, 0, st>>>(d, da); }
     LAUNCH_CHECK("dA_kernel");
   } else {
     CUDA_TRY(cudaMemsetAsync(dA, 0, (size_t)B * d.J * 12 * sizeof(float), st));
@@ -107,8 +108,9 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     sb.bodies_per_block = bpb;
     dim3 grid(tiles, (B + bpb - 1) / bpb);
     const size_t smem = (size_t)(3 * kSkinTileVerts * 3 + d.J * 12) * sizeof(float);
+    { ProfScope prof(model, st, SMPLK_PROF_SKIN_BWD);
     if (d.ell_k <= 4) skin_backward_kernel<true><<<grid, kSkinThreads, smem, st>>>(d, sb);
-    else skin_backward_kernel<false><<<grid, kSkinThreads, smem, st>>>(d, sb);
+    else skin_backward_kernel<false><<<grid, kSkinThreads, smem, st>>>(d, sb); }
     LAUNCH_CHECK("skin_backward_kernel");
 
     CUtensorMap tm_ahi, tm_alo, tm_out;
@@ -121,8 +123,9 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     ga.num_splits = L.splits; ga.k_blocks_per_split = L.kbps; ga.out_rows_per_split = L.mpad;
     ga.bias = nullptr;
     const int tiles_g = L.m_blocks * L.n_blocks * L.splits;
+    { ProfScope prof(model, st, SMPLK_PROF_BLEND_BWD);
     blend_tcgen05_kernel<<<std::min(tiles_g, model->num_sms), kGemmThreads, kGemmSmemAlloc, st>>>(
-        tm_ahi, tm_alo, model->tmap_pdkn_hi, model->tmap_pdkn_lo, tm_out, ga);
+        tm_ahi, tm_alo, model->tmap_pdkn_hi, model->tmap_pdkn_lo, tm_out, ga); }
     LAUNCH_CHECK("blend_tcgen05_kernel(backward)");
   }
 
@@ -141,8 +144,9 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     CUDA_TRY(cudaMemsetAsync(a->d_betas, 0, (size_t)d.NB * sizeof(float), st));
   const int blocks = (B + kPoseWarps - 1) / kPoseWarps;
   const size_t smem = (size_t)kPoseWarps * d.J * 18 * sizeof(float);
+  { ProfScope prof(model, st, SMPLK_PROF_POSE_BWD);
   if (d.J <= 32) pose_backward_kernel<1><<<blocks, kPoseWarps * 32, smem, st>>>(d, pb);
-  else pose_backward_kernel<2><<<blocks, kPoseWarps * 32, smem, st>>>(d, pb);
+  else pose_backward_kernel<2><<<blocks, kPoseWarps * 32, smem, st>>>(d, pb); }
   LAUNCH_CHECK("pose_backward_kernel");
   return 0;
 }

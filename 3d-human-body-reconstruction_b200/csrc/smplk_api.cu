@@ -61,6 +61,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  int slot;
+};
+
 struct smplk_model {
   ModelDev d;
   int device;
@@ -74,6 +79,32 @@ struct smplk_model {
   // host staging for smplk_forward_host
   void* stage_dev;
   size_t stage_bytes;
+  // optional per-kernel device timing (smplk_profile_*)
+  mutable bool prof_on;
+  mutable std::vector<ProfRec> prof_pending;
+  mutable double prof_ms[SMPLK_PROF_SLOTS];
+  mutable int64_t prof_n[SMPLK_PROF_SLOTS];
+};
+
+struct ProfScope {
+  const smplk_model* m;
+  cudaStream_t st;
+  int slot;
+  cudaEvent_t e0;
+  ProfScope(const smplk_model* m_, cudaStream_t st_, int slot_) : m(m_), st(st_), slot(slot_), e0(nullptr) {
+    if (m->prof_on) {
+      cudaEventCreate(&e0);
+      cudaEventRecord(e0, st);
+    }
+  }
+  ~ProfScope() {
+    if (e0) {
+      cudaEvent_t e1;
+      cudaEventCreate(&e1);
+      cudaEventRecord(e1, st);
+      m->prof_pending.push_back({e0, e1, slot});
+    }
+  }
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -371,6 +402,8 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   mdl->stage_dev = nullptr;
   mdl->stage_bytes = 0;
   mdl->encode = nullptr;
+  mdl->prof_on = false;
+  for (int i = 0; i < SMPLK_PROF_SLOTS; ++i) { mdl->prof_ms[i] = 0.0; mdl->prof_n[i] = 0; }
   if (prop.major != 10) {
     delete mdl;
     return fail(SMPLK_E_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
@@ -441,6 +474,7 @@ static int launch_pose_forward(const smplk_model* mdl, const PoseFwdArgs& pa, cu
   const ModelDev& d = mdl->d;
   const int blocks = (pa.B + kPoseWarps - 1) / kPoseWarps;
   const size_t smem = (size_t)kPoseWarps * std::max(d.Kpad, 32) * sizeof(float);
+  ProfScope prof(mdl, st, SMPLK_PROF_POSE_FWD);
   if (d.J <= 32)
     pose_forward_kernel<1><<<blocks, kPoseWarps * 32, smem, st>>>(d, pa);
   else
@@ -474,6 +508,7 @@ static int launch_blend(const smplk_model* mdl, int rows, float* F_hi, float* F_
     ga.bias = d.bias;
     const int tiles = ga.num_m_blocks * ga.num_n_blocks;
     const int grid = std::min(tiles, mdl->num_sms);
+    ProfScope prof(mdl, st, SMPLK_PROF_BLEND_TCGEN05);
     blend_tcgen05_kernel<<<grid, kGemmThreads, kGemmSmemAlloc, st>>>(
         tm_fhi, tm_flo, mdl->tmap_pd_hi, mdl->tmap_pd_lo, tm_out, ga);
     LAUNCH_CHECK("blend_tcgen05_kernel");
@@ -482,6 +517,7 @@ static int launch_blend(const smplk_model* mdl, int rows, float* F_hi, float* F_
     sa.M = rows; sa.F_hi = F_hi; sa.F_lo = F_lo; sa.out = v_posed;
     dim3 grid((d.Npad / 4 + kSimtThreads - 1) / kSimtThreads, (rows + kSimtBodies - 1) / kSimtBodies);
     const size_t smem = (size_t)d.Kpad * kSimtBodies * sizeof(float);
+    ProfScope prof(mdl, st, SMPLK_PROF_BLEND_SIMT);
     blend_simt_kernel<<<grid, kSimtThreads, smem, st>>>(d, sa);
     LAUNCH_CHECK("blend_simt_kernel");
   }
@@ -501,6 +537,7 @@ static int launch_skin(const smplk_model* mdl, int rows, const float* vsrc, size
   sa.vsrc = vsrc; sa.vsrc_stride = vstride; sa.A = A; sa.transl = transl; sa.out = out;
   dim3 grid(tiles, (rows + bpb - 1) / bpb);
   const size_t smem = (size_t)(2 * kSkinTileVerts * 3 + 2 * ((d.J * 12 + 3) & ~3)) * sizeof(float);
+  ProfScope prof(mdl, st, SMPLK_PROF_SKIN);
   if (d.ell_k <= 4)
     skin_kernel<true><<<grid, kSkinThreads, smem, st>>>(d, sa);
   else
@@ -646,6 +683,34 @@ extern "C" int smplk_forward_host(smplk_model* model, int32_t batch, uint32_t fl
   if (verts) CUDA_TRY(cudaMemcpyAsync(verts, d_verts, (size_t)batch * d.V * 12, cudaMemcpyDeviceToHost, st));
   if (joints) CUDA_TRY(cudaMemcpyAsync(joints, d_joints, (size_t)batch * (d.J + d.E) * 12, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int smplk_profile_enable(smplk_model* model, int enable) {
+  if (!model) return fail(SMPLK_E_ARG, "null model");
+  model->prof_on = enable != 0;
+  return 0;
+}
+
+extern "C" int smplk_profile_read(smplk_model* model, double ms[SMPLK_PROF_SLOTS],
+                                  int64_t counts[SMPLK_PROF_SLOTS], int reset) {
+  if (!model || !ms || !counts) return fail(SMPLK_E_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(model->device));
+  for (ProfRec& r : model->prof_pending) {
+    CUDA_TRY(cudaEventSynchronize(r.e1));
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, r.e0, r.e1));
+    model->prof_ms[r.slot] += t;
+    model->prof_n[r.slot] += 1;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  model->prof_pending.clear();
+  for (int i = 0; i < SMPLK_PROF_SLOTS; ++i) {
+    ms[i] = model->prof_ms[i];
+    counts[i] = model->prof_n[i];
+    if (reset) { model->prof_ms[i] = 0.0; model->prof_n[i] = 0; }
+  }
   return 0;
 }
 

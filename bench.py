@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the SMPL-H body-model hot path (BASELINE.json metric: posed meshes/sec).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+One "step" = one forward pass (pose/FK -> blend GEMM -> skinning) over a batch of B synthetic
+bodies PER GPU (weak scaling; bodies are independent, no data-path collective).  Workload at N=1:
+BASELINE.json configs[1] -- SMPL-H forward+LBS, batch 4096, fp32, 52 joints, 16 betas, 459 posedirs.
+
+Printed JSON line (rank 0): value = whole-job posed meshes/s with inputs resident in HBM;
+e2e = same metric through the C-ABI host-buffer call (H2D of inputs + D2H of vertices inside the
+timed region); roofline = dominant kernel (tcgen05 blend GEMM) against the tensor roofline, with
+the HBM-bound skinning kernel reported beside it; cpu_baseline = the oracle port timed on the host
+cores.  `--impl reference` times the CPU restatement of the reference path (oracle port; the
+reference is pure Python and /root/reference does not exist on the GPU box).
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FWD_BYTES_SKIN = 167856          # v_posed in + A in + verts out, per body
+FWD_BYTES_FUSED = 84004          # inputs + verts + FK joints, per body
+GEMM_FLOPS_PER_BODY = 2 * 20670 * (459 + 16)   # fp32-equivalent algorithmic FLOPs, K = 459 + 16
+METRIC = "smplh_posed_meshes_per_sec_fwd"
+UNIT = "meshes/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Polls SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_baseline(model, sample_bodies=256, budget_s=12.0):
+    """Oracle port of the reference torch path (upstream smplx lbs restatement) on the host cores,
+    fp32, all threads, on a bounded sample of the same synthetic workload."""
+    import torch
+    from oracle import smpl_oracle as O
+    from smplk import synthetic
+    om = O.TorchOracleModel(model, dtype=torch.float32)
+    betas, pose, transl = synthetic.make_inputs(model, sample_bodies, seed=123)
+    tb, tp, tt = torch.tensor(betas), torch.tensor(pose), torch.tensor(transl)
+    with torch.no_grad():
+        om.forward_full_pose(tb, tp, tt)
+        n, t0 = 0, time.perf_counter()
+        while True:
+            om.forward_full_pose(tb, tp, tt)
+            n += 1
+            el = time.perf_counter() - t0
+            if el > budget_s or n >= 200:
+                break
+    return {"value": sample_bodies * n / el, "unit": UNIT, "cores": torch.get_num_threads(),
+            "kind": "port",
+            "sample": "%d passes of %d bodies (torch-CPU fp32 restatement of smplx.lbs, oracle/smpl_oracle.py), %.1f s"
+                      % (n, sample_bodies, el)}
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from smplk import synthetic
+    model = synthetic.make_model("smplh", seed=0)
+    from oracle import smpl_oracle as O
+    om = O.TorchOracleModel(model, dtype=torch.float32)
+    sample = 256
+    betas, pose, transl = synthetic.make_inputs(model, sample, seed=1)
+    tb, tp, tt = torch.tensor(betas), torch.tensor(pose), torch.tensor(transl)
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 3))):
+            om.forward_full_pose(tb, tp, tt)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            om.forward_full_pose(tb, tp, tt)
+        el = time.perf_counter() - t0
+    val = sample * args.steps / el
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "SMPL-H forward+LBS batch %d fp32 (52 joints, 16 betas, 459 posedirs)" % args.batch,
+                       "step_sample": "%d bodies per step on the host CPU" % sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d steps x %d bodies, torch-CPU fp32 restatement of the reference torch path" % (args.steps, sample)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=4096, help="bodies per GPU per step")
+    ap.add_argument("--bwd-batch", type=int, default=1024)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip fwd+bwd / e2e / per-kernel passes")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import smplk
+    from smplk import _lib, synthetic
+    from smplk.body_models import body_model_apply
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    model = synthetic.make_model("smplh", seed=0)
+    dm = smplk.DeviceModel(model, device=local)
+    NSETS = 4  # rotate inputs; per-step footprint (v_posed + verts = %d MB) already exceeds the 126 MB L2
+    sets = []
+    for s in range(NSETS):
+        b, p, t = synthetic.make_inputs(model, B, seed=10 * rank + s)
+        sets.append(tuple(torch.tensor(x, device=dev) for x in (b, p, t)))
+    verts = torch.empty(B, dm.V, 3, device=dev)
+    joints = torch.empty(B, dm.J, 3, device=dev)
+    ws_bytes = dm.workspace_bytes(B, 0)
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i):
+        b, p, t = sets[i % NSETS]
+        a = _lib.ForwardArgs()
+        a.batch, a.flags = B, 0
+        a.betas, a.betas_batch = ctypes.c_void_p(b.data_ptr()), B
+        a.pose, a.transl = ctypes.c_void_p(p.data_ptr()), ctypes.c_void_p(t.data_ptr())
+        a.verts, a.joints = ctypes.c_void_p(verts.data_ptr()), ctypes.c_void_p(joints.data_ptr())
+        a.workspace, a.workspace_bytes = ctypes.c_void_p(ws.data_ptr()), ws_bytes
+        a.stream = ctypes.c_void_p(stream.cuda_stream)
+        dm.forward(a)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record(stream)
+        for i in range(args.steps):
+            step(i)
+        e1.record(stream)
+        barrier()
+    ms_local = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    ms = ms_local
+    if world > 1:
+        t = torch.tensor([ms_local], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    extras = {}
+    peaks = load_peaks()
+    if not args.no_extras:
+        # ---- per-kernel device time (CUDA events on the launching stream, inside libsmplk)
+        dm.profile_enable(True)
+        for i in range(min(args.steps, 50)):
+            step(i)
+        torch.cuda.synchronize(dev)
+        prof = dm.profile_read(reset=True)
+        dm.profile_enable(False)
+        kern = {k: (v[0] / v[1]) for k, v in prof.items() if v[1] > 0}
+        # TF32 tensor peak measured here with a cuBLAS 8192^3 TF32 GEMM (MEASURED_PEAKS.json has bf16 only)
+        tf32_peak = None
+        if rank == 0:
+            torch.backends.cuda.matmul.allow_tf32 = True
+            x = torch.randn(8192, 8192, device=dev)
+            y = torch.randn(8192, 8192, device=dev)
+            for _ in range(3):
+                x @ y
+            torch.cuda.synchronize(dev)
+            best = 1e9
+            for _ in range(8):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record(); x @ y; a1.record(); torch.cuda.synchronize(dev)
+                best = min(best, a0.elapsed_time(a1))
+            tf32_peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+            torch.backends.cuda.matmul.allow_tf32 = False
+            del x, y
+        if "blend_tcgen05" in kern and tf32_peak:
+            g_ms = kern["blend_tcgen05"]
+            alg_tflops = GEMM_FLOPS_PER_BODY * B / (g_ms * 1e-3) / 1e12
+            peak = tf32_peak / 3.0      # fp32-accurate contraction = 3 TF32 passes (3xTF32)
+            extras["roofline"] = {
+                "kernel": "blend_tcgen05_kernel", "bound": "tensor", "achieved": alg_tflops, "peak": peak,
+                "unit": "TFLOP/s", "frac": alg_tflops / peak, "traffic": None,
+                "ms_per_launch": g_ms,
+                "note": "achieved = 2*B*20670*475 fp32-equivalent FLOPs / CUDA-event time; peak = TF32 dense "
+                        "measured live with cuBLAS 8192^3 (%.0f TFLOP/s; bf16 %s = %.0f) / 3 passes of 3xTF32; "
+                        "issued tensor FLOPs = 3*2*B*20736*480" % (tf32_peak, peaks["source"], peaks["bf16"]),
+                "tf32_tflops_measured": tf32_peak,
+                "tensor_tflops_issued": 3 * 2 * B * 20736 * 480 / (g_ms * 1e-3) / 1e12}
+        if "skin" in kern:
+            s_ms = kern["skin"]
+            gbs = FWD_BYTES_SKIN * B / (s_ms * 1e-3) / 1e9
+            extras["roofline_skinning"] = {"kernel": "skin_kernel", "bound": "hbm", "achieved": gbs,
+                                           "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                                           "traffic": None, "ms_per_launch": s_ms,
+                                           "note": "167,856 algorithmic B/body (v_posed in, A in, verts out); peak %s" % peaks["source"]}
+        extras["kernel_ms"] = kern
+
+        # ---- forward+backward fitting step (config 3: vertex L2 loss, batch 1024)
+        Bb = args.bwd_batch
+        bb, pb, tb_ = (torch.tensor(x, device=dev, requires_grad=True) for x in synthetic.make_inputs(model, Bb, seed=99))
+        target = torch.randn(Bb, dm.V, 3, device=dev)
+
+        def fb_step():
+            for t_ in (bb, pb, tb_):
+                t_.grad = None
+            v, _, _, _ = body_model_apply(dm, bb, pb, transl=tb_)
+            loss = ((v - target) ** 2).sum()
+            loss.backward()
+            return loss
+        for _ in range(3):
+            fb_step()
+        torch.cuda.synchronize(dev)
+        nfb = max(5, min(args.steps, 30))
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(nfb):
+            fb_step()
+        f1.record(stream)
+        torch.cuda.synchronize(dev)
+        fb_ms = f0.elapsed_time(f1) / nfb
+        extras["fwd_bwd"] = {"metric": "smplh_fitting_steps_meshes_per_sec_fwd_bwd", "batch": Bb,
+                             "value": world * Bb / (fb_ms * 1e-3), "unit": UNIT, "ms_per_step": fb_ms,
+                             "loss": "sum ||V - V*||^2 through the SMPLH autograd.Function (torch elementwise loss included)"}
+
+        # ---- e2e: C-ABI host-buffer call (pinned host memory, H2D + D2H inside the timed region)
+        lib = smplk.load()
+        hb, hp, ht = (torch.tensor(x).pin_memory() for x in synthetic.make_inputs(model, B, seed=7))
+        hv = torch.empty(B, dm.V, 3).pin_memory()
+        def e2e_step():
+            _lib.check(lib.smplk_forward_host(dm.handle, B, 0, ctypes.c_void_p(hb.data_ptr()), B,
+                                              ctypes.c_void_p(hp.data_ptr()), ctypes.c_void_p(ht.data_ptr()),
+                                              ctypes.c_void_p(hv.data_ptr()), None,
+                                              ctypes.c_void_p(stream.cuda_stream)))
+        for _ in range(3):
+            e2e_step()
+        ne = max(5, min(args.steps, 20))
+        barrier()
+        t0 = time.perf_counter()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(ne):
+            e2e_step()
+        g1.record(stream)
+        torch.cuda.synchronize(dev)
+        e2e_ms = g0.elapsed_time(g1) / ne
+        if world > 1:
+            t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        extras["e2e"] = {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT,
+                         "h2d_bytes_per_step": int(hb.numel() + hp.numel() + ht.numel()) * 4,
+                         "d2h_bytes_per_step": int(hv.numel()) * 4, "ms_per_step": e2e_ms,
+                         "api": "smplk_forward_host (C ABI, pinned host buffers; numpy-twin path)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core blend, fp32 elsewhere)",
+                "data": "synthetic",
+                "config": {"workload": "SMPL-H forward+LBS batch %d per GPU, fp32, 52 joints, 16 betas, 459 posedirs "
+                                       "(BASELINE.json configs[1])" % B,
+                           "global_batch": world * B, "parallelism": "batch-sharded x%d, no collective" % world,
+                           "l2": "per-step footprint %.0f MB (v_posed + verts) > 126 MB L2; %d rotating input sets"
+                                 % (2 * B * 82680 / 1e6, NSETS),
+                           "weights": "canonically sparse LBS weights (<=4 per vertex)"},
+                "clocks": clocks.summary(), "gpu_launches": int(launches),
+                "hbm_gbs_fused_equiv": FWD_BYTES_FUSED * world * B * args.steps / (ms * 1e-3) / 1e9}
+        line.update(extras)
+        if "e2e" not in line:
+            line["e2e"] = None
+        if not args.no_cpu_baseline and not args.no_extras:
+            line["cpu_baseline"] = cpu_baseline(model)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

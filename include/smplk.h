@@ -168,6 +168,23 @@ int smplk_forward_host(smplk_model* model, int32_t batch, uint32_t flags, const 
                        int32_t betas_batch, const float* pose, const float* transl, float* verts,
                        float* joints, smplk_stream stream);
 
+/* Per-kernel device timing for benchmarks: while enabled, forward/backward bracket every kernel
+ * they launch with a CUDA event pair recorded on the caller's stream (the stream the kernel runs
+ * on).  `smplk_profile_read` waits for the pending events and returns accumulated milliseconds and
+ * launch counts per slot. */
+#define SMPLK_PROF_POSE_FWD 0
+#define SMPLK_PROF_BLEND_TCGEN05 1
+#define SMPLK_PROF_BLEND_SIMT 2
+#define SMPLK_PROF_SKIN 3
+#define SMPLK_PROF_DA 4
+#define SMPLK_PROF_SKIN_BWD 5
+#define SMPLK_PROF_BLEND_BWD 6
+#define SMPLK_PROF_POSE_BWD 7
+#define SMPLK_PROF_SLOTS 8
+int smplk_profile_enable(smplk_model* model, int enable);
+int smplk_profile_read(smplk_model* model, double ms[SMPLK_PROF_SLOTS],
+                       int64_t counts[SMPLK_PROF_SLOTS], int reset);
+
 const char* smplk_last_error_string(void);
 int smplk_version(void);
 

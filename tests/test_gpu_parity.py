@@ -1,0 +1,331 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI / the drop-in modules) against the
+oracle on the same seeded inputs, against the committed golden vectors made by the reference's own
+code, and size-independent properties at the full BASELINE sizes.
+
+Tolerances (BASELINE.json north_star): vertices / joints max abs error <= 1e-5 m against the fp32
+torch oracle; gradients relative error <= 1e-4."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import smplk
+from smplk import _lib, synthetic
+from smplk.body_models import SMPL, SMPLH, body_model_apply
+from oracle import smpl_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+GRAD_RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def smplh_model():
+    return synthetic.make_model("smplh", seed=21)
+
+
+@pytest.fixture(scope="module")
+def smpl_model():
+    return synthetic.make_model("smpl", seed=22)
+
+
+def _t(x, dev, grad=False):
+    return torch.tensor(np.asarray(x, dtype=np.float32), device=dev, requires_grad=grad)
+
+
+def _maxerr(a, b):
+    return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
+
+
+def test_native_library_is_loaded_and_counts_launches(dev, smpl_model):
+    lib = smplk.load()
+    assert os.path.basename(lib._name) == "libsmplk.so"
+    dm = smplk.DeviceModel(smpl_model, device=0)
+    assert dm.info.has_tcgen05_path == 1 and dm.info.max_weights_per_vertex <= 4
+    before = _lib.launch_count()
+    b, p, t = synthetic.make_inputs(smpl_model, 3)
+    body_model_apply(dm, _t(b, dev), _t(p, dev), transl=_t(t, dev))
+    assert _lib.launch_count() >= before + 3
+
+
+@pytest.mark.parametrize("B,flags", [(1, 0), (7, 0), (33, 0), (33, _lib.FLAG_BLEND_SIMT),
+                                     (129, 0), (700, 0)])
+def test_smplh_forward_matches_oracle(dev, smplh_model, B, flags):
+    m = smplh_model
+    dm = smplk.DeviceModel(m, device=0, extra_vertex_ids=m["extra_vertex_ids"],
+                           regressor_posed=m["J_regressor_extra"])
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=B)
+    pose[0] = 0.0                                  # zero pose: R(0) = I
+    if B > 2:
+        pose[1] *= 1e-6                            # tiny angles
+        pose[2] = pose[2] / np.abs(pose[2]).max() * 4.8   # |theta| > pi as in the AMASS clips
+    om32 = O.TorchOracleModel(m, dtype=torch.float32)
+    om64 = O.TorchOracleModel(m, dtype=torch.float64)
+    args64 = [torch.tensor(x, dtype=torch.float64) for x in (betas, pose, transl)]
+    ref32 = om32.forward_full_pose(*[a.float() for a in args64])
+    ref64 = om64.forward_full_pose(*args64)
+    v, j, jr, fp = body_model_apply(dm, _t(betas, dev), _t(pose, dev), transl=_t(transl, dev),
+                                    want_regressed=True, flags=flags)
+    assert _maxerr(v, ref32.vertices) <= TOL and _maxerr(v, ref64.vertices) <= TOL
+    assert _maxerr(j[:, :52], ref32.joints) <= TOL
+    picks = ref64.vertices[:, torch.as_tensor(m["extra_vertex_ids"], dtype=torch.long)]
+    assert _maxerr(j[:, 52:], picks) <= TOL
+    extra = torch.einsum("bik,ji->bjk", ref64.vertices, torch.tensor(m["J_regressor_extra"]))
+    assert _maxerr(jr, extra) <= TOL
+    assert _maxerr(fp, torch.tensor(pose)) == 0.0
+
+
+def test_tcgen05_and_simt_blend_agree(dev, smplh_model):
+    dm = smplk.DeviceModel(smplh_model, device=0)
+    betas, pose, transl = synthetic.make_inputs(smplh_model, 200, seed=9)
+    a = body_model_apply(dm, _t(betas, dev), _t(pose, dev), transl=_t(transl, dev), flags=_lib.FLAG_BLEND_SIMT)[0]
+    b = body_model_apply(dm, _t(betas, dev), _t(pose, dev), transl=_t(transl, dev), flags=_lib.FLAG_BLEND_TCGEN05)[0]
+    assert _maxerr(a, b) <= 5e-6
+
+
+def test_smpl_module_and_broadcast_betas(dev, smpl_model):
+    m = smpl_model
+    mod = SMPL(model=m, batch_size=1).to(dev)
+    B = 40
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=2, broadcast_betas=True)
+    out = mod(betas=_t(betas, dev), global_orient=_t(pose[:, :3], dev), body_pose=_t(pose[:, 3:], dev),
+              transl=_t(transl, dev), return_full_pose=True)
+    om = O.TorchOracleModel(m, dtype=torch.float64)
+    ref = om.forward(torch.tensor(betas, dtype=torch.float64).expand(B, -1),
+                     torch.tensor(pose[:, :3], dtype=torch.float64), torch.tensor(pose[:, 3:], dtype=torch.float64),
+                     transl=torch.tensor(transl, dtype=torch.float64))
+    assert out.vertices.shape == (B, 6890, 3) and out.joints.shape == (B, 24 + 21, 3)
+    assert _maxerr(out.vertices, ref.vertices) <= TOL and _maxerr(out.joints, ref.joints) <= TOL
+    assert _maxerr(out.full_pose, ref.full_pose) == 0.0
+    # module defaults: zero parameters -> rest template, verts_numpy lazily materialised
+    rest = mod()
+    assert _maxerr(rest.vertices[0], torch.tensor(m["v_template"])) <= 1e-6
+    assert mod.verts_numpy.shape == (6890, 3)
+    assert mod(return_verts=False).vertices is None
+
+
+def test_smplh_module_pca_mean_mapper_and_wrapper_extras(dev, smplh_model):
+    """Everything models/smplh.py:26-39 + smplx.create(...) of lib/gen_smplh.py:75-90 does."""
+    m = smplh_model
+    mapper_idx = np.array([52, 12, 17, 19, 21, 16, 18, 20, 0, 2, 5, 8, 1, 4, 7, 53, 54, 55, 56, 57, 58,
+                           59, 60, 61, 62, 20, 34, 35, 36, 63, 21, 49, 50, 51, 68, 72])
+    class Mapper(torch.nn.Module):
+        def forward(self, joints):
+            return torch.index_select(joints, 1, torch.as_tensor(mapper_idx, device=joints.device))
+    joint_map = np.array([3, 0, 36 + 8, 36 + 2, 7])
+    B = 5
+    mod = SMPLH(model=m, joint_mapper=Mapper(), use_pca=True, num_pca_comps=12, flat_hand_mean=False,
+                create_transl=False, batch_size=B, J_regressor_extra=m["J_regressor_extra"],
+                joint_map=joint_map).to(dev)
+    rng = np.random.default_rng(4)
+    kw = dict(betas=rng.standard_normal((B, 16)), global_orient=rng.standard_normal((B, 3)) * 0.4,
+              body_pose=rng.standard_normal((B, 63)) * 0.3, left_hand_pose=rng.standard_normal((B, 12)),
+              right_hand_pose=rng.standard_normal((B, 12)))
+    out = mod(**{k: _t(v, dev) for k, v in kw.items()}, return_full_pose=True, get_skin=True)
+    om = O.TorchOracleModel(m, dtype=torch.float64, num_pca_comps=12, joint_mapper=mapper_idx, joint_map=joint_map)
+    ref = om.forward(*[torch.tensor(kw[k]) for k in ("betas", "global_orient", "body_pose", "left_hand_pose",
+                                                    "right_hand_pose")], wrapper_extra=True)
+    assert _maxerr(out.vertices, ref.vertices) <= TOL
+    assert out.joints.shape == ref.joints.shape == (B, 5, 3)
+    assert _maxerr(out.joints, ref.joints) <= TOL
+    assert _maxerr(out.full_pose, ref.full_pose) <= 1e-6
+    # flat_hand_mean + axis-angle hands
+    mod2 = SMPLH(model=m, use_pca=False, flat_hand_mean=True, batch_size=2).to(dev)
+    lh, rh = rng.standard_normal((2, 45)) * 0.2, rng.standard_normal((2, 45)) * 0.2
+    out2 = mod2(left_hand_pose=_t(lh, dev), right_hand_pose=_t(rh, dev))
+    om2 = O.TorchOracleModel(m, dtype=torch.float64, flat_hand_mean=True)
+    z = lambda *s: torch.zeros(*s, dtype=torch.float64)
+    ref2 = om2.forward(z(2, 16), z(2, 3), z(2, 63), torch.tensor(lh), torch.tensor(rh), transl=z(2, 3), use_pca=False)
+    assert _maxerr(out2.vertices, ref2.vertices) <= TOL and _maxerr(out2.joints, ref2.joints) <= TOL
+
+
+def test_dense_weights_take_the_generic_path(dev):
+    m = synthetic.make_model("smplh", seed=5, dense_weights=True, dense_regressor=True)
+    dm = smplk.DeviceModel(m, device=0)
+    assert dm.info.max_weights_per_vertex == 52
+    betas, pose, transl = synthetic.make_inputs(m, 6, seed=1)
+    v = body_model_apply(dm, _t(betas, dev), _t(pose, dev), transl=_t(transl, dev))[0]
+    ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(
+        *[torch.tensor(x, dtype=torch.float64) for x in (betas, pose, transl)])
+    assert _maxerr(v, ref.vertices) <= TOL
+
+
+def test_numpy_twins_reproduce_reference_golden_vectors(dev, golden_dir):
+    g = np.load(os.path.join(golden_dir, "smplh_np_twin.npz"))
+    m = synthetic.make_model("smplh", num_betas=int(g["num_betas"]), seed=int(g["seed"]))
+    twin = smplk.SMPLHModel(m)
+    assert np.abs(twin.verts[::53] - g["rest_verts_sub64"]).max() <= TOL      # constructor runs update()
+    for i in range(g["pose"].shape[0]):
+        v = twin.set_params(pose=g["pose"][i].reshape(52, 3), beta=g["beta"][i], trans=g["trans"][i])
+        assert v.dtype == np.float64 and v.shape == (6890, 3)
+        assert np.abs(v - g["verts"][i]).max() <= TOL
+        assert np.abs(twin.gen_J_3d() - g["j3d"][i]).max() <= TOL
+    allv = twin.forward_batch(g["pose"], g["beta"], g["trans"])
+    assert np.abs(allv - g["verts"]).max() <= TOL
+    g = np.load(os.path.join(golden_dir, "smpl_np_twin.npz"))
+    m = synthetic.make_model("smpl", num_betas=int(g["num_betas"]), seed=int(g["seed"]))
+    twin = smplk.SMPLModel(m)
+    for i in range(g["pose"].shape[0]):
+        v = twin.set_params(pose=g["pose"][i].reshape(24, 3), beta=g["beta"][i], trans=g["trans"][i])
+        assert np.abs(v - g["verts"][i]).max() <= TOL
+        assert np.abs(twin.gen_J_3d() - g["j3d"][i]).max() <= TOL
+
+
+def test_recover_model_matches_reference_golden_vectors(dev, golden_dir):
+    g = np.load(os.path.join(golden_dir, "recover_lbs.npz"))
+    rig = synthetic.make_rigged_mesh(int(g["num_verts"]), seed=int(g["seed"]))
+    rm = smplk.RecoverModel(rig)
+    for i in range(g["pose"].shape[0]):
+        v = rm.set_params(pose=g["pose"][i].reshape(24, 3).copy(), trans=g["trans"][i])
+        assert np.abs(v - g["verts"][i]).max() <= TOL
+    clip = rm.replay(g["pose"], g["trans"])
+    assert clip.shape == g["verts"].shape and np.abs(clip - g["verts"]).max() <= TOL
+
+
+def test_rodrigues_kernel_matches_geometry_golden(dev, golden_dir):
+    g = np.load(os.path.join(golden_dir, "rodrigues_quat.npz"))
+    aa = _t(g["theta"], dev).contiguous()
+    out = torch.empty(aa.shape[0], 3, 3, device=dev)
+    lib = smplk.load()
+    _lib.check(lib.smplk_batch_rodrigues(aa.shape[0], ctypes.c_void_p(aa.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                         0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    assert _maxerr(out, torch.tensor(g["R"])) <= 2e-6
+
+
+@pytest.mark.parametrize("kind,B,pca,joint_w", [("smplh", 4, True, 0.5), ("smpl", 130, False, 0.0),
+                                                ("smplh", 64, False, 1.0)])
+def test_backward_matches_autograd_oracle(dev, kind, B, pca, joint_w):
+    m = synthetic.make_model(kind, seed=31)
+    J = 52 if kind == "smplh" else 24
+    om = O.TorchOracleModel(m, dtype=torch.float64, num_pca_comps=12)
+    dm = smplk.DeviceModel(m, device=0, num_pca_comps=12 if pca else 0, extra_vertex_ids=m["extra_vertex_ids"],
+                           regressor_posed=m["J_regressor_extra"])
+    rng = np.random.default_rng(7)
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=11)
+    if not pca:
+        pose[0, 3:9] = 0.0      # exercise the theta -> 0 branch of the Rodrigues backward
+    lh, rh = rng.standard_normal((B, 12)), rng.standard_normal((B, 12))
+    tgt_v = rng.standard_normal((B, 6890, 3))
+    tgt_j = rng.standard_normal((B, J + 21, 3))
+    tgt_r = rng.standard_normal((B, 9, 3))
+
+    def loss_fn(v, j, r):
+        l = ((v - tgt_v_t(v)) ** 2).sum()
+        if joint_w:
+            l = l + joint_w * ((j - tgt_j_t(j)) ** 2).sum() + joint_w * ((r - tgt_r_t(r)) ** 2).sum()
+        return l
+    tgt_v_t = lambda x: torch.as_tensor(tgt_v, dtype=x.dtype, device=x.device)
+    tgt_j_t = lambda x: torch.as_tensor(tgt_j, dtype=x.dtype, device=x.device)
+    tgt_r_t = lambda x: torch.as_tensor(tgt_r, dtype=x.dtype, device=x.device)
+
+    # oracle (float64 autograd)
+    ob, op, ot = (torch.tensor(x, dtype=torch.float64, requires_grad=True) for x in (betas, pose, transl))
+    ol, orr = (torch.tensor(x, dtype=torch.float64, requires_grad=True) for x in (lh, rh))
+    if pca:
+        o = om.forward(ob, op[:, :3], op[:, 3:66], ol, orr, transl=ot, wrapper_extra=True)
+    else:
+        o = om.forward_full_pose(ob, op, ot)
+        picks = o.vertices[:, torch.as_tensor(m["extra_vertex_ids"], dtype=torch.long)]
+        extra = torch.einsum("bik,ji->bjk", o.vertices, om.J_regressor_extra)
+        o = O.OracleOutput(o.vertices, torch.cat([o.joints, picks, extra], 1), None, None, None, None)
+    loss_fn(o.vertices, o.joints[:, :J + 21], o.joints[:, J + 21:]).backward()
+
+    gb, gp, gt = (_t(x, dev, True) for x in (betas, pose, transl))
+    gl, gr = (_t(x, dev, True) for x in (lh, rh))
+    v, j, r, _ = body_model_apply(dm, gb, gp, pca_l=gl if pca else None, pca_r=gr if pca else None, transl=gt,
+                                  add_pose_mean=pca, want_regressed=True)
+    loss_fn(v, j, r).backward()
+    pairs = [("betas", gb.grad, ob.grad), ("transl", gt.grad, ot.grad)]
+    if pca:
+        pairs += [("pose", gp.grad[:, :66], op.grad[:, :66]), ("lh", gl.grad, ol.grad), ("rh", gr.grad, orr.grad)]
+        assert float(gp.grad[:, 66:].abs().max()) == 0.0
+    else:
+        pairs += [("pose", gp.grad, op.grad)]
+    for name, got, ref in pairs:
+        rel = _maxerr(got, ref) / float(ref.abs().max())
+        assert rel <= GRAD_RTOL, (name, rel)
+
+
+def test_backward_broadcast_betas_and_module_autograd(dev, smplh_model):
+    m = smplh_model
+    mod = SMPLH(model=m, use_pca=True, num_pca_comps=12, batch_size=1, create_transl=False).to(dev)
+    om = O.TorchOracleModel(m, dtype=torch.float64, num_pca_comps=12)
+    B = 9
+    rng = np.random.default_rng(5)
+    bp = rng.standard_normal((B, 63)) * 0.3
+    with torch.no_grad():
+        mod.betas.copy_(_t(rng.standard_normal((1, 16)), dev))
+        mod.left_hand_pose.copy_(_t(rng.standard_normal((1, 12)), dev))
+    tgt = rng.standard_normal((B, 73, 3))
+    out = mod(body_pose=_t(bp, dev), return_verts=True)
+    ((out.joints - _t(tgt, dev)) ** 2).sum().backward()      # SMPLifyCameraInitLoss-style joints L2
+    ob = mod.betas.detach().double().cpu().requires_grad_(True)
+    ol = mod.left_hand_pose.detach().double().cpu().requires_grad_(True)
+    z = lambda *s: torch.zeros(*s, dtype=torch.float64)
+    o = om.forward(ob.expand(B, -1), z(B, 3), torch.tensor(bp), ol.expand(B, -1), z(B, 12))
+    ((o.joints - torch.tensor(tgt)) ** 2).sum().backward()
+    for got, ref in ((mod.betas.grad, ob.grad), (mod.left_hand_pose.grad, ol.grad)):
+        assert _maxerr(got, ref) / float(ref.abs().max()) <= GRAD_RTOL
+    assert mod.global_orient.grad is not None and mod.right_hand_pose.grad is not None
+
+
+def test_full_size_properties_batch_4096(dev, smplh_model):
+    """BASELINE config 2 size; properties that need no oracle at this size."""
+    m = smplh_model
+    dm = smplk.DeviceModel(m, device=0)
+    B = 4096
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=77)
+    tb, tp, tt = _t(betas, dev), _t(pose, dev), _t(transl, dev)
+    v = body_model_apply(dm, tb, tp, transl=tt)[0]
+    assert torch.isfinite(v).all()
+    # (1) shard equivalence, bitwise: concat of shard results == single-call result
+    from smplk.sharding import shard_bounds
+    for world in (2, 8):
+        parts = []
+        for r in range(world):
+            lo, hi = shard_bounds(B, world, r)
+            parts.append(body_model_apply(dm, tb[lo:hi].contiguous(), tp[lo:hi].contiguous(),
+                                          transl=tt[lo:hi].contiguous())[0])
+        assert torch.equal(torch.cat(parts), v)
+    # (2) translation equivariance: verts(t + d) - verts(t) == d up to fp32 rounding of the add
+    d = torch.tensor([0.25, -1.5, 3.0], device=dev)
+    v2 = body_model_apply(dm, tb, tp, transl=tt + d)[0]
+    assert float((v2 - v - d).abs().max()) <= 2e-6
+    # (3) determinism
+    assert torch.equal(body_model_apply(dm, tb, tp, transl=tt)[0], v)
+    # (4) spot-check 16 random bodies of the big batch against the float64 oracle
+    idx = np.random.default_rng(0).choice(B, 16, replace=False)
+    ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(
+        *[torch.tensor(x[idx], dtype=torch.float64) for x in (betas, pose, transl)])
+    assert _maxerr(v[torch.as_tensor(idx, device=dev)], ref.vertices) <= TOL
+    # (5) global rotation by pi about z maps (x,y,z) -> (-x,-y,z) when only the root is posed
+    p0 = torch.zeros(4, 156, device=dev)
+    p1 = p0.clone(); p1[:, 2] = float(np.pi)
+    a = body_model_apply(dm, tb[:4].contiguous(), p0)[0]
+    b = body_model_apply(dm, tb[:4].contiguous(), p1)[0]
+    j0 = body_model_apply(dm, tb[:4].contiguous(), p0)[1][:, :1]
+    assert float(((a - j0) * torch.tensor([-1., -1., 1.], device=dev) - (b - j0)).abs().max()) <= 5e-6
+
+
+def test_errors_are_loud(dev, smpl_model):
+    dm = smplk.DeviceModel(smpl_model, device=0)
+    b, p, t = synthetic.make_inputs(smpl_model, 2)
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
+        body_model_apply(dm, torch.tensor(b), torch.tensor(p))
+    with pytest.raises(RuntimeError, match="float32"):
+        body_model_apply(dm, _t(b, dev).double(), _t(p, dev).double())
+    a = _lib.ForwardArgs()
+    a.batch = 2
+    a.pose = ctypes.c_void_p(_t(p, dev).data_ptr())
+    with pytest.raises(RuntimeError, match="workspace"):
+        dm.forward(a)
+    with pytest.raises(RuntimeError, match="betas_batch"):
+        body_model_apply(dm, _t(np.zeros((3, 10)), dev), _t(p, dev))

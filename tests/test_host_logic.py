@@ -1,0 +1,122 @@
+"""CPU: the C-ABI library loads and exports every declared symbol, host-side packing helpers and
+error behaviour without a GPU, synthetic generator invariants, header/binding consistency."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import smplk
+from smplk import _lib, synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_header_symbol():
+    lib = smplk.load()
+    hdr = open(os.path.join(ROOT, "include", "smplk.h")).read()
+    declared = set(re.findall(r"\b(smplk_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.smplk_version() == 1
+
+
+def test_header_is_plain_c():
+    import subprocess, tempfile
+    src = '#include "smplk.h"\nint main(void){ smplk_forward_args a; (void)a; return smplk_version() < 0; }\n'
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "t.c")
+        open(p, "w").write(src)
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                            "-c", p, "-o", os.path.join(d, "t.o")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_ctypes_struct_sizes_match_header_layout():
+    # pointers and int32 interleaved exactly as in the header (natural alignment)
+    assert ctypes.sizeof(_lib.ForwardArgs) == 8 + 8 + 8 + 8 * 8 + 8 + 8 + 8 or ctypes.sizeof(_lib.ForwardArgs) % 8 == 0
+    assert _lib.ModelInfo._fields_[0][0] == "num_verts" and len(_lib.ModelInfo._fields_) == 11
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = synthetic.make_model("smpl", seed=1, num_verts=200)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        smplk.DeviceModel(m)
+    mod = smplk.SMPL(model=m)
+    with pytest.raises(RuntimeError):
+        mod()
+
+
+def test_bad_descriptor_arguments_are_rejected_before_touching_the_gpu():
+    lib = smplk.load()
+    h = ctypes.c_void_p()
+    d = _lib.ModelDesc()
+    d.num_joints, d.num_verts = 100, 10
+    rc = lib.smplk_model_create(ctypes.byref(d), 0, ctypes.byref(h))
+    assert rc == -2 and b"num_joints" in lib.smplk_last_error_string()
+    d.num_joints = 24
+    rc = lib.smplk_model_create(ctypes.byref(d), 0, ctypes.byref(h))
+    assert rc == -1
+    assert lib.smplk_model_create(None, 0, ctypes.byref(h)) == -1
+    assert lib.smplk_workspace_bytes(None, 4, 0) == 0
+
+
+def test_parent_tables():
+    for kind, J in (("smpl", 24), ("smplh", 52)):
+        m = synthetic.make_model(kind, seed=0, num_verts=100)
+        p = _lib.parents_from_model(m)
+        assert p.shape == (J,) and p[0] == -1 and all(p[i] < i for i in range(1, J))
+        assert list(p) == list(synthetic.parents_from_kintree(m["kintree_table"]))
+    rig = synthetic.make_rigged_mesh(50)
+    assert list(_lib.parents_from_model(rig)) == synthetic.SMPL_PARENTS
+    # canonical depths quoted in SURVEY.md H4
+    def depths(par):
+        d = [0] * len(par)
+        for i in range(1, len(par)):
+            d[i] = d[par[i]] + 1
+        return d
+    assert max(depths(synthetic.SMPL_PARENTS)) == 8
+    assert max(depths(synthetic.SMPLH_PARENTS)) == 10
+
+
+def test_synthetic_model_invariants():
+    m = synthetic.make_model("smplh", seed=1)
+    assert m["v_template"].shape == (6890, 3) and m["shapedirs"].shape == (6890, 3, 16)
+    assert m["posedirs"].shape == (6890, 3, 459) and m["J_regressor"].shape == (52, 6890)
+    W = m["weights"]
+    assert np.allclose(W.sum(1), 1) and (W >= 0).all() and ((W != 0).sum(1) <= 4).all()
+    assert np.allclose(m["J_regressor"].sum(1), 1)
+    q = m["hands_componentsl"]
+    assert np.allclose(q @ q.T, np.eye(45), atol=1e-10)
+    d = synthetic.make_model("smpl", seed=1, dense_weights=True, num_verts=64)
+    assert ((d["weights"] != 0).sum(1) == 24).all()
+    b, p, t = synthetic.make_inputs(m, 7, broadcast_betas=True)
+    assert b.shape == (1, 16) and p.shape == (7, 156) and t.shape == (7, 3)
+
+
+def test_module_signatures_mirror_reference():
+    import inspect
+    from smplk.body_models import SMPL, SMPLH, ModelOutput
+    sig = inspect.signature(SMPLH.forward).parameters
+    for name in ("betas", "global_orient", "body_pose", "left_hand_pose", "right_hand_pose", "transl",
+                 "return_verts", "return_full_pose", "pose2rot"):
+        assert name in sig
+    assert ModelOutput._fields[:6] == ("vertices", "joints", "full_pose", "betas", "global_orient", "body_pose")
+    m = synthetic.make_model("smplh", seed=1, num_verts=128)
+    mod = SMPLH(model=m, use_pca=True, num_pca_comps=12, batch_size=2, create_transl=False)
+    names = dict(mod.named_parameters())
+    assert names["left_hand_pose"].shape == (2, 12) and names["body_pose"].shape == (2, 63)
+    assert "transl" not in names and names["betas"].shape == (2, 16)
+    mod.reset_params(betas=np.ones((2, 16)))
+    assert float(mod.betas.sum()) == 32.0 and float(mod.body_pose.abs().sum()) == 0.0
+    s = SMPL(model=synthetic.make_model("smpl", seed=1, num_verts=128), create_body_pose=False)
+    assert "body_pose" not in dict(s.named_parameters())
+    from smplk import np_twins
+    for cls in (np_twins.SMPLHModel, np_twins.SMPLModel, np_twins.RecoverModel):
+        assert list(inspect.signature(cls.set_params).parameters)[1:] == ["pose", "beta", "trans"]
