@@ -11,6 +11,7 @@ constexpr int kBlendBM = 128;      // bodies per blend-GEMM tile (UMMA M)
 constexpr int kBlendBN = 256;      // vertex coordinates per blend-GEMM tile (UMMA N)
 constexpr int kBlendBK = 32;       // tf32 elements per k-block = one 128-byte swizzle row
 constexpr int kSkinTileVerts = 1024;
+constexpr int kGrpJoints = 8;      // distinct joints a 4-vertex group may reference on the fast path
 
 // Device pointers + sizes of one packed body model. Passed by value to kernels.
 struct ModelDev {
@@ -35,6 +36,9 @@ struct ModelDev {
   const float4* skin_w4;      // [V] four weights      (ell_k <= 4)
   const int* ell_idx;         // [ell_k][V]
   const float* ell_w;         // [ell_k][V]
+  int grp_ok;                 // 1 when every 4-vertex group touches <= 8 distinct joints
+  const uint2* grp_joints;    // [ceil(V/4)] eight u8 joint ids of the group (most weight first)
+  const float4* grp_w;        // [ceil(V/4)][8] weight of joint u for the group's 4 vertices
   const int* csc_ptr;         // [J+1] joint -> (vertex, weight) lists for the backward
   const int* csc_vert;        // [nnz]
   const float* csc_w;         // [nnz]

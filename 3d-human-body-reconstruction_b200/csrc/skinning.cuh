@@ -145,6 +145,165 @@ skin_kernel(const ModelDev m, const SkinArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// skin_grouped_kernel -- the product path for sparse weights.
+//
+// ncu on skin_kernel (profiles/r01_ncu_full_first_path.csv) showed it bound by shared-memory
+// wavefronts and block barriers, not HBM: every vertex gathered 4 x 48 B of transforms per body
+// (61 M wavefronts per launch at B=4096) and every body cost three __syncthreads.  Here:
+//  * a thread owns a group of 4 CONSECUTIVE vertices; neighbouring vertices share most of their
+//    joints, so the packer stores the <= 8 distinct joints of the group with a 4x8 weight block and
+//    each transform is fetched from shared memory once per group (typ. 4-6 x 48 B per 4 vertices
+//    instead of 16 x 48 B);
+//  * each WARP streams its own 128 vertices (1536 contiguous bytes per body) through a private
+//    ring of cp.async stages: coalesced 16-byte copies two bodies ahead, in-place compute, coalesced
+//    8-byte stores; only __syncwarp inside the body loop;
+//  * the bodies' 3x4 transforms are staged for 8 bodies at a time (double buffered), so the block
+//    meets at a barrier once per 8 bodies.
+// ------------------------------------------------------------------------------------------
+constexpr int kGrpThreads = 256;     // 8 warps x 128 vertices = one 1024-vertex tile
+constexpr int kGrpStages = 3;        // cp.async ring depth per warp
+constexpr int kGrpABodies = 8;       // transforms staged per A-group
+constexpr int kWarpFloats = 384;     // 128 vertices x 3
+
+__host__ __device__ inline int grp_a_pad(int J) { return (J * 12 + 3) & ~3; }
+__host__ __device__ inline size_t skin_grouped_smem_bytes(int J) {
+  return (size_t)(kGrpStages * kSkinTileVerts * 3 + 2 * kGrpABodies * grp_a_pad(J) + 4 * kGrpABodies * 2) *
+         sizeof(float);
+}
+
+template <bool kSharedTemplate>
+__global__ void __launch_bounds__(kGrpThreads, 2)
+skin_grouped_kernel(const ModelDev m, const SkinArgs a) {
+  extern __shared__ __align__(16) float sg_smem[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int v0 = blockIdx.x * kSkinTileVerts;
+  const int a_floats = m.J * 12;
+  const int a_chunks = m.J * 3;
+  const int a_pad = grp_a_pad(m.J);
+  float* ring = sg_smem;                                         // [stages][1024*3]
+  float* Abuf = sg_smem + kGrpStages * kSkinTileVerts * 3;       // [2][8][a_pad]
+  float* Tbuf = Abuf + 2 * kGrpABodies * a_pad;                  // [2][8][4] translations
+
+  const int b0 = blockIdx.y * a.bodies_per_block;
+  const int b1 = min(a.B, b0 + a.bodies_per_block);
+  if (b0 >= b1) return;
+
+  // this warp's slice of the row: floats [wf0, wf0 + 384)
+  const int wf0 = v0 * 3 + warp * kWarpFloats;
+  const int w_nfloat = max(0, min(kWarpFloats, m.V * 3 - wf0));   // valid output floats of the warp
+  const int g = (v0 >> 2) + tid;                                  // global 4-vertex group of this thread
+  const bool g_valid = 4 * g < m.V;
+  uint2 jid = make_uint2(0u, 0u);
+  float4 w[kGrpJoints];
+  uint32_t used = 0;
+#pragma unroll
+  for (int u = 0; u < kGrpJoints; ++u) {
+    w[u] = g_valid ? m.grp_w[(size_t)g * kGrpJoints + u] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (w[u].x != 0.f || w[u].y != 0.f || w[u].z != 0.f || w[u].w != 0.f) used |= 1u << u;
+  }
+  if (g_valid) jid = m.grp_joints[g];
+  used = __reduce_or_sync(0xffffffffu, used);   // warp-uniform: no divergence in the joint loop
+
+  // ---- async copy helpers (every thread commits the same number of groups)
+  auto issue_A = [&](int grp) {                 // transforms + translations of bodies b0+8grp ..
+    const int bb0 = b0 + grp * kGrpABodies;
+    const int nb = min(kGrpABodies, b1 - bb0);
+    float* dstA = Abuf + (grp & 1) * kGrpABodies * a_pad;
+    for (int c = tid; c < nb * a_chunks; c += kGrpThreads) {
+      const int bi = c / a_chunks, cc = c - bi * a_chunks;
+      ptx::cp_async_16(dstA + bi * a_pad + 4 * cc, a.A + (size_t)(bb0 + bi) * a_floats + 4 * cc);
+    }
+    if (tid < nb * 3) {
+      float* dstT = Tbuf + (grp & 1) * kGrpABodies * 4;
+      const int bi = tid / 3, k = tid - bi * 3;
+      dstT[bi * 4 + k] = a.transl ? a.transl[(size_t)(bb0 + bi) * 3 + k] : 0.f;
+    }
+  };
+  auto issue_v = [&](int b) {                   // this warp's 1536 B of body b -> ring slot
+    if (b < b1 && (!kSharedTemplate || b == b0)) {
+      const float* src = a.vsrc + (size_t)b * a.vsrc_stride + wf0;
+      float* dst = ring + ((b - b0) % kGrpStages) * (kSkinTileVerts * 3) + warp * kWarpFloats;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int c = lane + 32 * i;                          // 16-byte chunk of the warp slice
+        if (wf0 + 4 * c + 4 <= m.Npad) ptx::cp_async_16(dst + 4 * c, src + 4 * c);
+      }
+    }
+    ptx::cp_async_commit();
+  };
+
+  issue_A(0);
+  issue_v(b0);
+  issue_v(b0 + 1);
+  const bool even_rows = ((m.V * 3) & 1) == 0;
+
+  for (int b = b0; b < b1; ++b) {
+    const int rel = b - b0;
+    const int agrp = rel / kGrpABodies;
+    if ((rel % kGrpABodies) == 0) {
+      // transforms of this group were issued >= 8 bodies ago (or in the prologue)
+      ptx::cp_async_wait<1>();
+      __syncthreads();
+      if (b + kGrpABodies < b1) issue_A(agrp + 1);            // overwrites the buffer of group agrp-1
+    }
+    issue_v(b + 2);
+    ptx::cp_async_wait<2>();                                  // body b (and everything older) landed
+    __syncwarp();
+    const float* Ab = Abuf + ((agrp & 1) * kGrpABodies + (rel % kGrpABodies)) * a_pad;
+    const float* Tb = Tbuf + ((agrp & 1) * kGrpABodies + (rel % kGrpABodies)) * 4;
+    const float tx = Tb[0], ty = Tb[1], tz = Tb[2];
+    float* slot = ring + (kSharedTemplate ? 0 : (rel % kGrpStages)) * (kSkinTileVerts * 3) + warp * kWarpFloats;
+    float4* mine = reinterpret_cast<float4*>(slot) + 3 * lane;
+    const float4 c0 = mine[0], c1 = mine[1], c2 = mine[2];
+    // vertices of the group: (c0.x c0.y c0.z) (c0.w c1.x c1.y) (c1.z c1.w c2.x) (c2.y c2.z c2.w)
+    const float vx[4] = {c0.x, c0.w, c1.z, c2.y};
+    const float vy[4] = {c0.y, c1.x, c1.w, c2.z};
+    const float vz[4] = {c0.z, c1.y, c2.x, c2.w};
+    float ox[4] = {0.f, 0.f, 0.f, 0.f}, oy[4] = {0.f, 0.f, 0.f, 0.f}, oz[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < kGrpJoints; ++u) {
+      if (used & (1u << u)) {
+        const int j = ((u < 4 ? jid.x : jid.y) >> (8 * (u & 3))) & 0xff;
+        const float4* Aj = reinterpret_cast<const float4*>(Ab + j * 12);
+        const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+        const float wu[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float px = fmaf(r0.x, vx[i], fmaf(r0.y, vy[i], fmaf(r0.z, vz[i], r0.w)));
+          const float py = fmaf(r1.x, vx[i], fmaf(r1.y, vy[i], fmaf(r1.z, vz[i], r1.w)));
+          const float pz = fmaf(r2.x, vx[i], fmaf(r2.y, vy[i], fmaf(r2.z, vz[i], r2.w)));
+          ox[i] = fmaf(wu[i], px, ox[i]);
+          oy[i] = fmaf(wu[i], py, oy[i]);
+          oz[i] = fmaf(wu[i], pz, oz[i]);
+        }
+      }
+    }
+    float* orow = a.out + (size_t)b * m.V * 3 + wf0;
+    float* stage = kSharedTemplate ? ring + kSkinTileVerts * 3 + warp * kWarpFloats : slot;
+    float4* ot = reinterpret_cast<float4*>(stage) + 3 * lane;
+    ot[0] = make_float4(ox[0] + tx, oy[0] + ty, oz[0] + tz, ox[1] + tx);
+    ot[1] = make_float4(oy[1] + ty, oz[1] + tz, ox[2] + tx, oy[2] + ty);
+    ot[2] = make_float4(oz[2] + tz, ox[3] + tx, oy[3] + ty, oz[3] + tz);
+    __syncwarp();
+    if (even_rows) {                 // row base, tile and warp offsets are all even -> 8-byte aligned
+      const float2* s2 = reinterpret_cast<const float2*>(stage);
+      float2* o2 = reinterpret_cast<float2*>(orow);
+      if (w_nfloat == kWarpFloats) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) __stcs(o2 + lane + 32 * i, s2[lane + 32 * i]);
+      } else {
+        for (int c = lane; c < (w_nfloat >> 1); c += 32) __stcs(o2 + c, s2[c]);
+        if ((w_nfloat & 1) && lane == 0) orow[w_nfloat - 1] = stage[w_nfloat - 1];
+      }
+    } else {
+      for (int c = lane; c < w_nfloat; c += 32) __stcs(orow + c, stage[c]);
+    }
+    __syncwarp();                    // slot is refilled by issue_v two iterations later
+  }
+}
+
 // joints[b, J + e] = verts[b, extra_vids[e]]  (upstream VertexJointSelector; verts already + transl)
 __global__ void gather_extra_joints_kernel(const ModelDev m, int B, const float* __restrict__ verts,
                                            float* __restrict__ joints, int joints_ld) {

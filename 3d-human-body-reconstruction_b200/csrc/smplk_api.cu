@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -80,6 +81,7 @@ struct smplk_model {
   void* stage_dev;
   size_t stage_bytes;
   // optional per-kernel device timing (smplk_profile_*)
+  bool force_skin_v1;   // SMPLK_SKIN_V1=1 in the environment: per-vertex gather kernel (A/B testing)
   mutable bool prof_on;
   mutable std::vector<ProfRec> prof_pending;
   mutable double prof_ms[SMPLK_PROF_SLOTS];
@@ -294,6 +296,47 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
         cvert[pos] = v;
         cw[pos] = e.first;
       }
+    // 4-vertex groups: distinct joints of the group (<= kGrpJoints on the fast path), weights per vertex
+    {
+      const int G = (V + 3) / 4;
+      std::vector<uint2> gj(G, make_uint2(0u, 0u));
+      std::vector<float4> gw((size_t)G * kGrpJoints, make_float4(0.f, 0.f, 0.f, 0.f));
+      bool ok = ell_k <= 4;
+      for (int g = 0; g < G && ok; ++g) {
+        std::vector<std::pair<float, int>> uniq;   // (total weight, joint)
+        for (int i = 0; i < 4; ++i) {
+          const int v = 4 * g + i;
+          if (v >= V) break;
+          for (auto& e : rows[v]) {
+            bool found = false;
+            for (auto& u : uniq) if (u.second == e.second) { u.first += e.first; found = true; }
+            if (!found) uniq.push_back({e.first, e.second});
+          }
+        }
+        if ((int)uniq.size() > kGrpJoints) { ok = false; break; }
+        std::sort(uniq.begin(), uniq.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) {
+          return a.first > b.first || (a.first == b.first && a.second < b.second);
+        });
+        uint32_t packed[2] = {0u, 0u};
+        for (size_t u = 0; u < uniq.size(); ++u) {
+          packed[u / 4] |= (uint32_t)uniq[u].second << (8 * (u % 4));
+          float wv[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int i = 0; i < 4; ++i) {
+            const int v = 4 * g + i;
+            if (v >= V) break;
+            for (auto& e : rows[v]) if (e.second == uniq[u].second) wv[i] = e.first;
+          }
+          gw[(size_t)g * kGrpJoints + u] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+        }
+        // unused slots repeat the group's first joint with zero weight (no extra smem line touched)
+        for (size_t u = uniq.size(); u < (size_t)kGrpJoints; ++u)
+          packed[u / 4] |= (uint32_t)(uniq.empty() ? 0 : uniq[0].second) << (8 * (u % 4));
+        gj[g] = make_uint2(packed[0], packed[1]);
+      }
+      d.grp_ok = ok ? 1 : 0;
+      if (int r = upload(mdl, gj, &d.grp_joints)) return r;
+      if (int r = upload(mdl, gw, &d.grp_w)) return r;
+    }
     if (int r = upload(mdl, eidx, &d.ell_idx)) return r;
     if (int r = upload(mdl, ew, &d.ell_w)) return r;
     if (int r = upload(mdl, idx4, &d.skin_idx4)) return r;
@@ -371,6 +414,11 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
                                   kGemmSmemAlloc));
     mdl->has_tma = true;
   }
+  {
+    const int smem_g = (int)skin_grouped_smem_bytes(d.J);
+    CUDA_TRY(cudaFuncSetAttribute(skin_grouped_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g));
+    CUDA_TRY(cudaFuncSetAttribute(skin_grouped_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g));
+  }
   return 0;
 }
 
@@ -403,6 +451,7 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   mdl->stage_bytes = 0;
   mdl->encode = nullptr;
   mdl->prof_on = false;
+  { const char* e = getenv("SMPLK_SKIN_V1"); mdl->force_skin_v1 = e && e[0] == '1'; }
   for (int i = 0; i < SMPLK_PROF_SLOTS; ++i) { mdl->prof_ms[i] = 0.0; mdl->prof_n[i] = 0; }
   if (prop.major != 10) {
     delete mdl;
@@ -530,18 +579,25 @@ static int launch_skin(const smplk_model* mdl, int rows, const float* vsrc, size
   SkinArgs sa;
   sa.B = rows;
   const int tiles = (d.V + kSkinTileVerts - 1) / kSkinTileVerts;
-  // enough blocks for >= ~4 waves of 4 CTAs/SM, at most 16 bodies per block
-  int bpb = 16;
-  while (bpb > 1 && (long)tiles * ((rows + bpb - 1) / bpb) < 4L * 4 * mdl->num_sms) bpb >>= 1;
-  sa.bodies_per_block = bpb;
   sa.vsrc = vsrc; sa.vsrc_stride = vstride; sa.A = A; sa.transl = transl; sa.out = out;
+  const bool grouped = d.grp_ok && !mdl->force_skin_v1;
+  const size_t smem = grouped ? skin_grouped_smem_bytes(d.J)
+                              : (size_t)(2 * kSkinTileVerts * 3 + 2 * ((d.J * 12 + 3) & ~3)) * sizeof(float);
+  // bodies per block: as many as possible while keeping >= ~3 waves of resident blocks
+  const int resident = (grouped ? 2 : 4) * mdl->num_sms;
+  int bpb = 32;
+  while (bpb > 1 && (long)tiles * ((rows + bpb - 1) / bpb) < 3L * resident) bpb >>= 1;
+  sa.bodies_per_block = bpb;
   dim3 grid(tiles, (rows + bpb - 1) / bpb);
-  const size_t smem = (size_t)(2 * kSkinTileVerts * 3 + 2 * ((d.J * 12 + 3) & ~3)) * sizeof(float);
   ProfScope prof(mdl, st, SMPLK_PROF_SKIN);
-  if (d.ell_k <= 4)
+  if (grouped) {
+    if (vstride == 0) skin_grouped_kernel<true><<<grid, kGrpThreads, smem, st>>>(d, sa);
+    else skin_grouped_kernel<false><<<grid, kGrpThreads, smem, st>>>(d, sa);
+  } else if (d.ell_k <= 4) {
     skin_kernel<true><<<grid, kSkinThreads, smem, st>>>(d, sa);
-  else
+  } else {
     skin_kernel<false><<<grid, kSkinThreads, smem, st>>>(d, sa);
+  }
   LAUNCH_CHECK("skin_kernel");
   return 0;
 }
