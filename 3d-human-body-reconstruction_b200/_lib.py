@@ -12,7 +12,7 @@ import sys
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmplk.so")
+LIB_PATH = os.environ.get("SMPLK_LIB") or os.path.join(_HERE, "libsmplk.so")  # SMPLK_LIB: A/B variants
 CSRC = os.path.join(_HERE, "csrc")
 
 FLAG_SAVE_FOR_BACKWARD = 1

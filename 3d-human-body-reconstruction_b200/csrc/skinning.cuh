@@ -162,7 +162,10 @@ skin_kernel(const ModelDev m, const SkinArgs a) {
 //    meets at a barrier once per 8 bodies.
 // ------------------------------------------------------------------------------------------
 constexpr int kGrpThreads = 256;     // 8 warps x 128 vertices = one 1024-vertex tile
-constexpr int kGrpStages = 3;        // cp.async ring depth per warp
+#ifndef SMPLK_GRP_STAGES
+#define SMPLK_GRP_STAGES 5
+#endif
+constexpr int kGrpStages = SMPLK_GRP_STAGES;   // cp.async ring depth per warp (prefetch S-1 bodies ahead)
 constexpr int kGrpABodies = 8;       // transforms staged per A-group
 constexpr int kWarpFloats = 384;     // 128 vertices x 3
 
@@ -234,23 +237,24 @@ skin_grouped_kernel(const ModelDev m, const SkinArgs a) {
     ptx::cp_async_commit();
   };
 
-  issue_A(0);
-  issue_v(b0);
-  issue_v(b0 + 1);
+  issue_A(0);                                   // joins the first commit group
+#pragma unroll
+  for (int i = 0; i < kGrpStages - 1; ++i) issue_v(b0 + i);
   const bool even_rows = ((m.V * 3) & 1) == 0;
 
   for (int b = b0; b < b1; ++b) {
     const int rel = b - b0;
     const int agrp = rel / kGrpABodies;
+    issue_v(b + kGrpStages - 1);
+    ptx::cp_async_wait<kGrpStages - 1>();                     // body b (and everything older) landed
     if ((rel % kGrpABodies) == 0) {
-      // transforms of this group were issued >= 8 bodies ago (or in the prologue)
-      ptx::cp_async_wait<1>();
+      // this thread's share of the group's transforms was issued >= 8 bodies ago (or in the
+      // prologue) and is covered by the wait above; the barrier publishes it block-wide
       __syncthreads();
-      if (b + kGrpABodies < b1) issue_A(agrp + 1);            // overwrites the buffer of group agrp-1
+      if (b + kGrpABodies < b1) issue_A(agrp + 1);            // overwrites group agrp-1; joins next commit
+    } else {
+      __syncwarp();
     }
-    issue_v(b + 2);
-    ptx::cp_async_wait<2>();                                  // body b (and everything older) landed
-    __syncwarp();
     const float* Ab = Abuf + ((agrp & 1) * kGrpABodies + (rel % kGrpABodies)) * a_pad;
     const float* Tb = Tbuf + ((agrp & 1) * kGrpABodies + (rel % kGrpABodies)) * 4;
     const float tx = Tb[0], ty = Tb[1], tz = Tb[2];
@@ -300,7 +304,7 @@ skin_grouped_kernel(const ModelDev m, const SkinArgs a) {
     } else {
       for (int c = lane; c < w_nfloat; c += 32) __stcs(orow + c, stage[c]);
     }
-    __syncwarp();                    // slot is refilled by issue_v two iterations later
+    __syncwarp();                    // slot is refilled by a later issue_v of this warp
   }
 }
 
