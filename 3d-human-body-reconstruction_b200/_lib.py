@@ -19,6 +19,7 @@ FLAG_SAVE_FOR_BACKWARD = 1
 FLAG_ADD_POSE_MEAN = 2
 FLAG_BLEND_SIMT = 4
 FLAG_BLEND_TCGEN05 = 8
+FLAG_BLEND_TF32 = 16
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -121,10 +121,11 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     BlendGemmArgs ga;
     ga.num_m_blocks = L.m_blocks; ga.num_n_blocks = L.n_blocks; ga.num_k_blocks = L.k_blocks;
     ga.num_splits = L.splits; ga.k_blocks_per_split = L.kbps; ga.out_rows_per_split = L.mpad;
+    ga.k_elems = d.Npad; ga.out_scale = 1.0f;
     ga.bias = nullptr;
     const int tiles_g = L.m_blocks * L.n_blocks * L.splits;
     { ProfScope prof(model, st, SMPLK_PROF_BLEND_BWD);
-    blend_tcgen05_kernel<<<std::min(tiles_g, model->num_sms), kGemmThreads, kGemmSmemAlloc, st>>>(
+    blend_tcgen05_kernel<false><<<std::min(tiles_g, model->num_sms), kGemmThreads, kGemmSmemAlloc, st>>>(
         tm_ahi, tm_alo, model->tmap_pdkn_hi, model->tmap_pdkn_lo, tm_out, ga); }
     LAUNCH_CHECK("blend_tcgen05_kernel(backward)");
   }

@@ -13,6 +13,10 @@
 //    as hi = tf32(x) and lo = x - hi; each k-step issues hi*hi + lo*hi + hi*lo into the same TMEM
 //    accumulator (the lo*lo term, ~2^-22 relative, is dropped).  TMEM holds two 128x256 fp32
 //    accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+//    The same kernel has a second operand format (template kF16): both operands split into two
+//    fp16 terms (hi = half(x), lo = half(x - hi); posedirs pre-scaled by a power of two so the lo
+//    terms stay in the normal fp16 range) and kind::f16 MMAs (K=16 per instruction).  Same three
+//    products, same ~2^-22 relative accuracy, but half the operand bytes and twice the MMA rate.
 //  * blend_simt_kernel -- exact fp32 CUDA-core kernel for tiny batches (B < 32: the batch-1
 //    fitting loop of lib/Gen_SMPLH/fitting.py, where a 128-row MMA tile would be >75 % padding
 //    and the contraction is bound by streaming posedirs once) and for validating the GEMM.
@@ -42,6 +46,8 @@ struct BlendGemmArgs {
   int num_splits;          // split-K factor (1 for the forward blend)
   int k_blocks_per_split;  // ceil(num_k_blocks / num_splits)
   int out_rows_per_split;  // output row offset per split (partials stacked along rows)
+  int k_elems;             // contraction length in elements (multiple of the MMA K: 8 tf32 / 16 f16)
+  float out_scale;         // accumulator scale applied in the epilogue (1/posedirs scale for f16)
   const float* bias;       // [num_n_blocks * 256] added in the epilogue, or null
 };
 
@@ -63,6 +69,7 @@ __device__ __forceinline__ TileCoord tile_coord(const BlendGemmArgs& a, int tile
   return t;
 }
 
+template <bool kF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 blend_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
                      const __grid_constant__ CUtensorMap tmap_f_lo,
@@ -123,7 +130,7 @@ blend_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = stage_base + stage * kStageBytes;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-          const int k0 = kb * kBlendBK;
+          const int k0 = kb * (kF16 ? 2 * kBlendBK : kBlendBK);   // elements per 128-byte row
           ptx::tma_load_2d(st, &tmap_f_hi, &full_bar[stage], k0, m0);
           ptx::tma_load_2d(st + kTileABytes, &tmap_f_lo, &full_bar[stage], k0, m0);
           ptx::tma_load_2d(st + 2 * kTileABytes, &tmap_pd_hi, &full_bar[stage], k0, n0);
@@ -135,7 +142,10 @@ blend_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_tf32(kBlendBM, kBlendBN);
+      constexpr uint32_t idesc = kF16 ? ptx::make_idesc_f16(kBlendBM, kBlendBN)
+                                      : ptx::make_idesc_tf32(kBlendBM, kBlendBN);
+      constexpr int kElemsPerBlock = kF16 ? 2 * kBlendBK : kBlendBK;
+      constexpr int kUmmaK = kF16 ? 16 : 8;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -153,12 +163,17 @@ blend_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
           const uint64_t a_lo = ptx::make_sw128_kmajor_desc(st + kTileABytes);
           const uint64_t b_hi = ptx::make_sw128_kmajor_desc(st + 2 * kTileABytes);
           const uint64_t b_lo = ptx::make_sw128_kmajor_desc(st + 2 * kTileABytes + kTileBBytes);
+          // the last k-block may be partial (TMA zero-fills past k_elems; skip those MMAs)
+          const int ksteps = min(4, (args.k_elems - kb * kElemsPerBlock) / kUmmaK);
 #pragma unroll
-          for (int k = 0; k < kBlendBK / 8; ++k) {
-            const uint64_t adv = static_cast<uint64_t>((k * 8 * 4) >> 4);  // +32 B per UMMA_K
-            ptx::umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb != tc.kb0 || k != 0) ? 1u : 0u);
-            ptx::umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
-            ptx::umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+          for (int k = 0; k < 4; ++k) {
+            if (k < ksteps) {
+              const uint64_t adv = static_cast<uint64_t>((k * 32) >> 4);  // +32 B per UMMA_K
+              const uint32_t first = (kb != tc.kb0 || k != 0) ? 1u : 0u;
+              ptx::umma<kF16>(d_tmem, a_lo + adv, b_hi + adv, idesc, first);
+              ptx::umma<kF16>(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+              ptx::umma<kF16>(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+            }
           }
           ptx::umma_commit(&empty_bar[stage]);   // smem slot free once these MMAs retire
           if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
@@ -173,6 +188,7 @@ blend_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
     const int row = ewarp * 32 + lane;             // row of the 128-row tile == TMEM lane
     const int etid = threadIdx.x - 64;             // 0..127
     const bool store_thread = (etid == 0);
+    const float oscale = args.out_scale;
     int acc = 0;
     uint32_t acc_phase = 0;
     int ebuf = 0;
@@ -198,10 +214,10 @@ blend_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
         for (int q = 0; q < 8; ++q) {
           const float4 bq = *reinterpret_cast<const float4*>(bias_s + c * kEpiCols + 4 * q);
           float4 o;
-          o.x = __uint_as_float(v[4 * q + 0]) + bq.x;
-          o.y = __uint_as_float(v[4 * q + 1]) + bq.y;
-          o.z = __uint_as_float(v[4 * q + 2]) + bq.z;
-          o.w = __uint_as_float(v[4 * q + 3]) + bq.w;
+          o.x = fmaf(__uint_as_float(v[4 * q + 0]), oscale, bq.x);
+          o.y = fmaf(__uint_as_float(v[4 * q + 1]), oscale, bq.y);
+          o.z = fmaf(__uint_as_float(v[4 * q + 2]), oscale, bq.z);
+          o.w = fmaf(__uint_as_float(v[4 * q + 3]), oscale, bq.w);
           *reinterpret_cast<float4*>(ebase + ((q ^ (row & 7)) << 4)) = o;   // 128B swizzle
         }
         ptx::fence_proxy_async_smem();

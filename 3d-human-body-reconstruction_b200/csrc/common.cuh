@@ -1,6 +1,7 @@
 // Shared definitions: packed device-side model constants and small helpers.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -25,6 +26,9 @@ struct ModelDev {
   const float* bias;          // [Npad] v_template flattened (zero padded)
   const float* pd_nk_hi;      // [Npad][Kpad] tf32-rounded (posedirs|shapedirs)^T, K contiguous
   const float* pd_nk_lo;      // [Npad][Kpad] residual  x - hi
+  const __half* pd_nk_h_hi;   // [Npad][Kpad] fp16 hi term of posedirs * pd_scale
+  const __half* pd_nk_h_lo;   // [Npad][Kpad] fp16 lo term
+  float pd_scale;             // power of two; the f16 GEMM epilogue multiplies by 1/pd_scale
   const float* pd_kn;         // [Kpad][Npad] exact fp32, N contiguous
   const float* pd_kn_hi;      // [Kpad][Npad] tf32-rounded (backward GEMM operand)
   const float* pd_kn_lo;      // [Kpad][Npad] residual

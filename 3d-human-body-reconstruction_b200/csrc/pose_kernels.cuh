@@ -26,8 +26,10 @@ struct PoseFwdArgs {
   const float* pca_r;    // (B,C) or null
   int add_mean;
   const float* transl;   // (B,3) or null
-  float* F_hi;           // [rows][Kpad] or null
+  float* F_hi;           // [rows][Kpad] tf32 hi/lo rows, or null
   float* F_lo;
+  __half* H_hi;          // [rows][Kpad] fp16 hi/lo rows (f16 blend GEMM), or null
+  __half* H_lo;
   float* A;              // [B][J][12]
   float* joints;         // (B, joints_ld) or null; FK joints written to the first 3J entries
   int joints_ld;
@@ -222,7 +224,7 @@ pose_forward_kernel(const ModelDev m, const PoseFwdArgs a) {
   pose_forward_core<SLOTS>(m, betas_row, rv, R, Jr, Jrel, G, lane);
 
   // ---- GEMM A-operand row: [ (R_j - I) j=1..J-1 | betas | 0 pad ] split into TF32 hi / lo
-  if (a.F_hi != nullptr) {
+  if (a.F_hi != nullptr || a.H_hi != nullptr) {
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
       const int j = lane + 32 * s;
@@ -234,13 +236,26 @@ pose_forward_kernel(const ModelDev m, const PoseFwdArgs a) {
     for (int i = lane; i < m.Kpad - m.P; i += 32)
       feat[m.P + i] = (i < m.NB && betas_row) ? betas_row[i] : 0.f;
     __syncwarp();
-    float* fh = a.F_hi + (size_t)b * m.Kpad;
-    float* fl = a.F_lo + (size_t)b * m.Kpad;
-    for (int k = lane; k < m.Kpad; k += 32) {
-      float x = feat[k];
-      float h = ptx::tf32_round(x);
-      fh[k] = h;
-      fl[k] = x - h;
+    if (a.F_hi != nullptr) {
+      float* fh = a.F_hi + (size_t)b * m.Kpad;
+      float* fl = a.F_lo + (size_t)b * m.Kpad;
+      for (int k = lane; k < m.Kpad; k += 32) {
+        float x = feat[k];
+        float h = ptx::tf32_round(x);
+        fh[k] = h;
+        fl[k] = x - h;
+      }
+    }
+    if (a.H_hi != nullptr) {   // two-term fp16 split: x = hi + lo + O(2^-22 |x|)
+      __half2* hh = reinterpret_cast<__half2*>(a.H_hi + (size_t)b * m.Kpad);
+      __half2* hl = reinterpret_cast<__half2*>(a.H_lo + (size_t)b * m.Kpad);
+      for (int k = lane; k < m.Kpad / 2; k += 32) {
+        const float x0 = feat[2 * k], x1 = feat[2 * k + 1];
+        const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+        hh[k] = __halves2half2(h0, h1);
+        hl[k] = __halves2half2(__float2half_rn(x0 - __half2float(h0)),
+                               __float2half_rn(x1 - __half2float(h1)));
+      }
     }
   }
 

@@ -62,6 +62,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+enum BlendPath : int { BLEND_SIMT = 0, BLEND_TF32 = 1, BLEND_F16 = 2 };
 struct ProfRec {
   cudaEvent_t e0, e1;
   int slot;
@@ -76,11 +77,13 @@ struct smplk_model {
   EncodeTiledFn encode;
   bool has_tma;
   CUtensorMap tmap_pd_hi, tmap_pd_lo;      // forward: B operand rows = vertex coords
+  CUtensorMap tmap_pdh_hi, tmap_pdh_lo;    // forward, fp16-split operand
   CUtensorMap tmap_pdkn_hi, tmap_pdkn_lo;  // backward: B operand rows = blend features
   // host staging for smplk_forward_host
   void* stage_dev;
   size_t stage_bytes;
   // optional per-kernel device timing (smplk_profile_*)
+  BlendPath default_tc;  // BLEND_F16 unless SMPLK_BLEND=tf32 in the environment
   bool force_skin_v1;   // SMPLK_SKIN_V1=1 in the environment: per-vertex gather kernel (A/B testing)
   mutable bool prof_on;
   mutable std::vector<ProfRec> prof_pending;
@@ -135,12 +138,13 @@ static int upload(smplk_model* mdl, const std::vector<T>& h, const T** out) {
 
 static int make_tmap_2d(const smplk_model* mdl, CUtensorMap* map, const void* ptr, uint64_t inner,
                         uint64_t outer, uint32_t box_inner, uint32_t box_outer,
-                        CUtensorMapL2promotion promo) {
+                        CUtensorMapL2promotion promo, bool f16 = false) {
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {inner * sizeof(float)};
+  cuuint64_t strides[1] = {inner * (f16 ? sizeof(__half) : sizeof(float))};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = mdl->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims,
+  CUresult r = mdl->encode(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                           2, const_cast<void*>(ptr), dims,
                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SMPLK_E_DEVICE, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
@@ -241,6 +245,26 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
         knl[(size_t)k * d.Npad + n] = x - h;
       }
     }
+    {
+      // fp16 two-term split of posedirs * 2^e, e chosen so the largest entry lands in [2^14, 2^15)
+      float amax = 0.f;
+      for (int n = 0; n < d.N; ++n)
+        for (int k = 0; k < d.K; ++k) amax = std::max(amax, std::fabs(kn[(size_t)k * d.Npad + n]));
+      int e = 0;
+      if (amax > 0.f) e = 14 - (int)std::floor(std::log2(amax));
+      e = std::max(-20, std::min(e, 40));
+      d.pd_scale = std::ldexp(1.0f, e);
+      std::vector<__half> hh(nk, __float2half(0.f)), hl(nk, __float2half(0.f));
+      for (int n = 0; n < d.N; ++n)
+        for (int k = 0; k < d.K; ++k) {
+          const float x = kn[(size_t)k * d.Npad + n] * d.pd_scale;
+          const __half h = __float2half_rn(x);
+          hh[(size_t)n * d.Kpad + k] = h;
+          hl[(size_t)n * d.Kpad + k] = __float2half_rn(x - __half2float(h));
+        }
+      if (int r = upload(mdl, hh, &d.pd_nk_h_hi)) return r;
+      if (int r = upload(mdl, hl, &d.pd_nk_h_lo)) return r;
+    }
     if (int r = upload(mdl, hi, &d.pd_nk_hi)) return r;
     if (int r = upload(mdl, lo, &d.pd_nk_lo)) return r;
     if (int r = upload(mdl, kn, &d.pd_kn)) return r;
@@ -248,6 +272,8 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     if (int r = upload(mdl, knl, &d.pd_kn_lo)) return r;
   } else {
     d.pd_nk_hi = d.pd_nk_lo = d.pd_kn = d.pd_kn_hi = d.pd_kn_lo = nullptr;
+    d.pd_nk_h_hi = d.pd_nk_h_lo = nullptr;
+    d.pd_scale = 1.f;
   }
 
   // ---- LBS weights: ELL (k-major) + packed 4-wide form + CSC for the backward
@@ -410,7 +436,13 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return r;
     if (int r = make_tmap_2d(mdl, &mdl->tmap_pdkn_lo, d.pd_kn_lo, d.Npad, d.Kpad, kBlendBK, kBlendBN,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return r;
-    CUDA_TRY(cudaFuncSetAttribute(blend_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (int r = make_tmap_2d(mdl, &mdl->tmap_pdh_hi, d.pd_nk_h_hi, d.Kpad, d.Npad, 2 * kBlendBK, kBlendBN,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, true)) return r;
+    if (int r = make_tmap_2d(mdl, &mdl->tmap_pdh_lo, d.pd_nk_h_lo, d.Kpad, d.Npad, 2 * kBlendBK, kBlendBN,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, true)) return r;
+    CUDA_TRY(cudaFuncSetAttribute(blend_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kGemmSmemAlloc));
+    CUDA_TRY(cudaFuncSetAttribute(blend_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kGemmSmemAlloc));
     mdl->has_tma = true;
   }
@@ -452,6 +484,7 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   mdl->encode = nullptr;
   mdl->prof_on = false;
   { const char* e = getenv("SMPLK_SKIN_V1"); mdl->force_skin_v1 = e && e[0] == '1'; }
+  { const char* e = getenv("SMPLK_BLEND"); mdl->default_tc = (e && strcmp(e, "tf32") == 0) ? BLEND_TF32 : BLEND_F16; }
   for (int i = 0; i < SMPLK_PROF_SLOTS; ++i) { mdl->prof_ms[i] = 0.0; mdl->prof_n[i] = 0; }
   if (prop.major != 10) {
     delete mdl;
@@ -532,34 +565,46 @@ static int launch_pose_forward(const smplk_model* mdl, const PoseFwdArgs& pa, cu
   return 0;
 }
 
-static int launch_blend(const smplk_model* mdl, int rows, float* F_hi, float* F_lo, float* v_posed,
-                        uint32_t flags, cudaStream_t st) {
+static BlendPath choose_blend(const smplk_model* mdl, int rows, uint32_t flags) {
+  if (flags & SMPLK_FLAG_BLEND_SIMT) return BLEND_SIMT;
+  if (flags & SMPLK_FLAG_BLEND_TF32) return BLEND_TF32;
+  if (flags & SMPLK_FLAG_BLEND_TCGEN05) return mdl->default_tc;
+  return rows >= 32 ? mdl->default_tc : BLEND_SIMT;
+}
+
+static int launch_blend(const smplk_model* mdl, int rows, BlendPath path, float* F_hi, float* F_lo,
+                        float* v_posed, cudaStream_t st) {
   const ModelDev& d = mdl->d;
-  bool use_tc = rows >= 32;
-  if (flags & SMPLK_FLAG_BLEND_SIMT) use_tc = false;
-  if (flags & SMPLK_FLAG_BLEND_TCGEN05) use_tc = true;
-  if (use_tc) {
+  if (path != BLEND_SIMT) {
     if (!mdl->has_tma) return fail(SMPLK_E_DEVICE, "tcgen05 blend path unavailable on this device");
+    const bool f16 = path == BLEND_F16;
     CUtensorMap tm_fhi, tm_flo, tm_out;
-    if (int r = make_tmap_2d(mdl, &tm_fhi, F_hi, d.Kpad, rows, kBlendBK, kBlendBM,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return r;
-    if (int r = make_tmap_2d(mdl, &tm_flo, F_lo, d.Kpad, rows, kBlendBK, kBlendBM,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return r;
+    if (int r = make_tmap_2d(mdl, &tm_fhi, F_hi, d.Kpad, rows, f16 ? 2 * kBlendBK : kBlendBK, kBlendBM,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, f16)) return r;
+    if (int r = make_tmap_2d(mdl, &tm_flo, F_lo, d.Kpad, rows, f16 ? 2 * kBlendBK : kBlendBK, kBlendBM,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, f16)) return r;
     if (int r = make_tmap_2d(mdl, &tm_out, v_posed, d.Npad, rows, kEpiCols, kBlendBM,
                              CU_TENSOR_MAP_L2_PROMOTION_NONE)) return r;
     BlendGemmArgs ga;
+    const int elems_per_block = f16 ? 2 * kBlendBK : kBlendBK;
     ga.num_m_blocks = (rows + kBlendBM - 1) / kBlendBM;
     ga.num_n_blocks = d.Npad / kBlendBN;
-    ga.num_k_blocks = d.Kpad / kBlendBK;
+    ga.num_k_blocks = (d.Kpad + elems_per_block - 1) / elems_per_block;
     ga.num_splits = 1;
     ga.k_blocks_per_split = ga.num_k_blocks;
     ga.out_rows_per_split = 0;
+    ga.k_elems = d.Kpad;
+    ga.out_scale = f16 ? 1.0f / d.pd_scale : 1.0f;
     ga.bias = d.bias;
     const int tiles = ga.num_m_blocks * ga.num_n_blocks;
     const int grid = std::min(tiles, mdl->num_sms);
     ProfScope prof(mdl, st, SMPLK_PROF_BLEND_TCGEN05);
-    blend_tcgen05_kernel<<<grid, kGemmThreads, kGemmSmemAlloc, st>>>(
-        tm_fhi, tm_flo, mdl->tmap_pd_hi, mdl->tmap_pd_lo, tm_out, ga);
+    if (f16)
+      blend_tcgen05_kernel<true><<<grid, kGemmThreads, kGemmSmemAlloc, st>>>(
+          tm_fhi, tm_flo, mdl->tmap_pdh_hi, mdl->tmap_pdh_lo, tm_out, ga);
+    else
+      blend_tcgen05_kernel<false><<<grid, kGemmThreads, kGemmSmemAlloc, st>>>(
+          tm_fhi, tm_flo, mdl->tmap_pd_hi, mdl->tmap_pd_lo, tm_out, ga);
     LAUNCH_CHECK("blend_tcgen05_kernel");
   } else {
     BlendSimtArgs sa;
@@ -644,15 +689,19 @@ extern "C" int smplk_forward(const smplk_model* model, const smplk_forward_args*
     pa.pca_r = a->hand_pca_r ? a->hand_pca_r + (size_t)c0 * d.C : nullptr;
     pa.add_mean = (a->flags & SMPLK_FLAG_ADD_POSE_MEAN) ? 1 : 0;
     pa.transl = a->transl ? a->transl + (size_t)c0 * 3 : nullptr;
-    pa.F_hi = d.lbs_only ? nullptr : F_hi;
-    pa.F_lo = d.lbs_only ? nullptr : F_lo;
+    const BlendPath path = d.lbs_only ? BLEND_SIMT : choose_blend(model, rows, a->flags);
+    const bool f16 = !d.lbs_only && path == BLEND_F16;
+    pa.F_hi = (d.lbs_only || f16) ? nullptr : F_hi;
+    pa.F_lo = (d.lbs_only || f16) ? nullptr : F_lo;
+    pa.H_hi = f16 ? reinterpret_cast<__half*>(F_hi) : nullptr;   // fp16 rows alias the fp32 regions
+    pa.H_lo = f16 ? reinterpret_cast<__half*>(F_lo) : nullptr;
     pa.A = A;
     pa.joints = a->joints ? a->joints + (size_t)c0 * joints_ld : nullptr;
     pa.joints_ld = joints_ld;
     pa.full_pose = a->full_pose ? a->full_pose + (size_t)c0 * 3 * d.J : nullptr;
     if (int r = launch_pose_forward(model, pa, st)) return r;
     if (!d.lbs_only && (a->verts || (a->flags & SMPLK_FLAG_SAVE_FOR_BACKWARD))) {
-      if (int r = launch_blend(model, rows, F_hi, F_lo, v_posed, a->flags, st)) return r;
+      if (int r = launch_blend(model, rows, path, F_hi, F_lo, v_posed, st)) return r;
     }
     if (a->verts) {
       float* vout = a->verts + (size_t)c0 * d.V * 3;

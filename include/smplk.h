@@ -86,7 +86,8 @@ int smplk_model_get_info(const smplk_model* model, smplk_model_info* info);
 #define SMPLK_FLAG_SAVE_FOR_BACKWARD 1u /* keep v_posed & transforms of ALL bodies in the workspace */
 #define SMPLK_FLAG_ADD_POSE_MEAN 2u     /* full_pose += pose_mean (flat_hand_mean=False upstream)   */
 #define SMPLK_FLAG_BLEND_SIMT 4u        /* force the exact-fp32 SIMT blend kernel (small batch / bring-up) */
-#define SMPLK_FLAG_BLEND_TCGEN05 8u     /* force the tcgen05 3xTF32 blend GEMM                       */
+#define SMPLK_FLAG_BLEND_TCGEN05 8u     /* force a tcgen05 blend GEMM even for tiny batches           */
+#define SMPLK_FLAG_BLEND_TF32 16u       /* force the 3xTF32 operand format (default: fp16 two-term split) */
 
 /* Bytes of device workspace `smplk_forward` needs for `batch` bodies (256-byte aligned base). */
 size_t smplk_workspace_bytes(const smplk_model* model, int32_t batch, uint32_t flags);

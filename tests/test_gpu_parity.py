@@ -57,7 +57,8 @@ def test_native_library_is_loaded_and_counts_launches(dev, smpl_model):
 
 
 @pytest.mark.parametrize("B,flags", [(1, 0), (7, 0), (33, 0), (33, _lib.FLAG_BLEND_SIMT),
-                                     (129, 0), (700, 0)])
+                                     (129, 0), (700, 0), (129, _lib.FLAG_BLEND_TF32),
+                                     (700, _lib.FLAG_BLEND_TF32), (5, _lib.FLAG_BLEND_TCGEN05)])
 def test_smplh_forward_matches_oracle(dev, smplh_model, B, flags):
     m = smplh_model
     dm = smplk.DeviceModel(m, device=0, extra_vertex_ids=m["extra_vertex_ids"],
@@ -83,12 +84,32 @@ def test_smplh_forward_matches_oracle(dev, smplh_model, B, flags):
     assert _maxerr(fp, torch.tensor(pose)) == 0.0
 
 
-def test_tcgen05_and_simt_blend_agree(dev, smplh_model):
+def test_blend_operand_formats_agree(dev, smplh_model):
+    """exact-fp32 SIMT kernel vs tcgen05 fp16 two-term split (default) vs tcgen05 3xTF32."""
     dm = smplk.DeviceModel(smplh_model, device=0)
     betas, pose, transl = synthetic.make_inputs(smplh_model, 200, seed=9)
-    a = body_model_apply(dm, _t(betas, dev), _t(pose, dev), transl=_t(transl, dev), flags=_lib.FLAG_BLEND_SIMT)[0]
-    b = body_model_apply(dm, _t(betas, dev), _t(pose, dev), transl=_t(transl, dev), flags=_lib.FLAG_BLEND_TCGEN05)[0]
-    assert _maxerr(a, b) <= 5e-6
+    run = lambda f: body_model_apply(dm, _t(betas, dev), _t(pose, dev), transl=_t(transl, dev), flags=f)[0]
+    simt, f16, tf32 = run(_lib.FLAG_BLEND_SIMT), run(_lib.FLAG_BLEND_TCGEN05), run(_lib.FLAG_BLEND_TF32)
+    assert _maxerr(simt, f16) <= 5e-6 and _maxerr(simt, tf32) <= 5e-6 and _maxerr(f16, tf32) <= 2e-6
+
+
+def test_split_operands_hold_fp32_accuracy_on_large_blendshapes(dev):
+    """Stress the two-term splits: blendshape magnitudes 30x the synthetic default (cm-scale pose
+    correctives, dm-scale shape directions), betas up to |5|, pose up to pi."""
+    m = synthetic.make_model("smplh", seed=41)
+    m["posedirs"] = m["posedirs"] * 30.0
+    m["shapedirs"] = m["shapedirs"] * 10.0
+    m["posedirs"][5, 1, 7] = 0.9            # one huge entry sets the fp16 scale; tiny ones must survive
+    m["posedirs"][6, 2, 8] = 1e-7
+    dm = smplk.DeviceModel(m, device=0)
+    B = 256
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=3, pose_sigma=0.8)
+    betas = np.clip(betas * 2.5, -5, 5).astype(np.float32)
+    ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(
+        *[torch.tensor(x, dtype=torch.float64) for x in (betas, pose, transl)])
+    for flags in (0, _lib.FLAG_BLEND_TF32):
+        v = body_model_apply(dm, _t(betas, dev), _t(pose, dev), transl=_t(transl, dev), flags=flags)[0]
+        assert _maxerr(v, ref.vertices) <= TOL, flags
 
 
 def test_smpl_module_and_broadcast_betas(dev, smpl_model):

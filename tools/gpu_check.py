@@ -83,6 +83,8 @@ def main():
         worst = max(worst, check_forward("smpl", 37, _lib.FLAG_BLEND_SIMT, "simt/smpl"))
         worst = max(worst, check_forward("smplh", 9, _lib.FLAG_BLEND_SIMT, "simt/smplh-denseW", dense=True))
     elif mode == "tc":
+        worst = max(worst, check_forward("smplh", 128, _lib.FLAG_BLEND_TF32, "tcgen05-tf32/smplh"))
+        worst = max(worst, check_forward("smplh", 2500, _lib.FLAG_BLEND_TF32, "tcgen05-tf32/smplh"))
         worst = max(worst, check_forward("smplh", 128, _lib.FLAG_BLEND_TCGEN05, "tcgen05/smplh"))
         worst = max(worst, check_forward("smplh", 300, _lib.FLAG_BLEND_TCGEN05, "tcgen05/smplh"))
         worst = max(worst, check_forward("smpl", 1, _lib.FLAG_BLEND_TCGEN05, "tcgen05/smpl"))
