@@ -9,16 +9,18 @@ static BwdLayout bwd_layout(const smplk_model* mdl, int batch) {
   const ModelDev& d = mdl->d;
   BwdLayout L;
   memset(&L, 0, sizeof(L));
-  L.m_blocks = (batch + kBlendBM - 1) / kBlendBM;
-  L.mpad = L.m_blocks * kBlendBM;
+  const bool pair = mdl->use_2cta && batch > kBlendBM;      // CTA-pair GEMM: 256-row m blocks
+  const int bm = pair ? 2 * kBlendBM : kBlendBM;
+  L.m_blocks = (batch + bm - 1) / bm;
+  L.mpad = L.m_blocks * bm;
   size_t off = 0;
   L.off_dverts = off; off += align_up((size_t)batch * d.V * 3 * sizeof(float), 1024);
   L.off_dA = off;     off += align_up((size_t)batch * d.J * 12 * sizeof(float), 1024);
   L.off_dtr = off;    off += align_up((size_t)batch * 3 * sizeof(float), 1024);
   if (!d.lbs_only) {
     L.n_blocks = (d.Kpad + kBlendBN - 1) / kBlendBN;
-    L.k_blocks = d.Npad / kBlendBK;
-    int splits = std::max(1, mdl->num_sms / (L.m_blocks * L.n_blocks));
+    L.k_blocks = d.Npad / ((pair ? 128 : kRowBytes) / 4);
+    int splits = std::max(1, (pair ? mdl->num_sms / 2 : mdl->num_sms) / (L.m_blocks * L.n_blocks));
     splits = std::min(splits, L.k_blocks);
     L.kbps = (L.k_blocks + splits - 1) / splits;
     L.splits = (L.k_blocks + L.kbps - 1) / L.kbps;
@@ -114,8 +116,25 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     LAUNCH_CHECK("skin_backward_kernel");
 
     CUtensorMap tm_ahi, tm_alo, tm_out;
-    if (int r = make_tmap_2d(model, &tm_ahi, dvp_hi, d.Npad, B, kBlendBK, kBlendBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return r;
-    if (int r = make_tmap_2d(model, &tm_alo, dvp_lo, d.Npad, B, kBlendBK, kBlendBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return r;
+    const bool pair = model->use_2cta && B > kBlendBM;
+    if (pair) {
+      if (int r = make_operand_tmap_2cta(model, &tm_ahi, dvp_hi, d.Npad, B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, false)) return r;
+      if (int r = make_operand_tmap_2cta(model, &tm_alo, dvp_lo, d.Npad, B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, false)) return r;
+      if (int r = make_tmap_2d(model, &tm_out, dfeat, d.Kpad, (uint64_t)L.splits * L.mpad, kEpiCols, kBlendBM,
+                               CU_TENSOR_MAP_L2_PROMOTION_NONE)) return r;
+      BlendGemmArgs ga;
+      ga.num_m_blocks = L.m_blocks; ga.num_n_blocks = L.n_blocks; ga.num_k_blocks = L.k_blocks;
+      ga.num_splits = L.splits; ga.k_blocks_per_split = L.kbps; ga.out_rows_per_split = L.mpad;
+      ga.k_elems = d.Npad; ga.out_scale = 1.0f;
+      ga.bias = nullptr;
+      const int tiles_g = L.m_blocks * L.n_blocks * L.splits;
+      ProfScope prof(model, st, SMPLK_PROF_BLEND_BWD);
+      blend_tcgen05_2cta_kernel<false><<<2 * std::min(tiles_g, model->num_sms / 2), kGemmThreads, k2SmemAlloc, st>>>(
+          tm_ahi, tm_alo, model->tmap2_pdkn_hi, model->tmap2_pdkn_lo, tm_out, ga);
+      LAUNCH_CHECK("blend_tcgen05_2cta_kernel(backward)");
+    } else {
+    if (int r = make_operand_tmap(model, &tm_ahi, dvp_hi, d.Npad, B, kBlendBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, false)) return r;
+    if (int r = make_operand_tmap(model, &tm_alo, dvp_lo, d.Npad, B, kBlendBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, false)) return r;
     if (int r = make_tmap_2d(model, &tm_out, dfeat, d.Kpad, (uint64_t)L.splits * L.mpad, kEpiCols, kBlendBM,
                              CU_TENSOR_MAP_L2_PROMOTION_NONE)) return r;
     BlendGemmArgs ga;
@@ -128,6 +147,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     blend_tcgen05_kernel<false><<<std::min(tiles_g, model->num_sms), kGemmThreads, kGemmSmemAlloc, st>>>(
         tm_ahi, tm_alo, model->tmap_pdkn_hi, model->tmap_pdkn_lo, tm_out, ga); }
     LAUNCH_CHECK("blend_tcgen05_kernel(backward)");
+    }
   }
 
   PoseBwdArgs pb;

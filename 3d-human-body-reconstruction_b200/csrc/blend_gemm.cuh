@@ -29,11 +29,17 @@ namespace smplk {
 // ------------------------------------------------------------------------------------------
 // tcgen05 path
 // ------------------------------------------------------------------------------------------
-constexpr int kGemmStages = 2;
+#ifndef SMPLK_GEMM_ROW_BYTES
+#define SMPLK_GEMM_ROW_BYTES 128
+#endif
+constexpr int kRowBytes = SMPLK_GEMM_ROW_BYTES;        // bytes of K per smem row = swizzle span (128 or 64)
+static_assert(kRowBytes == 128 || kRowBytes == 64, "row bytes must match a TMA/UMMA swizzle mode");
+constexpr int kGemmStages = kRowBytes == 128 ? 2 : 4;  // 192 KB of operand stages either way
+constexpr int kKSteps = kRowBytes / 32;                // UMMA k-steps (32 B each) per k-block
 constexpr int kGemmThreads = 192;
-constexpr int kTileABytes = kBlendBM * kBlendBK * 4;   // 16 KB
-constexpr int kTileBBytes = kBlendBN * kBlendBK * 4;   // 32 KB
-constexpr int kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;  // hi+lo of both operands: 96 KB
+constexpr int kTileABytes = kBlendBM * kRowBytes;      // 16 KB (8 KB at 64 B rows)
+constexpr int kTileBBytes = kBlendBN * kRowBytes;      // 32 KB (16 KB)
+constexpr int kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;  // hi+lo of both operands
 constexpr int kEpiCols = 32;
 constexpr int kEpiBufBytes = kBlendBM * kEpiCols * 4;  // 16 KB
 constexpr int kGemmSmemBytes = kGemmStages * kStageBytes + 2 * kEpiBufBytes + kBlendBN * 4 + 256;
@@ -130,7 +136,7 @@ blend_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = stage_base + stage * kStageBytes;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-          const int k0 = kb * (kF16 ? 2 * kBlendBK : kBlendBK);   // elements per 128-byte row
+          const int k0 = kb * (kRowBytes / (kF16 ? 2 : 4));       // elements per smem row
           ptx::tma_load_2d(st, &tmap_f_hi, &full_bar[stage], k0, m0);
           ptx::tma_load_2d(st + kTileABytes, &tmap_f_lo, &full_bar[stage], k0, m0);
           ptx::tma_load_2d(st + 2 * kTileABytes, &tmap_pd_hi, &full_bar[stage], k0, n0);
@@ -144,7 +150,7 @@ blend_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
     if (lane == 0) {
       constexpr uint32_t idesc = kF16 ? ptx::make_idesc_f16(kBlendBM, kBlendBN)
                                       : ptx::make_idesc_tf32(kBlendBM, kBlendBN);
-      constexpr int kElemsPerBlock = kF16 ? 2 * kBlendBK : kBlendBK;
+      constexpr int kElemsPerBlock = kRowBytes / (kF16 ? 2 : 4);
       constexpr int kUmmaK = kF16 ? 16 : 8;
       int stage = 0;
       uint32_t phase = 0;
@@ -159,14 +165,14 @@ blend_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tcgen05_fence_after();
           const uint32_t st = ptx::smem_u32(stage_base + stage * kStageBytes);
-          const uint64_t a_hi = ptx::make_sw128_kmajor_desc(st);
-          const uint64_t a_lo = ptx::make_sw128_kmajor_desc(st + kTileABytes);
-          const uint64_t b_hi = ptx::make_sw128_kmajor_desc(st + 2 * kTileABytes);
-          const uint64_t b_lo = ptx::make_sw128_kmajor_desc(st + 2 * kTileABytes + kTileBBytes);
+          const uint64_t a_hi = ptx::make_kmajor_desc<kRowBytes>(st);
+          const uint64_t a_lo = ptx::make_kmajor_desc<kRowBytes>(st + kTileABytes);
+          const uint64_t b_hi = ptx::make_kmajor_desc<kRowBytes>(st + 2 * kTileABytes);
+          const uint64_t b_lo = ptx::make_kmajor_desc<kRowBytes>(st + 2 * kTileABytes + kTileBBytes);
           // the last k-block may be partial (TMA zero-fills past k_elems; skip those MMAs)
-          const int ksteps = min(4, (args.k_elems - kb * kElemsPerBlock) / kUmmaK);
+          const int ksteps = min(kKSteps, (args.k_elems - kb * kElemsPerBlock) / kUmmaK);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < kKSteps; ++k) {
             if (k < ksteps) {
               const uint64_t adv = static_cast<uint64_t>((k * 32) >> 4);  // +32 B per UMMA_K
               const uint32_t first = (kb != tc.kb0 || k != 0) ? 1u : 0u;

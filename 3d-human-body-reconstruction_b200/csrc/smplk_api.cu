@@ -14,6 +14,7 @@
 #include "../../include/smplk.h"
 #include "backward.cuh"
 #include "blend_gemm.cuh"
+#include "blend_gemm_2cta.cuh"
 #include "common.cuh"
 #include "pose_kernels.cuh"
 #include "skinning.cuh"
@@ -78,6 +79,9 @@ struct smplk_model {
   bool has_tma;
   CUtensorMap tmap_pd_hi, tmap_pd_lo;      // forward: B operand rows = vertex coords
   CUtensorMap tmap_pdh_hi, tmap_pdh_lo;    // forward, fp16-split operand
+  // CTA-pair kernel: 128-byte rows, 128-row boxes (each CTA loads half of the B tile)
+  CUtensorMap tmap2_pd_hi, tmap2_pd_lo, tmap2_pdh_hi, tmap2_pdh_lo, tmap2_pdkn_hi, tmap2_pdkn_lo;
+  bool use_2cta;
   CUtensorMap tmap_pdkn_hi, tmap_pdkn_lo;  // backward: B operand rows = blend features
   // host staging for smplk_forward_host
   void* stage_dev;
@@ -138,7 +142,8 @@ static int upload(smplk_model* mdl, const std::vector<T>& h, const T** out) {
 
 static int make_tmap_2d(const smplk_model* mdl, CUtensorMap* map, const void* ptr, uint64_t inner,
                         uint64_t outer, uint32_t box_inner, uint32_t box_outer,
-                        CUtensorMapL2promotion promo, bool f16 = false) {
+                        CUtensorMapL2promotion promo, bool f16 = false,
+                        CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {inner * (f16 ? sizeof(__half) : sizeof(float))};
   cuuint32_t box[2] = {box_inner, box_outer};
@@ -146,9 +151,23 @@ static int make_tmap_2d(const smplk_model* mdl, CUtensorMap* map, const void* pt
   CUresult r = mdl->encode(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                            2, const_cast<void*>(ptr), dims,
                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           swz, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SMPLK_E_DEVICE, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
   return 0;
+}
+
+// GEMM operand tile: rows of kRowBytes (the smem swizzle span), `box_rows` rows per TMA box.
+static int make_operand_tmap(const smplk_model* mdl, CUtensorMap* map, const void* ptr, uint64_t inner,
+                             uint64_t outer, uint32_t box_rows, CUtensorMapL2promotion promo, bool f16) {
+  return make_tmap_2d(mdl, map, ptr, inner, outer, kRowBytes / (f16 ? 2 : 4), box_rows, promo, f16,
+                      kRowBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+// Operand tile of the CTA-pair kernel: always 128-byte rows / 128B swizzle, 128 rows per box.
+static int make_operand_tmap_2cta(const smplk_model* mdl, CUtensorMap* map, const void* ptr, uint64_t inner,
+                                  uint64_t outer, CUtensorMapL2promotion promo, bool f16) {
+  return make_tmap_2d(mdl, map, ptr, inner, outer, 128 / (f16 ? 2 : 4), kBlendBM, promo, f16,
+                      CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 extern "C" int smplk_model_destroy(smplk_model* model) {
@@ -428,18 +447,29 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || fn == nullptr)
       return fail(SMPLK_E_DEVICE, "cuTensorMapEncodeTiled not available from the driver");
     mdl->encode = reinterpret_cast<EncodeTiledFn>(fn);
-    if (int r = make_tmap_2d(mdl, &mdl->tmap_pd_hi, d.pd_nk_hi, d.Kpad, d.Npad, kBlendBK, kBlendBN,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return r;
-    if (int r = make_tmap_2d(mdl, &mdl->tmap_pd_lo, d.pd_nk_lo, d.Kpad, d.Npad, kBlendBK, kBlendBN,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return r;
-    if (int r = make_tmap_2d(mdl, &mdl->tmap_pdkn_hi, d.pd_kn_hi, d.Npad, d.Kpad, kBlendBK, kBlendBN,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return r;
-    if (int r = make_tmap_2d(mdl, &mdl->tmap_pdkn_lo, d.pd_kn_lo, d.Npad, d.Kpad, kBlendBK, kBlendBN,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return r;
-    if (int r = make_tmap_2d(mdl, &mdl->tmap_pdh_hi, d.pd_nk_h_hi, d.Kpad, d.Npad, 2 * kBlendBK, kBlendBN,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, true)) return r;
-    if (int r = make_tmap_2d(mdl, &mdl->tmap_pdh_lo, d.pd_nk_h_lo, d.Kpad, d.Npad, 2 * kBlendBK, kBlendBN,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, true)) return r;
+    if (int r = make_operand_tmap(mdl, &mdl->tmap_pd_hi, d.pd_nk_hi, d.Kpad, d.Npad, kBlendBN,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, false)) return r;
+    if (int r = make_operand_tmap(mdl, &mdl->tmap_pd_lo, d.pd_nk_lo, d.Kpad, d.Npad, kBlendBN,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, false)) return r;
+    if (int r = make_operand_tmap(mdl, &mdl->tmap_pdkn_hi, d.pd_kn_hi, d.Npad, d.Kpad, kBlendBN,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, false)) return r;
+    if (int r = make_operand_tmap(mdl, &mdl->tmap_pdkn_lo, d.pd_kn_lo, d.Npad, d.Kpad, kBlendBN,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, false)) return r;
+    if (int r = make_operand_tmap(mdl, &mdl->tmap_pdh_hi, d.pd_nk_h_hi, d.Kpad, d.Npad, kBlendBN,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, true)) return r;
+    if (int r = make_operand_tmap(mdl, &mdl->tmap_pdh_lo, d.pd_nk_h_lo, d.Kpad, d.Npad, kBlendBN,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, true)) return r;
+    const CUtensorMapL2promotion p256 = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pd_hi, d.pd_nk_hi, d.Kpad, d.Npad, p256, false)) return r;
+    if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pd_lo, d.pd_nk_lo, d.Kpad, d.Npad, p256, false)) return r;
+    if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdh_hi, d.pd_nk_h_hi, d.Kpad, d.Npad, p256, true)) return r;
+    if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdh_lo, d.pd_nk_h_lo, d.Kpad, d.Npad, p256, true)) return r;
+    if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdkn_hi, d.pd_kn_hi, d.Npad, d.Kpad, p256, false)) return r;
+    if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdkn_lo, d.pd_kn_lo, d.Npad, d.Kpad, p256, false)) return r;
+    CUDA_TRY(cudaFuncSetAttribute(blend_tcgen05_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  k2SmemAlloc));
+    CUDA_TRY(cudaFuncSetAttribute(blend_tcgen05_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  k2SmemAlloc));
     CUDA_TRY(cudaFuncSetAttribute(blend_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kGemmSmemAlloc));
     CUDA_TRY(cudaFuncSetAttribute(blend_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -484,6 +514,7 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   mdl->encode = nullptr;
   mdl->prof_on = false;
   { const char* e = getenv("SMPLK_SKIN_V1"); mdl->force_skin_v1 = e && e[0] == '1'; }
+  { const char* e = getenv("SMPLK_GEMM_1CTA"); mdl->use_2cta = !(e && e[0] == '1'); }
   { const char* e = getenv("SMPLK_BLEND"); mdl->default_tc = (e && strcmp(e, "tf32") == 0) ? BLEND_TF32 : BLEND_F16; }
   for (int i = 0; i < SMPLK_PROF_SLOTS; ++i) { mdl->prof_ms[i] = 0.0; mdl->prof_n[i] = 0; }
   if (prop.major != 10) {
@@ -579,14 +610,43 @@ static int launch_blend(const smplk_model* mdl, int rows, BlendPath path, float*
     if (!mdl->has_tma) return fail(SMPLK_E_DEVICE, "tcgen05 blend path unavailable on this device");
     const bool f16 = path == BLEND_F16;
     CUtensorMap tm_fhi, tm_flo, tm_out;
-    if (int r = make_tmap_2d(mdl, &tm_fhi, F_hi, d.Kpad, rows, f16 ? 2 * kBlendBK : kBlendBK, kBlendBM,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, f16)) return r;
-    if (int r = make_tmap_2d(mdl, &tm_flo, F_lo, d.Kpad, rows, f16 ? 2 * kBlendBK : kBlendBK, kBlendBM,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, f16)) return r;
+    if (mdl->use_2cta && rows > kBlendBM) {
+      // CTA pairs: 256-body x 256-coord tiles, B operand halved per CTA
+      if (int r = make_operand_tmap_2cta(mdl, &tm_fhi, F_hi, d.Kpad, rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, f16)) return r;
+      if (int r = make_operand_tmap_2cta(mdl, &tm_flo, F_lo, d.Kpad, rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, f16)) return r;
+      if (int r = make_tmap_2d(mdl, &tm_out, v_posed, d.Npad, rows, kEpiCols, kBlendBM,
+                               CU_TENSOR_MAP_L2_PROMOTION_NONE)) return r;
+      BlendGemmArgs ga;
+      const int epb = 128 / (f16 ? 2 : 4);
+      ga.num_m_blocks = (rows + 2 * kBlendBM - 1) / (2 * kBlendBM);
+      ga.num_n_blocks = d.Npad / kBlendBN;
+      ga.num_k_blocks = (d.Kpad + epb - 1) / epb;
+      ga.num_splits = 1;
+      ga.k_blocks_per_split = ga.num_k_blocks;
+      ga.out_rows_per_split = 0;
+      ga.k_elems = d.Kpad;
+      ga.out_scale = f16 ? 1.0f / d.pd_scale : 1.0f;
+      ga.bias = d.bias;
+      const int tiles = ga.num_m_blocks * ga.num_n_blocks;
+      const int grid = 2 * std::min(tiles, mdl->num_sms / 2);
+      ProfScope prof(mdl, st, SMPLK_PROF_BLEND_TCGEN05);
+      if (f16)
+        blend_tcgen05_2cta_kernel<true><<<grid, kGemmThreads, k2SmemAlloc, st>>>(
+            tm_fhi, tm_flo, mdl->tmap2_pdh_hi, mdl->tmap2_pdh_lo, tm_out, ga);
+      else
+        blend_tcgen05_2cta_kernel<false><<<grid, kGemmThreads, k2SmemAlloc, st>>>(
+            tm_fhi, tm_flo, mdl->tmap2_pd_hi, mdl->tmap2_pd_lo, tm_out, ga);
+      LAUNCH_CHECK("blend_tcgen05_2cta_kernel");
+      return 0;
+    }
+    if (int r = make_operand_tmap(mdl, &tm_fhi, F_hi, d.Kpad, rows, kBlendBM,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, f16)) return r;
+    if (int r = make_operand_tmap(mdl, &tm_flo, F_lo, d.Kpad, rows, kBlendBM,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, f16)) return r;
     if (int r = make_tmap_2d(mdl, &tm_out, v_posed, d.Npad, rows, kEpiCols, kBlendBM,
                              CU_TENSOR_MAP_L2_PROMOTION_NONE)) return r;
     BlendGemmArgs ga;
-    const int elems_per_block = f16 ? 2 * kBlendBK : kBlendBK;
+    const int elems_per_block = kRowBytes / (f16 ? 2 : 4);
     ga.num_m_blocks = (rows + kBlendBM - 1) / kBlendBM;
     ga.num_n_blocks = d.Npad / kBlendBN;
     ga.num_k_blocks = (d.Kpad + elems_per_block - 1) / elems_per_block;
