@@ -127,6 +127,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
       ga.num_splits = L.splits; ga.k_blocks_per_split = L.kbps; ga.out_rows_per_split = L.mpad;
       ga.k_elems = d.Npad; ga.out_scale = 1.0f;
       ga.bias = nullptr;
+      ga.out = dfeat; ga.out_ld = d.Kpad; ga.out_rows = L.splits * L.mpad; ga.out_cols = d.Kpad;
       const int tiles_g = L.m_blocks * L.n_blocks * L.splits;
       ProfScope prof(model, st, SMPLK_PROF_BLEND_BWD);
       blend_tcgen05_2cta_kernel<false><<<2 * std::min(tiles_g, model->num_sms / 2), kGemmThreads, k2SmemAlloc, st>>>(
@@ -142,6 +143,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     ga.num_splits = L.splits; ga.k_blocks_per_split = L.kbps; ga.out_rows_per_split = L.mpad;
     ga.k_elems = d.Npad; ga.out_scale = 1.0f;
     ga.bias = nullptr;
+    ga.out = dfeat; ga.out_ld = d.Kpad; ga.out_rows = L.splits * L.mpad; ga.out_cols = d.Kpad;
     const int tiles_g = L.m_blocks * L.n_blocks * L.splits;
     { ProfScope prof(model, st, SMPLK_PROF_BLEND_BWD);
     blend_tcgen05_kernel<false><<<std::min(tiles_g, model->num_sms), kGemmThreads, kGemmSmemAlloc, st>>>(

@@ -55,6 +55,9 @@ struct BlendGemmArgs {
   int k_elems;             // contraction length in elements (multiple of the MMA K: 8 tf32 / 16 f16)
   float out_scale;         // accumulator scale applied in the epilogue (1/posedirs scale for f16)
   const float* bias;       // [num_n_blocks * 256] added in the epilogue, or null
+  float* out;              // output matrix for the direct (register -> global) epilogue
+  int out_ld;              // floats per output row
+  int out_rows, out_cols;  // valid extent (rows / columns beyond it are not written)
 };
 
 // tile -> (m block, n block, k range); m fastest so CTAs running together share the B operand

@@ -18,6 +18,14 @@
 
 namespace smplk {
 
+#ifndef SMPLK_EPI_DIRECT
+#define SMPLK_EPI_DIRECT 0
+#endif
+// Epilogue store path.  0 (default): swizzled smem staging + TMA store.  1: each thread writes its
+// row's 32 fp32 (one 128-byte line) straight from registers with 16-byte stores -- measured SLOWER
+// on B200 (f16 blend 0.213 ms vs 0.160 ms at B=4096): 32 partial lines per store instruction cost
+// more L2 write transactions than the smem round trip saves.  Kept for A/B runs only.
+constexpr bool k2DirectStore = SMPLK_EPI_DIRECT != 0;
 constexpr int k2Stages = 3;
 constexpr int k2TileABytes = kBlendBM * 128;        // this CTA's 128 rows of the A operand, 128 B of K
 constexpr int k2TileBBytes = (kBlendBN / 2) * 128;  // this CTA's half (128 rows) of the B operand
@@ -173,8 +181,35 @@ blend_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
       ptx::named_bar_sync(1, 128);
       bias_s[etid] = args.bias ? args.bias[n0 + etid] : 0.f;
       bias_s[etid + 128] = args.bias ? args.bias[n0 + etid + 128] : 0.f;
+      if (k2DirectStore) ptx::named_bar_sync(1, 128);   // bias visible to all epilogue warps
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tcgen05_fence_after();
+      if (k2DirectStore) {
+        const int grow = orow + row;                     // global output row of this thread
+        float* orow_ptr = args.out + (size_t)grow * args.out_ld + n0;
+        const bool row_ok = grow < args.out_rows;
+#pragma unroll 2
+        for (int c = 0; c < kBlendBN / kEpiCols; ++c) {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) +
+                                 static_cast<uint32_t>(acc * kBlendBN + c * kEpiCols);
+          ptx::tmem_ld_32x32b_x32(taddr, v);
+          ptx::tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int col = c * kEpiCols + 4 * q;
+              const float4 bq = *reinterpret_cast<const float4*>(bias_s + col);
+              float4 o;
+              o.x = fmaf(__uint_as_float(v[4 * q + 0]), oscale, bq.x);
+              o.y = fmaf(__uint_as_float(v[4 * q + 1]), oscale, bq.y);
+              o.z = fmaf(__uint_as_float(v[4 * q + 2]), oscale, bq.z);
+              o.w = fmaf(__uint_as_float(v[4 * q + 3]), oscale, bq.w);
+              if (n0 + col + 4 <= args.out_cols) *reinterpret_cast<float4*>(orow_ptr + col) = o;
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < kBlendBN / kEpiCols; ++c) {
         uint32_t v[32];
@@ -202,6 +237,7 @@ blend_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
           ptx::tma_store_commit();
         }
         ebuf ^= 1;
+      }
       }
       ptx::tcgen05_fence_before();
       ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);    // leader's barrier collects both CTAs

@@ -627,6 +627,7 @@ static int launch_blend(const smplk_model* mdl, int rows, BlendPath path, float*
       ga.k_elems = d.Kpad;
       ga.out_scale = f16 ? 1.0f / d.pd_scale : 1.0f;
       ga.bias = d.bias;
+      ga.out = v_posed; ga.out_ld = d.Npad; ga.out_rows = rows; ga.out_cols = d.Npad;
       const int tiles = ga.num_m_blocks * ga.num_n_blocks;
       const int grid = 2 * std::min(tiles, mdl->num_sms / 2);
       ProfScope prof(mdl, st, SMPLK_PROF_BLEND_TCGEN05);
@@ -656,6 +657,7 @@ static int launch_blend(const smplk_model* mdl, int rows, BlendPath path, float*
     ga.k_elems = d.Kpad;
     ga.out_scale = f16 ? 1.0f / d.pd_scale : 1.0f;
     ga.bias = d.bias;
+    ga.out = v_posed; ga.out_ld = d.Npad; ga.out_rows = rows; ga.out_cols = d.Npad;
     const int tiles = ga.num_m_blocks * ga.num_n_blocks;
     const int grid = std::min(tiles, mdl->num_sms);
     ProfScope prof(mdl, st, SMPLK_PROF_BLEND_TCGEN05);

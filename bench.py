@@ -261,19 +261,29 @@ def main():
             tf32_peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
             torch.backends.cuda.matmul.allow_tf32 = False
             del x, y
-        if "blend_tcgen05" in kern and tf32_peak:
+        if "blend_tcgen05" in kern:
             g_ms = kern["blend_tcgen05"]
             alg_tflops = GEMM_FLOPS_PER_BODY * B / (g_ms * 1e-3) / 1e12
-            peak = tf32_peak / 3.0      # fp32-accurate contraction = 3 TF32 passes (3xTF32)
+            fmt = os.environ.get("SMPLK_BLEND", "f16")
+            # fp32-accurate contraction = 3 tensor-core passes over two-term-split operands:
+            #   default: fp16 split, kind::f16 -> ceiling = measured bf16/fp16 dense peak / 3
+            #   SMPLK_BLEND=tf32: 3xTF32   -> ceiling = TF32 dense peak (cuBLAS, measured here) / 3
+            dense_peak = peaks["bf16"] if fmt != "tf32" else (tf32_peak or peaks["bf16"] / 2)
+            peak = dense_peak / 3.0
+            issued = 3 * 2 * B * 20736 * 480 / (g_ms * 1e-3) / 1e12
             extras["roofline"] = {
-                "kernel": "blend_tcgen05_kernel", "bound": "tensor", "achieved": alg_tflops, "peak": peak,
+                "kernel": "blend_tcgen05_2cta_kernel<%s>" % ("f16" if fmt != "tf32" else "tf32"),
+                "bound": "tensor", "achieved": alg_tflops, "peak": peak,
                 "unit": "TFLOP/s", "frac": alg_tflops / peak, "traffic": None,
                 "ms_per_launch": g_ms,
-                "note": "achieved = 2*B*20670*475 fp32-equivalent FLOPs / CUDA-event time; peak = TF32 dense "
-                        "measured live with cuBLAS 8192^3 (%.0f TFLOP/s; bf16 %s = %.0f) / 3 passes of 3xTF32; "
-                        "issued tensor FLOPs = 3*2*B*20736*480" % (tf32_peak, peaks["source"], peaks["bf16"]),
+                "note": "achieved = 2*B*20670*475 fp32-equivalent FLOPs / CUDA-event time on the launching stream; "
+                        "peak = dense tensor peak / 3 passes (%s: %.0f TFLOP/s, %s burst figure; sustained %.0f); "
+                        "issued tensor FLOPs = 3*2*B*20736*480" % (
+                            "bf16/fp16" if fmt != "tf32" else "tf32 cuBLAS 8192^3 measured in this run",
+                            dense_peak, peaks["source"], peaks["bf16_sustained"]),
                 "tf32_tflops_measured": tf32_peak,
-                "tensor_tflops_issued": 3 * 2 * B * 20736 * 480 / (g_ms * 1e-3) / 1e12}
+                "tensor_tflops_issued": issued,
+                "tensor_frac_issued": issued / dense_peak}
         if "skin" in kern:
             s_ms = kern["skin"]
             gbs = FWD_BYTES_SKIN * B / (s_ms * 1e-3) / 1e9
