@@ -36,6 +36,8 @@ struct ModelDev {
   const float* J_shapedirs;   // [J][3][NB]
   const int* parents;         // [J]
   const int* depth;           // [J]
+  const int* order;           // [J] joints sorted by depth (level-major)
+  const int* level_start;     // [max_depth+2] offsets into `order`
   const uint32_t* skin_idx4;  // [V] four u8 joint ids (ell_k <= 4)
   const float4* skin_w4;      // [V] four weights      (ell_k <= 4)
   const int* ell_idx;         // [ell_k][V]

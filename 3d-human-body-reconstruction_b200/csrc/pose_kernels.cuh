@@ -198,65 +198,133 @@ __device__ __forceinline__ void pose_forward_core(const ModelDev& m, const float
   }
 }
 
+// Forward kernel.  The chain runs through a per-warp shared-memory table of 3x4 transforms:
+// joints are visited level by level (`order` / `level_start` from the packer), one lane per joint
+// of the level, each reading its parent's world transform (3 x LDS.128) and writing its own --
+// max_depth (<= 10) short rounds instead of 51 dependent products.  (The backward kernel keeps
+// the register/shuffle variant of the walk, `pose_forward_core`, because it needs every lane's
+// forward values in registers.)
 template <int SLOTS>
 __global__ void __launch_bounds__(kPoseWarps * 32)
 pose_forward_kernel(const ModelDev m, const PoseFwdArgs a) {
-  extern __shared__ float pose_smem[];
+  extern __shared__ __align__(16) float pose_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kPoseWarps + warp;
   if (b >= a.B) return;
-  float* feat = pose_smem + warp * m.Kpad;
+  const int per_warp = max(m.Kpad, 32) + m.J * 12;
+  float* feat = pose_smem + warp * per_warp;                 // [Kpad] blend features
+  float* Gs = feat + max(m.Kpad, 32);                        // [J][12] transforms
   const float* betas_row = a.betas ? a.betas + (size_t)(a.betas_B == 1 ? 0 : b) * m.NB : nullptr;
 
-  float rv[SLOTS][3], R[SLOTS][9], Jr[SLOTS][3], Jrel[SLOTS][3], G[SLOTS][12];
+  // ---- per joint: pose -> R, rest joint; local transform [R | J] into the table
+  float Jr[SLOTS][3];
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
     const int j = lane + 32 * s;
-    rv[s][0] = rv[s][1] = rv[s][2] = 0.f;
+    Jr[s][0] = Jr[s][1] = Jr[s][2] = 0.f;
     if (j < m.J) {
-      load_joint_pose(m, a.pose, a.pca_l, a.pca_r, a.add_mean, b, j, rv[s]);
+      float rv[3], R[9];
+      load_joint_pose(m, a.pose, a.pca_l, a.pca_r, a.add_mean, b, j, rv);
       if (a.full_pose) {
         float* fp = a.full_pose + (size_t)b * 3 * m.J + 3 * j;
-        fp[0] = rv[s][0]; fp[1] = rv[s][1]; fp[2] = rv[s][2];
+        fp[0] = rv[0]; fp[1] = rv[1]; fp[2] = rv[2];
+      }
+      rodrigues(rv[0], rv[1], rv[2], R);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = m.J_template[3 * j + c];
+        if (betas_row != nullptr) {
+          const float* sd = m.J_shapedirs + (size_t)(3 * j + c) * m.NB;
+          for (int i = 0; i < m.NB; ++i) v = fmaf(sd[i], betas_row[i], v);
+        }
+        Jr[s][c] = v;
+      }
+      float4* g = reinterpret_cast<float4*>(Gs + j * 12);
+      g[0] = make_float4(R[0], R[1], R[2], Jr[s][0]);
+      g[1] = make_float4(R[3], R[4], R[5], Jr[s][1]);
+      g[2] = make_float4(R[6], R[7], R[8], Jr[s][2]);
+      if ((a.F_hi != nullptr || a.H_hi != nullptr) && j >= 1) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) feat[9 * (j - 1) + i] = R[i] - ((i % 4 == 0) ? 1.f : 0.f);
       }
     }
   }
-  pose_forward_core<SLOTS>(m, betas_row, rv, R, Jr, Jrel, G, lane);
-
-  // ---- GEMM A-operand row: [ (R_j - I) j=1..J-1 | betas | 0 pad ] split into TF32 hi / lo
   if (a.F_hi != nullptr || a.H_hi != nullptr) {
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-      const int j = lane + 32 * s;
-      if (j >= 1 && j < m.J) {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) feat[9 * (j - 1) + i] = R[s][i] - ((i % 4 == 0) ? 1.f : 0.f);
-      }
-    }
     for (int i = lane; i < m.Kpad - m.P; i += 32)
       feat[m.P + i] = (i < m.NB && betas_row) ? betas_row[i] : 0.f;
+  }
+  __syncwarp();
+  // ---- translation column -> offset from the parent's rest joint
+  float pj[SLOTS][3];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int j = lane + 32 * s;
+    pj[s][0] = pj[s][1] = pj[s][2] = 0.f;
+    if (j >= 1 && j < m.J) {
+      const float* gp = Gs + m.parents[j] * 12;
+      pj[s][0] = gp[3]; pj[s][1] = gp[7]; pj[s][2] = gp[11];
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int j = lane + 32 * s;
+    if (j >= 1 && j < m.J) {
+      Gs[j * 12 + 3] = Jr[s][0] - pj[s][0];
+      Gs[j * 12 + 7] = Jr[s][1] - pj[s][1];
+      Gs[j * 12 + 11] = Jr[s][2] - pj[s][2];
+    }
+  }
+  __syncwarp();
+
+  // ---- blend-feature rows (independent of the chain; issue the stores before walking it)
+  if (a.F_hi != nullptr) {
+    float* fh = a.F_hi + (size_t)b * m.Kpad;
+    float* fl = a.F_lo + (size_t)b * m.Kpad;
+    for (int k = lane; k < m.Kpad; k += 32) {
+      float x = feat[k];
+      float h = ptx::tf32_round(x);
+      fh[k] = h;
+      fl[k] = x - h;
+    }
+  }
+  if (a.H_hi != nullptr) {   // two-term fp16 split: x = hi + lo + O(2^-22 |x|)
+    __half2* hh = reinterpret_cast<__half2*>(a.H_hi + (size_t)b * m.Kpad);
+    __half2* hl = reinterpret_cast<__half2*>(a.H_lo + (size_t)b * m.Kpad);
+    for (int k = lane; k < m.Kpad / 2; k += 32) {
+      const float2 x = *reinterpret_cast<const float2*>(feat + 2 * k);
+      const __half h0 = __float2half_rn(x.x), h1 = __float2half_rn(x.y);
+      hh[k] = __halves2half2(h0, h1);
+      hl[k] = __halves2half2(__float2half_rn(x.x - __half2float(h0)),
+                             __float2half_rn(x.y - __half2float(h1)));
+    }
+  }
+
+  // ---- walk the tree level by level: G_j = G_parent(j) * L_j
+  for (int d = 1; d <= m.max_depth; ++d) {
+    const int l0 = m.level_start[d], l1 = m.level_start[d + 1];
+    for (int i = l0 + lane; i < l1; i += 32) {
+      const int j = m.order[i];
+      const float4* P4 = reinterpret_cast<const float4*>(Gs + m.parents[j] * 12);
+      float4* L4 = reinterpret_cast<float4*>(Gs + j * 12);
+      const float4 p0 = P4[0], p1 = P4[1], p2 = P4[2];
+      const float4 q0 = L4[0], q1 = L4[1], q2 = L4[2];
+      float4 o0, o1, o2;
+      o0.x = fmaf(p0.x, q0.x, fmaf(p0.y, q1.x, p0.z * q2.x));
+      o0.y = fmaf(p0.x, q0.y, fmaf(p0.y, q1.y, p0.z * q2.y));
+      o0.z = fmaf(p0.x, q0.z, fmaf(p0.y, q1.z, p0.z * q2.z));
+      o0.w = fmaf(p0.x, q0.w, fmaf(p0.y, q1.w, fmaf(p0.z, q2.w, p0.w)));
+      o1.x = fmaf(p1.x, q0.x, fmaf(p1.y, q1.x, p1.z * q2.x));
+      o1.y = fmaf(p1.x, q0.y, fmaf(p1.y, q1.y, p1.z * q2.y));
+      o1.z = fmaf(p1.x, q0.z, fmaf(p1.y, q1.z, p1.z * q2.z));
+      o1.w = fmaf(p1.x, q0.w, fmaf(p1.y, q1.w, fmaf(p1.z, q2.w, p1.w)));
+      o2.x = fmaf(p2.x, q0.x, fmaf(p2.y, q1.x, p2.z * q2.x));
+      o2.y = fmaf(p2.x, q0.y, fmaf(p2.y, q1.y, p2.z * q2.y));
+      o2.z = fmaf(p2.x, q0.z, fmaf(p2.y, q1.z, p2.z * q2.z));
+      o2.w = fmaf(p2.x, q0.w, fmaf(p2.y, q1.w, fmaf(p2.z, q2.w, p2.w)));
+      L4[0] = o0; L4[1] = o1; L4[2] = o2;
+    }
     __syncwarp();
-    if (a.F_hi != nullptr) {
-      float* fh = a.F_hi + (size_t)b * m.Kpad;
-      float* fl = a.F_lo + (size_t)b * m.Kpad;
-      for (int k = lane; k < m.Kpad; k += 32) {
-        float x = feat[k];
-        float h = ptx::tf32_round(x);
-        fh[k] = h;
-        fl[k] = x - h;
-      }
-    }
-    if (a.H_hi != nullptr) {   // two-term fp16 split: x = hi + lo + O(2^-22 |x|)
-      __half2* hh = reinterpret_cast<__half2*>(a.H_hi + (size_t)b * m.Kpad);
-      __half2* hl = reinterpret_cast<__half2*>(a.H_lo + (size_t)b * m.Kpad);
-      for (int k = lane; k < m.Kpad / 2; k += 32) {
-        const float x0 = feat[2 * k], x1 = feat[2 * k + 1];
-        const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-        hh[k] = __halves2half2(h0, h1);
-        hl[k] = __halves2half2(__float2half_rn(x0 - __half2float(h0)),
-                               __float2half_rn(x1 - __half2float(h1)));
-      }
-    }
   }
 
   // ---- skinning transforms A_j = [G_R | G_t - G_R J_j]  and FK joints
@@ -267,19 +335,17 @@ pose_forward_kernel(const ModelDev m, const PoseFwdArgs a) {
   for (int s = 0; s < SLOTS; ++s) {
     const int j = lane + 32 * s;
     if (j < m.J) {
-      float4* dst = reinterpret_cast<float4*>(a.A + ((size_t)b * m.J + j) * 12);
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        float t = G[s][r * 4 + 3] - (G[s][r * 4 + 0] * Jr[s][0] + G[s][r * 4 + 1] * Jr[s][1] +
-                                     G[s][r * 4 + 2] * Jr[s][2]);
-        dst[r] = make_float4(G[s][r * 4 + 0], G[s][r * 4 + 1], G[s][r * 4 + 2], t);
-      }
+      const float4* G4 = reinterpret_cast<const float4*>(Gs + j * 12);
+      float4 g0 = G4[0], g1 = G4[1], g2 = G4[2];
       if (a.joints) {
         float* jo = a.joints + (size_t)b * a.joints_ld + 3 * j;
-        jo[0] = G[s][3] + tx;
-        jo[1] = G[s][7] + ty;
-        jo[2] = G[s][11] + tz;
+        jo[0] = g0.w + tx; jo[1] = g1.w + ty; jo[2] = g2.w + tz;
       }
+      g0.w -= g0.x * Jr[s][0] + g0.y * Jr[s][1] + g0.z * Jr[s][2];
+      g1.w -= g1.x * Jr[s][0] + g1.y * Jr[s][1] + g1.z * Jr[s][2];
+      g2.w -= g2.x * Jr[s][0] + g2.y * Jr[s][1] + g2.z * Jr[s][2];
+      float4* dst = reinterpret_cast<float4*>(a.A + ((size_t)b * m.J + j) * 12);
+      dst[0] = g0; dst[1] = g1; dst[2] = g2;
     }
   }
 }

@@ -211,6 +211,16 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
   d.max_depth = max_depth;
   if (int r = upload(mdl, parents, &d.parents)) return r;
   if (int r = upload(mdl, depth, &d.depth)) return r;
+  {
+    std::vector<int> order, lstart(max_depth + 2, 0);
+    for (int dd = 0; dd <= max_depth; ++dd) {
+      lstart[dd] = (int)order.size();
+      for (int j = 0; j < J; ++j) if (depth[j] == dd) order.push_back(j);
+    }
+    lstart[max_depth + 1] = (int)order.size();
+    if (int r = upload(mdl, order, &d.order)) return r;
+    if (int r = upload(mdl, lstart, &d.level_start)) return r;
+  }
 
   // ---- template / bias
   std::vector<float> bias(d.Npad, 0.f);
@@ -586,7 +596,7 @@ extern "C" int smplk_workspace_layout(const smplk_model* model, int32_t batch, u
 static int launch_pose_forward(const smplk_model* mdl, const PoseFwdArgs& pa, cudaStream_t st) {
   const ModelDev& d = mdl->d;
   const int blocks = (pa.B + kPoseWarps - 1) / kPoseWarps;
-  const size_t smem = (size_t)kPoseWarps * std::max(d.Kpad, 32) * sizeof(float);
+  const size_t smem = (size_t)kPoseWarps * (std::max(d.Kpad, 32) + d.J * 12) * sizeof(float);
   ProfScope prof(mdl, st, SMPLK_PROF_POSE_FWD);
   if (d.J <= 32)
     pose_forward_kernel<1><<<blocks, kPoseWarps * 32, smem, st>>>(d, pa);

@@ -353,7 +353,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core blend, fp32 elsewhere)",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (blend contraction on tensor cores with two-term split operands, %s; fp32 accumulate and fp32 everywhere else)" % ("3xTF32" if os.environ.get("SMPLK_BLEND") == "tf32" else "fp16 hi+lo"),
                 "data": "synthetic",
                 "config": {"workload": "SMPL-H forward+LBS batch %d per GPU, fp32, 52 joints, 16 betas, 459 posedirs "
                                        "(BASELINE.json configs[1])" % B,

@@ -336,6 +336,48 @@ def test_full_size_properties_batch_4096(dev, smplh_model):
     assert float(((a - j0) * torch.tensor([-1., -1., 1.], device=dev) - (b - j0)).abs().max()) <= 5e-6
 
 
+def test_chunked_large_batch_and_sequence_replay(dev, smplh_model):
+    """BASELINE configs 4/5 shapes: batches beyond the 8192-body chunk and a long motion sequence
+    with ONE broadcast betas row (the 100k-frame replay of config 5, shortened to 20k frames here;
+    frames are independent so the property is size independent)."""
+    m = smplh_model
+    dm = smplk.DeviceModel(m, device=0)
+    N = 20000
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal((97, 156)).astype(np.float32) * 0.3     # a 97-frame clip, tiled
+    pose = np.tile(base, (N // 97 + 1, 1))[:N]
+    trans = np.cumsum(rng.standard_normal((N, 3)).astype(np.float32) * 0.01, axis=0)
+    betas = rng.standard_normal((1, 16)).astype(np.float32)
+    v, j, _, _ = body_model_apply(dm, _t(betas, dev), _t(pose, dev), transl=_t(trans, dev))
+    assert v.shape == (N, 6890, 3) and torch.isfinite(v).all()
+    # periodicity: frame i and i+97 differ exactly by their translation difference
+    d = (v[97:97 + 500] - v[:500]) - (_t(trans[97:597], dev) - _t(trans[:500], dev))[:, None]
+    assert float(d.abs().max()) <= 4e-6
+    # spot-check frames on both sides of the 8192 chunk boundaries against the oracle
+    idx = np.array([0, 8191, 8192, 8193, 16383, 16384, 19999])
+    ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(
+        torch.tensor(np.repeat(betas, len(idx), 0), dtype=torch.float64),
+        torch.tensor(pose[idx], dtype=torch.float64), torch.tensor(trans[idx], dtype=torch.float64))
+    ii = torch.as_tensor(idx, device=dev)
+    assert _maxerr(v[ii], ref.vertices) <= TOL and _maxerr(j[ii], ref.joints) <= TOL
+
+
+def test_rigged_mesh_replay_large_vertex_count(dev):
+    """config 5, LBS-only variant: recovered mesh with Nv = 50,001 (odd 3*Nv -> scalar store path)
+    and Nv = 200,000, replayed over a clip in one call."""
+    for nv in (50001, 200000):
+        rig = synthetic.make_rigged_mesh(nv, seed=13)
+        rm = smplk.RecoverModel(rig)
+        rng = np.random.default_rng(nv)
+        poses = rng.standard_normal((40, 72)) * 0.4
+        trans = rng.standard_normal((40, 3))
+        out = rm.replay(poses, trans)
+        assert out.shape == (40, nv, 3)
+        for i in (0, 39):
+            ref = O.np_lbs_only(rig, poses[i], trans[i])["verts"]
+            assert np.abs(out[i] - ref).max() <= TOL
+
+
 def test_errors_are_loud(dev, smpl_model):
     dm = smplk.DeviceModel(smpl_model, device=0)
     b, p, t = synthetic.make_inputs(smpl_model, 2)
