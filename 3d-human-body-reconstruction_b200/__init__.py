@@ -11,7 +11,7 @@ from ._lib import DeviceModel, build, load  # noqa: F401
 
 
 def __getattr__(name):  # torch-dependent modules load lazily
-    if name in ("SMPL", "SMPLH", "ModelOutput", "create", "body_model_apply", "load_model_file"):
+    if name in ("SMPL", "SMPLH", "ModelOutput", "create", "body_model_apply", "load_model_file", "vertex_l2_loss"):
         from . import body_models
         return getattr(body_models, name)
     if name in ("SMPLModel", "SMPLHModel", "RecoverModel"):

@@ -83,7 +83,7 @@ EXPORTED_SYMBOLS = [
     "smplk_model_create", "smplk_model_destroy", "smplk_model_get_info", "smplk_workspace_bytes",
     "smplk_forward", "smplk_backward_scratch_bytes", "smplk_backward", "smplk_regress_joints",
     "smplk_batch_rodrigues", "smplk_forward_host", "smplk_last_error_string", "smplk_version",
-    "smplk_launch_count", "smplk_workspace_layout", "smplk_profile_enable", "smplk_profile_read",
+    "smplk_launch_count", "smplk_workspace_layout", "smplk_profile_enable", "smplk_profile_read", "smplk_vertex_l2",
 ]
 PROF_SLOTS = ["pose_fwd", "blend_tcgen05", "blend_simt", "skin", "dA", "skin_bwd", "blend_bwd",
               "pose_bwd"]
@@ -150,6 +150,10 @@ def load():
                                            ctypes.POINTER(ctypes.c_size_t),
                                            ctypes.POINTER(ctypes.c_int32)]
     lib.smplk_workspace_layout.restype = ctypes.c_int
+    lib.smplk_vertex_l2.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                    ctypes.c_void_p]
+    lib.smplk_vertex_l2.restype = ctypes.c_int
     lib.smplk_profile_enable.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.smplk_profile_enable.restype = ctypes.c_int
     lib.smplk_profile_read.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),

@@ -127,6 +127,38 @@ class _BodyModelFn(torch.autograd.Function):
         return None, None, None, d_betas, d_pose, d_pl, d_pr, d_tr
 
 
+class _VertexL2Fn(torch.autograd.Function):
+    """loss (B,) = scale * sum ||V - V*||^2 per body, gradient produced in the same pass."""
+
+    @staticmethod
+    def forward(ctx, verts, target, scale):
+        v, t = verts.contiguous(), target.contiguous()
+        B = v.shape[0]
+        n = v[0].numel()
+        loss = torch.empty(B, device=v.device, dtype=torch.float32)
+        grad = torch.empty_like(v) if verts.requires_grad else None
+        lib = _lib.load()
+        with torch.cuda.device(v.device):
+            _lib.check(lib.smplk_vertex_l2(B, n, _ptr(v), _ptr(t), float(scale), _ptr(grad), _ptr(loss),
+                                           v.device.index or 0,
+                                           ctypes.c_void_p(torch.cuda.current_stream(v.device).cuda_stream)))
+        ctx.grad = grad
+        return loss
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        g = ctx.grad
+        if g is None:
+            return None, None, None
+        return g * d_loss.view(-1, *([1] * (g.dim() - 1))), None, None
+
+
+def vertex_l2_loss(verts, target, scale=1.0):
+    """Per-body squared-L2 vertex (or joint) data term, fused loss + gradient kernel.
+    `vertex_l2_loss(v, t).sum().backward()` is the fitting step of BASELINE config 3."""
+    return _VertexL2Fn.apply(verts, target, scale)
+
+
 def body_model_apply(dm, betas, pose, pca_l=None, pca_r=None, transl=None, add_pose_mean=False,
                      want_regressed=False, flags=0):
     """Functional entry point: (verts, joints_fk_plus_picks, joints_regressed|None, full_pose)."""

@@ -39,6 +39,35 @@ __global__ void scatter_joint_grads_kernel(const ModelDev m, int B, const float*
   }
 }
 
+// Fused vertex L2 data term of the fitting step (config 3; squared-L2 form of
+// lib/Gen_SMPLH/fitting.py:491-495 applied to vertices):  loss[b] = scale * sum ||V - V*||^2,
+// grad = 2 * scale * (V - V*).  One pass over V and V* instead of ~6 elementwise torch kernels.
+__global__ void __launch_bounds__(256)
+vertex_l2_kernel(int n_per_body, const float* __restrict__ verts, const float* __restrict__ target,
+                 float scale, float* __restrict__ grad, float* __restrict__ loss) {
+  __shared__ float red[8];
+  const int b = blockIdx.y;
+  const size_t base = (size_t)b * n_per_body;
+  const int chunk = (n_per_body + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * chunk, i1 = min(n_per_body, i0 + chunk);
+  float acc = 0.f;
+  const float s2 = 2.f * scale;
+  for (int i = i0 + threadIdx.x; i < i1; i += 256) {
+    const float d = verts[base + i] - __ldcs(target + base + i);
+    acc = fmaf(d, d, acc);
+    if (grad) grad[base + i] = s2 * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(loss + b, scale * t);
+  }
+}
+
 struct SkinBwdArgs {
   int B;
   int bodies_per_block;
@@ -141,6 +170,148 @@ skin_backward_kernel(const ModelDev m, const SkinBwdArgs a) {
   }
 }
 
+// Grouped / warp-streamed version of skin_backward_kernel (same structure as skin_grouped_kernel):
+// each warp streams its 128 vertices of d_verts through a private cp.async ring (8-byte copies:
+// rows of (B,V,3) are only 8-byte aligned), a thread owns 4 consecutive vertices and fetches each
+// of the group's <= 8 distinct transforms once, d_v_posed = sum_u w_u R_u^T g is written as TF32
+// hi/lo rows with 16-byte coalesced stores (pad columns up to Npad are zeroed: they are the K
+// padding of the backward GEMM).
+constexpr int kSkinBwdStages = 3;
+
+template <int kStages>
+__global__ void __launch_bounds__(kGrpThreads, 2)
+skin_backward_grouped_kernel(const ModelDev m, const SkinBwdArgs a) {
+  extern __shared__ __align__(16) float sbg_smem[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int v0 = blockIdx.x * kSkinTileVerts;
+  const int a_floats = m.J * 12;
+  const int a_chunks = m.J * 3;
+  const int a_pad = grp_a_pad(m.J);
+  float* ring = sbg_smem;                                        // [stages][3072] g in, hi out
+  float* lobuf = sbg_smem + kStages * kSkinTileVerts * 3;        // [3072] lo out
+  float* Abuf = lobuf + kSkinTileVerts * 3;                      // [2][8][a_pad]
+  const int b0 = blockIdx.y * a.bodies_per_block;
+  const int b1 = min(a.B, b0 + a.bodies_per_block);
+  if (b0 >= b1) return;
+
+  const int wf0 = v0 * 3 + warp * kWarpFloats;
+  const int n_in = max(0, min(kWarpFloats, m.V * 3 - wf0));      // valid input floats
+  const int n_out = max(0, min(kWarpFloats, m.Npad - wf0));      // output floats incl. zero padding
+  const int g = (v0 >> 2) + tid;
+  const bool g_valid = 4 * g < m.V;
+  uint2 jid = make_uint2(0u, 0u);
+  float4 w[kGrpJoints];
+  uint32_t used = 0;
+#pragma unroll
+  for (int u = 0; u < kGrpJoints; ++u) {
+    w[u] = g_valid ? m.grp_w[(size_t)g * kGrpJoints + u] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (w[u].x != 0.f || w[u].y != 0.f || w[u].z != 0.f || w[u].w != 0.f) used |= 1u << u;
+  }
+  if (g_valid) jid = m.grp_joints[g];
+  used = __reduce_or_sync(0xffffffffu, used);
+  // never-copied tail floats of the ring must be finite (they are multiplied by zero weights)
+  for (int i = tid; i < kStages * kSkinTileVerts * 3; i += kGrpThreads) ring[i] = 0.f;
+  __syncthreads();
+
+  auto issue_A = [&](int grp) {
+    const int bb0 = b0 + grp * kGrpABodies;
+    const int nb = min(kGrpABodies, b1 - bb0);
+    float* dstA = Abuf + (grp & 1) * kGrpABodies * a_pad;
+    for (int c = tid; c < nb * a_chunks; c += kGrpThreads) {
+      const int bi = c / a_chunks, cc = c - bi * a_chunks;
+      ptx::cp_async_16(dstA + bi * a_pad + 4 * cc, a.A + (size_t)(bb0 + bi) * a_floats + 4 * cc);
+    }
+  };
+  auto issue_g = [&](int b) {
+    if (b < b1) {
+      const float* src = a.dverts + (size_t)b * m.V * 3 + wf0;
+      float* dst = ring + ((b - b0) % kStages) * (kSkinTileVerts * 3) + warp * kWarpFloats;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int c = lane + 32 * i;                       // 8-byte chunk of the warp slice
+        if (2 * c + 2 <= n_in) ptx::cp_async_8(dst + 2 * c, src + 2 * c);
+      }
+      if ((n_in & 1) && lane == 0) dst[n_in - 1] = src[n_in - 1];
+    }
+    ptx::cp_async_commit();
+  };
+
+  issue_A(0);
+#pragma unroll
+  for (int i = 0; i < kStages - 1; ++i) issue_g(b0 + i);
+
+  for (int b = b0; b < b1; ++b) {
+    const int rel = b - b0;
+    const int agrp = rel / kGrpABodies;
+    issue_g(b + kStages - 1);
+    ptx::cp_async_wait<kStages - 1>();
+    if ((rel % kGrpABodies) == 0) {
+      __syncthreads();
+      if (b + kGrpABodies < b1) issue_A(agrp + 1);
+    } else {
+      __syncwarp();
+    }
+    const float* Ab = Abuf + ((agrp & 1) * kGrpABodies + (rel % kGrpABodies)) * a_pad;
+    float* slot = ring + (rel % kStages) * (kSkinTileVerts * 3) + warp * kWarpFloats;
+    float* lo = lobuf + warp * kWarpFloats;
+    float4* mine = reinterpret_cast<float4*>(slot) + 3 * lane;
+    const float4 c0 = mine[0], c1 = mine[1], c2 = mine[2];
+    const float gx[4] = {c0.x, c0.w, c1.z, c2.y};
+    const float gy[4] = {c0.y, c1.x, c1.w, c2.z};
+    const float gz[4] = {c0.z, c1.y, c2.x, c2.w};
+    float ox[4] = {0.f, 0.f, 0.f, 0.f}, oy[4] = {0.f, 0.f, 0.f, 0.f}, oz[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < kGrpJoints; ++u) {
+      if (used & (1u << u)) {
+        const int j = ((u < 4 ? jid.x : jid.y) >> (8 * (u & 3))) & 0xff;
+        const float4* Aj = reinterpret_cast<const float4*>(Ab + j * 12);
+        const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+        const float wu[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {   // R_u^T g
+          const float px = fmaf(r0.x, gx[i], fmaf(r1.x, gy[i], r2.x * gz[i]));
+          const float py = fmaf(r0.y, gx[i], fmaf(r1.y, gy[i], r2.y * gz[i]));
+          const float pz = fmaf(r0.z, gx[i], fmaf(r1.z, gy[i], r2.z * gz[i]));
+          ox[i] = fmaf(wu[i], px, ox[i]);
+          oy[i] = fmaf(wu[i], py, oy[i]);
+          oz[i] = fmaf(wu[i], pz, oz[i]);
+        }
+      }
+    }
+    float o[12] = {ox[0], oy[0], oz[0], ox[1], oy[1], oz[1], ox[2], oy[2], oz[2], ox[3], oy[3], oz[3]};
+    float h[12], l[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const bool ok = 4 * g + i / 3 < m.V;           // zero (not garbage*0) beyond the last vertex
+      const float x = ok ? o[i] : 0.f;
+      h[i] = ptx::tf32_round(x);
+      l[i] = x - h[i];
+    }
+    __syncwarp();                                    // everyone has read its inputs from the slot
+    float4* hs = reinterpret_cast<float4*>(slot) + 3 * lane;
+    float4* ls = reinterpret_cast<float4*>(lo) + 3 * lane;
+    hs[0] = make_float4(h[0], h[1], h[2], h[3]); hs[1] = make_float4(h[4], h[5], h[6], h[7]);
+    hs[2] = make_float4(h[8], h[9], h[10], h[11]);
+    ls[0] = make_float4(l[0], l[1], l[2], l[3]); ls[1] = make_float4(l[4], l[5], l[6], l[7]);
+    ls[2] = make_float4(l[8], l[9], l[10], l[11]);
+    __syncwarp();
+    float4* oh = reinterpret_cast<float4*>(a.dvp_hi + (size_t)b * m.Npad + wf0);
+    float4* ol = reinterpret_cast<float4*>(a.dvp_lo + (size_t)b * m.Npad + wf0);
+    const float4* sh4 = reinterpret_cast<const float4*>(slot);
+    const float4* sl4 = reinterpret_cast<const float4*>(lo);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int c = lane + 32 * i;
+      if (4 * c + 4 <= n_out) {
+        oh[c] = sh4[c];
+        ol[c] = sl4[c];
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // dA[b,j] (3x4) = sum over the vertices bound to joint j of  w * g (x) [v_posed; 1];
 // also dtr[b] = sum_v g[b,v].  One block per body; warps walk the joint -> vertex (CSC) lists.
 struct DAArgs {
@@ -164,14 +335,36 @@ __global__ void __launch_bounds__(kDAThreads) dA_kernel(const ModelDev m, const 
     float acc[12];
 #pragma unroll
     for (int q = 0; q < 12; ++q) acc[q] = 0.f;
-    for (int n = m.csc_ptr[j] + lane; n < m.csc_ptr[j + 1]; n += 32) {
-      const int v = m.csc_vert[n];
-      const float w = m.csc_w[n];
-      const float gx = w * g[3 * v + 0], gy = w * g[3 * v + 1], gz = w * g[3 * v + 2];
-      const float x = vp[3 * v + 0], y = vp[3 * v + 1], z = vp[3 * v + 2];
-      acc[0] = fmaf(gx, x, acc[0]); acc[1] = fmaf(gx, y, acc[1]); acc[2] = fmaf(gx, z, acc[2]); acc[3] += gx;
-      acc[4] = fmaf(gy, x, acc[4]); acc[5] = fmaf(gy, y, acc[5]); acc[6] = fmaf(gy, z, acc[6]); acc[7] += gy;
-      acc[8] = fmaf(gz, x, acc[8]); acc[9] = fmaf(gz, y, acc[9]); acc[10] = fmaf(gz, z, acc[10]); acc[11] += gz;
+    // 4 list entries per lane per trip: the index loads, then all 8 gathers, are independent
+    // (the plain one-entry loop was bound by two dependent L2 round trips per entry)
+    const int beg = m.csc_ptr[j], end = m.csc_ptr[j + 1];
+    for (int n0 = beg + lane; n0 < end; n0 += 128) {
+      int vv[4];
+      float ww[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int n = n0 + 32 * u;
+        const bool ok = n < end;
+        vv[u] = ok ? m.csc_vert[n] : 0;
+        ww[u] = ok ? m.csc_w[n] : 0.f;
+      }
+      float gq[4][3], xq[4][3];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          gq[u][c] = g[3 * vv[u] + c];
+          xq[u][c] = vp[3 * vv[u] + c];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float gx = ww[u] * gq[u][0], gy = ww[u] * gq[u][1], gz = ww[u] * gq[u][2];
+        const float x = xq[u][0], y = xq[u][1], z = xq[u][2];
+        acc[0] = fmaf(gx, x, acc[0]); acc[1] = fmaf(gx, y, acc[1]); acc[2] = fmaf(gx, z, acc[2]); acc[3] += gx;
+        acc[4] = fmaf(gy, x, acc[4]); acc[5] = fmaf(gy, y, acc[5]); acc[6] = fmaf(gy, z, acc[6]); acc[7] += gy;
+        acc[8] = fmaf(gz, x, acc[8]); acc[9] = fmaf(gz, y, acc[9]); acc[10] = fmaf(gz, z, acc[10]); acc[11] += gz;
+      }
     }
 #pragma unroll
     for (int q = 0; q < 12; ++q) {

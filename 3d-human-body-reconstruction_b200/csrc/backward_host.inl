@@ -105,15 +105,28 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     SkinBwdArgs sb;
     sb.B = B; sb.dverts = dverts; sb.A = A; sb.dvp_hi = dvp_hi; sb.dvp_lo = dvp_lo;
     const int tiles = (d.V + kSkinTileVerts - 1) / kSkinTileVerts;
-    int bpb = 16;
-    while (bpb > 1 && (long)tiles * ((B + bpb - 1) / bpb) < 4L * 4 * model->num_sms) bpb >>= 1;
-    sb.bodies_per_block = bpb;
-    dim3 grid(tiles, (B + bpb - 1) / bpb);
-    const size_t smem = (size_t)(3 * kSkinTileVerts * 3 + d.J * 12) * sizeof(float);
-    { ProfScope prof(model, st, SMPLK_PROF_SKIN_BWD);
-    if (d.ell_k <= 4) skin_backward_kernel<true><<<grid, kSkinThreads, smem, st>>>(d, sb);
-    else skin_backward_kernel<false><<<grid, kSkinThreads, smem, st>>>(d, sb); }
-    LAUNCH_CHECK("skin_backward_kernel");
+    const bool grouped = d.grp_ok && !model->force_skin_v1 && ((d.V * 3) % 2 == 0);
+    if (grouped) {
+      constexpr int kS = kSkinBwdStages;
+      int bpb = 32;
+      while (bpb > 8 && (long)tiles * ((B + bpb - 1) / bpb) < 3L * 2 * model->num_sms) bpb >>= 1;
+      sb.bodies_per_block = bpb;
+      dim3 grid(tiles, (B + bpb - 1) / bpb);
+      const size_t smem = (size_t)((kS + 1) * kSkinTileVerts * 3 + 2 * kGrpABodies * grp_a_pad(d.J)) * sizeof(float);
+      ProfScope prof(model, st, SMPLK_PROF_SKIN_BWD);
+      skin_backward_grouped_kernel<kS><<<grid, kGrpThreads, smem, st>>>(d, sb);
+      LAUNCH_CHECK("skin_backward_grouped_kernel");
+    } else {
+      int bpb = 16;
+      while (bpb > 1 && (long)tiles * ((B + bpb - 1) / bpb) < 4L * 4 * model->num_sms) bpb >>= 1;
+      sb.bodies_per_block = bpb;
+      dim3 grid(tiles, (B + bpb - 1) / bpb);
+      const size_t smem = (size_t)(3 * kSkinTileVerts * 3 + d.J * 12) * sizeof(float);
+      { ProfScope prof(model, st, SMPLK_PROF_SKIN_BWD);
+      if (d.ell_k <= 4) skin_backward_kernel<true><<<grid, kSkinThreads, smem, st>>>(d, sb);
+      else skin_backward_kernel<false><<<grid, kSkinThreads, smem, st>>>(d, sb); }
+      LAUNCH_CHECK("skin_backward_kernel");
+    }
 
     CUtensorMap tm_ahi, tm_alo, tm_out;
     const bool pair = model->use_2cta && B > kBlendBM;

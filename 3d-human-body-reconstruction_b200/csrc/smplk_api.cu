@@ -490,6 +490,8 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     const int smem_g = (int)skin_grouped_smem_bytes(d.J);
     CUDA_TRY(cudaFuncSetAttribute(skin_grouped_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g));
     CUDA_TRY(cudaFuncSetAttribute(skin_grouped_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g));
+    CUDA_TRY(cudaFuncSetAttribute(skin_backward_grouped_kernel<kSkinBwdStages>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   }
   return 0;
 }
@@ -860,6 +862,21 @@ extern "C" int smplk_forward_host(smplk_model* model, int32_t batch, uint32_t fl
   if (verts) CUDA_TRY(cudaMemcpyAsync(verts, d_verts, (size_t)batch * d.V * 12, cudaMemcpyDeviceToHost, st));
   if (joints) CUDA_TRY(cudaMemcpyAsync(joints, d_joints, (size_t)batch * (d.J + d.E) * 12, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int smplk_vertex_l2(int32_t batch, int32_t floats_per_body, const float* verts,
+                               const float* target, float scale, float* grad, float* loss,
+                               int device, smplk_stream stream) {
+  if (batch < 1 || floats_per_body < 1 || !verts || !target || !loss)
+    return fail(SMPLK_E_ARG, "bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemsetAsync(loss, 0, (size_t)batch * sizeof(float), st));
+  int gx = 8;
+  while (gx > 1 && (long)gx * batch > 16384) gx >>= 1;
+  vertex_l2_kernel<<<dim3(gx, batch), 256, 0, st>>>(floats_per_body, verts, target, scale, grad, loss);
+  LAUNCH_CHECK("vertex_l2_kernel");
   return 0;
 }
 

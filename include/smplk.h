@@ -161,6 +161,13 @@ int smplk_regress_joints(const smplk_model* model, int32_t batch, const float* v
 int smplk_batch_rodrigues(int32_t n, const float* axis_angle, float* rotmats, int device,
                           smplk_stream stream);
 
+/* Fused vertex data term of a fitting step (the squared-L2 loss of
+ * lib/Gen_SMPLH/fitting.py:491-495 on vertices; BASELINE config 3): loss[b] = scale * sum over
+ * the body's floats of (verts - target)^2 and, if `grad` is given, grad = 2 * scale * (verts -
+ * target), in one pass.  Feed `grad` to smplk_backward as d_verts. */
+int smplk_vertex_l2(int32_t batch, int32_t floats_per_body, const float* verts, const float* target,
+                    float scale, float* grad, float* loss, int device, smplk_stream stream);
+
 /* End-to-end call with HOST buffers (the reference's numpy API works on host arrays:
  * set_params(pose, beta, trans) -> verts, models/smplh_np.py:39-47).  Copies inputs H2D,
  * runs the forward on `stream`, copies verts/joints D2H and synchronises the stream.  Device

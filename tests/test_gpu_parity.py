@@ -378,6 +378,26 @@ def test_rigged_mesh_replay_large_vertex_count(dev):
             assert np.abs(out[i] - ref).max() <= TOL
 
 
+def test_fused_vertex_l2_loss_matches_torch(dev, smpl_model):
+    from smplk.body_models import vertex_l2_loss
+    m = smpl_model
+    dm = smplk.DeviceModel(m, device=0)
+    B = 37
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=4)
+    tgt = torch.randn(B, 6890, 3, device=dev)
+    grads = []
+    for fused in (True, False):
+        tb, tp, tt = (_t(x, dev, True) for x in (betas, pose, transl))
+        v = body_model_apply(dm, tb, tp, transl=tt)[0]
+        per_body = vertex_l2_loss(v, tgt, 0.5) if fused else 0.5 * ((v - tgt) ** 2).sum(dim=(1, 2))
+        (per_body * torch.arange(1, B + 1, device=dev)).sum().backward()
+        grads.append((per_body.detach(), tb.grad, tp.grad, tt.grad))
+    for a, b in zip(*grads):
+        assert _maxerr(a, b) <= 1e-5 * float(b.abs().max())
+    no_grad = vertex_l2_loss(v.detach(), tgt)
+    assert no_grad.shape == (B,) and not no_grad.requires_grad
+
+
 def test_errors_are_loud(dev, smpl_model):
     dm = smplk.DeviceModel(smpl_model, device=0)
     b, p, t = synthetic.make_inputs(smpl_model, 2)
