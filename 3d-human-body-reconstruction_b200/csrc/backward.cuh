@@ -323,7 +323,10 @@ struct DAArgs {
   float* dtr;             // (B,3)
 };
 
-constexpr int kDAThreads = 256;
+#ifndef SMPLK_DA_THREADS
+#define SMPLK_DA_THREADS 256
+#endif
+constexpr int kDAThreads = SMPLK_DA_THREADS;   // one body per block; fewer, fatter blocks keep a body's rows in L1
 
 __global__ void __launch_bounds__(kDAThreads) dA_kernel(const ModelDev m, const DAArgs a) {
   __shared__ float red[3][kDAThreads / 32];
@@ -445,27 +448,89 @@ struct PoseBwdArgs {
   float* d_transl;           // (B,3) or null
 };
 
+// smem floats per warp of pose_backward_kernel: world G, local L, dG (12 each), dR (9), dJ, dfull (3 each)
+__host__ __device__ inline int pose_bwd_smem_floats(int J) { return J * 51; }
+
 template <int SLOTS>
 __global__ void __launch_bounds__(kPoseWarps * 32)
 pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
-  extern __shared__ float pb_smem[];
+  extern __shared__ __align__(16) float pb_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kPoseWarps + warp;
   if (b >= a.B) return;
-  const int per_warp = m.J * 18;
-  float* dG = pb_smem + warp * per_warp;   // [J][12]
-  float* dJ = dG + m.J * 12;               // [J][3]
-  float* dfull = dJ + m.J * 3;             // [3J]
+  float* Gw = pb_smem + warp * pose_bwd_smem_floats(m.J);   // [J][12] world transforms
+  float* Lc = Gw + m.J * 12;                                // [J][12] local [R | Jrel]
+  float* dG = Lc + m.J * 12;                                // [J][12]
+  float* dRs = dG + m.J * 12;                               // [J][9]
+  float* dJ = dRs + m.J * 9;                                // [J][3]
+  float* dfull = dJ + m.J * 3;                              // [3J]
   const float* betas_row = a.betas ? a.betas + (size_t)(a.betas_B == 1 ? 0 : b) * m.NB : nullptr;
 
-  float rv[SLOTS][3], R[SLOTS][9], Jr[SLOTS][3], Jrel[SLOTS][3], G[SLOTS][12];
+  // ---- forward recompute (same walk as pose_forward_kernel; cheaper than saving it)
+  float rv[SLOTS][3], Jr[SLOTS][3];
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
     const int j = lane + 32 * s;
     rv[s][0] = rv[s][1] = rv[s][2] = 0.f;
-    if (j < m.J) load_joint_pose(m, a.pose, a.pca_l, a.pca_r, a.add_mean, b, j, rv[s]);
+    Jr[s][0] = Jr[s][1] = Jr[s][2] = 0.f;
+    if (j < m.J) {
+      float R[9];
+      load_joint_pose(m, a.pose, a.pca_l, a.pca_r, a.add_mean, b, j, rv[s]);
+      rodrigues(rv[s][0], rv[s][1], rv[s][2], R);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = m.J_template[3 * j + c];
+        if (betas_row != nullptr) {
+          const float* sd = m.J_shapedirs + (size_t)(3 * j + c) * m.NB;
+          for (int i = 0; i < m.NB; ++i) v = fmaf(sd[i], betas_row[i], v);
+        }
+        Jr[s][c] = v;
+      }
+      float4* l4 = reinterpret_cast<float4*>(Lc + j * 12);
+      l4[0] = make_float4(R[0], R[1], R[2], Jr[s][0]);
+      l4[1] = make_float4(R[3], R[4], R[5], Jr[s][1]);
+      l4[2] = make_float4(R[6], R[7], R[8], Jr[s][2]);
+    }
   }
-  pose_forward_core<SLOTS>(m, betas_row, rv, R, Jr, Jrel, G, lane);
+  __syncwarp();
+  float pj[SLOTS][3];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int j = lane + 32 * s;
+    pj[s][0] = pj[s][1] = pj[s][2] = 0.f;
+    if (j >= 1 && j < m.J) {
+      const float* lp = Lc + m.parents[j] * 12;
+      pj[s][0] = lp[3]; pj[s][1] = lp[7]; pj[s][2] = lp[11];
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int j = lane + 32 * s;
+    if (j < m.J) {
+      if (j >= 1) {
+        Lc[j * 12 + 3] = Jr[s][0] - pj[s][0];
+        Lc[j * 12 + 7] = Jr[s][1] - pj[s][1];
+        Lc[j * 12 + 11] = Jr[s][2] - pj[s][2];
+      }
+      const float4* l4 = reinterpret_cast<const float4*>(Lc + j * 12);
+      float4* g4 = reinterpret_cast<float4*>(Gw + j * 12);
+      g4[0] = l4[0]; g4[1] = l4[1]; g4[2] = l4[2];
+    }
+  }
+  __syncwarp();
+  for (int d = 1; d <= m.max_depth; ++d) {
+    const int l0 = m.level_start[d], l1 = m.level_start[d + 1];
+    for (int i = l0 + lane; i < l1; i += 32) {
+      const int j = m.order[i];
+      const float* Pm = Gw + m.parents[j] * 12;
+      float out[12];
+      affine_mul(Pm, Lc + j * 12, out);
+#pragma unroll
+      for (int q = 0; q < 12; ++q) Gw[j * 12 + q] = out[q];
+    }
+    __syncwarp();
+  }
 
   // ---- seed: A_j = [G_R | G_t - G_R J_j], joints_fk = G_t
 #pragma unroll
@@ -473,6 +538,7 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
     const int j = lane + 32 * s;
     if (j < m.J) {
       const float* g = a.dA + ((size_t)b * m.J + j) * 12;
+      const float* G = Gw + j * 12;
       float gt[3] = {g[3], g[7], g[11]};
       float djr[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -480,7 +546,7 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           dG[j * 12 + r * 4 + c] = g[r * 4 + c] - gt[r] * Jr[s][c];
-          djr[c] -= G[s][r * 4 + c] * gt[r];
+          djr[c] -= G[r * 4 + c] * gt[r];
         }
       }
       if (a.d_joints) {
@@ -494,46 +560,35 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
   __syncwarp();
 
   // ---- chain backward, deepest level first:  G_j = G_p [R_j | Jrel_j]
-  float dRl[SLOTS][9];
-#pragma unroll
-  for (int s = 0; s < SLOTS; ++s)
-#pragma unroll
-    for (int i = 0; i < 9; ++i) dRl[s][i] = 0.f;
   for (int d = m.max_depth; d >= 1; --d) {
+    const int l0 = m.level_start[d], l1 = m.level_start[d + 1];
+    for (int i = l0 + lane; i < l1; i += 32) {
+      const int j = m.order[i];
+      const int p = m.parents[j];
+      const float* Pm = Gw + p * 12;
+      const float* L = Lc + j * 12;
+      float dg[12];
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-      const int j = lane + 32 * s;
-      const bool act = (j < m.J) && (m.depth[j] == d);
-      const int p = act ? m.parents[j] : 0;
-      float Pm[12];
-      fetch_parent<SLOTS>(G, p, Pm);
-      if (act) {
-        float dg[12];
+      for (int q = 0; q < 12; ++q) dg[q] = dG[j * 12 + q];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) dg[i] = dG[j * 12 + i];
-        // G (world) of this joint is no longer needed by the forward; but children were handled
-        // already, so G[s] may still be fetched by nobody at shallower levels except as a parent
-        // of deeper joints -- keep it untouched.
+      for (int r = 0; r < 3; ++r) {
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c)
+          dRs[j * 9 + r * 3 + c] = Pm[0 * 4 + r] * dg[0 * 4 + c] + Pm[1 * 4 + r] * dg[1 * 4 + c] +
+                                   Pm[2 * 4 + r] * dg[2 * 4 + c];
+        const float djrel = Pm[0 * 4 + r] * dg[3] + Pm[1 * 4 + r] * dg[7] + Pm[2 * 4 + r] * dg[11];
+        dJ[j * 3 + r] += djrel;
+        atomicAdd(&dJ[p * 3 + r], -djrel);
+      }
 #pragma unroll
-          for (int c = 0; c < 3; ++c)
-            dRl[s][r * 3 + c] = Pm[0 * 4 + r] * dg[0 * 4 + c] + Pm[1 * 4 + r] * dg[1 * 4 + c] +
-                                Pm[2 * 4 + r] * dg[2 * 4 + c];
-          const float djrel = Pm[0 * 4 + r] * dg[3] + Pm[1 * 4 + r] * dg[7] + Pm[2 * 4 + r] * dg[11];
-          dJ[j * 3 + r] += djrel;
-          atomicAdd(&dJ[p * 3 + r], -djrel);
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float v = dg[r * 4 + 0] * L[k * 4 + 0] + dg[r * 4 + 1] * L[k * 4 + 1] +
+                          dg[r * 4 + 2] * L[k * 4 + 2] + dg[r * 4 + 3] * L[k * 4 + 3];
+          atomicAdd(&dG[p * 12 + r * 4 + k], v);
         }
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const float v = dg[i * 4 + 0] * R[s][k * 3 + 0] + dg[i * 4 + 1] * R[s][k * 3 + 1] +
-                            dg[i * 4 + 2] * R[s][k * 3 + 2] + dg[i * 4 + 3] * Jrel[s][k];
-            atomicAdd(&dG[p * 12 + i * 4 + k], v);
-          }
-          atomicAdd(&dG[p * 12 + i * 4 + 3], dg[i * 4 + 3]);
-        }
+        atomicAdd(&dG[p * 12 + r * 4 + 3], dg[r * 4 + 3]);
       }
     }
     __syncwarp();
@@ -542,11 +597,18 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) dRl[0][r * 3 + c] = dG[r * 4 + c];
+      for (int c = 0; c < 3; ++c) dRs[r * 3 + c] = dG[r * 4 + c];
       dJ[r] += dG[r * 4 + 3];
     }
   }
   __syncwarp();
+  float dRl[SLOTS][9];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int j = lane + 32 * s;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) dRl[s][q] = (j < m.J) ? dRs[j * 9 + q] : 0.f;
+  }
 
   // ---- pose-feature gradient from the blend GEMM, Rodrigues backward
 #pragma unroll

@@ -490,6 +490,8 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     const int smem_g = (int)skin_grouped_smem_bytes(d.J);
     CUDA_TRY(cudaFuncSetAttribute(skin_grouped_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g));
     CUDA_TRY(cudaFuncSetAttribute(skin_grouped_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g));
+    CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(skin_backward_grouped_kernel<kSkinBwdStages>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   }
