@@ -45,6 +45,9 @@ struct ModelDev {
   int grp_ok;                 // 1 when every 4-vertex group touches <= 8 distinct joints
   const uint2* grp_joints;    // [ceil(V/4)] eight u8 joint ids of the group (most weight first)
   const float4* grp_w;        // [ceil(V/4)][8] weight of joint u for the group's 4 vertices
+  int grp8_ok;                // same for 8-vertex groups
+  const uint2* grp8_joints;   // [ceil(V/8)]
+  const float4* grp8_w;       // [ceil(V/8)][8 joints][2] weights of the group's 8 vertices
   const int* csc_ptr;         // [J+1] joint -> (vertex, weight) lists for the backward
   const int* csc_vert;        // [nnz]
   const float* csc_w;         // [nnz]

@@ -25,6 +25,7 @@ struct SkinArgs {
   const float* A;         // (B,J,12)
   const float* transl;    // (B,3) or null
   float* out;             // (B,V,3)
+  int debug_copy_only;    // tuning aid: skip the transform blend (measures the streaming skeleton)
 };
 
 template <bool kReg4>
@@ -208,6 +209,7 @@ skin_grouped_kernel(const ModelDev m, const SkinArgs a) {
   }
   if (g_valid) jid = m.grp_joints[g];
   used = __reduce_or_sync(0xffffffffu, used);   // warp-uniform: no divergence in the joint loop
+  if (a.debug_copy_only) used = 0;
 
   // ---- async copy helpers (every thread commits the same number of groups)
   auto issue_A = [&](int grp) {                 // transforms + translations of bodies b0+8grp ..
@@ -306,6 +308,198 @@ skin_grouped_kernel(const ModelDev m, const SkinArgs a) {
     }
     __syncwarp();                    // slot is refilled by a later issue_v of this warp
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// skin_tma_kernel -- skin_grouped_kernel with the streaming data moved off the LSU pipe.
+//
+// ncu on skin_grouped_kernel (profiles/r01_ncu_skin_grouped_v3.csv): L1TEX data pipe 63 % busy
+// (the cp.async writes, the LDS.64/STG.64 copy-out and the transform gathers all share it) and
+// 17 % of the stall samples on the block barrier.  Here every warp runs a private TMA pipeline:
+//   lane 0 issues one 1536-byte cp.async.bulk (global -> this warp's ring slot, mbarrier
+//   complete_tx) three bodies ahead; the warp waits on the slot's mbarrier, computes in place,
+//   and lane 0 issues one cp.async.bulk smem -> global for the result.  Output rows of (B,V,3)
+//   are only 8-byte aligned for odd bodies: those results are written 8 bytes shifted inside the
+//   (16-byte padded) slot so the bulk store's source and destination are both 16-byte aligned,
+//   with the first and last 8 bytes stored by two lanes.
+// The 8-body transform groups are bulk-loaded by warp 0 behind full/empty mbarriers, so there is
+// no __syncthreads in the body loop.
+// ------------------------------------------------------------------------------------------
+constexpr int kTmaStages = 5;                  // ring slots per warp; loads run kTmaStages-2 ahead
+constexpr int kTmaDist = kTmaStages - 2;
+constexpr int kSlotFloats = kWarpFloats + 4;   // 1536 B + 16 B pad (shifted odd-row results)
+
+__host__ __device__ inline size_t skin_tma_smem_bytes(int J) {
+  return (size_t)(8 * kTmaStages * kSlotFloats + 2 * kGrpABodies * grp_a_pad(J)) * sizeof(float) +
+         (8 * kTmaStages + 4) * sizeof(uint64_t) + 16;
+}
+
+__global__ void __launch_bounds__(kGrpThreads, 2)
+skin_tma_kernel(const ModelDev m, const SkinArgs a) {
+  extern __shared__ __align__(16) float st_smem[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int v0 = blockIdx.x * kSkinTileVerts;
+  const int a_floats = m.J * 12;
+  const int a_pad = grp_a_pad(m.J);
+  float* ring = st_smem + warp * (kTmaStages * kSlotFloats);      // this warp's slots
+  float* Abuf = st_smem + 8 * kTmaStages * kSlotFloats;           // [2][8][a_pad]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Abuf + 2 * kGrpABodies * a_pad);
+  uint64_t* vfull = bars + warp * kTmaStages;                     // [kTmaStages] per warp
+  uint64_t* afull = bars + 8 * kTmaStages;                        // [2]
+  uint64_t* aempty = afull + 2;                                   // [2]
+
+  const int b0 = blockIdx.y * a.bodies_per_block;
+  const int b1 = min(a.B, b0 + a.bodies_per_block);
+  if (b0 >= b1) return;
+
+  const int wf0 = v0 * 3 + warp * kWarpFloats;
+  const int w_nfloat = max(0, min(kWarpFloats, m.V * 3 - wf0));
+  const uint32_t in_bytes = (uint32_t)max(0, min(kWarpFloats, m.Npad - wf0)) * 4u;   // multiple of 16
+  const bool full_slice = w_nfloat == kWarpFloats;
+  const int g = (v0 >> 2) + tid;
+  const bool g_valid = 4 * g < m.V;
+  uint2 jid = make_uint2(0u, 0u);
+  float4 w[kGrpJoints];
+  uint32_t used = 0;
+#pragma unroll
+  for (int u = 0; u < kGrpJoints; ++u) {
+    w[u] = g_valid ? m.grp_w[(size_t)g * kGrpJoints + u] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (w[u].x != 0.f || w[u].y != 0.f || w[u].z != 0.f || w[u].w != 0.f) used |= 1u << u;
+  }
+  if (g_valid) jid = m.grp_joints[g];
+  used = __reduce_or_sync(0xffffffffu, used);
+
+  if (tid == 0) {
+    for (int i = 0; i < 8 * kTmaStages; ++i) ptx::mbar_init(&bars[i], 1);
+    ptx::mbar_init(&afull[0], 1); ptx::mbar_init(&afull[1], 1);
+    ptx::mbar_init(&aempty[0], 8); ptx::mbar_init(&aempty[1], 8);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto issue_v = [&](int b) {            // lane 0 only
+    if (b < b1 && in_bytes > 0) {
+      const int s = (b - b0) % kTmaStages;
+      ptx::mbar_arrive_expect_tx(&vfull[s], in_bytes);
+      ptx::bulk_load(ring + s * kSlotFloats, a.vsrc + (size_t)b * a.vsrc_stride + wf0, in_bytes, &vfull[s]);
+    }
+  };
+  auto issue_A = [&](int grp) {          // warp 0 lane 0 only
+    const int bb0 = b0 + grp * kGrpABodies;
+    const int nb = min(kGrpABodies, b1 - bb0);
+    const uint32_t bytes = (uint32_t)(nb * a_floats) * 4u;      // J*48 bytes per body: multiple of 16
+    float* dst = Abuf + (grp & 1) * kGrpABodies * a_pad;
+    ptx::mbar_arrive_expect_tx(&afull[grp & 1], bytes);
+    if (a_pad == a_floats) {
+      ptx::bulk_load(dst, a.A + (size_t)bb0 * a_floats, bytes, &afull[grp & 1]);
+    } else {
+      for (int i = 0; i < nb; ++i)
+        ptx::bulk_load(dst + i * a_pad, a.A + (size_t)(bb0 + i) * a_floats, (uint32_t)a_floats * 4u, &afull[grp & 1]);
+    }
+  };
+
+  if (lane == 0) {
+    if (warp == 0) issue_A(0);
+    for (int i = 0; i < kTmaDist; ++i) issue_v(b0 + i);
+  }
+  const bool even_rows = ((m.V * 3) & 1) == 0;
+  float tn[3] = {0.f, 0.f, 0.f};         // translation of the next body, prefetched
+  if (a.transl && lane < 3) tn[0] = a.transl[(size_t)b0 * 3 + lane];
+
+  for (int b = b0; b < b1; ++b) {
+    const int rel = b - b0;
+    const int agrp = rel / kGrpABodies;
+    const int s = rel % kTmaStages;
+    if (lane == 0) {
+      ptx::tma_store_wait_read<1>();                 // stores of bodies <= b-2 have left their slots
+      issue_v(b + kTmaDist);
+    }
+    // translation: lanes 0..2 hold x,y,z of this body; prefetch the next one
+    const float tcur = tn[0];
+    if (a.transl && lane < 3 && b + 1 < b1) tn[0] = a.transl[(size_t)(b + 1) * 3 + lane];
+    const float tx = __shfl_sync(0xffffffffu, tcur, 0), ty = __shfl_sync(0xffffffffu, tcur, 1),
+                tz = __shfl_sync(0xffffffffu, tcur, 2);
+    if ((rel % kGrpABodies) == 0) {
+      ptx::mbar_wait(&afull[agrp & 1], (agrp >> 1) & 1);
+      if (warp == 0 && lane == 0 && b + kGrpABodies < b1) {
+        if (agrp >= 1) ptx::mbar_wait(&aempty[(agrp + 1) & 1], ((agrp - 1) >> 1) & 1);
+        issue_A(agrp + 1);
+      }
+    }
+    if (in_bytes > 0) ptx::mbar_wait(&vfull[s], (rel / kTmaStages) & 1);
+    const float* Ab = Abuf + ((agrp & 1) * kGrpABodies + (rel % kGrpABodies)) * a_pad;
+    float* slot = ring + s * kSlotFloats;
+    const float4* mine = reinterpret_cast<const float4*>(slot) + 3 * lane;
+    const float4 c0 = mine[0], c1 = mine[1], c2 = mine[2];
+    const float vx[4] = {c0.x, c0.w, c1.z, c2.y};
+    const float vy[4] = {c0.y, c1.x, c1.w, c2.z};
+    const float vz[4] = {c0.z, c1.y, c2.x, c2.w};
+    float ox[4] = {0.f, 0.f, 0.f, 0.f}, oy[4] = {0.f, 0.f, 0.f, 0.f}, oz[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < kGrpJoints; ++u) {
+      if (used & (1u << u)) {
+        const int j = ((u < 4 ? jid.x : jid.y) >> (8 * (u & 3))) & 0xff;
+        const float4* Aj = reinterpret_cast<const float4*>(Ab + j * 12);
+        const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+        const float wu[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float px = fmaf(r0.x, vx[i], fmaf(r0.y, vy[i], fmaf(r0.z, vz[i], r0.w)));
+          const float py = fmaf(r1.x, vx[i], fmaf(r1.y, vy[i], fmaf(r1.z, vz[i], r1.w)));
+          const float pz = fmaf(r2.x, vx[i], fmaf(r2.y, vy[i], fmaf(r2.z, vz[i], r2.w)));
+          ox[i] = fmaf(wu[i], px, ox[i]);
+          oy[i] = fmaf(wu[i], py, oy[i]);
+          oz[i] = fmaf(wu[i], pz, oz[i]);
+        }
+      }
+    }
+    const float r[12] = {ox[0] + tx, oy[0] + ty, oz[0] + tz, ox[1] + tx, oy[1] + ty, oz[1] + tz,
+                         ox[2] + tx, oy[2] + ty, oz[2] + tz, ox[3] + tx, oy[3] + ty, oz[3] + tz};
+    float* orow = a.out + (size_t)b * m.V * 3 + wf0;
+    const uint32_t misalign = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(orow) & 15);
+    if (full_slice && even_rows && misalign == 0) {
+      float4* ot = reinterpret_cast<float4*>(slot) + 3 * lane;
+      ot[0] = make_float4(r[0], r[1], r[2], r[3]);
+      ot[1] = make_float4(r[4], r[5], r[6], r[7]);
+      ot[2] = make_float4(r[8], r[9], r[10], r[11]);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::bulk_store(orow, slot, kWarpFloats * 4);
+        ptx::tma_store_commit();
+      }
+    } else if (full_slice && even_rows && misalign == 8) {
+      // row base = 8 (mod 16): results shifted by 8 bytes inside the padded slot
+      __syncwarp();                                   // all lanes hold their inputs in registers
+      float2* o2 = reinterpret_cast<float2*>(slot + 2) + 6 * lane;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) o2[i] = make_float2(r[2 * i], r[2 * i + 1]);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::bulk_store(orow + 2, slot + 4, kWarpFloats * 4 - 16);     // 16-byte aligned middle
+        ptx::tma_store_commit();
+        *reinterpret_cast<float2*>(orow) = *reinterpret_cast<const float2*>(slot + 2);
+      } else if (lane == 31) {
+        *reinterpret_cast<float2*>(orow + kWarpFloats - 2) =
+            *reinterpret_cast<const float2*>(slot + kWarpFloats);
+      }
+    } else {
+      // partial slice (mesh tail) or odd 3V: coalesced LSU copy-out
+      float4* ot = reinterpret_cast<float4*>(slot) + 3 * lane;
+      ot[0] = make_float4(r[0], r[1], r[2], r[3]);
+      ot[1] = make_float4(r[4], r[5], r[6], r[7]);
+      ot[2] = make_float4(r[8], r[9], r[10], r[11]);
+      __syncwarp();
+      for (int c = lane; c < w_nfloat; c += 32) __stcs(orow + c, slot[c]);
+      __syncwarp();
+      if (lane == 0) ptx::tma_store_commit();         // keep bulk-group accounting uniform
+    }
+    if (lane == 0 && ((rel % kGrpABodies) == kGrpABodies - 1 || b + 1 == b1))
+      ptx::mbar_arrive(&aempty[agrp & 1]);
+  }
+  if (lane == 0) ptx::tma_store_wait<0>();
 }
 
 // joints[b, J + e] = verts[b, extra_vids[e]]  (upstream VertexJointSelector; verts already + transl)

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "pose_kernels.cuh"
 #include "skinning.cuh"
+#include "skinning8.cuh"
 
 using namespace smplk;
 
@@ -88,6 +89,9 @@ struct smplk_model {
   size_t stage_bytes;
   // optional per-kernel device timing (smplk_profile_*)
   BlendPath default_tc;  // BLEND_F16 unless SMPLK_BLEND=tf32 in the environment
+  int skin_bpb;         // SMPLK_SKIN_BPB: override bodies per block (tuning)
+  bool skin_g8;         // 8 vertices per thread (default; SMPLK_SKIN_G8=0 selects the 4-vertex kernel)
+  bool skin_tma;        // SMPLK_SKIN_TMA=1: per-warp cp.async.bulk pipeline (measured slower: 0.210 vs 0.182 ms)
   bool force_skin_v1;   // SMPLK_SKIN_V1=1 in the environment: per-vertex gather kernel (A/B testing)
   mutable bool prof_on;
   mutable std::vector<ProfRec> prof_pending;
@@ -392,6 +396,47 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
       if (int r = upload(mdl, gj, &d.grp_joints)) return r;
       if (int r = upload(mdl, gw, &d.grp_w)) return r;
     }
+    // 8-vertex groups (skin_grouped8_kernel): same idea, twice the reuse of every fetched transform
+    {
+      const int G = (V + 7) / 8;
+      std::vector<uint2> gj(G, make_uint2(0u, 0u));
+      std::vector<float4> gw((size_t)G * kGrpJoints * 2, make_float4(0.f, 0.f, 0.f, 0.f));
+      bool ok = ell_k <= 4;
+      for (int g = 0; g < G && ok; ++g) {
+        std::vector<std::pair<float, int>> uniq;
+        for (int i = 0; i < 8; ++i) {
+          const int v = 8 * g + i;
+          if (v >= V) break;
+          for (auto& e : rows[v]) {
+            bool found = false;
+            for (auto& u : uniq) if (u.second == e.second) { u.first += e.first; found = true; }
+            if (!found) uniq.push_back({e.first, e.second});
+          }
+        }
+        if ((int)uniq.size() > kGrpJoints) { ok = false; break; }
+        std::sort(uniq.begin(), uniq.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) {
+          return a.first > b.first || (a.first == b.first && a.second < b.second);
+        });
+        uint32_t packed[2] = {0u, 0u};
+        for (size_t u = 0; u < (size_t)kGrpJoints; ++u) {
+          const int jj = uniq.empty() ? 0 : (u < uniq.size() ? uniq[u].second : uniq[0].second);
+          packed[u / 4] |= (uint32_t)jj << (8 * (u % 4));
+          if (u >= uniq.size()) continue;
+          float wv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int i = 0; i < 8; ++i) {
+            const int v = 8 * g + i;
+            if (v >= V) break;
+            for (auto& e : rows[v]) if (e.second == uniq[u].second) wv[i] = e.first;
+          }
+          gw[((size_t)g * kGrpJoints + u) * 2 + 0] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+          gw[((size_t)g * kGrpJoints + u) * 2 + 1] = make_float4(wv[4], wv[5], wv[6], wv[7]);
+        }
+        gj[g] = make_uint2(packed[0], packed[1]);
+      }
+      d.grp8_ok = ok ? 1 : 0;
+      if (int r = upload(mdl, gj, &d.grp8_joints)) return r;
+      if (int r = upload(mdl, gw, &d.grp8_w)) return r;
+    }
     if (int r = upload(mdl, eidx, &d.ell_idx)) return r;
     if (int r = upload(mdl, ew, &d.ell_w)) return r;
     if (int r = upload(mdl, idx4, &d.skin_idx4)) return r;
@@ -490,6 +535,12 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     const int smem_g = (int)skin_grouped_smem_bytes(d.J);
     CUDA_TRY(cudaFuncSetAttribute(skin_grouped_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g));
     CUDA_TRY(cudaFuncSetAttribute(skin_grouped_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g));
+    CUDA_TRY(cudaFuncSetAttribute(skin_grouped8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)skin_grouped8_smem_bytes(d.J)));
+    CUDA_TRY(cudaFuncSetAttribute(skin_grouped8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)skin_grouped8_smem_bytes(d.J)));
+    CUDA_TRY(cudaFuncSetAttribute(skin_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)skin_tma_smem_bytes(d.J)));
     CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(skin_backward_grouped_kernel<kSkinBwdStages>,
@@ -527,6 +578,9 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   mdl->stage_bytes = 0;
   mdl->encode = nullptr;
   mdl->prof_on = false;
+  { const char* e = getenv("SMPLK_SKIN_BPB"); mdl->skin_bpb = e ? atoi(e) : 0; }
+  { const char* e = getenv("SMPLK_SKIN_G8"); mdl->skin_g8 = !(e && e[0] == '0'); }
+  { const char* e = getenv("SMPLK_SKIN_TMA"); mdl->skin_tma = (e && e[0] == '1'); }
   { const char* e = getenv("SMPLK_SKIN_V1"); mdl->force_skin_v1 = e && e[0] == '1'; }
   { const char* e = getenv("SMPLK_GEMM_1CTA"); mdl->use_2cta = !(e && e[0] == '1'); }
   { const char* e = getenv("SMPLK_BLEND"); mdl->default_tc = (e && strcmp(e, "tf32") == 0) ? BLEND_TF32 : BLEND_F16; }
@@ -701,17 +755,32 @@ static int launch_skin(const smplk_model* mdl, int rows, const float* vsrc, size
   sa.B = rows;
   const int tiles = (d.V + kSkinTileVerts - 1) / kSkinTileVerts;
   sa.vsrc = vsrc; sa.vsrc_stride = vstride; sa.A = A; sa.transl = transl; sa.out = out;
+  { const char* e = getenv("SMPLK_SKIN_COPYONLY"); sa.debug_copy_only = (e && e[0] == '1') ? 1 : 0; }
   const bool grouped = d.grp_ok && !mdl->force_skin_v1;
   const size_t smem = grouped ? skin_grouped_smem_bytes(d.J)
                               : (size_t)(2 * kSkinTileVerts * 3 + 2 * ((d.J * 12 + 3) & ~3)) * sizeof(float);
-  // bodies per block: as many as possible while keeping >= ~3 waves of resident blocks
+  // bodies per block: measured sweep at B=4096 (0.220/0.187/0.177/0.183/0.204 ms for 4/8/16/32/64):
+  // long enough to amortise the weight load and pipeline fill, short enough for >= ~6 waves
   const int resident = (grouped ? 2 : 4) * mdl->num_sms;
   int bpb = 32;
-  while (bpb > 1 && (long)tiles * ((rows + bpb - 1) / bpb) < 3L * resident) bpb >>= 1;
+  while (bpb > 8 && (long)tiles * ((rows + bpb - 1) / bpb) < 6L * resident) bpb >>= 1;
+  while (bpb > 1 && (long)tiles * ((rows + bpb - 1) / bpb) < resident) bpb >>= 1;
+  if (mdl->skin_bpb > 0) bpb = mdl->skin_bpb;
   sa.bodies_per_block = bpb;
   dim3 grid(tiles, (rows + bpb - 1) / bpb);
   ProfScope prof(mdl, st, SMPLK_PROF_SKIN);
-  if (grouped) {
+  if (grouped && d.grp8_ok && mdl->skin_g8) {
+    const int res8 = 3 * mdl->num_sms;
+    int bpb8 = 32;
+    while (bpb8 > 4 && (long)tiles * ((rows + bpb8 - 1) / bpb8) < 3L * res8) bpb8 >>= 1;
+    if (mdl->skin_bpb > 0) bpb8 = mdl->skin_bpb;
+    sa.bodies_per_block = bpb8;
+    dim3 grid8(tiles, (rows + bpb8 - 1) / bpb8);
+    if (vstride == 0) skin_grouped8_kernel<true><<<grid8, k8Threads, skin_grouped8_smem_bytes(d.J), st>>>(d, sa);
+    else skin_grouped8_kernel<false><<<grid8, k8Threads, skin_grouped8_smem_bytes(d.J), st>>>(d, sa);
+  } else if (grouped && vstride != 0 && mdl->skin_tma) {
+    skin_tma_kernel<<<grid, kGrpThreads, skin_tma_smem_bytes(d.J), st>>>(d, sa);
+  } else if (grouped) {
     if (vstride == 0) skin_grouped_kernel<true><<<grid, kGrpThreads, smem, st>>>(d, sa);
     else skin_grouped_kernel<false><<<grid, kGrpThreads, smem, st>>>(d, sa);
   } else if (d.ell_k <= 4) {

@@ -179,6 +179,29 @@ def test_dense_weights_take_the_generic_path(dev):
     assert _maxerr(v, ref.vertices) <= TOL
 
 
+def test_rigid_and_smooth_weights_take_the_8_vertex_group_kernel(dev):
+    """Weights whose 8-vertex groups touch <= 8 joints (rigid binding; smooth two-joint blends)
+    run skin_grouped8_kernel; the synthetic default (random secondary joints) does not."""
+    import ctypes as C
+    for max_nnz in (1, 2):
+        m = synthetic.make_model("smplh", seed=17, max_nnz=max_nnz)
+        if max_nnz == 2:   # smooth blend between a joint and its parent along each range
+            W = np.zeros_like(m["weights"])
+            prim = m["weights"].argmax(1)
+            par = np.array(synthetic.SMPLH_PARENTS)
+            t = (np.arange(6890) % 50) / 50.0
+            for v in range(6890):
+                j = prim[v]; p = par[j] if par[j] >= 0 else j
+                W[v, j] += 1.0 - 0.5 * t[v]; W[v, p] += 0.5 * t[v]
+            m["weights"] = W
+        dm = smplk.DeviceModel(m, device=0)
+        betas, pose, transl = synthetic.make_inputs(m, 70, seed=2)
+        v = body_model_apply(dm, _t(betas, dev), _t(pose, dev), transl=_t(transl, dev))[0]
+        ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(
+            *[torch.tensor(x, dtype=torch.float64) for x in (betas, pose, transl)])
+        assert _maxerr(v, ref.vertices) <= TOL
+
+
 def test_numpy_twins_reproduce_reference_golden_vectors(dev, golden_dir):
     g = np.load(os.path.join(golden_dir, "smplh_np_twin.npz"))
     m = synthetic.make_model("smplh", num_betas=int(g["num_betas"]), seed=int(g["seed"]))
