@@ -86,7 +86,7 @@ EXPORTED_SYMBOLS = [
     "smplk_launch_count", "smplk_workspace_layout", "smplk_profile_enable", "smplk_profile_read", "smplk_vertex_l2",
 ]
 PROF_SLOTS = ["pose_fwd", "blend_tcgen05", "blend_simt", "skin", "dA", "skin_bwd", "blend_bwd",
-              "pose_bwd"]
+              "pose_bwd", "blend_skin_fused", "transpose"]
 
 
 def build(force=False, verbose=False):

@@ -1,0 +1,388 @@
+// Fused forward: blendshape GEMM (tcgen05, CTA pairs) whose epilogue applies linear-blend skinning
+// straight from the TMEM accumulators, so v_posed never goes to HBM.
+//
+//   verts[b,v] = sum_k w[v,k] A[b, j[v,k]] [v_template[v] + sum_f F[b,f] PD[3v.., f]; 1] + transl[b]
+//
+// Reference math: models/smplh_np.py:50,59 (shape + pose blend), :79-82 (T = W.A; v = T [v_posed;1];
+// + trans); upstream smplx lbs().  Algorithmic HBM traffic per body drops from 84,580 (GEMM) +
+// 167,856 (skinning) bytes to 84,004 (SURVEY 8d "forward, fused end-to-end").
+//
+// Mapping
+//   * GEMM main loop = blend_tcgen05_2cta_kernel (TMA producer warp, one MMA-issuing thread in the
+//     leader CTA, 256-body x 256-column tiles, 3 smem stages, two TMEM accumulators).
+//   * The B operand is re-packed so that a 256-column tile holds 85 WHOLE vertices (255 columns,
+//     interleaved xyz, + 1 zero column): column c of tile t is flat output coordinate 255 t + c.
+//   * Epilogue = 2 sets of 4 warps.  Set s owns TMEM accumulator s, i.e. every second tile of the
+//     CTA, so a set has two tile-times to finish a tile and the two sets never synchronise.  A thread
+//     is one body (TMEM lane); a warp covers the 32 bodies of its TMEM lane quarter.
+//   * Per 16-vertex chunk (48 TMEM columns -> 48 registers): the chunk's distinct joints come from a
+//     table built at model-create time.  For each joint the warp loads the body's 3x4 transform from
+//     the TRANSPOSED transform array At[128-body block][joint][12][128] -- lane = body, so each of the
+//     12 loads is one coalesced 128-byte line -- and applies it to the vertices that use the joint
+//     (weights are warp-uniform loads; a zero weight is a uniform branch).  The next joint's
+//     transform is prefetched while the current one is applied.
+//   * The 32 x 48 result block is transposed through a warp-private smem buffer (two passes of 24
+//     columns, row stride 25 words -> conflict free both ways) and written with row-contiguous
+//     96-byte stores.  (The caller's (B, V, 3) fp32 rows are 82,680 bytes = 8 mod 16, so neither a
+//     2-D TMA store nor 16-byte bulk stores can target them.)
+#pragma once
+#include "blend_gemm_2cta.cuh"
+
+namespace smplk {
+
+#ifndef SMPLK_FZ_SLOTS
+#define SMPLK_FZ_SLOTS 2     // transform slots of the epilogue's prefetch ring (3 spills at 168 registers)
+#endif
+constexpr int kFzEpiWarps = 8;
+constexpr int kFzThreads = 64 + kFzEpiWarps * 32;   // producer warp, MMA warp, 2 x 4 epilogue warps
+constexpr int kFzTileVerts = 84;                    // whole vertices per 256-column tile
+constexpr int kFzTileCols = 3 * kFzTileVerts;       // 252 output coordinates per tile (+ 4 zero columns)
+constexpr int kFzChunkVerts = 12;
+constexpr int kFzChunkCols = 36;
+constexpr int kFzChunks = 7;                        // 7 x 12 vertices
+constexpr int kFzStageStride = 33;                  // words per staged row of the 32-column window
+constexpr int kFzStageWords = 32 * kFzStageStride;
+constexpr int kFzSmemBytes = k2Stages * k2StageBytes + kFzEpiWarps * kFzStageWords * 4 + 256;
+constexpr int kFzSmemAlloc = kFzSmemBytes + 1024;
+static_assert(kFzSmemAlloc <= 232448, "fused kernel shared memory exceeds the sm_100 limit");
+
+struct FusedArgs {
+  int num_m_blocks;        // 256-body blocks
+  int num_n_blocks;        // 85-vertex tiles
+  int num_k_blocks;
+  int k_elems;
+  float out_scale;         // 1 / pd_scale
+  const float* bias;       // [num_n_blocks * 256 + 64] v_template in the fused column layout
+  const int* ch_off;       // [num_n_blocks * 6 + 1] first entry of every 16-vertex chunk
+  const int* ch_joint;     // [entries] joint id
+  const float4* ch_w;      // [entries][4] weight of that joint for the chunk's 16 vertices
+  const float* At;         // [ceil(rows/128)][J*12][128] transposed transforms (transl folded in)
+  int J;
+  float* out;              // (rows, N) posed vertices
+  int rows;
+  int N;                   // 3 V
+};
+
+// A [rows][J*12] -> At [ceil(rows/128)][J*12][128] (+ transl on the translation column), so that the
+// fused epilogue (lane = body) reads every transform component as one 128-byte line.
+__global__ void __launch_bounds__(256)
+transpose_transforms_kernel(int rows, int JC, const float* __restrict__ A,
+                            const float* __restrict__ transl, float* __restrict__ At) {
+  __shared__ float tile[32][33];
+  const int b0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int b = b0 + r, c = c0 + tx;
+    float v = 0.f;
+    if (b < rows && c < JC) {
+      v = A[(size_t)b * JC + c];
+      if (transl != nullptr && (c & 3) == 3) v += transl[3 * b + ((c % 12) >> 2)];
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, b = b0 + tx;
+    if (c < JC) At[((size_t)(b >> 7) * JC + c) * 128 + (b & 127)] = tile[tx][r];
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFzThreads, 1)
+blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
+                        const __grid_constant__ CUtensorMap tmap_f_lo,
+                        const __grid_constant__ CUtensorMap tmap_pd_hi,
+                        const __grid_constant__ CUtensorMap tmap_pd_lo, const FusedArgs args) {
+  extern __shared__ uint8_t fz_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(fz_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* stage_base = smem;
+  float* epi_base = reinterpret_cast<float*>(smem + k2Stages * k2StageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2Stages * k2StageBytes + kFzEpiWarps * kFzStageWords * 4);
+  uint64_t* full_bar = bars;                        // [k2Stages]   (used in the leader)
+  uint64_t* empty_bar = bars + k2Stages;            // [k2Stages]
+  uint64_t* tmem_full = bars + 2 * k2Stages;        // [2]
+  uint64_t* tmem_empty = bars + 2 * k2Stages + 2;   // [2]          (used in the leader)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * k2Stages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_clusters = gridDim.x >> 1;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_tiles = args.num_m_blocks * args.num_n_blocks;
+  constexpr int kElemsPerBlock = 64;   // fp16 elements per 128-byte k-block
+  constexpr int kUmmaK = 16;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_f_hi);
+    ptx::prefetch_tmap(&tmap_f_lo);
+    ptx::prefetch_tmap(&tmap_pd_hi);
+    ptx::prefetch_tmap(&tmap_pd_lo);
+    for (int s = 0; s < k2Stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 2);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_empty[s], 256);   // the 4 warps of one epilogue set, in both CTAs
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2cta<kTmemCols>(tmem_ptr);
+    ptx::tmem_relinquish_2cta();
+  }
+  ptx::tcgen05_fence_before();
+  ptx::cluster_sync();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int mb = tile % args.num_m_blocks;
+        const int nb = tile / args.num_m_blocks;
+        const int m0 = mb * 2 * kBlendBM + (int)rank * kBlendBM;
+        const int nb0 = nb * kBlendBN + (int)rank * (kBlendBN / 2);   // this CTA's half of the B tile
+        for (int kb = 0; kb < args.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = stage_base + stage * k2StageBytes;
+          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * k2StageBytes);
+          else ptx::mbar_arrive_cluster(&full_bar[stage], 0);
+          const int k0 = kb * kElemsPerBlock;
+          ptx::tma_load_2d_2sm(st, &tmap_f_hi, &full_bar[stage], k0, m0);
+          ptx::tma_load_2d_2sm(st + k2TileABytes, &tmap_f_lo, &full_bar[stage], k0, m0);
+          ptx::tma_load_2d_2sm(st + 2 * k2TileABytes, &tmap_pd_hi, &full_bar[stage], k0, nb0);
+          ptx::tma_load_2d_2sm(st + 2 * k2TileABytes + k2TileBBytes, &tmap_pd_lo, &full_bar[stage], k0, nb0);
+          if (++stage == k2Stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(2 * kBlendBM, kBlendBN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kBlendBN;
+        for (int kb = 0; kb < args.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tcgen05_fence_after();
+          const uint32_t st = ptx::smem_u32(stage_base + stage * k2StageBytes);
+          const uint64_t a_hi = ptx::make_kmajor_desc<128>(st);
+          const uint64_t a_lo = ptx::make_kmajor_desc<128>(st + k2TileABytes);
+          const uint64_t b_hi = ptx::make_kmajor_desc<128>(st + 2 * k2TileABytes);
+          const uint64_t b_lo = ptx::make_kmajor_desc<128>(st + 2 * k2TileABytes + k2TileBBytes);
+          const int ksteps = min(4, (args.k_elems - kb * kElemsPerBlock) / kUmmaK);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < ksteps) {
+              const uint64_t adv = static_cast<uint64_t>((k * 32) >> 4);
+              const uint32_t first = (kb != 0 || k != 0) ? 1u : 0u;
+              ptx::umma_2cta<true>(d_tmem, a_lo + adv, b_hi + adv, idesc, first);
+              ptx::umma_2cta<true>(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+              ptx::umma_2cta<true>(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+            }
+          }
+          ptx::umma_commit_2cta(&empty_bar[stage]);
+          if (++stage == k2Stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit_2cta(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== skinning epilogue (warps 2..9) =====================
+    const int set = (warp - 2) >> 2;          // accumulator buffer / tile parity this warp serves
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const uint32_t stage_u32 = ptx::smem_u32(epi_base + (warp - 2) * kFzStageWords);
+    const uint32_t stage_row = stage_u32 + lane * (kFzStageStride * 4);   // this body's staged row
+    const uint32_t stage_col = stage_u32 + lane * 4;                      // this lane's staged column
+    const float oscale = args.out_scale;
+    const int JC128 = args.J * 12 * 128;
+    const float* wflat = reinterpret_cast<const float*>(args.ch_w);
+    constexpr unsigned kFull = 0xffffffffu;
+    for (int it = set;; it += 2) {
+      const int tile = cluster_id + it * num_clusters;
+      if (tile >= num_tiles) break;
+      const int mb = tile % args.num_m_blocks;
+      const int nb = tile / args.num_m_blocks;
+      const int m0 = mb * 2 * kBlendBM + (int)rank * kBlendBM;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const float* At_w = args.At + (size_t)(m0 >> 7) * JC128 + q * 32 + lane;
+      const float* bias_t = args.bias + nb * kBlendBN;
+      const int row0 = m0 + q * 32;
+      const int nrows = min(32, args.rows - row0);
+      float* out_t = args.out + (size_t)row0 * args.N + (size_t)nb * kFzTileCols;
+      const int cols_left = args.N - nb * kFzTileCols;     // valid output columns from this tile on
+      // chunk offsets (lane i <- off[i], i <= 7), first window of joint ids, first bias lines: all
+      // independent of the accumulator, so issue them before waiting for the MMAs
+      const int ol = __ldg(args.ch_off + nb * kFzChunks + min(lane, kFzChunks));
+      int e = __shfl_sync(kFull, ol, 0);
+      const int e_end = __shfl_sync(kFull, ol, kFzChunks);
+      int wb = e;                                          // base of the joint-id window
+      int jl = __ldg(args.ch_joint + wb + lane);
+      float bn0 = __ldg(bias_t + lane), bn1 = __ldg(bias_t + 32 + (lane & 3));
+      float sa0[12], sa1[12];
+      float sw0 = 0.f, sw1 = 0.f;
+#if SMPLK_FZ_SLOTS == 3
+      float sa2[12];
+      float sw2 = 0.f;
+#endif
+      float p[kFzChunkCols], o[kFzChunkCols];
+
+      // entry ee -> registers: the joint's 3x4 transform of this lane's body (12 coalesced lines)
+      // and the joint's weight for vertex (lane & 15) of the chunk (12 weights + 4 zeros per entry)
+      auto load_slot = [&](float (&sa)[12], float& sw, int ee) {
+        if (ee >= wb + 32) {
+          wb += 32;
+          jl = __ldg(args.ch_joint + wb + lane);
+        }
+        const int jj = __shfl_sync(kFull, jl, ee - wb);
+        const float* ap = At_w + (size_t)jj * (12 * 128);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) sa[i] = __ldg(ap + i * 128);
+        sw = __ldg(wflat + (size_t)ee * 16 + (lane & 15));
+      };
+      // branch-free: a vertex that does not use the joint has w = 0 and adds exactly 0 (p and the
+      // transforms are finite, padding rows / columns included)
+      auto apply_slot = [&](const float (&a)[12], float sw) {
+#pragma unroll
+        for (int v = 0; v < kFzChunkVerts; ++v) {
+          const float w = __shfl_sync(kFull, sw, v);
+          const float x = p[3 * v], y = p[3 * v + 1], z = p[3 * v + 2];
+          const float qx = fmaf(a[0], x, fmaf(a[1], y, fmaf(a[2], z, a[3])));
+          const float qy = fmaf(a[4], x, fmaf(a[5], y, fmaf(a[6], z, a[7])));
+          const float qz = fmaf(a[8], x, fmaf(a[9], y, fmaf(a[10], z, a[11])));
+          o[3 * v] = fmaf(w, qx, o[3 * v]);
+          o[3 * v + 1] = fmaf(w, qy, o[3 * v + 1]);
+          o[3 * v + 2] = fmaf(w, qz, o[3 * v + 2]);
+        }
+      };
+      // 32 staged columns (one 128-byte segment per body row) -> global
+      auto store_window = [&](int wnd, int ncols) {
+        const int col = 32 * wnd + lane;
+        if (lane < ncols && col < cols_left) {
+          float* dst = out_t + col;
+          if (nrows == 32) {
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r)
+              dst[r * args.N] = ptx::ld_shared_f32(stage_col + r * (kFzStageStride * 4));
+          } else {
+            for (int r = 0; r < nrows; ++r)
+              dst[r * args.N] = ptx::ld_shared_f32(stage_col + r * (kFzStageStride * 4));
+          }
+        }
+      };
+
+      if (e < e_end) load_slot(sa0, sw0, e);
+#if SMPLK_FZ_SLOTS == 3
+      if (e + 1 < e_end) load_slot(sa1, sw1, e + 1);
+#endif
+      ptx::mbar_wait(&tmem_full[set], acc_phase);
+      ptx::tcgen05_fence_after();
+
+      int ph = 0;                                          // slot holding entry e
+#pragma unroll 1
+      for (int c = 0; c < kFzChunks; ++c) {
+        // ---- TMEM accumulator columns of chunk c -> p (+ v_template), o = 0
+        {
+          uint32_t pr[kFzChunkCols];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 static_cast<uint32_t>(set * kBlendBN + c * kFzChunkCols);
+          ptx::tmem_ld_32x32b_x16(taddr, pr);
+          ptx::tmem_ld_32x32b_x16(taddr + 16, pr + 16);
+          ptx::tmem_ld_32x32b_x4(taddr + 32, pr + 32);
+          ptx::tmem_ld_wait();
+          if (c == kFzChunks - 1) {             // accumulator fully read: hand it back to the MMA warp
+            ptx::tcgen05_fence_before();
+            ptx::mbar_arrive_cluster(&tmem_empty[set], 0);
+          }
+          const float b0 = bn0, b1 = bn1;
+          if (c < kFzChunks - 1) {              // next chunk's v_template line (bias is padded by 64)
+            bn0 = __ldg(bias_t + (c + 1) * kFzChunkCols + lane);
+            bn1 = __ldg(bias_t + (c + 1) * kFzChunkCols + 32 + (lane & 3));
+          }
+#pragma unroll
+          for (int i = 0; i < kFzChunkCols; ++i) {
+            const float bi = i < 32 ? __shfl_sync(kFull, b0, i) : __shfl_sync(kFull, b1, i - 32);
+            p[i] = fmaf(__uint_as_float(pr[i]), oscale, bi);
+            o[i] = 0.f;
+          }
+        }
+        // ---- the chunk's (joint, weights) entries.  The transform slots form a ring that rotates
+        // statically (Duff's device over the slot that holds entry e), so entry e is applied from
+        // one slot while the next entries -- of this chunk or the next -- are in flight in the others.
+        const int cend = __shfl_sync(kFull, ol, c + 1);
+        while (e < cend) {
+          switch (ph) {
+#if SMPLK_FZ_SLOTS == 3
+            case 0:
+              if (e + 2 < e_end) load_slot(sa2, sw2, e + 2);
+              apply_slot(sa0, sw0);
+              ph = 1;
+              if (++e == cend) break;
+            case 1:
+              if (e + 2 < e_end) load_slot(sa0, sw0, e + 2);
+              apply_slot(sa1, sw1);
+              ph = 2;
+              if (++e == cend) break;
+            default:
+              if (e + 2 < e_end) load_slot(sa1, sw1, e + 2);
+              apply_slot(sa2, sw2);
+              ph = 0;
+              ++e;
+#else
+            case 0:
+              if (e + 1 < e_end) load_slot(sa1, sw1, e + 1);
+              apply_slot(sa0, sw0);
+              ph = 1;
+              if (++e == cend) break;
+            default:
+              if (e + 1 < e_end) load_slot(sa0, sw0, e + 1);
+              apply_slot(sa1, sw1);
+              ph = 0;
+              ++e;
+#endif
+          }
+        }
+        // ---- o (32 bodies x 36 columns) -> rolling 32-column staging window -> global.  Chunk c
+        // starts at window column w0 = 36 c mod 32; its first 32 - w0 columns complete the window.
+        const int w0 = (c * kFzChunkCols) & 31;
+        const int split = 32 - w0;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < kFzChunkCols; ++i)
+          if (i < split) ptx::st_shared_f32(stage_row + (w0 + i) * 4, o[i]);
+        __syncwarp();
+        store_window((c * kFzChunkCols) >> 5, 32);
+        __syncwarp();
+#pragma unroll
+        for (int i = 4; i < kFzChunkCols; ++i)
+          if (i >= split) ptx::st_shared_f32(stage_row + (i - split) * 4, o[i]);
+        if (c == kFzChunks - 1) {                // the last window of the tile is partial
+          __syncwarp();
+          store_window(kFzTileCols >> 5, kFzTileCols & 31);
+        }
+      }
+    }
+  }
+
+  ptx::tcgen05_fence_before();
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc_2cta<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace smplk

@@ -15,6 +15,7 @@
 #include "backward.cuh"
 #include "blend_gemm.cuh"
 #include "blend_gemm_2cta.cuh"
+#include "blend_skin_fused.cuh"
 #include "common.cuh"
 #include "pose_kernels.cuh"
 #include "skinning.cuh"
@@ -83,6 +84,8 @@ struct smplk_model {
   // CTA-pair kernel: 128-byte rows, 128-row boxes (each CTA loads half of the B tile)
   CUtensorMap tmap2_pd_hi, tmap2_pd_lo, tmap2_pdh_hi, tmap2_pdh_lo, tmap2_pdkn_hi, tmap2_pdkn_lo;
   bool use_2cta;
+  CUtensorMap tmapf_pdh_hi, tmapf_pdh_lo;  // fused blend+skinning kernel: 85-vertex column tiles
+  bool use_fused;       // SMPLK_FUSED=0 in the environment selects the two-kernel forward (A/B runs)
   CUtensorMap tmap_pdkn_hi, tmap_pdkn_lo;  // backward: B operand rows = blend features
   // host staging for smplk_forward_host
   void* stage_dev;
@@ -297,6 +300,24 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
         }
       if (int r = upload(mdl, hh, &d.pd_nk_h_hi)) return r;
       if (int r = upload(mdl, hl, &d.pd_nk_h_lo)) return r;
+      // same operand in the fused kernel's column layout: tile t = vertices [85 t, 85 t + 85),
+      // row 256 t + c <-> flat coordinate 255 t + c (c < 255), row 256 t + 255 = 0
+      d.fz_tiles = (V + kFzTileVerts - 1) / kFzTileVerts;
+      const size_t nf = (size_t)d.fz_tiles * kBlendBN;
+      std::vector<__half> fh(nf * d.Kpad, __float2half(0.f)), fl(nf * d.Kpad, __float2half(0.f));
+      std::vector<float> bf(nf + 64, 0.f);
+      for (int t = 0; t < d.fz_tiles; ++t)
+        for (int c = 0; c < kFzTileCols; ++c) {
+          const int n = t * kFzTileCols + c;
+          if (n >= d.N) break;
+          const size_t row = (size_t)t * kBlendBN + c;
+          memcpy(&fh[row * d.Kpad], &hh[(size_t)n * d.Kpad], (size_t)d.Kpad * sizeof(__half));
+          memcpy(&fl[row * d.Kpad], &hl[(size_t)n * d.Kpad], (size_t)d.Kpad * sizeof(__half));
+          bf[row] = (float)desc->v_template[n];
+        }
+      if (int r = upload(mdl, fh, &d.pdf_h_hi)) return r;
+      if (int r = upload(mdl, fl, &d.pdf_h_lo)) return r;
+      if (int r = upload(mdl, bf, &d.bias_f)) return r;
     }
     if (int r = upload(mdl, hi, &d.pd_nk_hi)) return r;
     if (int r = upload(mdl, lo, &d.pd_nk_lo)) return r;
@@ -306,6 +327,9 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
   } else {
     d.pd_nk_hi = d.pd_nk_lo = d.pd_kn = d.pd_kn_hi = d.pd_kn_lo = nullptr;
     d.pd_nk_h_hi = d.pd_nk_h_lo = nullptr;
+    d.pdf_h_hi = d.pdf_h_lo = nullptr;
+    d.bias_f = nullptr;
+    d.fz_tiles = 0;
     d.pd_scale = 1.f;
   }
 
@@ -444,6 +468,46 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     if (int r = upload(mdl, cptr, &d.csc_ptr)) return r;
     if (int r = upload(mdl, cvert, &d.csc_vert)) return r;
     if (int r = upload(mdl, cw, &d.csc_w)) return r;
+    // fused epilogue tables: for every 16-vertex chunk of every 85-vertex tile, the distinct joints
+    // its vertices are bound to and, per joint, the 16 weights (0 where a vertex does not use it)
+    if (!lbs_only) {
+      const int tiles = (V + kFzTileVerts - 1) / kFzTileVerts;
+      std::vector<int> off(1, 0), cj;
+      std::vector<float4> cwv;
+      for (int t = 0; t < tiles; ++t)
+        for (int c = 0; c < kFzChunks; ++c) {
+          std::vector<int> js;
+          for (int i = 0; i < kFzChunkVerts; ++i) {
+            const int lv = c * kFzChunkVerts + i, v = t * kFzTileVerts + lv;
+            if (lv >= kFzTileVerts || v >= V) break;
+            for (auto& e : rows[v])
+              if (std::find(js.begin(), js.end(), e.second) == js.end()) js.push_back(e.second);
+          }
+          std::sort(js.begin(), js.end());
+          for (int j : js) {
+            float wv[16];
+            for (int i = 0; i < 16; ++i) {
+              wv[i] = 0.f;
+              const int lv = c * kFzChunkVerts + i, v = t * kFzTileVerts + lv;
+              if (i >= kFzChunkVerts || lv >= kFzTileVerts || v >= V) continue;
+              for (auto& e : rows[v]) if (e.second == j) wv[i] = e.first;
+            }
+            cj.push_back(j);
+            for (int i = 0; i < 4; ++i) cwv.push_back(make_float4(wv[4 * i], wv[4 * i + 1], wv[4 * i + 2], wv[4 * i + 3]));
+          }
+          off.push_back((int)cj.size());
+        }
+      // the fused epilogue pays per (chunk, joint) entry; canonical (<= 4 weights, locally coherent)
+      // rigs have ~4-8 joints per chunk, dense weight matrices have all J -> keep those on the
+      // two-kernel path
+      d.fz_ok = (cj.size() <= (size_t)12 * tiles * kFzChunks) ? 1 : 0;
+      cj.resize(cj.size() + 64, 0);      // the epilogue reads joint ids in 32-entry windows
+      if (int r = upload(mdl, off, &d.fz_off)) return r;
+      if (int r = upload(mdl, cj, &d.fz_joint)) return r;
+      if (int r = upload(mdl, cwv, &d.fz_w)) return r;
+    } else {
+      d.fz_ok = 0;
+    }
   }
 
   // ---- hand PCA, pose mean
@@ -521,6 +585,9 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdh_lo, d.pd_nk_h_lo, d.Kpad, d.Npad, p256, true)) return r;
     if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdkn_hi, d.pd_kn_hi, d.Npad, d.Kpad, p256, false)) return r;
     if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdkn_lo, d.pd_kn_lo, d.Npad, d.Kpad, p256, false)) return r;
+    if (int r = make_operand_tmap_2cta(mdl, &mdl->tmapf_pdh_hi, d.pdf_h_hi, d.Kpad, (uint64_t)d.fz_tiles * kBlendBN, p256, true)) return r;
+    if (int r = make_operand_tmap_2cta(mdl, &mdl->tmapf_pdh_lo, d.pdf_h_lo, d.Kpad, (uint64_t)d.fz_tiles * kBlendBN, p256, true)) return r;
+    CUDA_TRY(cudaFuncSetAttribute(blend_skin_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFzSmemAlloc));
     CUDA_TRY(cudaFuncSetAttribute(blend_tcgen05_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   k2SmemAlloc));
     CUDA_TRY(cudaFuncSetAttribute(blend_tcgen05_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -583,6 +650,7 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   { const char* e = getenv("SMPLK_SKIN_TMA"); mdl->skin_tma = (e && e[0] == '1'); }
   { const char* e = getenv("SMPLK_SKIN_V1"); mdl->force_skin_v1 = e && e[0] == '1'; }
   { const char* e = getenv("SMPLK_GEMM_1CTA"); mdl->use_2cta = !(e && e[0] == '1'); }
+  { const char* e = getenv("SMPLK_FUSED"); mdl->use_fused = !(e && e[0] == '0'); }
   { const char* e = getenv("SMPLK_BLEND"); mdl->default_tc = (e && strcmp(e, "tf32") == 0) ? BLEND_TF32 : BLEND_F16; }
   for (int i = 0; i < SMPLK_PROF_SLOTS; ++i) { mdl->prof_ms[i] = 0.0; mdl->prof_n[i] = 0; }
   if (prop.major != 10) {
@@ -616,7 +684,7 @@ constexpr int kDefaultChunk = 8192;
 
 struct WsLayout {
   int chunk;
-  size_t off_fhi, off_flo, off_A, off_vposed, total;
+  size_t off_fhi, off_flo, off_A, off_At, off_vposed, total;
 };
 
 static WsLayout ws_layout(const ModelDev& d, int batch, uint32_t flags) {
@@ -628,6 +696,8 @@ static WsLayout ws_layout(const ModelDev& d, int batch, uint32_t flags) {
   w.off_fhi = off; off += align_up(rows_pad * d.Kpad * sizeof(float), 1024);
   w.off_flo = off; off += align_up(rows_pad * d.Kpad * sizeof(float), 1024);
   w.off_A = off;   off += align_up((size_t)w.chunk * d.J * 12 * sizeof(float), 1024);
+  // transposed transforms of the fused blend+skinning kernel (256-body blocks)
+  w.off_At = off;  if (!d.lbs_only) off += align_up((size_t)round_up(w.chunk, 2 * kBlendBM) * d.J * 12 * sizeof(float), 1024);
   w.off_vposed = off;
   if (!d.lbs_only) off += align_up((size_t)w.chunk * d.Npad * sizeof(float), 1024);
   w.total = off;
@@ -748,6 +818,46 @@ static int launch_blend(const smplk_model* mdl, int rows, BlendPath path, float*
   return 0;
 }
 
+// Fused forward (blend GEMM + skinning epilogue): true when this call can take it.
+static bool fused_applies(const smplk_model* mdl, int rows, BlendPath path, uint32_t flags, bool want_verts) {
+  const ModelDev& d = mdl->d;
+  return mdl->use_fused && mdl->has_tma && mdl->use_2cta && !d.lbs_only && d.fz_ok && want_verts &&
+         path == BLEND_F16 && rows > kBlendBM && !(flags & SMPLK_FLAG_SAVE_FOR_BACKWARD);
+}
+
+static int launch_fused(const smplk_model* mdl, int rows, float* F_hi, float* F_lo, const float* A,
+                        float* At, const float* transl, float* out, cudaStream_t st) {
+  const ModelDev& d = mdl->d;
+  const int JC = d.J * 12;
+  const int rows_pad = round_up(rows, 2 * kBlendBM);
+  {
+    ProfScope prof(mdl, st, SMPLK_PROF_TRANSPOSE);
+    dim3 grid((JC + 31) / 32, rows_pad / 32);
+    transpose_transforms_kernel<<<grid, 256, 0, st>>>(rows, JC, A, transl, At);
+    LAUNCH_CHECK("transpose_transforms_kernel");
+  }
+  CUtensorMap tm_fhi, tm_flo;
+  if (int r = make_operand_tmap_2cta(mdl, &tm_fhi, F_hi, d.Kpad, rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, true)) return r;
+  if (int r = make_operand_tmap_2cta(mdl, &tm_flo, F_lo, d.Kpad, rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, true)) return r;
+  FusedArgs fa;
+  fa.num_m_blocks = rows_pad / (2 * kBlendBM);
+  fa.num_n_blocks = d.fz_tiles;
+  fa.num_k_blocks = (d.Kpad + 63) / 64;
+  fa.k_elems = d.Kpad;
+  fa.out_scale = 1.0f / d.pd_scale;
+  fa.bias = d.bias_f;
+  fa.ch_off = d.fz_off; fa.ch_joint = d.fz_joint; fa.ch_w = d.fz_w;
+  fa.At = At; fa.J = d.J;
+  fa.out = out; fa.rows = rows; fa.N = d.N;
+  const int tiles = fa.num_m_blocks * fa.num_n_blocks;
+  const int grid = 2 * std::min(tiles, mdl->num_sms / 2);
+  ProfScope prof(mdl, st, SMPLK_PROF_BLEND_SKIN_FUSED);
+  blend_skin_fused_kernel<<<grid, kFzThreads, kFzSmemAlloc, st>>>(tm_fhi, tm_flo, mdl->tmapf_pdh_hi,
+                                                                  mdl->tmapf_pdh_lo, fa);
+  LAUNCH_CHECK("blend_skin_fused_kernel");
+  return 0;
+}
+
 static int launch_skin(const smplk_model* mdl, int rows, const float* vsrc, size_t vstride,
                        const float* A, const float* transl, float* out, cudaStream_t st) {
   const ModelDev& d = mdl->d;
@@ -820,6 +930,7 @@ extern "C" int smplk_forward(const smplk_model* model, const smplk_forward_args*
   float* F_hi = reinterpret_cast<float*>(ws + w.off_fhi);
   float* F_lo = reinterpret_cast<float*>(ws + w.off_flo);
   float* A = reinterpret_cast<float*>(ws + w.off_A);
+  float* At = reinterpret_cast<float*>(ws + w.off_At);
   float* v_posed = reinterpret_cast<float*>(ws + w.off_vposed);
   const int joints_ld = 3 * (d.J + d.E);
 
@@ -845,13 +956,18 @@ extern "C" int smplk_forward(const smplk_model* model, const smplk_forward_args*
     pa.joints_ld = joints_ld;
     pa.full_pose = a->full_pose ? a->full_pose + (size_t)c0 * 3 * d.J : nullptr;
     if (int r = launch_pose_forward(model, pa, st)) return r;
-    if (!d.lbs_only && (a->verts || (a->flags & SMPLK_FLAG_SAVE_FOR_BACKWARD))) {
+    const bool fused = fused_applies(model, rows, path, a->flags, a->verts != nullptr);
+    if (!fused && !d.lbs_only && (a->verts || (a->flags & SMPLK_FLAG_SAVE_FOR_BACKWARD))) {
       if (int r = launch_blend(model, rows, path, F_hi, F_lo, v_posed, st)) return r;
     }
     if (a->verts) {
       float* vout = a->verts + (size_t)c0 * d.V * 3;
-      if (int r = launch_skin(model, rows, d.lbs_only ? d.bias : v_posed,
-                              d.lbs_only ? 0 : (size_t)d.Npad, A, pa.transl, vout, st)) return r;
+      if (fused) {
+        if (int r = launch_fused(model, rows, F_hi, F_lo, A, At, pa.transl, vout, st)) return r;
+      } else {
+        if (int r = launch_skin(model, rows, d.lbs_only ? d.bias : v_posed,
+                                d.lbs_only ? 0 : (size_t)d.Npad, A, pa.transl, vout, st)) return r;
+      }
       if (a->joints && d.E > 0) {
         const int n = rows * d.E;
         gather_extra_joints_kernel<<<(n + 127) / 128, 128, 0, st>>>(d, rows, vout, pa.joints, joints_ld);

@@ -188,7 +188,9 @@ int smplk_forward_host(smplk_model* model, int32_t batch, uint32_t flags, const 
 #define SMPLK_PROF_SKIN_BWD 5
 #define SMPLK_PROF_BLEND_BWD 6
 #define SMPLK_PROF_POSE_BWD 7
-#define SMPLK_PROF_SLOTS 8
+#define SMPLK_PROF_BLEND_SKIN_FUSED 8 /* fused blend GEMM + skinning epilogue (forward without SAVE_FOR_BACKWARD) */
+#define SMPLK_PROF_TRANSPOSE 9        /* transform transposition feeding the fused kernel */
+#define SMPLK_PROF_SLOTS 10
 int smplk_profile_enable(smplk_model* model, int enable);
 int smplk_profile_read(smplk_model* model, double ms[SMPLK_PROF_SLOTS],
                        int64_t counts[SMPLK_PROF_SLOTS], int reset);

@@ -93,6 +93,54 @@ def test_blend_operand_formats_agree(dev, smplh_model):
     assert _maxerr(simt, f16) <= 5e-6 and _maxerr(simt, tf32) <= 5e-6 and _maxerr(f16, tf32) <= 2e-6
 
 
+@pytest.mark.parametrize("B", [129, 257, 300, 1000, 2049])
+def test_fused_blend_skinning_matches_two_kernel_path_and_oracle(dev, smplh_model, B, monkeypatch):
+    """The forward without SAVE_FOR_BACKWARD runs the fused kernel (blend GEMM whose epilogue skins
+    straight from TMEM); SMPLK_FUSED=0 selects blend GEMM -> v_posed -> skinning kernel.  Ragged
+    batches exercise partial 256-body blocks and the last 85-vertex tile (5 vertices)."""
+    m = smplh_model
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=100 + B)
+    pose[0] = 0.0
+    pose[B - 1] = pose[B - 1] / np.abs(pose[B - 1]).max() * 4.8
+    dm_f = smplk.DeviceModel(m, device=0, extra_vertex_ids=m["extra_vertex_ids"])
+    monkeypatch.setenv("SMPLK_FUSED", "0")
+    dm_u = smplk.DeviceModel(m, device=0, extra_vertex_ids=m["extra_vertex_ids"])
+    monkeypatch.delenv("SMPLK_FUSED")
+    args = (_t(betas, dev), _t(pose, dev))
+    dm_f.profile_enable(True)
+    vf, jf, _, _ = body_model_apply(dm_f, *args, transl=_t(transl, dev))
+    vf0, _, _, _ = body_model_apply(dm_f, *args)                     # no translation
+    torch.cuda.synchronize()
+    prof = dm_f.profile_read()
+    assert prof["blend_skin_fused"][1] == 2 and prof["skin"][1] == 0 and prof["blend_tcgen05"][1] == 0
+    dm_u.profile_enable(True)
+    vu, ju, _, _ = body_model_apply(dm_u, *args, transl=_t(transl, dev))
+    torch.cuda.synchronize()
+    prof = dm_u.profile_read()
+    assert prof["blend_skin_fused"][1] == 0 and prof["skin"][1] == 1
+    ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(
+        *[torch.tensor(x, dtype=torch.float64) for x in (betas, pose, transl)])
+    assert _maxerr(vf, ref.vertices) <= TOL and _maxerr(vu, ref.vertices) <= TOL
+    assert _maxerr(vf, vu) <= 3e-6 and _maxerr(jf[:, :52], ju[:, :52]) == 0.0 and _maxerr(jf, ju) <= 3e-6
+    assert _maxerr(vf0 + _t(transl, dev)[:, None, :], vf) <= 3e-6
+    assert torch.isfinite(vf).all()
+
+
+def test_fused_path_smpl_24_joints_and_broadcast_betas(dev, smpl_model):
+    m = smpl_model
+    B = 513
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=5)
+    dm = smplk.DeviceModel(m, device=0)
+    dm.profile_enable(True)
+    v, j, _, _ = body_model_apply(dm, _t(betas[:1], dev), _t(pose, dev), transl=_t(transl, dev))
+    torch.cuda.synchronize()
+    assert dm.profile_read()["blend_skin_fused"][1] == 1
+    ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(
+        torch.tensor(betas[:1], dtype=torch.float64).expand(B, -1),
+        torch.tensor(pose, dtype=torch.float64), torch.tensor(transl, dtype=torch.float64))
+    assert _maxerr(v, ref.vertices) <= TOL and _maxerr(j, ref.joints) <= TOL
+
+
 def test_split_operands_hold_fp32_accuracy_on_large_blendshapes(dev):
     """Stress the two-term splits: blendshape magnitudes 30x the synthetic default (cm-scale pose
     correctives, dm-scale shape directions), betas up to |5|, pose up to pi."""
@@ -174,6 +222,18 @@ def test_dense_weights_take_the_generic_path(dev):
     assert dm.info.max_weights_per_vertex == 52
     betas, pose, transl = synthetic.make_inputs(m, 6, seed=1)
     v = body_model_apply(dm, _t(betas, dev), _t(pose, dev), transl=_t(transl, dev))[0]
+    ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(
+        *[torch.tensor(x, dtype=torch.float64) for x in (betas, pose, transl)])
+    assert _maxerr(v, ref.vertices) <= TOL
+    # dense weights at a GEMM-sized batch: every 16-vertex chunk would list all 52 joints, so the
+    # packer keeps this model off the fused kernel (blend GEMM + generic skinning kernel instead)
+    B = 200
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=2)
+    dm.profile_enable(True)
+    v = body_model_apply(dm, _t(betas, dev), _t(pose, dev), transl=_t(transl, dev))[0]
+    torch.cuda.synchronize()
+    prof = dm.profile_read()
+    assert prof["blend_skin_fused"][1] == 0 and prof["skin"][1] == 1
     ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(
         *[torch.tensor(x, dtype=torch.float64) for x in (betas, pose, transl)])
     assert _maxerr(v, ref.vertices) <= TOL
