@@ -30,9 +30,25 @@
 
 namespace smplk {
 
-#ifndef SMPLK_FZ_SLOTS
-#define SMPLK_FZ_SLOTS 2     // transform slots of the epilogue's prefetch ring (3 spills at 168 registers)
+#ifndef SMPLK_FZ_RING
+#define SMPLK_FZ_RING 4      // transform entries in flight per epilogue warp (cp.async ring in smem)
 #endif
+#ifndef SMPLK_FZ_ROW_BYTES
+#define SMPLK_FZ_ROW_BYTES 64
+#endif
+// GEMM operand stages: rows of kFzRowBytes of K (= swizzle span).  64-byte rows x 4 stages hold
+// 128 KB in flight (3 stages of prefetch ~ 2400 MMA cycles, enough to cover the TMA latency) and
+// leave room for the epilogue's transform ring; 128-byte rows x 3 stages (the stand-alone GEMM's
+// choice) would fill shared memory.
+constexpr int kFzRowBytes = SMPLK_FZ_ROW_BYTES;
+constexpr int kFzStages = kFzRowBytes == 64 ? 4 : 2;
+constexpr int kFzKSteps = kFzRowBytes / 32;                 // UMMA k-steps (16 fp16 = 32 B) per k-block
+constexpr int kFzElemsPerBlock = kFzRowBytes / 2;           // fp16 elements per k-block
+constexpr int kFzTileABytes = kBlendBM * kFzRowBytes;       // this CTA's 128 feature rows
+constexpr int kFzTileBBytes = (kBlendBN / 2) * kFzRowBytes; // this CTA's half of the posedirs tile
+constexpr int kFzStageBytes = 2 * kFzTileABytes + 2 * kFzTileBBytes;
+constexpr int kFzRing = SMPLK_FZ_RING;
+constexpr int kFzRingEntryBytes = 13 * 128;                 // 12 transform lines + 1 weight line per warp
 constexpr int kFzEpiWarps = 8;
 constexpr int kFzThreads = 64 + kFzEpiWarps * 32;   // producer warp, MMA warp, 2 x 4 epilogue warps
 constexpr int kFzTileVerts = 84;                    // whole vertices per 256-column tile
@@ -42,7 +58,8 @@ constexpr int kFzChunkCols = 36;
 constexpr int kFzChunks = 7;                        // 7 x 12 vertices
 constexpr int kFzStageStride = 33;                  // words per staged row of the 32-column window
 constexpr int kFzStageWords = 32 * kFzStageStride;
-constexpr int kFzSmemBytes = k2Stages * k2StageBytes + kFzEpiWarps * kFzStageWords * 4 + 256;
+constexpr int kFzSmemBytes = kFzStages * kFzStageBytes + kFzEpiWarps * kFzStageWords * 4 +
+                             kFzEpiWarps * kFzRing * kFzRingEntryBytes + 256;
 constexpr int kFzSmemAlloc = kFzSmemBytes + 1024;
 static_assert(kFzSmemAlloc <= 232448, "fused kernel shared memory exceeds the sm_100 limit");
 
@@ -61,6 +78,7 @@ struct FusedArgs {
   float* out;              // (rows, N) posed vertices
   int rows;
   int N;                   // 3 V
+  int zero;                // always 0 (opaque to the compiler; see load_slot)
 };
 
 // A [rows][J*12] -> At [ceil(rows/128)][J*12][128] (+ transl on the translation column), so that the
@@ -96,13 +114,14 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(fz_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* stage_base = smem;
-  float* epi_base = reinterpret_cast<float*>(smem + k2Stages * k2StageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2Stages * k2StageBytes + kFzEpiWarps * kFzStageWords * 4);
-  uint64_t* full_bar = bars;                        // [k2Stages]   (used in the leader)
-  uint64_t* empty_bar = bars + k2Stages;            // [k2Stages]
-  uint64_t* tmem_full = bars + 2 * k2Stages;        // [2]
-  uint64_t* tmem_empty = bars + 2 * k2Stages + 2;   // [2]          (used in the leader)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * k2Stages + 4);
+  float* epi_base = reinterpret_cast<float*>(smem + kFzStages * kFzStageBytes);
+  uint8_t* ring_base = smem + kFzStages * kFzStageBytes + kFzEpiWarps * kFzStageWords * 4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_base + kFzEpiWarps * kFzRing * kFzRingEntryBytes);
+  uint64_t* full_bar = bars;                        // [kFzStages]   (used in the leader)
+  uint64_t* empty_bar = bars + kFzStages;           // [kFzStages]
+  uint64_t* tmem_full = bars + 2 * kFzStages;       // [2]
+  uint64_t* tmem_empty = bars + 2 * kFzStages + 2;  // [2]          (used in the leader)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kFzStages + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -111,7 +130,6 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
   const int num_clusters = gridDim.x >> 1;
   const int cluster_id = blockIdx.x >> 1;
   const int num_tiles = args.num_m_blocks * args.num_n_blocks;
-  constexpr int kElemsPerBlock = 64;   // fp16 elements per 128-byte k-block
   constexpr int kUmmaK = 16;
 
   if (warp == 0 && lane == 0) {
@@ -119,13 +137,13 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
     ptx::prefetch_tmap(&tmap_f_lo);
     ptx::prefetch_tmap(&tmap_pd_hi);
     ptx::prefetch_tmap(&tmap_pd_lo);
-    for (int s = 0; s < k2Stages; ++s) {
+    for (int s = 0; s < kFzStages; ++s) {
       ptx::mbar_init(&full_bar[s], 2);
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], 256);   // the 4 warps of one epilogue set, in both CTAs
+      ptx::mbar_init(&tmem_empty[s], 512);   // all 8 epilogue warps, in both CTAs
     }
     ptx::fence_barrier_init();
   }
@@ -150,15 +168,15 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
         const int nb0 = nb * kBlendBN + (int)rank * (kBlendBN / 2);   // this CTA's half of the B tile
         for (int kb = 0; kb < args.num_k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* st = stage_base + stage * k2StageBytes;
-          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * k2StageBytes);
+          uint8_t* st = stage_base + stage * kFzStageBytes;
+          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * kFzStageBytes);
           else ptx::mbar_arrive_cluster(&full_bar[stage], 0);
-          const int k0 = kb * kElemsPerBlock;
+          const int k0 = kb * kFzElemsPerBlock;
           ptx::tma_load_2d_2sm(st, &tmap_f_hi, &full_bar[stage], k0, m0);
-          ptx::tma_load_2d_2sm(st + k2TileABytes, &tmap_f_lo, &full_bar[stage], k0, m0);
-          ptx::tma_load_2d_2sm(st + 2 * k2TileABytes, &tmap_pd_hi, &full_bar[stage], k0, nb0);
-          ptx::tma_load_2d_2sm(st + 2 * k2TileABytes + k2TileBBytes, &tmap_pd_lo, &full_bar[stage], k0, nb0);
-          if (++stage == k2Stages) { stage = 0; phase ^= 1; }
+          ptx::tma_load_2d_2sm(st + kFzTileABytes, &tmap_f_lo, &full_bar[stage], k0, m0);
+          ptx::tma_load_2d_2sm(st + 2 * kFzTileABytes, &tmap_pd_hi, &full_bar[stage], k0, nb0);
+          ptx::tma_load_2d_2sm(st + 2 * kFzTileABytes + kFzTileBBytes, &tmap_pd_lo, &full_bar[stage], k0, nb0);
+          if (++stage == kFzStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -177,14 +195,14 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
         for (int kb = 0; kb < args.num_k_blocks; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tcgen05_fence_after();
-          const uint32_t st = ptx::smem_u32(stage_base + stage * k2StageBytes);
-          const uint64_t a_hi = ptx::make_kmajor_desc<128>(st);
-          const uint64_t a_lo = ptx::make_kmajor_desc<128>(st + k2TileABytes);
-          const uint64_t b_hi = ptx::make_kmajor_desc<128>(st + 2 * k2TileABytes);
-          const uint64_t b_lo = ptx::make_kmajor_desc<128>(st + 2 * k2TileABytes + k2TileBBytes);
-          const int ksteps = min(4, (args.k_elems - kb * kElemsPerBlock) / kUmmaK);
+          const uint32_t st = ptx::smem_u32(stage_base + stage * kFzStageBytes);
+          const uint64_t a_hi = ptx::make_kmajor_desc<kFzRowBytes>(st);
+          const uint64_t a_lo = ptx::make_kmajor_desc<kFzRowBytes>(st + kFzTileABytes);
+          const uint64_t b_hi = ptx::make_kmajor_desc<kFzRowBytes>(st + 2 * kFzTileABytes);
+          const uint64_t b_lo = ptx::make_kmajor_desc<kFzRowBytes>(st + 2 * kFzTileABytes + kFzTileBBytes);
+          const int ksteps = min(kFzKSteps, (args.k_elems - kb * kFzElemsPerBlock) / kUmmaK);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < kFzKSteps; ++k) {
             if (k < ksteps) {
               const uint64_t adv = static_cast<uint64_t>((k * 32) >> 4);
               const uint32_t first = (kb != 0 || k != 0) ? 1u : 0u;
@@ -194,7 +212,7 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
             }
           }
           ptx::umma_commit_2cta(&empty_bar[stage]);
-          if (++stage == k2Stages) { stage = 0; phase ^= 1; }
+          if (++stage == kFzStages) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit_2cta(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -202,22 +220,30 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
     }
   } else {
     // ===================== skinning epilogue (warps 2..9) =====================
-    const int set = (warp - 2) >> 2;          // accumulator buffer / tile parity this warp serves
+    const int half = (warp - 2) >> 2;         // which part of every tile's chunk range this warp takes
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
     const uint32_t stage_u32 = ptx::smem_u32(epi_base + (warp - 2) * kFzStageWords);
     const uint32_t stage_row = stage_u32 + lane * (kFzStageStride * 4);   // this body's staged row
     const uint32_t stage_col = stage_u32 + lane * 4;                      // this lane's staged column
+    const uint32_t ring_lane = ptx::smem_u32(ring_base) + (warp - 2) * (kFzRing * kFzRingEntryBytes) + lane * 4;
+    int ps = 0, cs = 0;                       // ring slots: next to fill / next to apply
     const float oscale = args.out_scale;
     const int JC128 = args.J * 12 * 128;
     const float* wflat = reinterpret_cast<const float*>(args.ch_w);
     constexpr unsigned kFull = 0xffffffffu;
-    for (int it = set;; it += 2) {
+    for (int it = 0;; ++it) {
       const int tile = cluster_id + it * num_clusters;
       if (tile >= num_tiles) break;
       const int mb = tile % args.num_m_blocks;
       const int nb = tile / args.num_m_blocks;
       const int m0 = mb * 2 * kBlendBM + (int)rank * kBlendBM;
+      const int acc = it & 1;                   // TMEM accumulator buffer of this tile
       const uint32_t acc_phase = (it >> 1) & 1;
+      // Both warps of a TMEM lane quarter work on EVERY tile, one on chunks [0, cb) and the other on
+      // [cb, 7) (the 4/3 split alternates), so an accumulator is held for about half an epilogue:
+      // with 2 accumulators the per-tile time is max(T_mma, (T_mma + T_hold) / 2).
+      const int cb = 3 + (it & 1);
+      const int c_lo = half ? cb : 0, c_hi = half ? kFzChunks : cb;
       const float* At_w = args.At + (size_t)(m0 >> 7) * JC128 + q * 32 + lane;
       const float* bias_t = args.bias + nb * kBlendBN;
       const int row0 = m0 + q * 32;
@@ -227,35 +253,43 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
       // chunk offsets (lane i <- off[i], i <= 7), first window of joint ids, first bias lines: all
       // independent of the accumulator, so issue them before waiting for the MMAs
       const int ol = __ldg(args.ch_off + nb * kFzChunks + min(lane, kFzChunks));
-      int e = __shfl_sync(kFull, ol, 0);
-      const int e_end = __shfl_sync(kFull, ol, kFzChunks);
+      int e = __shfl_sync(kFull, ol, c_lo);
+      const int e_end = __shfl_sync(kFull, ol, c_hi);
       int wb = e;                                          // base of the joint-id window
       int jl = __ldg(args.ch_joint + wb + lane);
-      float bn0 = __ldg(bias_t + lane), bn1 = __ldg(bias_t + 32 + (lane & 3));
-      float sa0[12], sa1[12];
-      float sw0 = 0.f, sw1 = 0.f;
-#if SMPLK_FZ_SLOTS == 3
-      float sa2[12];
-      float sw2 = 0.f;
-#endif
+      float bn0 = __ldg(bias_t + c_lo * kFzChunkCols + lane), bn1 = __ldg(bias_t + c_lo * kFzChunkCols + 32 + (lane & 3));
       float p[kFzChunkCols], o[kFzChunkCols];
 
-      // entry ee -> registers: the joint's 3x4 transform of this lane's body (12 coalesced lines)
-      // and the joint's weight for vertex (lane & 15) of the chunk (12 weights + 4 zeros per entry)
-      auto load_slot = [&](float (&sa)[12], float& sw, int ee) {
-        if (ee >= wb + 32) {
-          wb += 32;
-          jl = __ldg(args.ch_joint + wb + lane);
-        }
-        const int jj = __shfl_sync(kFull, jl, ee - wb);
-        const float* ap = At_w + (size_t)jj * (12 * 128);
+      // (chunk, joint) entry ee -> ring slot: this lane's element of the 12 transform lines (lane =
+      // body, one coalesced 128-byte line per component) and of the entry's weight line, by 4-byte
+      // cp.async.  Every lane later reads back exactly the words it copied, so completion needs only
+      // cp.async.wait_group -- no barrier, and no register scoreboard is held while the loads fly.
+      auto issue_entry = [&](int ee) {
+        if (ee < e_end) {
+          if (ee >= wb + 32) {
+            wb += 32;
+            jl = __ldg(args.ch_joint + wb + lane);
+          }
+          const int jj = __shfl_sync(kFull, jl, ee - wb);
+          const float* ap = At_w + (size_t)jj * (12 * 128);
+          const uint32_t dst = ring_lane + ps * kFzRingEntryBytes;
 #pragma unroll
-        for (int i = 0; i < 12; ++i) sa[i] = __ldg(ap + i * 128);
-        sw = __ldg(wflat + (size_t)ee * 16 + (lane & 15));
+          for (int i = 0; i < 12; ++i) ptx::cp_async_4(dst + i * 128, ap + i * 128);
+          ptx::cp_async_4(dst + 12 * 128, wflat + (size_t)ee * 16 + (lane & 15));
+        }
+        ptx::cp_async_commit();                 // one group per entry, empty past the tile's end
+        ps = (ps + 1 == kFzRing) ? 0 : ps + 1;
       };
       // branch-free: a vertex that does not use the joint has w = 0 and adds exactly 0 (p and the
       // transforms are finite, padding rows / columns included)
-      auto apply_slot = [&](const float (&a)[12], float sw) {
+      auto apply_entry = [&]() {
+        ptx::cp_async_wait<kFzRing - 1>();
+        const uint32_t src = ring_lane + cs * kFzRingEntryBytes;
+        cs = (cs + 1 == kFzRing) ? 0 : cs + 1;
+        float a[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) a[i] = ptx::ld_shared_f32(src + i * 128);
+        const float sw = ptx::ld_shared_f32(src + 12 * 128);
 #pragma unroll
         for (int v = 0; v < kFzChunkVerts; ++v) {
           const float w = __shfl_sync(kFull, sw, v);
@@ -269,9 +303,9 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
         }
       };
       // 32 staged columns (one 128-byte segment per body row) -> global
-      auto store_window = [&](int wnd, int ncols) {
+      auto store_window = [&](int wnd, int lane_lo, int lane_hi) {
         const int col = 32 * wnd + lane;
-        if (lane < ncols && col < cols_left) {
+        if (lane >= lane_lo && lane < lane_hi && col < cols_left) {
           float* dst = out_t + col;
           if (nrows == 32) {
 #pragma unroll 8
@@ -284,31 +318,30 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
         }
       };
 
-      if (e < e_end) load_slot(sa0, sw0, e);
-#if SMPLK_FZ_SLOTS == 3
-      if (e + 1 < e_end) load_slot(sa1, sw1, e + 1);
-#endif
-      ptx::mbar_wait(&tmem_full[set], acc_phase);
+      ps = 0;                                   // every group of the previous tile has been consumed
+      cs = 0;
+#pragma unroll
+      for (int i = 0; i < kFzRing - 1; ++i) issue_entry(e + i);
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tcgen05_fence_after();
 
-      int ph = 0;                                          // slot holding entry e
 #pragma unroll 1
-      for (int c = 0; c < kFzChunks; ++c) {
+      for (int c = c_lo; c < c_hi; ++c) {
         // ---- TMEM accumulator columns of chunk c -> p (+ v_template), o = 0
         {
           uint32_t pr[kFzChunkCols];
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                 static_cast<uint32_t>(set * kBlendBN + c * kFzChunkCols);
+                                 static_cast<uint32_t>(acc * kBlendBN + c * kFzChunkCols);
           ptx::tmem_ld_32x32b_x16(taddr, pr);
           ptx::tmem_ld_32x32b_x16(taddr + 16, pr + 16);
           ptx::tmem_ld_32x32b_x4(taddr + 32, pr + 32);
           ptx::tmem_ld_wait();
-          if (c == kFzChunks - 1) {             // accumulator fully read: hand it back to the MMA warp
+          if (c == c_hi - 1) {                  // this warp's last read of the accumulator
             ptx::tcgen05_fence_before();
-            ptx::mbar_arrive_cluster(&tmem_empty[set], 0);
+            ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);
           }
           const float b0 = bn0, b1 = bn1;
-          if (c < kFzChunks - 1) {              // next chunk's v_template line (bias is padded by 64)
+          if (c < c_hi - 1) {                   // next chunk's v_template line (bias is padded by 64)
             bn0 = __ldg(bias_t + (c + 1) * kFzChunkCols + lane);
             bn1 = __ldg(bias_t + (c + 1) * kFzChunkCols + 32 + (lane & 3));
           }
@@ -319,41 +352,12 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
             o[i] = 0.f;
           }
         }
-        // ---- the chunk's (joint, weights) entries.  The transform slots form a ring that rotates
-        // statically (Duff's device over the slot that holds entry e), so entry e is applied from
-        // one slot while the next entries -- of this chunk or the next -- are in flight in the others.
+        // ---- the chunk's (joint, weights) entries: entry e is applied from its ring slot while
+        // entries e+1 .. e+kFzRing-1 -- of this chunk or the next -- are in flight
         const int cend = __shfl_sync(kFull, ol, c + 1);
-        while (e < cend) {
-          switch (ph) {
-#if SMPLK_FZ_SLOTS == 3
-            case 0:
-              if (e + 2 < e_end) load_slot(sa2, sw2, e + 2);
-              apply_slot(sa0, sw0);
-              ph = 1;
-              if (++e == cend) break;
-            case 1:
-              if (e + 2 < e_end) load_slot(sa0, sw0, e + 2);
-              apply_slot(sa1, sw1);
-              ph = 2;
-              if (++e == cend) break;
-            default:
-              if (e + 2 < e_end) load_slot(sa1, sw1, e + 2);
-              apply_slot(sa2, sw2);
-              ph = 0;
-              ++e;
-#else
-            case 0:
-              if (e + 1 < e_end) load_slot(sa1, sw1, e + 1);
-              apply_slot(sa0, sw0);
-              ph = 1;
-              if (++e == cend) break;
-            default:
-              if (e + 1 < e_end) load_slot(sa0, sw0, e + 1);
-              apply_slot(sa1, sw1);
-              ph = 0;
-              ++e;
-#endif
-          }
+        for (; e < cend; ++e) {
+          issue_entry(e + kFzRing - 1);
+          apply_entry();
         }
         // ---- o (32 bodies x 36 columns) -> rolling 32-column staging window -> global.  Chunk c
         // starts at window column w0 = 36 c mod 32; its first 32 - w0 columns complete the window.
@@ -364,14 +368,14 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
         for (int i = 0; i < kFzChunkCols; ++i)
           if (i < split) ptx::st_shared_f32(stage_row + (w0 + i) * 4, o[i]);
         __syncwarp();
-        store_window((c * kFzChunkCols) >> 5, 32);
+        store_window((c * kFzChunkCols) >> 5, c == c_lo ? w0 : 0, 32);   // columns below w0 of the range's first window are the other warp's
         __syncwarp();
 #pragma unroll
         for (int i = 4; i < kFzChunkCols; ++i)
           if (i >= split) ptx::st_shared_f32(stage_row + (i - split) * 4, o[i]);
-        if (c == kFzChunks - 1) {                // the last window of the tile is partial
+        if (c == c_hi - 1) {                     // the last window of this warp's range is partial
           __syncwarp();
-          store_window(kFzTileCols >> 5, kFzTileCols & 31);
+          store_window(((c + 1) * kFzChunkCols) >> 5, 0, ((c + 1) * kFzChunkCols) & 31);
         }
       }
     }

@@ -177,6 +177,13 @@ static int make_operand_tmap_2cta(const smplk_model* mdl, CUtensorMap* map, cons
                       CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+// fp16 operand tile of the fused kernel: kFzRowBytes of K per row (= swizzle span), 128 rows per box.
+static int make_operand_tmap_fused(const smplk_model* mdl, CUtensorMap* map, const void* ptr, uint64_t inner,
+                                   uint64_t outer, CUtensorMapL2promotion promo) {
+  return make_tmap_2d(mdl, map, ptr, inner, outer, kFzRowBytes / 2, kBlendBM, promo, true,
+                      kFzRowBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
 extern "C" int smplk_model_destroy(smplk_model* model) {
   if (!model) return 0;
   cudaSetDevice(model->device);
@@ -585,8 +592,8 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdh_lo, d.pd_nk_h_lo, d.Kpad, d.Npad, p256, true)) return r;
     if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdkn_hi, d.pd_kn_hi, d.Npad, d.Kpad, p256, false)) return r;
     if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdkn_lo, d.pd_kn_lo, d.Npad, d.Kpad, p256, false)) return r;
-    if (int r = make_operand_tmap_2cta(mdl, &mdl->tmapf_pdh_hi, d.pdf_h_hi, d.Kpad, (uint64_t)d.fz_tiles * kBlendBN, p256, true)) return r;
-    if (int r = make_operand_tmap_2cta(mdl, &mdl->tmapf_pdh_lo, d.pdf_h_lo, d.Kpad, (uint64_t)d.fz_tiles * kBlendBN, p256, true)) return r;
+    if (int r = make_operand_tmap_fused(mdl, &mdl->tmapf_pdh_hi, d.pdf_h_hi, d.Kpad, (uint64_t)d.fz_tiles * kBlendBN, p256)) return r;
+    if (int r = make_operand_tmap_fused(mdl, &mdl->tmapf_pdh_lo, d.pdf_h_lo, d.Kpad, (uint64_t)d.fz_tiles * kBlendBN, p256)) return r;
     CUDA_TRY(cudaFuncSetAttribute(blend_skin_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFzSmemAlloc));
     CUDA_TRY(cudaFuncSetAttribute(blend_tcgen05_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   k2SmemAlloc));
@@ -837,18 +844,18 @@ static int launch_fused(const smplk_model* mdl, int rows, float* F_hi, float* F_
     LAUNCH_CHECK("transpose_transforms_kernel");
   }
   CUtensorMap tm_fhi, tm_flo;
-  if (int r = make_operand_tmap_2cta(mdl, &tm_fhi, F_hi, d.Kpad, rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, true)) return r;
-  if (int r = make_operand_tmap_2cta(mdl, &tm_flo, F_lo, d.Kpad, rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, true)) return r;
+  if (int r = make_operand_tmap_fused(mdl, &tm_fhi, F_hi, d.Kpad, rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return r;
+  if (int r = make_operand_tmap_fused(mdl, &tm_flo, F_lo, d.Kpad, rows, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return r;
   FusedArgs fa;
   fa.num_m_blocks = rows_pad / (2 * kBlendBM);
   fa.num_n_blocks = d.fz_tiles;
-  fa.num_k_blocks = (d.Kpad + 63) / 64;
+  fa.num_k_blocks = (d.Kpad + kFzElemsPerBlock - 1) / kFzElemsPerBlock;
   fa.k_elems = d.Kpad;
   fa.out_scale = 1.0f / d.pd_scale;
   fa.bias = d.bias_f;
   fa.ch_off = d.fz_off; fa.ch_joint = d.fz_joint; fa.ch_w = d.fz_w;
   fa.At = At; fa.J = d.J;
-  fa.out = out; fa.rows = rows; fa.N = d.N;
+  fa.out = out; fa.rows = rows; fa.N = d.N; fa.zero = 0;
   const int tiles = fa.num_m_blocks * fa.num_n_blocks;
   const int grid = 2 * std::min(tiles, mdl->num_sms / 2);
   ProfScope prof(mdl, st, SMPLK_PROF_BLEND_SKIN_FUSED);
