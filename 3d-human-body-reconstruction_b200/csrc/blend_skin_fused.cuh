@@ -7,24 +7,27 @@
 // + trans); upstream smplx lbs().  Algorithmic HBM traffic per body drops from 84,580 (GEMM) +
 // 167,856 (skinning) bytes to 84,004 (SURVEY 8d "forward, fused end-to-end").
 //
-// Mapping
-//   * GEMM main loop = blend_tcgen05_2cta_kernel (TMA producer warp, one MMA-issuing thread in the
-//     leader CTA, 256-body x 256-column tiles, 3 smem stages, two TMEM accumulators).
-//   * The B operand is re-packed so that a 256-column tile holds 85 WHOLE vertices (255 columns,
-//     interleaved xyz, + 1 zero column): column c of tile t is flat output coordinate 255 t + c.
-//   * Epilogue = 2 sets of 4 warps.  Set s owns TMEM accumulator s, i.e. every second tile of the
-//     CTA, so a set has two tile-times to finish a tile and the two sets never synchronise.  A thread
-//     is one body (TMEM lane); a warp covers the 32 bodies of its TMEM lane quarter.
-//   * Per 16-vertex chunk (48 TMEM columns -> 48 registers): the chunk's distinct joints come from a
-//     table built at model-create time.  For each joint the warp loads the body's 3x4 transform from
-//     the TRANSPOSED transform array At[128-body block][joint][12][128] -- lane = body, so each of the
-//     12 loads is one coalesced 128-byte line -- and applies it to the vertices that use the joint
-//     (weights are warp-uniform loads; a zero weight is a uniform branch).  The next joint's
-//     transform is prefetched while the current one is applied.
-//   * The 32 x 48 result block is transposed through a warp-private smem buffer (two passes of 24
-//     columns, row stride 25 words -> conflict free both ways) and written with row-contiguous
-//     96-byte stores.  (The caller's (B, V, 3) fp32 rows are 82,680 bytes = 8 mod 16, so neither a
-//     2-D TMA store nor 16-byte bulk stores can target them.)
+// Mapping (10 warps per CTA, one CTA per SM, CTA pairs)
+//   * GEMM main loop as in blend_tcgen05_2cta_kernel (TMA producer warp, one MMA-issuing thread in
+//     the leader CTA, 256-body x 256-column tiles, two 256-column TMEM accumulators), but with
+//     64-byte operand rows x 4 stages (128 KB in flight) so that the epilogue's buffers fit.
+//   * The B operand is re-packed so that a 256-column tile holds 84 WHOLE vertices (252 columns,
+//     interleaved xyz, + 4 zero columns): column c of tile t is flat output coordinate 252 t + c.
+//   * Epilogue = 8 warps; a thread is one body (TMEM lane), a warp the 32 bodies of its TMEM lane
+//     quarter.  The two warps of a quarter split EVERY tile's 7 chunks of 12 vertices 3/4
+//     (alternating), so an accumulator is held for half an epilogue: with two accumulators the
+//     per-tile time is max(T_mma, (T_mma + T_hold) / 2).
+//   * Per chunk (36 TMEM columns -> 36 registers + v_template from smem): the chunk's distinct
+//     joints come from a table built at model-create time.  For each (chunk, joint) entry the body's
+//     3x4 transform is read from the TRANSPOSED transform array At[128-body block][joint][12][128]
+//     (lane = body: every component is one coalesced 128-byte line) and applied to the 12 vertices
+//     with the entry's weights (0 where a vertex does not use the joint; branch-free).
+//   * Transforms and weights travel through a per-warp cp.async ring in shared memory (kFzRing
+//     entries of 13 lines): ptxas tracks ALL global loads of a warp with ONE scoreboard, so a
+//     register prefetch cannot run more than one entry ahead -- cp.async groups can.
+//   * Results leave through a rolling 32-column staging window per warp (STS.128 rows, LDS columns)
+//     and are written as 128-byte row segments.  (The caller's (B, V, 3) fp32 rows are 82,680 bytes
+//     = 8 mod 16, so a 2-D TMA store cannot target them directly.)
 #pragma once
 #include "blend_gemm_2cta.cuh"
 
@@ -32,6 +35,9 @@ namespace smplk {
 
 #ifndef SMPLK_FZ_RING
 #define SMPLK_FZ_RING 4      // transform entries in flight per epilogue warp (cp.async ring in smem)
+#endif
+#ifndef SMPLK_FZ_BACKOFF_NS
+#define SMPLK_FZ_BACKOFF_NS 40
 #endif
 #ifndef SMPLK_FZ_ROW_BYTES
 #define SMPLK_FZ_ROW_BYTES 64
@@ -56,30 +62,41 @@ constexpr int kFzTileCols = 3 * kFzTileVerts;       // 252 output coordinates pe
 constexpr int kFzChunkVerts = 12;
 constexpr int kFzChunkCols = 36;
 constexpr int kFzChunks = 7;                        // 7 x 12 vertices
-constexpr int kFzStageStride = 33;                  // words per staged row of the 32-column window
+constexpr int kFzStageStride = 36;                  // words per staged row of the 32-column window: 16-byte
+                                                    // aligned rows, conflict-free for STS.128 rows and LDS columns
 constexpr int kFzStageWords = 32 * kFzStageStride;
+constexpr int kFzBiasBytes = 4 * kFzChunkCols * 4;          // v_template of a warp's (<= 4) chunks
 constexpr int kFzSmemBytes = kFzStages * kFzStageBytes + kFzEpiWarps * kFzStageWords * 4 +
-                             kFzEpiWarps * kFzRing * kFzRingEntryBytes + 256;
+                             kFzEpiWarps * kFzRing * kFzRingEntryBytes + kFzEpiWarps * kFzBiasBytes + 256;
 constexpr int kFzSmemAlloc = kFzSmemBytes + 1024;
 static_assert(kFzSmemAlloc <= 232448, "fused kernel shared memory exceeds the sm_100 limit");
 
 struct FusedArgs {
   int num_m_blocks;        // 256-body blocks
-  int num_n_blocks;        // 85-vertex tiles
+  int num_n_blocks;        // 84-vertex tiles
   int num_k_blocks;
   int k_elems;
   float out_scale;         // 1 / pd_scale
   const float* bias;       // [num_n_blocks * 256 + 64] v_template in the fused column layout
-  const int* ch_off;       // [num_n_blocks * 6 + 1] first entry of every 16-vertex chunk
+  const int* ch_off;       // [num_n_blocks * 7 + 1] first entry of every 12-vertex chunk
   const int* ch_joint;     // [entries] joint id
-  const float4* ch_w;      // [entries][4] weight of that joint for the chunk's 16 vertices
+  const float4* ch_w;      // [entries][4] weight of that joint for the chunk's 12 vertices (+ 4 zeros)
   const float* At;         // [ceil(rows/128)][J*12][128] transposed transforms (transl folded in)
   int J;
   float* out;              // (rows, N) posed vertices
   int rows;
   int N;                   // 3 V
-  int zero;                // always 0 (opaque to the compiler; see load_slot)
+  long long* dbg;          // tuning aid (SMPLK_FZ_TIMELINE builds): per-tile clock64 stamps of CTA 0
 };
+constexpr int kFzDbgTiles = 32;
+#ifndef SMPLK_FZ_TIMELINE
+#define SMPLK_FZ_TIMELINE 0
+#endif
+#if SMPLK_FZ_TIMELINE
+#define FZ_STAMP(cond, ptr_expr) do { if (cond) *(ptr_expr) = clock64(); } while (0)
+#else
+#define FZ_STAMP(cond, ptr_expr) do { } while (0)
+#endif
 
 // A [rows][J*12] -> At [ceil(rows/128)][J*12][128] (+ transl on the translation column), so that the
 // fused epilogue (lane = body) reads every transform component as one 128-byte line.
@@ -105,6 +122,9 @@ transpose_transforms_kernel(int rows, int JC, const float* __restrict__ A,
   }
 }
 
+// kN > 0: floats per output row known at compile time (3 * 6890 for SMPL / SMPL-H), so the 32 row
+// addresses of a window store are immediates; kN == 0: row pitch from args.N.
+template <int kN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFzThreads, 1)
 blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
                         const __grid_constant__ CUtensorMap tmap_f_lo,
@@ -116,7 +136,8 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
   uint8_t* stage_base = smem;
   float* epi_base = reinterpret_cast<float*>(smem + kFzStages * kFzStageBytes);
   uint8_t* ring_base = smem + kFzStages * kFzStageBytes + kFzEpiWarps * kFzStageWords * 4;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_base + kFzEpiWarps * kFzRing * kFzRingEntryBytes);
+  uint8_t* bias_base = ring_base + kFzEpiWarps * kFzRing * kFzRingEntryBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_base + kFzEpiWarps * kFzBiasBytes);
   uint64_t* full_bar = bars;                        // [kFzStages]   (used in the leader)
   uint64_t* empty_bar = bars + kFzStages;           // [kFzStages]
   uint64_t* tmem_full = bars + 2 * kFzStages;       // [2]
@@ -125,6 +146,7 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int outN = kN > 0 ? kN : args.N;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
   const int num_clusters = gridDim.x >> 1;
@@ -167,7 +189,7 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
         const int m0 = mb * 2 * kBlendBM + (int)rank * kBlendBM;
         const int nb0 = nb * kBlendBN + (int)rank * (kBlendBN / 2);   // this CTA's half of the B tile
         for (int kb = 0; kb < args.num_k_blocks; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_wait_backoff(&empty_bar[stage], phase ^ 1, SMPLK_FZ_BACKOFF_NS);
           uint8_t* st = stage_base + stage * kFzStageBytes;
           if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * kFzStageBytes);
           else ptx::mbar_arrive_cluster(&full_bar[stage], 0);
@@ -189,8 +211,11 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        const int dbg_it = (tile - cluster_id) / num_clusters;
+        FZ_STAMP(args.dbg && blockIdx.x == 0 && dbg_it < kFzDbgTiles, &args.dbg[(1 * kFzDbgTiles + dbg_it) * 4 + 0]);
+        ptx::mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1, SMPLK_FZ_BACKOFF_NS);
         ptx::tcgen05_fence_after();
+        FZ_STAMP(args.dbg && blockIdx.x == 0 && dbg_it < kFzDbgTiles, &args.dbg[(1 * kFzDbgTiles + dbg_it) * 4 + 1]);
         const uint32_t d_tmem = tmem_base + acc * kBlendBN;
         for (int kb = 0; kb < args.num_k_blocks; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
@@ -215,6 +240,7 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
           if (++stage == kFzStages) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit_2cta(&tmem_full[acc]);
+        FZ_STAMP(args.dbg && blockIdx.x == 0 && dbg_it < kFzDbgTiles, &args.dbg[(1 * kFzDbgTiles + dbg_it) * 4 + 2]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -225,7 +251,10 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
     const uint32_t stage_u32 = ptx::smem_u32(epi_base + (warp - 2) * kFzStageWords);
     const uint32_t stage_row = stage_u32 + lane * (kFzStageStride * 4);   // this body's staged row
     const uint32_t stage_col = stage_u32 + lane * 4;                      // this lane's staged column
-    const uint32_t ring_lane = ptx::smem_u32(ring_base) + (warp - 2) * (kFzRing * kFzRingEntryBytes) + lane * 4;
+    const uint32_t ring_warp = ptx::smem_u32(ring_base) + (warp - 2) * (kFzRing * kFzRingEntryBytes);
+    const uint32_t ring_lane = ring_warp + lane * 4;
+    const uint32_t ring_piece = ring_warp + lane * 16;    // this lane's 16-byte piece of lines l/8 + 4k
+    const uint32_t bias_warp = ptx::smem_u32(bias_base) + (warp - 2) * kFzBiasBytes;
     int ps = 0, cs = 0;                       // ring slots: next to fill / next to apply
     const float oscale = args.out_scale;
     const int JC128 = args.J * 12 * 128;
@@ -244,12 +273,13 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
       // with 2 accumulators the per-tile time is max(T_mma, (T_mma + T_hold) / 2).
       const int cb = 3 + (it & 1);
       const int c_lo = half ? cb : 0, c_hi = half ? kFzChunks : cb;
-      const float* At_w = args.At + (size_t)(m0 >> 7) * JC128 + q * 32 + lane;
+      // this lane's 16-byte piece (lane & 7) of transform line (lane >> 3) of the warp's 32 bodies
+      const float* At_w = args.At + (size_t)(m0 >> 7) * JC128 + q * 32 + (lane >> 3) * 128 + (lane & 7) * 4;
       const float* bias_t = args.bias + nb * kBlendBN;
       const int row0 = m0 + q * 32;
       const int nrows = min(32, args.rows - row0);
-      float* out_t = args.out + (size_t)row0 * args.N + (size_t)nb * kFzTileCols;
-      const int cols_left = args.N - nb * kFzTileCols;     // valid output columns from this tile on
+      float* out_t = args.out + (size_t)row0 * outN + (size_t)nb * kFzTileCols;
+      const int cols_left = outN - nb * kFzTileCols;     // valid output columns from this tile on
       // chunk offsets (lane i <- off[i], i <= 7), first window of joint ids, first bias lines: all
       // independent of the accumulator, so issue them before waiting for the MMAs
       const int ol = __ldg(args.ch_off + nb * kFzChunks + min(lane, kFzChunks));
@@ -257,13 +287,20 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
       const int e_end = __shfl_sync(kFull, ol, c_hi);
       int wb = e;                                          // base of the joint-id window
       int jl = __ldg(args.ch_joint + wb + lane);
-      float bn0 = __ldg(bias_t + c_lo * kFzChunkCols + lane), bn1 = __ldg(bias_t + c_lo * kFzChunkCols + 32 + (lane & 3));
+      // v_template of this warp's chunks -> smem (first cp.async group of the tile)
+      {
+        const int npieces = (c_hi - c_lo) * (kFzChunkCols / 4);
+        for (int i = lane; i < npieces; i += 32)
+          ptx::cp_async_16(bias_warp + i * 16, bias_t + c_lo * kFzChunkCols + i * 4);
+        ptx::cp_async_commit();
+      }
       float p[kFzChunkCols], o[kFzChunkCols];
 
-      // (chunk, joint) entry ee -> ring slot: this lane's element of the 12 transform lines (lane =
-      // body, one coalesced 128-byte line per component) and of the entry's weight line, by 4-byte
-      // cp.async.  Every lane later reads back exactly the words it copied, so completion needs only
-      // cp.async.wait_group -- no barrier, and no register scoreboard is held while the loads fly.
+      // (chunk, joint) entry ee -> ring slot: the joint's 12 transform lines of the warp's 32 bodies
+      // (128 bytes each, lane = body) + the entry's 64-byte weight line, as 16-byte cp.async pieces
+      // (3 per lane + 4 lanes for the weights).  No register scoreboard is held while the loads fly
+      // (ptxas tracks ALL global loads of a warp with one scoreboard, so register prefetching cannot
+      // run more than one entry ahead; cp.async groups can).
       auto issue_entry = [&](int ee) {
         if (ee < e_end) {
           if (ee >= wb + 32) {
@@ -272,27 +309,33 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
           }
           const int jj = __shfl_sync(kFull, jl, ee - wb);
           const float* ap = At_w + (size_t)jj * (12 * 128);
-          const uint32_t dst = ring_lane + ps * kFzRingEntryBytes;
+          const uint32_t dst = ring_piece + ps * kFzRingEntryBytes;
 #pragma unroll
-          for (int i = 0; i < 12; ++i) ptx::cp_async_4(dst + i * 128, ap + i * 128);
-          ptx::cp_async_4(dst + 12 * 128, wflat + (size_t)ee * 16 + (lane & 15));
+          for (int k = 0; k < 3; ++k) ptx::cp_async_16(dst + k * 512, ap + k * 512);
+          if (lane < 4) ptx::cp_async_16(dst + 12 * 128, wflat + (size_t)ee * 16 + lane * 4);
         }
         ptx::cp_async_commit();                 // one group per entry, empty past the tile's end
         ps = (ps + 1 == kFzRing) ? 0 : ps + 1;
       };
-      // branch-free: a vertex that does not use the joint has w = 0 and adds exactly 0 (p and the
-      // transforms are finite, padding rows / columns included)
-      auto apply_entry = [&]() {
-        ptx::cp_async_wait<kFzRing - 1>();
-        const uint32_t src = ring_lane + cs * kFzRingEntryBytes;
+      // Apply entry e (slot cs) and refill the slot of entry e-1 with entry e + kFzRing - 1.
+      // Branch-free: a vertex that does not use the joint has w = 0 and adds exactly 0 (p and the
+      // transforms are finite, padding rows / columns included).
+      auto apply_entry = [&](int ee) {
+        ptx::cp_async_wait<kFzRing - 2>();      // this lane's pieces of entry e have landed ...
+        __syncwarp();                           // ... and so have everyone else's; slot e-1 is drained
+        issue_entry(ee + kFzRing - 1);
+        const uint32_t src = ring_warp + cs * kFzRingEntryBytes;
         cs = (cs + 1 == kFzRing) ? 0 : cs + 1;
         float a[12];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) a[i] = ptx::ld_shared_f32(src + i * 128);
-        const float sw = ptx::ld_shared_f32(src + 12 * 128);
+        for (int i = 0; i < 12; ++i) a[i] = ptx::ld_shared_f32(src + i * 128 + lane * 4);
+        float wv[kFzChunkVerts];
+#pragma unroll
+        for (int i = 0; i < kFzChunkVerts / 4; ++i)
+          ptx::ld_shared_v4(src + 12 * 128 + i * 16, wv[4 * i], wv[4 * i + 1], wv[4 * i + 2], wv[4 * i + 3]);
 #pragma unroll
         for (int v = 0; v < kFzChunkVerts; ++v) {
-          const float w = __shfl_sync(kFull, sw, v);
+          const float w = wv[v];
           const float x = p[3 * v], y = p[3 * v + 1], z = p[3 * v + 2];
           const float qx = fmaf(a[0], x, fmaf(a[1], y, fmaf(a[2], z, a[3])));
           const float qy = fmaf(a[4], x, fmaf(a[5], y, fmaf(a[6], z, a[7])));
@@ -308,12 +351,19 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
         if (lane >= lane_lo && lane < lane_hi && col < cols_left) {
           float* dst = out_t + col;
           if (nrows == 32) {
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r)
-              dst[r * args.N] = ptx::ld_shared_f32(stage_col + r * (kFzStageStride * 4));
+            // batches of 8: the shared loads are volatile asm, so without explicit batching every
+            // store would wait for its own load (load latency x 32 per window)
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = ptx::ld_shared_f32(stage_col + (r0 + j) * (kFzStageStride * 4));
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[(r0 + j) * outN] = v[j];
+            }
           } else {
             for (int r = 0; r < nrows; ++r)
-              dst[r * args.N] = ptx::ld_shared_f32(stage_col + r * (kFzStageStride * 4));
+              dst[r * outN] = ptx::ld_shared_f32(stage_col + r * (kFzStageStride * 4));
           }
         }
       };
@@ -322,11 +372,19 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
       cs = 0;
 #pragma unroll
       for (int i = 0; i < kFzRing - 1; ++i) issue_entry(e + i);
+      ptx::cp_async_wait<kFzRing - 1>();        // the v_template group (older than the primed entries)
+      __syncwarp();
+      const bool dbg_on = args.dbg && blockIdx.x == 0 && lane == 0 && it < kFzDbgTiles;
+      FZ_STAMP(dbg_on, &args.dbg[(warp * kFzDbgTiles + it) * 4 + 0]);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tcgen05_fence_after();
+      FZ_STAMP(dbg_on, &args.dbg[(warp * kFzDbgTiles + it) * 4 + 1]);
 
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; ++c) {
+        const bool dbg_c = dbg_on && (warp == 2 || warp == 6) && it < 4;
+        long long* dbg_p = args.dbg ? args.dbg + (0 * kFzDbgTiles + it * 7 + c) * 4 : nullptr;
+        FZ_STAMP(dbg_c, &dbg_p[0]);
         // ---- TMEM accumulator columns of chunk c -> p (+ v_template), o = 0
         {
           uint32_t pr[kFzChunkCols];
@@ -339,45 +397,48 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
           if (c == c_hi - 1) {                  // this warp's last read of the accumulator
             ptx::tcgen05_fence_before();
             ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);
+            FZ_STAMP(dbg_on, &args.dbg[(warp * kFzDbgTiles + it) * 4 + 2]);
           }
-          const float b0 = bn0, b1 = bn1;
-          if (c < c_hi - 1) {                   // next chunk's v_template line (bias is padded by 64)
-            bn0 = __ldg(bias_t + (c + 1) * kFzChunkCols + lane);
-            bn1 = __ldg(bias_t + (c + 1) * kFzChunkCols + 32 + (lane & 3));
-          }
+          const uint32_t bsrc = bias_warp + (c - c_lo) * (kFzChunkCols * 4);
 #pragma unroll
-          for (int i = 0; i < kFzChunkCols; ++i) {
-            const float bi = i < 32 ? __shfl_sync(kFull, b0, i) : __shfl_sync(kFull, b1, i - 32);
-            p[i] = fmaf(__uint_as_float(pr[i]), oscale, bi);
-            o[i] = 0.f;
+          for (int i = 0; i < kFzChunkCols; i += 4) {
+            float b0, b1, b2, b3;
+            ptx::ld_shared_v4(bsrc + i * 4, b0, b1, b2, b3);      // warp-uniform address: broadcast
+            p[i] = fmaf(__uint_as_float(pr[i]), oscale, b0);
+            p[i + 1] = fmaf(__uint_as_float(pr[i + 1]), oscale, b1);
+            p[i + 2] = fmaf(__uint_as_float(pr[i + 2]), oscale, b2);
+            p[i + 3] = fmaf(__uint_as_float(pr[i + 3]), oscale, b3);
+            o[i] = o[i + 1] = o[i + 2] = o[i + 3] = 0.f;
           }
         }
         // ---- the chunk's (joint, weights) entries: entry e is applied from its ring slot while
         // entries e+1 .. e+kFzRing-1 -- of this chunk or the next -- are in flight
         const int cend = __shfl_sync(kFull, ol, c + 1);
-        for (; e < cend; ++e) {
-          issue_entry(e + kFzRing - 1);
-          apply_entry();
-        }
+
+        for (; e < cend; ++e) apply_entry(e);
+        FZ_STAMP(dbg_c, &dbg_p[1]);
         // ---- o (32 bodies x 36 columns) -> rolling 32-column staging window -> global.  Chunk c
         // starts at window column w0 = 36 c mod 32; its first 32 - w0 columns complete the window.
         const int w0 = (c * kFzChunkCols) & 31;
-        const int split = 32 - w0;
+        const int g0 = w0 >> 2;                  // window position of the chunk's first 4-column group
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < kFzChunkCols; ++i)
-          if (i < split) ptx::st_shared_f32(stage_row + (w0 + i) * 4, o[i]);
+        for (int g = 0; g < kFzChunkCols / 4; ++g)
+          if (g0 + g < 8) ptx::st_shared_v4(stage_row + (g0 + g) * 16, o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
         __syncwarp();
+        FZ_STAMP(dbg_c, &dbg_p[2]);
         store_window((c * kFzChunkCols) >> 5, c == c_lo ? w0 : 0, 32);   // columns below w0 of the range's first window are the other warp's
+        FZ_STAMP(dbg_c, &dbg_p[3]);
         __syncwarp();
 #pragma unroll
-        for (int i = 4; i < kFzChunkCols; ++i)
-          if (i >= split) ptx::st_shared_f32(stage_row + (i - split) * 4, o[i]);
+        for (int g = 1; g < kFzChunkCols / 4; ++g)
+          if (g0 + g >= 8) ptx::st_shared_v4(stage_row + (g0 + g - 8) * 16, o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
         if (c == c_hi - 1) {                     // the last window of this warp's range is partial
           __syncwarp();
           store_window(((c + 1) * kFzChunkCols) >> 5, 0, ((c + 1) * kFzChunkCols) & 31);
         }
       }
+      FZ_STAMP(dbg_on, &args.dbg[(warp * kFzDbgTiles + it) * 4 + 3]);
     }
   }
 

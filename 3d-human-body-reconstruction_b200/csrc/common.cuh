@@ -58,15 +58,15 @@ struct ModelDev {
   const int* reg_ptr;         // [R+1] CSR of regressor_posed
   const int* reg_col;         // [nnzR]
   const float* reg_val;       // [nnzR]
-  // fused blend+skinning kernel (blend_skin_fused.cuh): 85 whole vertices per 256-column tile
+  // fused blend+skinning kernel (blend_skin_fused.cuh): 84 whole vertices per 256-column tile
   int fz_ok;                  // 1 when the per-chunk joint lists are short enough for the fused epilogue
-  int fz_tiles;               // ceil(V / 85)
-  const __half* pdf_h_hi;     // [fz_tiles*256][Kpad] fp16 hi term, row 256 t + c <-> coordinate 255 t + c
+  int fz_tiles;               // ceil(V / 84)
+  const __half* pdf_h_hi;     // [fz_tiles*256][Kpad] fp16 hi term, row 256 t + c <-> coordinate 252 t + c
   const __half* pdf_h_lo;     // [fz_tiles*256][Kpad] fp16 lo term
   const float* bias_f;        // [fz_tiles*256 + 64] v_template in the same column layout
-  const int* fz_off;          // [fz_tiles*6 + 1] first (joint, weights) entry of every 16-vertex chunk
+  const int* fz_off;          // [fz_tiles*7 + 1] first (joint, weights) entry of every 12-vertex chunk
   const int* fz_joint;        // [entries]
-  const float4* fz_w;         // [entries][4] weights of the chunk's 16 vertices for that joint
+  const float4* fz_w;         // [entries][4] weights of the chunk's 12 vertices for that joint (+ 4 zeros)
 };
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }

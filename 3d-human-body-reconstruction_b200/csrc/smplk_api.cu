@@ -84,7 +84,7 @@ struct smplk_model {
   // CTA-pair kernel: 128-byte rows, 128-row boxes (each CTA loads half of the B tile)
   CUtensorMap tmap2_pd_hi, tmap2_pd_lo, tmap2_pdh_hi, tmap2_pdh_lo, tmap2_pdkn_hi, tmap2_pdkn_lo;
   bool use_2cta;
-  CUtensorMap tmapf_pdh_hi, tmapf_pdh_lo;  // fused blend+skinning kernel: 85-vertex column tiles
+  CUtensorMap tmapf_pdh_hi, tmapf_pdh_lo;  // fused blend+skinning kernel: 84-vertex column tiles
   bool use_fused;       // SMPLK_FUSED=0 in the environment selects the two-kernel forward (A/B runs)
   CUtensorMap tmap_pdkn_hi, tmap_pdkn_lo;  // backward: B operand rows = blend features
   // host staging for smplk_forward_host
@@ -307,8 +307,8 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
         }
       if (int r = upload(mdl, hh, &d.pd_nk_h_hi)) return r;
       if (int r = upload(mdl, hl, &d.pd_nk_h_lo)) return r;
-      // same operand in the fused kernel's column layout: tile t = vertices [85 t, 85 t + 85),
-      // row 256 t + c <-> flat coordinate 255 t + c (c < 255), row 256 t + 255 = 0
+      // same operand in the fused kernel's column layout: tile t = vertices [84 t, 84 t + 84),
+      // row 256 t + c <-> flat coordinate 252 t + c (c < 252), rows 256 t + 252.. = 0
       d.fz_tiles = (V + kFzTileVerts - 1) / kFzTileVerts;
       const size_t nf = (size_t)d.fz_tiles * kBlendBN;
       std::vector<__half> fh(nf * d.Kpad, __float2half(0.f)), fl(nf * d.Kpad, __float2half(0.f));
@@ -475,8 +475,8 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     if (int r = upload(mdl, cptr, &d.csc_ptr)) return r;
     if (int r = upload(mdl, cvert, &d.csc_vert)) return r;
     if (int r = upload(mdl, cw, &d.csc_w)) return r;
-    // fused epilogue tables: for every 16-vertex chunk of every 85-vertex tile, the distinct joints
-    // its vertices are bound to and, per joint, the 16 weights (0 where a vertex does not use it)
+    // fused epilogue tables: for every 12-vertex chunk of every 84-vertex tile, the distinct joints
+    // its vertices are bound to and, per joint, the chunk's weights (0 where a vertex does not use it)
     if (!lbs_only) {
       const int tiles = (V + kFzTileVerts - 1) / kFzTileVerts;
       std::vector<int> off(1, 0), cj;
@@ -594,7 +594,8 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdkn_lo, d.pd_kn_lo, d.Npad, d.Kpad, p256, false)) return r;
     if (int r = make_operand_tmap_fused(mdl, &mdl->tmapf_pdh_hi, d.pdf_h_hi, d.Kpad, (uint64_t)d.fz_tiles * kBlendBN, p256)) return r;
     if (int r = make_operand_tmap_fused(mdl, &mdl->tmapf_pdh_lo, d.pdf_h_lo, d.Kpad, (uint64_t)d.fz_tiles * kBlendBN, p256)) return r;
-    CUDA_TRY(cudaFuncSetAttribute(blend_skin_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFzSmemAlloc));
+    CUDA_TRY(cudaFuncSetAttribute(blend_skin_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFzSmemAlloc));
+    CUDA_TRY(cudaFuncSetAttribute(blend_skin_fused_kernel<3 * 6890>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFzSmemAlloc));
     CUDA_TRY(cudaFuncSetAttribute(blend_tcgen05_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   k2SmemAlloc));
     CUDA_TRY(cudaFuncSetAttribute(blend_tcgen05_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -855,13 +856,46 @@ static int launch_fused(const smplk_model* mdl, int rows, float* F_hi, float* F_
   fa.bias = d.bias_f;
   fa.ch_off = d.fz_off; fa.ch_joint = d.fz_joint; fa.ch_w = d.fz_w;
   fa.At = At; fa.J = d.J;
-  fa.out = out; fa.rows = rows; fa.N = d.N; fa.zero = 0;
+  fa.out = out; fa.rows = rows; fa.N = d.N;
+  fa.dbg = nullptr;
+  static long long* dbg_dev = nullptr;
+  const bool dbg = SMPLK_FZ_TIMELINE && getenv("SMPLK_FZ_DEBUG") != nullptr;   // tools/fz_timeline.py
+  if (dbg) {
+    if (!dbg_dev) cudaMalloc(&dbg_dev, 10 * kFzDbgTiles * 4 * sizeof(long long));
+    cudaMemsetAsync(dbg_dev, 0, 10 * kFzDbgTiles * 4 * sizeof(long long), st);
+    fa.dbg = dbg_dev;
+  }
   const int tiles = fa.num_m_blocks * fa.num_n_blocks;
   const int grid = 2 * std::min(tiles, mdl->num_sms / 2);
   ProfScope prof(mdl, st, SMPLK_PROF_BLEND_SKIN_FUSED);
-  blend_skin_fused_kernel<<<grid, kFzThreads, kFzSmemAlloc, st>>>(tm_fhi, tm_flo, mdl->tmapf_pdh_hi,
-                                                                  mdl->tmapf_pdh_lo, fa);
+  if (d.N == 3 * 6890)   // canonical SMPL-family vertex count: row pitch folded into the store addresses
+    blend_skin_fused_kernel<3 * 6890><<<grid, kFzThreads, kFzSmemAlloc, st>>>(tm_fhi, tm_flo, mdl->tmapf_pdh_hi,
+                                                                            mdl->tmapf_pdh_lo, fa);
+  else
+    blend_skin_fused_kernel<0><<<grid, kFzThreads, kFzSmemAlloc, st>>>(tm_fhi, tm_flo, mdl->tmapf_pdh_hi,
+                                                                     mdl->tmapf_pdh_lo, fa);
   LAUNCH_CHECK("blend_skin_fused_kernel");
+  if (dbg) {   // tuning aid: per-tile timeline of CTA 0 (cycles relative to the first stamp)
+    std::vector<long long> h(10 * kFzDbgTiles * 4);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), dbg_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long t0 = h[(1 * kFzDbgTiles + 0) * 4 + 0];
+    for (int it = 0; it < kFzDbgTiles; ++it) {
+      if (!h[(1 * kFzDbgTiles + it) * 4 + 0]) break;
+      fprintf(stderr, "tile %2d mma[wait %7lld go %7lld done %7lld]", it, h[(1 * kFzDbgTiles + it) * 4 + 0] - t0,
+              h[(1 * kFzDbgTiles + it) * 4 + 1] - t0, h[(1 * kFzDbgTiles + it) * 4 + 2] - t0);
+      for (int w = 2; w < 10; ++w) {
+        const long long* r = &h[(w * kFzDbgTiles + it) * 4];
+        fprintf(stderr, " | w%d %lld %lld %lld %lld", w, r[0] - t0, r[1] - t0, r[2] - t0, r[3] - t0);
+      }
+      fprintf(stderr, "\n");
+    }
+    for (int i = 0; i < 28; ++i) {
+      const long long* r = &h[i * 4];
+      if (r[0]) fprintf(stderr, "tile %d chunk %d: start %lld load+entries %lld stsA %lld store_window %lld\n", i / 7, i % 7,
+                        r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2]);
+    }
+  }
   return 0;
 }
 

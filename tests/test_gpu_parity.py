@@ -126,6 +126,22 @@ def test_fused_blend_skinning_matches_two_kernel_path_and_oracle(dev, smplh_mode
     assert torch.isfinite(vf).all()
 
 
+@pytest.mark.parametrize("V,B", [(1000, 300), (7001, 260)])
+def test_fused_path_other_vertex_counts(dev, V, B):
+    """Vertex counts other than 6890 take the runtime-row-pitch instance of the fused kernel; the
+    last 84-vertex tile / 12-vertex chunk are ragged."""
+    m = synthetic.make_model("smplh", seed=7, num_verts=V)
+    dm = smplk.DeviceModel(m, device=0)
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=V)
+    dm.profile_enable(True)
+    v, j, _, _ = body_model_apply(dm, _t(betas, dev), _t(pose, dev), transl=_t(transl, dev))
+    torch.cuda.synchronize()
+    assert dm.profile_read()["blend_skin_fused"][1] == 1
+    ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(
+        *[torch.tensor(x, dtype=torch.float64) for x in (betas, pose, transl)])
+    assert _maxerr(v, ref.vertices) <= TOL and _maxerr(j, ref.joints) <= TOL
+
+
 def test_fused_path_smpl_24_joints_and_broadcast_betas(dev, smpl_model):
     m = smpl_model
     B = 513
