@@ -9,8 +9,8 @@ BASELINE.json configs[1] -- SMPL-H forward+LBS, batch 4096, fp32, 52 joints, 16 
 
 Printed JSON line (rank 0): value = whole-job posed meshes/s with inputs resident in HBM;
 e2e = same metric through the C-ABI host-buffer call (H2D of inputs + D2H of vertices inside the
-timed region); roofline = dominant kernel (tcgen05 blend GEMM) against the tensor roofline, with
-the HBM-bound skinning kernel reported beside it; cpu_baseline = the oracle port timed on the host
+timed region); roofline = dominant kernel (fused tcgen05 blend GEMM + skinning epilogue) against the
+tensor roofline, with its HBM figure and the stand-alone GEMM / skinning kernels reported beside it; cpu_baseline = the oracle port timed on the host
 cores.  `--impl reference` times the CPU restatement of the reference path (oracle port; the
 reference is pure Python and /root/reference does not exist on the GPU box).
 """
@@ -261,33 +261,80 @@ def main():
             tf32_peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
             torch.backends.cuda.matmul.allow_tf32 = False
             del x, y
-        if "blend_tcgen05" in kern:
-            g_ms = kern["blend_tcgen05"]
+        fmt = os.environ.get("SMPLK_BLEND", "f16")
+        # fp32-accurate contraction = 3 tensor-core passes over two-term-split operands:
+        #   default: fp16 split, kind::f16 -> ceiling = measured bf16/fp16 dense peak / 3
+        #   SMPLK_BLEND=tf32: 3xTF32   -> ceiling = TF32 dense peak (cuBLAS, measured here) / 3
+        dense_peak = peaks["bf16"] if fmt != "tf32" else (tf32_peak or peaks["bf16"] / 2)
+        ncu_traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_ncu_fused_traffic.json")
+        if os.path.exists(tp):
+            ncu_traffic = json.load(open(tp))
+
+        def tensor_roofline(name, g_ms, npad, note_extra=""):
             alg_tflops = GEMM_FLOPS_PER_BODY * B / (g_ms * 1e-3) / 1e12
-            fmt = os.environ.get("SMPLK_BLEND", "f16")
-            # fp32-accurate contraction = 3 tensor-core passes over two-term-split operands:
-            #   default: fp16 split, kind::f16 -> ceiling = measured bf16/fp16 dense peak / 3
-            #   SMPLK_BLEND=tf32: 3xTF32   -> ceiling = TF32 dense peak (cuBLAS, measured here) / 3
-            dense_peak = peaks["bf16"] if fmt != "tf32" else (tf32_peak or peaks["bf16"] / 2)
-            peak = dense_peak / 3.0
-            issued = 3 * 2 * B * 20736 * 480 / (g_ms * 1e-3) / 1e12
-            extras["roofline"] = {
-                "kernel": "blend_tcgen05_2cta_kernel<%s>" % ("f16" if fmt != "tf32" else "tf32"),
-                "bound": "tensor", "achieved": alg_tflops, "peak": peak,
-                "unit": "TFLOP/s", "frac": alg_tflops / peak, "traffic": None,
-                "ms_per_launch": g_ms,
-                "note": "achieved = 2*B*20670*475 fp32-equivalent FLOPs / CUDA-event time on the launching stream; "
-                        "peak = dense tensor peak / 3 passes (%s: %.0f TFLOP/s, %s burst figure; sustained %.0f); "
-                        "issued tensor FLOPs = 3*2*B*20736*480" % (
-                            "bf16/fp16" if fmt != "tf32" else "tf32 cuBLAS 8192^3 measured in this run",
-                            dense_peak, peaks["source"], peaks["bf16_sustained"]),
-                "tf32_tflops_measured": tf32_peak,
-                "tensor_tflops_issued": issued,
-                "tensor_frac_issued": issued / dense_peak}
+            issued = 3 * 2 * B * npad * 480 / (g_ms * 1e-3) / 1e12
+            return {"kernel": name, "bound": "tensor", "achieved": alg_tflops, "peak": dense_peak / 3.0,
+                    "unit": "TFLOP/s", "frac": alg_tflops / (dense_peak / 3.0), "traffic": None,
+                    "ms_per_launch": g_ms,
+                    "note": "achieved = 2*B*20670*475 fp32-equivalent FLOPs / CUDA-event time on the launching stream; "
+                            "peak = dense tensor peak / 3 passes (%s: %.0f TFLOP/s, %s burst figure; sustained %.0f); "
+                            "issued tensor FLOPs = 3*2*B*%d*480%s" % (
+                                "bf16/fp16" if fmt != "tf32" else "tf32 cuBLAS 8192^3 measured in this run",
+                                dense_peak, peaks["source"], peaks["bf16_sustained"], npad, note_extra),
+                    "tf32_tflops_measured": tf32_peak, "tensor_tflops_issued": issued,
+                    "tensor_frac_issued": issued / dense_peak}
+
+        if "blend_skin_fused" in kern:
+            # the forward's dominant kernel: blend GEMM + skinning epilogue in one launch
+            f_ms = kern["blend_skin_fused"]
+            r = tensor_roofline("blend_skin_fused_kernel", f_ms, 83 * 256,
+                                "; the epilogue (LBS skinning from TMEM, CUDA cores) runs under the MMAs")
+            if ncu_traffic:
+                r["traffic"] = ncu_traffic.get("dram_bytes_per_launch")
+                r["traffic_note"] = ncu_traffic.get("note")
+            extras["roofline"] = r
+            gbs = FWD_BYTES_FUSED * B / (f_ms * 1e-3) / 1e9
+            extras["roofline_hbm_fused"] = {
+                "kernel": "blend_skin_fused_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"],
+                "unit": "GB/s", "frac": gbs / peaks["hbm"], "traffic": r["traffic"], "ms_per_launch": f_ms,
+                "note": "84,004 algorithmic B/body (inputs + verts + FK joints; v_posed never leaves the SM); "
+                        "this kernel is tensor-bound, the HBM figure shows how far below the memory roofline it sits"}
+        elif "blend_tcgen05" in kern:
+            extras["roofline"] = tensor_roofline("blend_tcgen05_2cta_kernel<%s>" % ("f16" if fmt != "tf32" else "tf32"),
+                                                 kern["blend_tcgen05"], 20736)
+        # the stand-alone kernels (forward with SAVE_FOR_BACKWARD, LBS-only models, dense weights):
+        # timed through a second handle created with SMPLK_FUSED=0
+        if "blend_skin_fused" in kern and rank == 0:
+            os.environ["SMPLK_FUSED"] = "0"
+            dm_u = smplk.DeviceModel(model, device=local)
+            del os.environ["SMPLK_FUSED"]
+            dm_u.profile_enable(True)
+            for i in range(20):
+                b_, p_, t_ = sets[i % NSETS]
+                a = _lib.ForwardArgs()
+                a.batch, a.flags = B, 0
+                a.betas, a.betas_batch = ctypes.c_void_p(b_.data_ptr()), B
+                a.pose, a.transl = ctypes.c_void_p(p_.data_ptr()), ctypes.c_void_p(t_.data_ptr())
+                a.verts, a.joints = ctypes.c_void_p(verts.data_ptr()), ctypes.c_void_p(joints.data_ptr())
+                wsb = dm_u.workspace_bytes(B, 0)
+                if wsb > ws.numel():
+                    ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+                a.workspace, a.workspace_bytes = ctypes.c_void_p(ws.data_ptr()), ws.numel()
+                a.stream = ctypes.c_void_p(stream.cuda_stream)
+                dm_u.forward(a)
+            torch.cuda.synchronize(dev)
+            pu = {k: (v[0] / v[1]) for k, v in dm_u.profile_read(reset=True).items() if v[1] > 0}
+            kern.update({"unfused_" + k: v for k, v in pu.items()})
+            if "blend_tcgen05" in pu:
+                extras["roofline_blend_gemm"] = tensor_roofline("blend_tcgen05_2cta_kernel<f16>", pu["blend_tcgen05"], 20736)
+            if "skin" in pu:
+                kern["skin"] = pu["skin"]
         if "skin" in kern:
             s_ms = kern["skin"]
             gbs = FWD_BYTES_SKIN * B / (s_ms * 1e-3) / 1e9
-            extras["roofline_skinning"] = {"kernel": "skin_kernel", "bound": "hbm", "achieved": gbs,
+            extras["roofline_skinning"] = {"kernel": "skin_grouped8_kernel (two-kernel forward: SAVE_FOR_BACKWARD / SMPLK_FUSED=0)",
+                                           "bound": "hbm", "achieved": gbs,
                                            "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                                            "traffic": None, "ms_per_launch": s_ms,
                                            "note": "167,856 algorithmic B/body (v_posed in, A in, verts out); peak %s" % peaks["source"]}
@@ -366,8 +413,8 @@ def main():
                 "config": {"workload": "SMPL-H forward+LBS batch %d per GPU, fp32, 52 joints, 16 betas, 459 posedirs "
                                        "(BASELINE.json configs[1])" % B,
                            "global_batch": world * B, "parallelism": "batch-sharded x%d, no collective" % world,
-                           "l2": "per-step footprint %.0f MB (v_posed + verts) > 126 MB L2; %d rotating input sets"
-                                 % (2 * B * 82680 / 1e6, NSETS),
+                           "l2": "per-step output %.0f MB (verts) > 126 MB L2; %d rotating input sets"
+                                 % (B * 82680 / 1e6, NSETS),
                            "weights": "canonically sparse LBS weights (<=4 per vertex)"},
                 "clocks": clocks.summary(), "gpu_launches": int(launches),
                 "hbm_gbs_fused_equiv": FWD_BYTES_FUSED * world * B * args.steps / (ms * 1e-3) / 1e9}
