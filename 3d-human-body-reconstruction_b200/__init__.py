@@ -14,6 +14,9 @@ def __getattr__(name):  # torch-dependent modules load lazily
     if name in ("SMPL", "SMPLH", "ModelOutput", "create", "body_model_apply", "load_model_file", "vertex_l2_loss"):
         from . import body_models
         return getattr(body_models, name)
+    if name in ("MeshTopology", "inverse_lbs", "inverse_joints", "transforms"):
+        from . import mesh_ops
+        return getattr(mesh_ops, name)
     if name in ("SMPLModel", "SMPLHModel", "RecoverModel"):
         from . import np_twins
         return getattr(np_twins, name)

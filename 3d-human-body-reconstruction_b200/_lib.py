@@ -20,6 +20,7 @@ FLAG_ADD_POSE_MEAN = 2
 FLAG_BLEND_SIMT = 4
 FLAG_BLEND_TCGEN05 = 8
 FLAG_BLEND_TF32 = 16
+FLAG_TRANSFORMS_ONLY = 32
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -84,6 +85,7 @@ EXPORTED_SYMBOLS = [
     "smplk_forward", "smplk_backward_scratch_bytes", "smplk_backward", "smplk_regress_joints",
     "smplk_batch_rodrigues", "smplk_forward_host", "smplk_last_error_string", "smplk_version",
     "smplk_launch_count", "smplk_workspace_layout", "smplk_profile_enable", "smplk_profile_read", "smplk_vertex_l2",
+    "smplk_inverse_lbs", "smplk_inverse_joints", "smplk_vertex_normals", "smplk_divide_faces",
 ]
 PROF_SLOTS = ["pose_fwd", "blend_tcgen05", "blend_simt", "skin", "dA", "skin_bwd", "blend_bwd",
               "pose_bwd", "blend_skin_fused", "transpose"]
@@ -146,6 +148,15 @@ def load():
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p]
     lib.smplk_forward_host.restype = ctypes.c_int
+    vp, i32 = ctypes.c_void_p, ctypes.c_int32
+    lib.smplk_inverse_lbs.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.smplk_inverse_lbs.restype = ctypes.c_int
+    lib.smplk_inverse_joints.argtypes = [i32, i32, vp, vp, i32, vp, vp, ctypes.c_int, vp]
+    lib.smplk_inverse_joints.restype = ctypes.c_int
+    lib.smplk_vertex_normals.argtypes = [i32, i32, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+    lib.smplk_vertex_normals.restype = ctypes.c_int
+    lib.smplk_divide_faces.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+    lib.smplk_divide_faces.restype = ctypes.c_int
     lib.smplk_workspace_layout.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint32,
                                            ctypes.POINTER(ctypes.c_size_t),
                                            ctypes.POINTER(ctypes.c_int32)]

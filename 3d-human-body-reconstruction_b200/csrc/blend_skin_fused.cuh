@@ -211,7 +211,7 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int dbg_it = (tile - cluster_id) / num_clusters;
+        [[maybe_unused]] const int dbg_it = (tile - cluster_id) / num_clusters;
         FZ_STAMP(args.dbg && blockIdx.x == 0 && dbg_it < kFzDbgTiles, &args.dbg[(1 * kFzDbgTiles + dbg_it) * 4 + 0]);
         ptx::mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1, SMPLK_FZ_BACKOFF_NS);
         ptx::tcgen05_fence_after();
@@ -252,7 +252,6 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
     const uint32_t stage_row = stage_u32 + lane * (kFzStageStride * 4);   // this body's staged row
     const uint32_t stage_col = stage_u32 + lane * 4;                      // this lane's staged column
     const uint32_t ring_warp = ptx::smem_u32(ring_base) + (warp - 2) * (kFzRing * kFzRingEntryBytes);
-    const uint32_t ring_lane = ring_warp + lane * 4;
     const uint32_t ring_piece = ring_warp + lane * 16;    // this lane's 16-byte piece of lines l/8 + 4k
     const uint32_t bias_warp = ptx::smem_u32(bias_base) + (warp - 2) * kFzBiasBytes;
     int ps = 0, cs = 0;                       // ring slots: next to fill / next to apply
@@ -374,7 +373,7 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
       for (int i = 0; i < kFzRing - 1; ++i) issue_entry(e + i);
       ptx::cp_async_wait<kFzRing - 1>();        // the v_template group (older than the primed entries)
       __syncwarp();
-      const bool dbg_on = args.dbg && blockIdx.x == 0 && lane == 0 && it < kFzDbgTiles;
+      [[maybe_unused]] const bool dbg_on = args.dbg && blockIdx.x == 0 && lane == 0 && it < kFzDbgTiles;
       FZ_STAMP(dbg_on, &args.dbg[(warp * kFzDbgTiles + it) * 4 + 0]);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tcgen05_fence_after();
@@ -382,8 +381,8 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
 
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; ++c) {
-        const bool dbg_c = dbg_on && (warp == 2 || warp == 6) && it < 4;
-        long long* dbg_p = args.dbg ? args.dbg + (0 * kFzDbgTiles + it * 7 + c) * 4 : nullptr;
+        [[maybe_unused]] const bool dbg_c = dbg_on && (warp == 2 || warp == 6) && it < 4;
+        [[maybe_unused]] long long* dbg_p = args.dbg ? args.dbg + (0 * kFzDbgTiles + it * 7 + c) * 4 : nullptr;
         FZ_STAMP(dbg_c, &dbg_p[0]);
         // ---- TMEM accumulator columns of chunk c -> p (+ v_template), o = 0
         {

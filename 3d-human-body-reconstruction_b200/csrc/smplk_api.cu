@@ -20,6 +20,7 @@
 #include "pose_kernels.cuh"
 #include "skinning.cuh"
 #include "skinning8.cuh"
+#include "mesh_ops.cuh"
 
 using namespace smplk;
 
@@ -953,7 +954,10 @@ extern "C" int smplk_forward(const smplk_model* model, const smplk_forward_args*
                 a->betas_batch, a->batch);
   if ((a->hand_pca_l || a->hand_pca_r) && d.C == 0)
     return fail(SMPLK_E_ARG, "hand PCA coefficients given but the model has no PCA components");
-  if ((a->joints && d.E > 0 && !a->verts) || (a->joints_regressed && !a->verts))
+  if ((a->flags & SMPLK_FLAG_TRANSFORMS_ONLY) && (a->verts || a->joints_regressed))
+    return fail(SMPLK_E_ARG, "SMPLK_FLAG_TRANSFORMS_ONLY excludes the verts / joints_regressed outputs");
+  if (!(a->flags & SMPLK_FLAG_TRANSFORMS_ONLY) &&
+      ((a->joints && d.E > 0 && !a->verts) || (a->joints_regressed && !a->verts)))
     return fail(SMPLK_E_ARG, "vertex picks / regressed joints need the verts output buffer");
   if (a->joints_regressed && d.R == 0)
     return fail(SMPLK_E_ARG, "joints_regressed requested but the model has no regressor_posed");
@@ -998,6 +1002,7 @@ extern "C" int smplk_forward(const smplk_model* model, const smplk_forward_args*
     pa.full_pose = a->full_pose ? a->full_pose + (size_t)c0 * 3 * d.J : nullptr;
     if (int r = launch_pose_forward(model, pa, st)) return r;
     const bool fused = fused_applies(model, rows, path, a->flags, a->verts != nullptr);
+    if (a->flags & SMPLK_FLAG_TRANSFORMS_ONLY) continue;    // pose / FK kernel only: A, joints, full_pose
     if (!fused && !d.lbs_only && (a->verts || (a->flags & SMPLK_FLAG_SAVE_FOR_BACKWARD))) {
       if (int r = launch_blend(model, rows, path, F_hi, F_lo, v_posed, st)) return r;
     }
@@ -1133,6 +1138,63 @@ extern "C" int smplk_profile_read(smplk_model* model, double ms[SMPLK_PROF_SLOTS
     counts[i] = model->prof_n[i];
     if (reset) { model->prof_ms[i] = 0.0; model->prof_n[i] = 0; }
   }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// mesh operations either side of the forward
+// ------------------------------------------------------------------------------------------
+extern "C" int smplk_inverse_lbs(const smplk_model* model, int32_t batch, const float* A,
+                                 const float* verts, const float* transl, float* v_rest,
+                                 smplk_stream stream) {
+  if (!model || batch < 1 || !A || !verts || !v_rest) return fail(SMPLK_E_ARG, "bad argument");
+  const ModelDev& d = model->d;
+  CUDA_TRY(cudaSetDevice(model->device));
+  dim3 grid((d.V + 255) / 256, batch);
+  inverse_lbs_kernel<<<grid, 256, (size_t)d.J * 12 * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+      d, batch, A, verts, transl, v_rest);
+  LAUNCH_CHECK("inverse_lbs_kernel");
+  return 0;
+}
+
+extern "C" int smplk_inverse_joints(int32_t batch, int32_t num_joints, const float* A, const float* joints,
+                                    int32_t joints_ld, const float* transl, float* out, int device,
+                                    smplk_stream stream) {
+  if (batch < 1 || num_joints < 1 || !A || !joints || !out || joints_ld < 3 * num_joints)
+    return fail(SMPLK_E_ARG, "bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  const int n = batch * num_joints;
+  inverse_joints_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      batch, num_joints, A, joints, joints_ld, transl, out);
+  LAUNCH_CHECK("inverse_joints_kernel");
+  return 0;
+}
+
+extern "C" int smplk_vertex_normals(int32_t batch, int32_t num_verts, const int32_t* faces,
+                                    const int32_t* vf_ptr, const int32_t* vf_face, const float* verts,
+                                    float* normals, int device, smplk_stream stream) {
+  if (batch < 1 || num_verts < 1 || !faces || !vf_ptr || !vf_face || !verts || !normals)
+    return fail(SMPLK_E_ARG, "bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  dim3 grid((num_verts + 255) / 256, batch);
+  vertex_normals_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      batch, num_verts, faces, vf_ptr, vf_face, verts, normals);
+  LAUNCH_CHECK("vertex_normals_kernel");
+  return 0;
+}
+
+extern "C" int smplk_divide_faces(int32_t batch, int32_t num_verts, int32_t num_faces, const int32_t* faces,
+                                  const float* verts, int32_t* faces_out, int32_t* vidx_out,
+                                  int32_t* counts, int device, smplk_stream stream) {
+  if (batch < 1 || num_verts < 1 || num_faces < 1 || !faces || !verts || !faces_out || !vidx_out || !counts)
+    return fail(SMPLK_E_ARG, "bad argument");
+  const size_t smem = ((size_t)2 * num_verts + 32) * sizeof(int);
+  if (smem > 200 * 1024) return fail(SMPLK_E_SHAPE, "divide_faces: %d vertices exceed the shared-memory table", num_verts);
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaFuncSetAttribute(divide_faces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  divide_faces_kernel<<<2 * batch, kDivThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      batch, num_verts, num_faces, faces, verts, faces_out, vidx_out, counts);
+  LAUNCH_CHECK("divide_faces_kernel");
   return 0;
 }
 

@@ -88,6 +88,8 @@ int smplk_model_get_info(const smplk_model* model, smplk_model_info* info);
 #define SMPLK_FLAG_BLEND_SIMT 4u        /* force the exact-fp32 SIMT blend kernel (small batch / bring-up) */
 #define SMPLK_FLAG_BLEND_TCGEN05 8u     /* force a tcgen05 blend GEMM even for tiny batches           */
 #define SMPLK_FLAG_BLEND_TF32 16u       /* force the 3xTF32 operand format (default: fp16 two-term split) */
+#define SMPLK_FLAG_TRANSFORMS_ONLY 32u  /* run the pose / FK kernel only: skinning transforms A (workspace), FK
+                                           joints, full_pose; with E > 0 the vertex-pick joints are left unwritten */
 
 /* Bytes of device workspace `smplk_forward` needs for `batch` bodies (256-byte aligned base). */
 size_t smplk_workspace_bytes(const smplk_model* model, int32_t batch, uint32_t flags);
@@ -175,6 +177,40 @@ int smplk_vertex_l2(int32_t batch, int32_t floats_per_body, const float* verts, 
 int smplk_forward_host(smplk_model* model, int32_t batch, uint32_t flags, const float* betas,
                        int32_t betas_batch, const float* pose, const float* transl, float* verts,
                        float* joints, smplk_stream stream);
+
+/* ---- mesh operations either side of the forward (SURVEY.md 8f "next" rows 2 and 4) ----------- */
+
+/* Inverse LBS (un-posing).  Replaces RecoverModel.to_T_pose / to_rest_pose
+ * (lib/mesh2smpl_model.py:183-207, :340-372) and models/smpl_np.py:239-246:
+ *   v_rest[b,v] = (sum_k w[v,k] A[b,j_k])^-1 [verts[b,v] - transl[b]; 1]
+ * `model` supplies the skin weights (any handle, rigged mesh included); `A` (B,J,12) are the 3x4
+ * skinning transforms of the pose being removed (the forward's workspace segment 2, see
+ * smplk_workspace_layout, with SMPLK_FLAG_SAVE_FOR_BACKWARD).  All pointers are device pointers. */
+int smplk_inverse_lbs(const smplk_model* model, int32_t batch, const float* A, const float* verts,
+                      const float* transl /* (B,3) or NULL */, float* v_rest /* out (B,V,3) */,
+                      smplk_stream stream);
+/* J_rest[b,j] = A[b,j]^-1 [J_posed[b,j] - transl[b]; 1]  (lib/mesh2smpl_model.py:205-207). */
+int smplk_inverse_joints(int32_t batch, int32_t num_joints, const float* A, const float* joints,
+                         int32_t joints_ld /* floats per body row of `joints` */, const float* transl,
+                         float* out /* (B,J,3) */, int device, smplk_stream stream);
+
+/* Per-vertex unit normals of posed meshes: area-weighted sum of the incident triangles' cross
+ * products (v1-v0)x(v2-v0), normalised.  Replaces VertNormals(verts, faces, True) at
+ * utils/render_model.py:36,63-81 (upstream opendr).  `vf_ptr` (V+1) / `vf_face` are the CSR lists
+ * vertex -> incident faces (host-built once per topology). */
+int smplk_vertex_normals(int32_t batch, int32_t num_verts, const int32_t* faces /* (F,3) */,
+                         const int32_t* vf_ptr, const int32_t* vf_face, const float* verts,
+                         float* normals /* out (B,V,3) */, int device, smplk_stream stream);
+
+/* Front / back split of posed meshes.  Replaces SMPLHModel.divide_face (models/smplh_np.py:126-182):
+ * a triangle is FRONT when the z of (v1-v0)x(v2-v1) is <= 0, BACK otherwise; each side's vertices
+ * are listed in order of first appearance (face order, then corner) and its faces re-indexed.
+ *   faces_out (B,2,F,3)  side 0 = front, 1 = back; first counts[b][side][0] rows valid
+ *   vidx_out  (B,2,V)    original vertex ids; first counts[b][side][1] entries valid
+ *   counts    (B,2,2)    {faces, vertices} per side */
+int smplk_divide_faces(int32_t batch, int32_t num_verts, int32_t num_faces, const int32_t* faces,
+                       const float* verts, int32_t* faces_out, int32_t* vidx_out, int32_t* counts,
+                       int device, smplk_stream stream);
 
 /* Per-kernel device timing for benchmarks: while enabled, forward/backward bracket every kernel
  * they launch with a CUDA event pair recorded on the caller's stream (the stream the kernel runs

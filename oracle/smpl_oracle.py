@@ -150,6 +150,57 @@ def np_inverse_lbs(rig_weights, A, verts):
     return np.einsum("vab,vb->va", Tinv, vh)[:, :3]
 
 
+def np_inverse_joints(A, joints):
+    """lib/mesh2smpl_model.py:205-207: J = inv(G) [or_J; 1] with G the rest-removed transforms."""
+    A4 = np.zeros((A.shape[0], 4, 4))
+    A4[:, :3, :] = np.asarray(A, np.float64).reshape(-1, 3, 4)
+    A4[:, 3, 3] = 1.0
+    jh = np.concatenate([np.asarray(joints, np.float64), np.ones((joints.shape[0], 1))], 1)
+    return np.einsum("jab,jb->ja", np.linalg.inv(A4), jh)[:, :3]
+
+
+def np_vertex_normals(verts, faces):
+    """utils/render_model.py:36 VertNormals(verts, faces, True) [upstream opendr, unpinned]: per-vertex
+    sum of the incident triangles' (un-normalised, i.e. area-weighted) cross products
+    (v1-v0)x(v2-v0), normalised to unit length."""
+    v = np.asarray(verts, np.float64)
+    f = np.asarray(faces, np.int64)
+    tn = np.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]])
+    n = np.zeros_like(v)
+    for c in range(3):
+        np.add.at(n, f[:, c], tn)
+    ln = np.linalg.norm(n, axis=1, keepdims=True)
+    return n / np.where(ln > 0, ln, 1.0)
+
+
+def np_divide_face(verts, faces):
+    """models/smplh_np.py:126-182 divide_face, restated with the same sequential semantics:
+    z = m0*n1 - n0*m1 with m = v1-v0, n = v2-v1 (:149-152); z <= 0 -> front (:155), else back;
+    vertices re-indexed in order of first appearance (:157-163)."""
+    v = np.asarray(verts)
+    f = np.asarray(faces)
+    out = []
+    v0, v1, v2 = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
+    m, n = v1 - v0, v2 - v1
+    z = m[:, 0] * n[:, 1] - n[:, 0] * m[:, 1]
+    for side_mask in (z <= 0, z > 0):
+        index_of = {}
+        order = []
+        new_faces = []
+        for tri in f[side_mask]:
+            row = []
+            for idx in tri:
+                idx = int(idx)
+                if idx not in index_of:
+                    index_of[idx] = len(order)
+                    order.append(idx)
+                row.append(index_of[idx])
+            new_faces.append(row)
+        order = np.asarray(order, dtype=np.int64)
+        out += [np.asarray(new_faces, dtype=np.int64).reshape(-1, 3), v[order], order]
+    return tuple(out)
+
+
 # ----------------------------------------------------------------------------------------
 # torch batched restatement of upstream smplx (differentiable)
 # ----------------------------------------------------------------------------------------

@@ -1,0 +1,108 @@
+"""GPU parity of the mesh operations either side of the forward against the
+oracle and the reference-made golden vectors.  Index work (face split, re-indexing) is bit-exact;
+floating point within the tolerances written below."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import smplk
+from smplk import synthetic
+from smplk.body_models import body_model_apply
+from smplk.mesh_ops import MeshTopology, inverse_joints, inverse_lbs, transforms
+from oracle import smpl_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(x):
+    return torch.tensor(np.asarray(x, dtype=np.float32), device="cuda:0")
+
+
+def test_transforms_only_flag_and_inverse_lbs_roundtrip():
+    """to_T_pose (lib/mesh2smpl_model.py:183-207): pose a rigged mesh, then remove the pose again."""
+    rig = synthetic.make_rigged_mesh(5003, seed=2)
+    dm = smplk.DeviceModel(rig, device=0, lbs_only=True)
+    rng = np.random.default_rng(0)
+    B = 5
+    pose = rng.standard_normal((B, 72)) * 0.5
+    trans = rng.standard_normal((B, 3))
+    A, joints = transforms(dm, None, _t(pose), _t(trans))
+    posed = body_model_apply(dm, None, _t(pose), transl=_t(trans))[0]
+    for b in (0, B - 1):
+        ref = O.np_lbs_only(rig, pose[b], trans[b], ignore_joints=())
+        assert np.abs(A[b].double().cpu().numpy() - ref["A"][:, :3, :]).max() <= 2e-6
+        assert np.abs(posed[b].double().cpu().numpy() - ref["verts"]).max() <= 1e-5
+        assert np.abs(joints[b].double().cpu().numpy() - (ref["G"][:, :3, 3] + trans[b])).max() <= 1e-5
+    rest = inverse_lbs(dm, A, posed, _t(trans))
+    # fp32 inverse of a blended transform: error scales with cond(T); these rigs stay below 3e-5 m
+    assert float((rest - _t(rig["v_template"])[None]).abs().max()) <= 3e-5
+    for b in (0, B - 1):
+        ref = O.np_lbs_only(rig, pose[b], trans[b], ignore_joints=())
+        want = O.np_inverse_lbs(rig["weights"], ref["A"], posed[b].double().cpu().numpy() - trans[b])
+        assert np.abs(rest[b].double().cpu().numpy() - want).max() <= 3e-5
+    jr = inverse_joints(A, joints, _t(trans))
+    assert float((jr - _t(rig["J"])[None]).abs().max()) <= 1e-5
+
+
+def test_inverse_lbs_with_smplh_weights_and_shape():
+    """The un-posing of models/smpl_np.py:239-246: weights of the body model itself, betas != 0."""
+    m = synthetic.make_model("smplh", seed=4)
+    dm = smplk.DeviceModel(m, device=0)
+    B = 3
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=8)
+    A, _ = transforms(dm, _t(betas), _t(pose))
+    v = body_model_apply(dm, _t(betas), _t(pose), transl=_t(transl))[0]
+    rest = inverse_lbs(dm, A, v, _t(transl))
+    om = O.TorchOracleModel(m, dtype=torch.float64)
+    ref = om.forward_full_pose(*[torch.tensor(x, dtype=torch.float64) for x in (betas, pose, transl)])
+    assert float((rest.double().cpu() - ref.v_posed).abs().max()) <= 3e-5
+
+
+def test_vertex_normals_match_oracle():
+    m = synthetic.make_model("smpl", seed=6)
+    dm = smplk.DeviceModel(m, device=0)
+    topo = MeshTopology(m["f"], dm.V)
+    B = 4
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=2)
+    v = body_model_apply(dm, _t(betas), _t(pose), transl=_t(transl))[0]
+    n = topo.vertex_normals(v)
+    vn = v.double().cpu().numpy()
+    for b in range(B):
+        ref = O.np_vertex_normals(vn[b], m["f"])
+        # unit vectors from fp32 cross products of random (large) triangles
+        assert np.abs(n[b].double().cpu().numpy() - ref).max() <= 2e-5
+    used = np.zeros(dm.V, bool)
+    used[np.asarray(m["f"]).ravel()] = True
+    ln = n.norm(dim=2).cpu().numpy()
+    assert np.abs(ln[:, used] - 1).max() <= 1e-5 and np.all(ln[:, ~used] == 0)
+
+
+def test_divide_face_matches_reference_golden_and_oracle(golden_dir):
+    g = np.load(os.path.join(golden_dir, "divide_face.npz"))
+    m = synthetic.make_model("smplh", num_betas=int(g["num_betas"]), seed=int(g["seed"]))
+    faces = np.asarray(m["f"])[:int(g["num_faces"])]
+    topo = MeshTopology(faces, 6890)
+    # (1) on the reference's own vertices: identical split and re-indexing as SMPLHModel.divide_face
+    verts = _t(np.stack([g["verts0"], g["verts1"]]))
+    res = topo.divide_face(verts)
+    for i in range(2):
+        ff, fv, fi, bf, bv, bi = res[i]
+        assert np.array_equal(ff.cpu().numpy(), g["front_face%d" % i])
+        assert np.array_equal(fi.cpu().numpy(), g["front_index%d" % i])
+        assert np.array_equal(bf.cpu().numpy(), g["back_face%d" % i])
+        assert np.array_equal(bi.cpu().numpy(), g["back_index%d" % i])
+        assert torch.equal(fv, verts[i][fi]) and torch.equal(bv, verts[i][bi])
+    # (2) full topology (13,776 faces), vertices from the CUDA forward, batch of 6: same as the oracle
+    dm = smplk.DeviceModel(m, device=0)
+    topo_full = MeshTopology(m["f"], 6890)
+    betas, pose, transl = synthetic.make_inputs(m, 6, seed=12)
+    v = body_model_apply(dm, _t(betas), _t(pose), transl=_t(transl))[0]
+    res = topo_full.divide_face(v)
+    vn = v.cpu().numpy()
+    for b in (0, 5):
+        want = O.np_divide_face(vn[b], m["f"])
+        got = res[b]
+        for w, gt in zip(want, got):
+            assert np.array_equal(np.asarray(w), gt.cpu().numpy())

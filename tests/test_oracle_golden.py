@@ -117,3 +117,46 @@ def test_oracle_gradients_match_finite_differences():
         e[idx] = 1e-6
         fd = (f(pose + e) - f(pose - e)) / 2e-6
         assert abs(fd - float(gp[idx])) < 1e-5 * max(1.0, abs(fd))
+
+
+def test_divide_face_oracle_matches_reference(golden_dir):
+    """oracle np_divide_face == SMPLHModel.divide_face of the reference (models/smplh_np.py:126-182),
+    on the reference's own float64 vertices: same faces per side, same first-appearance order."""
+    g = np.load(os.path.join(golden_dir, "divide_face.npz"))
+    m = synthetic.make_model("smplh", num_betas=int(g["num_betas"]), seed=int(g["seed"]))
+    assert abs(model_checksum(m) - float(g["checksum"])) < 1e-9
+    faces = np.asarray(m["f"])[:int(g["num_faces"])]
+    for i in range(2):
+        verts = g["verts%d" % i]
+        # the vertices themselves are the reference forward's
+        r = O.np_forward(m, g["pose"][i].reshape(-1), g["beta"][i], g["trans"][i])
+        assert np.abs(r["verts"] - verts).max() < 1e-12
+        ff, fv, fi, bf, bv, bi = O.np_divide_face(verts, faces)
+        assert np.array_equal(ff, g["front_face%d" % i]) and np.array_equal(fi, g["front_index%d" % i])
+        assert np.array_equal(bf, g["back_face%d" % i]) and np.array_equal(bi, g["back_index%d" % i])
+        assert np.array_equal(fv, verts[fi]) and np.array_equal(bv, verts[bi])
+        assert len(ff) + len(bf) == len(faces)
+
+
+def test_vertex_normals_and_inverse_joints_oracle_properties():
+    rng = np.random.default_rng(4)
+    m = synthetic.make_model("smpl", seed=3)
+    r = O.np_forward(m, rng.standard_normal(72) * 0.3, rng.standard_normal(10), rng.standard_normal(3))
+    faces = np.asarray(m["f"])
+    n = O.np_vertex_normals(r["verts"], faces)
+    used = np.zeros(len(n), bool)
+    used[faces.ravel()] = True
+    assert np.abs(np.linalg.norm(n[used], axis=1) - 1).max() < 1e-12 and np.all(n[~used] == 0)
+    # brute force for a few vertices
+    for v in np.flatnonzero(used)[:20]:
+        acc = np.zeros(3)
+        for f in faces[(faces == v).any(1)]:
+            acc += np.cross(r["verts"][f[1]] - r["verts"][f[0]], r["verts"][f[2]] - r["verts"][f[0]]) * (f == v).sum()
+        assert np.abs(acc / np.linalg.norm(acc) - n[v]).max() < 1e-12
+    # a flipped face flips its contribution; a rigid rotation rotates the normals
+    Rz = O.np_rodrigues(np.array([[0.3, -0.2, 0.5]]))[0]
+    assert np.abs(O.np_vertex_normals(r["verts"] @ Rz.T, faces) - n @ Rz.T).max() < 1e-10
+    # inverse joints: A_j^-1 maps the posed joint back to the rest joint
+    posed_J = r["G"][:, :3, 3]
+    back = O.np_inverse_joints(r["A"][:, :3, :], posed_J)
+    assert np.abs(back - r["J"]).max() < 1e-10
