@@ -79,6 +79,34 @@ class BackwardArgs(ctypes.Structure):
     ]
 
 
+class ReprojArgs(ctypes.Structure):
+    _fields_ = [
+        ("batch", ctypes.c_int32), ("num_joints", ctypes.c_int32),
+        ("joints", ctypes.c_void_p), ("rotation", ctypes.c_void_p), ("translation", ctypes.c_void_p),
+        ("focal", ctypes.c_void_p), ("center", ctypes.c_void_p), ("camera_batch", ctypes.c_int32),
+        ("gt_joints", ctypes.c_void_p), ("weights", ctypes.c_void_p), ("weights_batch", ctypes.c_int32),
+        ("rho", ctypes.c_float), ("data_weight", ctypes.c_float),
+        ("loss", ctypes.c_void_p), ("d_joints", ctypes.c_void_p), ("d_translation", ctypes.c_void_p),
+        ("device", ctypes.c_int), ("stream", ctypes.c_void_p),
+    ]
+
+
+class PriorArgs(ctypes.Structure):
+    _fields_ = [
+        ("batch", ctypes.c_int32),
+        ("betas", ctypes.c_void_p), ("num_betas", ctypes.c_int32),
+        ("pose_embedding", ctypes.c_void_p), ("num_embedding", ctypes.c_int32),
+        ("body_pose", ctypes.c_void_p), ("num_body_pose", ctypes.c_int32),
+        ("left_hand_pose", ctypes.c_void_p), ("right_hand_pose", ctypes.c_void_p), ("num_hand", ctypes.c_int32),
+        ("shape_weight", ctypes.c_float), ("body_pose_weight", ctypes.c_float),
+        ("bending_prior_weight", ctypes.c_float), ("hand_prior_weight", ctypes.c_float),
+        ("loss", ctypes.c_void_p),
+        ("d_betas", ctypes.c_void_p), ("d_pose_embedding", ctypes.c_void_p), ("d_body_pose", ctypes.c_void_p),
+        ("d_left_hand_pose", ctypes.c_void_p), ("d_right_hand_pose", ctypes.c_void_p),
+        ("device", ctypes.c_int), ("stream", ctypes.c_void_p),
+    ]
+
+
 # every symbol include/smplk.h declares
 EXPORTED_SYMBOLS = [
     "smplk_model_create", "smplk_model_destroy", "smplk_model_get_info", "smplk_workspace_bytes",
@@ -86,6 +114,7 @@ EXPORTED_SYMBOLS = [
     "smplk_batch_rodrigues", "smplk_forward_host", "smplk_last_error_string", "smplk_version",
     "smplk_launch_count", "smplk_workspace_layout", "smplk_profile_enable", "smplk_profile_read", "smplk_vertex_l2",
     "smplk_inverse_lbs", "smplk_inverse_joints", "smplk_vertex_normals", "smplk_divide_faces",
+    "smplk_reprojection_loss", "smplk_fit_priors",
 ]
 PROF_SLOTS = ["pose_fwd", "blend_tcgen05", "blend_simt", "skin", "dA", "skin_bwd", "blend_bwd",
               "pose_bwd", "blend_skin_fused", "transpose"]
@@ -157,6 +186,10 @@ def load():
     lib.smplk_vertex_normals.restype = ctypes.c_int
     lib.smplk_divide_faces.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, ctypes.c_int, vp]
     lib.smplk_divide_faces.restype = ctypes.c_int
+    lib.smplk_reprojection_loss.argtypes = [ctypes.POINTER(ReprojArgs)]
+    lib.smplk_reprojection_loss.restype = ctypes.c_int
+    lib.smplk_fit_priors.argtypes = [ctypes.POINTER(PriorArgs)]
+    lib.smplk_fit_priors.restype = ctypes.c_int
     lib.smplk_workspace_layout.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint32,
                                            ctypes.POINTER(ctypes.c_size_t),
                                            ctypes.POINTER(ctypes.c_int32)]

@@ -21,6 +21,7 @@
 #include "skinning.cuh"
 #include "skinning8.cuh"
 #include "mesh_ops.cuh"
+#include "fit_loss.cuh"
 
 using namespace smplk;
 
@@ -1195,6 +1196,47 @@ extern "C" int smplk_divide_faces(int32_t batch, int32_t num_verts, int32_t num_
   divide_faces_kernel<<<2 * batch, kDivThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       batch, num_verts, num_faces, faces, verts, faces_out, vidx_out, counts);
   LAUNCH_CHECK("divide_faces_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// fitting loss around the body model
+// ------------------------------------------------------------------------------------------
+extern "C" int smplk_reprojection_loss(const smplk_reprojection_args* a) {
+  if (!a || a->batch < 1 || a->num_joints < 1 || !a->joints || !a->rotation || !a->translation ||
+      !a->focal || !a->center || !a->gt_joints || !a->loss)
+    return fail(SMPLK_E_ARG, "bad argument");
+  if ((a->camera_batch != 1 && a->camera_batch != a->batch) ||
+      (a->weights && a->weights_batch != 1 && a->weights_batch != a->batch))
+    return fail(SMPLK_E_SHAPE, "camera_batch / weights_batch must be 1 or batch");
+  CUDA_TRY(cudaSetDevice(a->device));
+  ReprojArgs r;
+  r.B = a->batch; r.Jn = a->num_joints; r.joints = a->joints; r.rotation = a->rotation;
+  r.translation = a->translation; r.focal = a->focal; r.center = a->center; r.cam_batch = a->camera_batch;
+  r.gt = a->gt_joints; r.weights = a->weights; r.w_batch = a->weights ? a->weights_batch : 1;
+  r.rho = a->rho; r.data_weight = a->data_weight; r.loss = a->loss; r.d_joints = a->d_joints;
+  r.d_translation = a->d_translation;
+  const int warps_per_block = 4;
+  reprojection_loss_kernel<<<(a->batch + warps_per_block - 1) / warps_per_block, 32 * warps_per_block, 0,
+                             reinterpret_cast<cudaStream_t>(a->stream)>>>(r);
+  LAUNCH_CHECK("reprojection_loss_kernel");
+  return 0;
+}
+
+extern "C" int smplk_fit_priors(const smplk_prior_args* a) {
+  if (!a || a->batch < 1 || !a->loss) return fail(SMPLK_E_ARG, "bad argument");
+  if (a->body_pose && a->num_body_pose < 56) return fail(SMPLK_E_SHAPE, "body_pose needs >= 56 columns for the angle prior");
+  CUDA_TRY(cudaSetDevice(a->device));
+  PriorArgs p;
+  p.B = a->batch; p.betas = a->betas; p.nb = a->num_betas; p.pose_embedding = a->pose_embedding;
+  p.ne = a->num_embedding; p.body_pose = a->body_pose; p.np = a->num_body_pose; p.lhand = a->left_hand_pose;
+  p.rhand = a->right_hand_pose; p.nh = a->num_hand; p.shape_weight = a->shape_weight;
+  p.body_pose_weight = a->body_pose_weight; p.bending_weight = a->bending_prior_weight;
+  p.hand_weight = a->hand_prior_weight; p.loss = a->loss; p.d_betas = a->d_betas;
+  p.d_pose_embedding = a->d_pose_embedding; p.d_body_pose = a->d_body_pose; p.d_lhand = a->d_left_hand_pose;
+  p.d_rhand = a->d_right_hand_pose;
+  fit_priors_kernel<<<a->batch, 64, 0, reinterpret_cast<cudaStream_t>(a->stream)>>>(p);
+  LAUNCH_CHECK("fit_priors_kernel");
   return 0;
 }
 

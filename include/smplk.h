@@ -212,6 +212,53 @@ int smplk_divide_faces(int32_t batch, int32_t num_verts, int32_t num_faces, cons
                        const float* verts, int32_t* faces_out, int32_t* vidx_out, int32_t* counts,
                        int device, smplk_stream stream);
 
+/* ---- fitting loss around the body model (SURVEY.md 8f "next" row 1), batched over bodies ------ */
+
+/* Reprojection data term and its gradient.  Replaces, per closure call, PerspectiveCamera.forward
+ * (lib/Gen_SMPLH/camera.py:93-117), GMoF (lib/Gen_SMPLH/util.py:60-71) and the joint term of
+ * SMPLifyLoss.forward (lib/Gen_SMPLH/fitting.py:369-381); rho <= 0 gives the squared residual of
+ * SMPLifyCameraInitLoss (fitting.py:486-495).  All pointers are device pointers.
+ *   loss[b] = data_weight^2 sum_j w[b,j]^2 (rob(gt_x - img_x) + rob(gt_y - img_y)),
+ *   img = focal * (R p + t).xy / (R p + t).z + center,  rob(r) = rho^2 r^2 / (r^2 + rho^2) */
+typedef struct {
+  int32_t batch, num_joints;
+  const float* joints;        /* (B,Jn,3) model joints after the joint mapper                    */
+  const float* rotation;      /* (camera_batch,3,3) row-major                                    */
+  const float* translation;   /* (camera_batch,3)                                                */
+  const float* focal;         /* (camera_batch,2) fx, fy                                         */
+  const float* center;        /* (camera_batch,2)                                                */
+  int32_t camera_batch;       /* 1 (shared camera) or B                                          */
+  const float* gt_joints;     /* (B,Jn,2) 2-D detections                                         */
+  const float* weights;       /* (weights_batch,Jn) joint_weights * joints_conf, or NULL (= 1)   */
+  int32_t weights_batch;      /* 1 or B                                                          */
+  float rho, data_weight;
+  float* loss;                /* out (B)                                                         */
+  float* d_joints;            /* out (B,Jn,3) d loss[b] / d joints, or NULL                      */
+  float* d_translation;       /* out (B,3) d loss[b] / d camera translation, or NULL             */
+  int device;
+  smplk_stream stream;
+} smplk_reprojection_args;
+int smplk_reprojection_loss(const smplk_reprojection_args* args);
+
+/* Priors and their gradients (lib/Gen_SMPLH/fitting.py:383-413, lib/Gen_SMPLH/prior.py:53-97):
+ *   shape_weight^2 |betas|^2 + body_pose_weight^2 |pose_embedding|^2 (or |body_pose|^2 when no
+ *   embedding is given: L2Prior) + bending_prior_weight sum_k exp(s_k body_pose[i_k])^2 with
+ *   i = {55,58,12,15} - 3, s = {1,-1,-1,-1} + hand_prior_weight^2 (|lh|^2 + |rh|^2).
+ * body_pose is full_pose[:, 3:66].  NULL inputs drop their term; NULL gradients are skipped. */
+typedef struct {
+  int32_t batch;
+  const float* betas; int32_t num_betas;
+  const float* pose_embedding; int32_t num_embedding;
+  const float* body_pose; int32_t num_body_pose;
+  const float* left_hand_pose; const float* right_hand_pose; int32_t num_hand;
+  float shape_weight, body_pose_weight, bending_prior_weight, hand_prior_weight;
+  float* loss;                /* out (B) */
+  float* d_betas; float* d_pose_embedding; float* d_body_pose; float* d_left_hand_pose; float* d_right_hand_pose;
+  int device;
+  smplk_stream stream;
+} smplk_prior_args;
+int smplk_fit_priors(const smplk_prior_args* args);
+
 /* Per-kernel device timing for benchmarks: while enabled, forward/backward bracket every kernel
  * they launch with a CUDA event pair recorded on the caller's stream (the stream the kernel runs
  * on).  `smplk_profile_read` waits for the pending events and returns accumulated milliseconds and
