@@ -151,10 +151,12 @@ divide_faces_kernel(int B, int V, int F, const int* __restrict__ faces, const fl
   __syncthreads();
   auto face_side = [&](int f) {
     const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
-    const float m0 = vb[3 * i1] - vb[3 * i0], m1 = vb[3 * i1 + 1] - vb[3 * i0 + 1];
-    const float n0 = vb[3 * i2] - vb[3 * i1], n1 = vb[3 * i2 + 1] - vb[3 * i1 + 1];
-    const float z = m0 * n1 - n0 * m1;     // models/smplh_np.py:152
-    return z <= 0.f ? 0 : 1;
+    // evaluated in double: differences and products of fp32 values are exact there, so the sign --
+    // an index decision -- is the one the reference's float64 arithmetic gives for these vertices
+    const double m0 = (double)vb[3 * i1] - vb[3 * i0], m1 = (double)vb[3 * i1 + 1] - vb[3 * i0 + 1];
+    const double n0 = (double)vb[3 * i2] - vb[3 * i1], n1 = (double)vb[3 * i2 + 1] - vb[3 * i1 + 1];
+    const double z = m0 * n1 - n0 * m1;    // models/smplh_np.py:152
+    return z <= 0.0 ? 0 : 1;
   };
   // pass 1: first appearance of every vertex among this side's faces
   for (int f = threadIdx.x; f < F; f += blockDim.x) {

@@ -43,7 +43,7 @@ def test_oracle_matches_reference_modules(g):
 
 
 def _rel(a, b):
-    return float((a.double().cpu() - b).abs().max() / b.abs().max())
+    return float((a.detach().double().cpu() - b.detach()).abs().max() / b.detach().abs().max())
 
 
 @pytest.mark.gpu
@@ -70,7 +70,7 @@ def test_reprojection_kernel_matches_oracle(g, rho, shared_cam):
     (out * cw.float().to(dev)).sum().backward()
     assert _rel(out, ref.detach()) <= 1e-5
     if rho > 0 and not shared_cam:
-        assert np.abs(out.double().cpu().numpy() / g["joint_loss"] - 1).max() <= 1e-5    # the reference's numbers
+        assert np.abs(out.detach().double().cpu().numpy() / g["joint_loss"] - 1).max() <= 1e-5    # the reference's numbers
     assert _rel(jg.grad, j64.grad) <= 1e-4 and _rel(tg.grad, t64.grad) <= 1e-4
 
 
