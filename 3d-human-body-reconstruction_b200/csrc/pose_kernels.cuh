@@ -19,6 +19,7 @@ constexpr int kPoseWarps = 4;
 
 struct PoseFwdArgs {
   int B;
+  float* At;             // [ceil(B/256)*2][J*12][128] transposed transforms (+ transl), or null (block kernel only)
   const float* betas;
   int betas_B;
   const float* pose;     // (B,3J)
@@ -346,6 +347,262 @@ pose_forward_kernel(const ModelDev m, const PoseFwdArgs a) {
       g2.w -= g2.x * Jr[s][0] + g2.y * Jr[s][1] + g2.z * Jr[s][2];
       float4* dst = reinterpret_cast<float4*>(a.A + ((size_t)b * m.J + j) * 12);
       dst[0] = g0; dst[1] = g1; dst[2] = g2;
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Block version of the forward kernel: 32 warps = 32 consecutive bodies per block.
+//
+// ncu on the warp-per-body kernel above (4 bodies per block) shows 53 % of the stall samples on the
+// long scoreboard at an IPC of 0.03 per warp: every table access (parents / order / level_start /
+// J_template / J_shapedirs / pose_mean / PCA components) is a dependent global load (L1 hit, ~35
+// cycles each, a few hundred of them on the critical path).  Here the block stages those tables in
+// shared memory once, the warps read them with LDS, and because a block now holds 32 bodies it
+// also writes the TRANSPOSED transforms At[128-body block][J*12][128] that the fused blend+skinning
+// kernel reads (lane = body -> one 128-byte line per component), so no separate transposition pass.
+// ------------------------------------------------------------------------------------------
+constexpr int kPoseBlockWarps = 32;
+
+struct PoseBlockSmem {
+  int per_warp;      // floats per warp: feat[Kpad] + Gs[J*12], padded to 4 mod 32 (rows stay 16-byte
+                     // aligned for the float4 table accesses; the transposition reads are 4-way conflicted)
+  int off_Jt, off_Js, off_pm, off_cl, off_cr, off_par, off_ord, off_lvl, total;   // float offsets
+  int nbp;           // padded betas stride of J_shapedirs rows (odd)
+};
+
+__host__ __device__ inline PoseBlockSmem pose_block_layout(const ModelDev& m) {
+  PoseBlockSmem L;
+  const int base = max(m.Kpad, 32) + m.J * 12;
+  L.per_warp = base + ((36 - (base & 31)) & 31);             // == 4 (mod 32)
+  L.nbp = (max(m.NB, 1) | 1);
+  int o = kPoseBlockWarps * L.per_warp;
+  L.off_Jt = o;  o += 3 * m.J;
+  L.off_Js = o;  o += 3 * m.J * L.nbp;
+  L.off_pm = o;  o += 3 * m.J;
+  L.off_cl = o;  o += m.C * 45;
+  L.off_cr = o;  o += m.C * 45;
+  L.off_par = o; o += m.J;
+  L.off_ord = o; o += m.J;
+  L.off_lvl = o; o += m.max_depth + 2;
+  L.total = o;
+  return L;
+}
+
+template <int SLOTS>
+__global__ void __launch_bounds__(kPoseBlockWarps * 32, 1)
+pose_forward_block_kernel(const ModelDev m, const PoseFwdArgs a) {
+  extern __shared__ __align__(16) float pose_smem[];
+  const PoseBlockSmem L = pose_block_layout(m);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kPoseBlockWarps + warp;
+  const bool live = b < a.B;
+  float* feat = pose_smem + warp * L.per_warp;
+  float* Gs = feat + max(m.Kpad, 32);
+  float* sJt = pose_smem + L.off_Jt;
+  float* sJs = pose_smem + L.off_Js;
+  float* spm = pose_smem + L.off_pm;
+  float* scl = pose_smem + L.off_cl;
+  float* scr = pose_smem + L.off_cr;
+  int* spar = reinterpret_cast<int*>(pose_smem + L.off_par);
+  int* sord = reinterpret_cast<int*>(pose_smem + L.off_ord);
+  int* slvl = reinterpret_cast<int*>(pose_smem + L.off_lvl);
+
+  // ---- stage the model tables
+  for (int i = threadIdx.x; i < 3 * m.J; i += blockDim.x) {
+    sJt[i] = m.J_template[i];
+    spm[i] = (a.add_mean && m.pose_mean) ? m.pose_mean[i] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 3 * m.J * m.NB; i += blockDim.x) sJs[(i / m.NB) * L.nbp + (i % m.NB)] = m.J_shapedirs[i];
+  for (int i = threadIdx.x; i < m.C * 45; i += blockDim.x) { scl[i] = m.comp_l[i]; scr[i] = m.comp_r[i]; }
+  for (int i = threadIdx.x; i < m.J; i += blockDim.x) { spar[i] = m.parents[i]; sord[i] = m.order[i]; }
+  for (int i = threadIdx.x; i < m.max_depth + 2; i += blockDim.x) slvl[i] = m.level_start[i];
+  // ---- this body's small inputs into the warp's feature row: betas at feat[P..], PCA coefficients
+  // parked at feat[0..2C) until the features overwrite them
+  const float* betas_row = (a.betas && live) ? a.betas + (size_t)(a.betas_B == 1 ? 0 : b) * m.NB : nullptr;
+  for (int i = lane; i < m.Kpad - m.P; i += 32) feat[m.P + i] = (i < m.NB && betas_row) ? betas_row[i] : 0.f;
+  float pca_c = 0.f;                      // lane i < C: left coefficient i; lane 16 + i: right coefficient i
+  if (live && a.pca_l && lane < m.C) pca_c = a.pca_l[(size_t)b * m.C + lane];
+  if (live && a.pca_r && lane >= 16 && lane - 16 < m.C) pca_c = a.pca_r[(size_t)b * m.C + lane - 16];
+  __syncthreads();
+
+  const int hand0 = m.J - 30;
+  float Jr[SLOTS][3];
+  float rvs[SLOTS][3];
+  // hand PCA needs every lane for the coefficient broadcasts: evaluate it for all slots first
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int j = lane + 32 * s;
+    float x = 0.f, y = 0.f, z = 0.f;
+    const bool lh = a.pca_l != nullptr && j >= hand0 && j < hand0 + 15;
+    const bool rh = a.pca_r != nullptr && j >= hand0 + 15 && j < m.J;
+    if (a.pca_l != nullptr || a.pca_r != nullptr) {
+      const float* comp = lh ? scl + 3 * (j - hand0) : scr + 3 * (j - hand0 - 15);
+      for (int i = 0; i < m.C; ++i) {
+        const float cl = __shfl_sync(0xffffffffu, pca_c, i);
+        const float cr = __shfl_sync(0xffffffffu, pca_c, 16 + i);
+        if (lh || rh) {
+          const float ci = lh ? cl : cr;
+          x = fmaf(ci, comp[i * 45 + 0], x);
+          y = fmaf(ci, comp[i * 45 + 1], y);
+          z = fmaf(ci, comp[i * 45 + 2], z);
+        }
+      }
+    }
+    if (j < m.J && live) {
+      if (!(lh || rh)) {
+        const float* pp = a.pose + (size_t)b * 3 * m.J + 3 * j;
+        x = pp[0]; y = pp[1]; z = pp[2];
+      }
+      x += spm[3 * j]; y += spm[3 * j + 1]; z += spm[3 * j + 2];
+    }
+    rvs[s][0] = x; rvs[s][1] = y; rvs[s][2] = z;
+  }
+  // ---- per joint: R, rest joint; local transform [R | J] into the table
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int j = lane + 32 * s;
+    Jr[s][0] = Jr[s][1] = Jr[s][2] = 0.f;
+    if (j < m.J) {
+      float R[9];
+      if (a.full_pose && live) {
+        float* fp = a.full_pose + (size_t)b * 3 * m.J + 3 * j;
+        fp[0] = rvs[s][0]; fp[1] = rvs[s][1]; fp[2] = rvs[s][2];
+      }
+      rodrigues(rvs[s][0], rvs[s][1], rvs[s][2], R);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = sJt[3 * j + c];
+        const float* sd = sJs + (3 * j + c) * L.nbp;
+        for (int i = 0; i < m.NB; ++i) v = fmaf(sd[i], feat[m.P + i], v);
+        Jr[s][c] = v;
+      }
+      float4* g = reinterpret_cast<float4*>(Gs + j * 12);
+      g[0] = make_float4(R[0], R[1], R[2], Jr[s][0]);
+      g[1] = make_float4(R[3], R[4], R[5], Jr[s][1]);
+      g[2] = make_float4(R[6], R[7], R[8], Jr[s][2]);
+      if ((a.F_hi != nullptr || a.H_hi != nullptr) && j >= 1) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) feat[9 * (j - 1) + i] = R[i] - ((i % 4 == 0) ? 1.f : 0.f);
+      }
+    }
+  }
+  __syncwarp();
+  // ---- translation column -> offset from the parent's rest joint
+  float pj[SLOTS][3];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int j = lane + 32 * s;
+    pj[s][0] = pj[s][1] = pj[s][2] = 0.f;
+    if (j >= 1 && j < m.J) {
+      const float* gp = Gs + spar[j] * 12;
+      pj[s][0] = gp[3]; pj[s][1] = gp[7]; pj[s][2] = gp[11];
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int j = lane + 32 * s;
+    if (j >= 1 && j < m.J) {
+      Gs[j * 12 + 3] = Jr[s][0] - pj[s][0];
+      Gs[j * 12 + 7] = Jr[s][1] - pj[s][1];
+      Gs[j * 12 + 11] = Jr[s][2] - pj[s][2];
+    }
+  }
+  __syncwarp();
+
+  // ---- blend-feature rows (independent of the chain; issue the stores before walking it)
+  if (a.F_hi != nullptr && live) {
+    float* fh = a.F_hi + (size_t)b * m.Kpad;
+    float* fl = a.F_lo + (size_t)b * m.Kpad;
+    for (int k = lane; k < m.Kpad; k += 32) {
+      float x = feat[k];
+      float h = ptx::tf32_round(x);
+      fh[k] = h;
+      fl[k] = x - h;
+    }
+  }
+  if (a.H_hi != nullptr && live) {
+    __half2* hh = reinterpret_cast<__half2*>(a.H_hi + (size_t)b * m.Kpad);
+    __half2* hl = reinterpret_cast<__half2*>(a.H_lo + (size_t)b * m.Kpad);
+    for (int k = lane; k < m.Kpad / 2; k += 32) {
+      const float2 x = *reinterpret_cast<const float2*>(feat + 2 * k);
+      const __half h0 = __float2half_rn(x.x), h1 = __float2half_rn(x.y);
+      hh[k] = __halves2half2(h0, h1);
+      hl[k] = __halves2half2(__float2half_rn(x.x - __half2float(h0)),
+                             __float2half_rn(x.y - __half2float(h1)));
+    }
+  }
+
+  // ---- walk the tree level by level: G_j = G_parent(j) * L_j
+  for (int d = 1; d <= m.max_depth; ++d) {
+    const int l0 = slvl[d], l1 = slvl[d + 1];
+    for (int i = l0 + lane; i < l1; i += 32) {
+      const int j = sord[i];
+      const float4* P4 = reinterpret_cast<const float4*>(Gs + spar[j] * 12);
+      float4* L4 = reinterpret_cast<float4*>(Gs + j * 12);
+      const float4 p0 = P4[0], p1 = P4[1], p2 = P4[2];
+      const float4 q0 = L4[0], q1 = L4[1], q2 = L4[2];
+      float4 o0, o1, o2;
+      o0.x = fmaf(p0.x, q0.x, fmaf(p0.y, q1.x, p0.z * q2.x));
+      o0.y = fmaf(p0.x, q0.y, fmaf(p0.y, q1.y, p0.z * q2.y));
+      o0.z = fmaf(p0.x, q0.z, fmaf(p0.y, q1.z, p0.z * q2.z));
+      o0.w = fmaf(p0.x, q0.w, fmaf(p0.y, q1.w, fmaf(p0.z, q2.w, p0.w)));
+      o1.x = fmaf(p1.x, q0.x, fmaf(p1.y, q1.x, p1.z * q2.x));
+      o1.y = fmaf(p1.x, q0.y, fmaf(p1.y, q1.y, p1.z * q2.y));
+      o1.z = fmaf(p1.x, q0.z, fmaf(p1.y, q1.z, p1.z * q2.z));
+      o1.w = fmaf(p1.x, q0.w, fmaf(p1.y, q1.w, fmaf(p1.z, q2.w, p1.w)));
+      o2.x = fmaf(p2.x, q0.x, fmaf(p2.y, q1.x, p2.z * q2.x));
+      o2.y = fmaf(p2.x, q0.y, fmaf(p2.y, q1.y, p2.z * q2.y));
+      o2.z = fmaf(p2.x, q0.z, fmaf(p2.y, q1.z, p2.z * q2.z));
+      o2.w = fmaf(p2.x, q0.w, fmaf(p2.y, q1.w, fmaf(p2.z, q2.w, p2.w)));
+      L4[0] = o0; L4[1] = o1; L4[2] = o2;
+    }
+    __syncwarp();
+  }
+
+  // ---- skinning transforms A_j = [G_R | G_t - G_R J_j] (kept in the table), FK joints
+  const float tx = (a.transl && live) ? a.transl[3 * b + 0] : 0.f;
+  const float ty = (a.transl && live) ? a.transl[3 * b + 1] : 0.f;
+  const float tz = (a.transl && live) ? a.transl[3 * b + 2] : 0.f;
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int j = lane + 32 * s;
+    if (j < m.J) {
+      float4* G4 = reinterpret_cast<float4*>(Gs + j * 12);
+      float4 g0 = G4[0], g1 = G4[1], g2 = G4[2];
+      if (a.joints && live) {
+        float* jo = a.joints + (size_t)b * a.joints_ld + 3 * j;
+        jo[0] = g0.w + tx; jo[1] = g1.w + ty; jo[2] = g2.w + tz;
+      }
+      g0.w -= g0.x * Jr[s][0] + g0.y * Jr[s][1] + g0.z * Jr[s][2];
+      g1.w -= g1.x * Jr[s][0] + g1.y * Jr[s][1] + g1.z * Jr[s][2];
+      g2.w -= g2.x * Jr[s][0] + g2.y * Jr[s][1] + g2.z * Jr[s][2];
+      if (!live) g0 = g1 = g2 = make_float4(0.f, 0.f, 0.f, 0.f);
+      G4[0] = g0; G4[1] = g1; G4[2] = g2;
+      if (a.A && live) {
+        float4* dst = reinterpret_cast<float4*>(a.A + ((size_t)b * m.J + j) * 12);
+        dst[0] = g0; dst[1] = g1; dst[2] = g2;
+      }
+    }
+  }
+  // ---- transposed transforms for the fused kernel: warp w writes rows w, w+32, ... ; lane = body
+  if (a.At != nullptr) {
+    __syncthreads();
+    const int JC = m.J * 12;
+    const int bb = blockIdx.x * kPoseBlockWarps + lane;            // body this lane writes
+    const float* Gl = pose_smem + lane * L.per_warp + max(m.Kpad, 32);
+    float ttx = 0.f, tty = 0.f, ttz = 0.f;
+    if (a.transl && bb < a.B) { ttx = a.transl[3 * bb]; tty = a.transl[3 * bb + 1]; ttz = a.transl[3 * bb + 2]; }
+    float* dst = a.At + (size_t)(bb >> 7) * JC * 128 + (bb & 127);
+    for (int row = warp; row < JC; row += kPoseBlockWarps) {
+      float v = Gl[row];
+      if ((row & 3) == 3 && bb < a.B) {
+        const int ax = (row % 12) >> 2;
+        v += ax == 0 ? ttx : (ax == 1 ? tty : ttz);
+      }
+      dst[(size_t)row * 128] = v;
     }
   }
 }

@@ -88,6 +88,7 @@ struct smplk_model {
   bool use_2cta;
   CUtensorMap tmapf_pdh_hi, tmapf_pdh_lo;  // fused blend+skinning kernel: 84-vertex column tiles
   bool use_fused;       // SMPLK_FUSED=0 in the environment selects the two-kernel forward (A/B runs)
+  bool use_pose_block;  // SMPLK_POSE_V1=1 selects the warp-per-body pose kernel + transposition pass
   CUtensorMap tmap_pdkn_hi, tmap_pdkn_lo;  // backward: B operand rows = blend features
   // host staging for smplk_forward_host
   void* stage_dev;
@@ -618,6 +619,11 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
                                   (int)skin_grouped8_smem_bytes(d.J)));
     CUDA_TRY(cudaFuncSetAttribute(skin_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)skin_tma_smem_bytes(d.J)));
+    if ((size_t)pose_block_layout(d).total * sizeof(float) <= 200 * 1024) {
+      const int pb = (int)(pose_block_layout(d).total * sizeof(float));
+      CUDA_TRY(cudaFuncSetAttribute(pose_forward_block_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
+      CUDA_TRY(cudaFuncSetAttribute(pose_forward_block_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
+    }
     CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(skin_backward_grouped_kernel<kSkinBwdStages>,
@@ -661,6 +667,7 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   { const char* e = getenv("SMPLK_SKIN_V1"); mdl->force_skin_v1 = e && e[0] == '1'; }
   { const char* e = getenv("SMPLK_GEMM_1CTA"); mdl->use_2cta = !(e && e[0] == '1'); }
   { const char* e = getenv("SMPLK_FUSED"); mdl->use_fused = !(e && e[0] == '0'); }
+  { const char* e = getenv("SMPLK_POSE_V1"); mdl->use_pose_block = !(e && e[0] == '1'); }
   { const char* e = getenv("SMPLK_BLEND"); mdl->default_tc = (e && strcmp(e, "tf32") == 0) ? BLEND_TF32 : BLEND_F16; }
   for (int i = 0; i < SMPLK_PROF_SLOTS; ++i) { mdl->prof_ms[i] = 0.0; mdl->prof_n[i] = 0; }
   if (prop.major != 10) {
@@ -731,8 +738,26 @@ extern "C" int smplk_workspace_layout(const smplk_model* model, int32_t batch, u
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
+// The block kernel (tables in smem, 32 bodies per block, writes At itself) when its shared memory fits.
+static bool pose_block_applies(const smplk_model* mdl) {
+  return mdl->use_pose_block && (size_t)pose_block_layout(mdl->d).total * sizeof(float) <= 200 * 1024;
+}
+
 static int launch_pose_forward(const smplk_model* mdl, const PoseFwdArgs& pa, cudaStream_t st) {
   const ModelDev& d = mdl->d;
+  if (pose_block_applies(mdl)) {
+    const size_t smem = (size_t)pose_block_layout(d).total * sizeof(float);
+    // At is written for whole 256-body blocks (the fused kernel reads zero transforms for padding rows)
+    const int bodies = pa.At ? round_up(pa.B, 2 * kBlendBM) : pa.B;
+    const int blocks = (bodies + kPoseBlockWarps - 1) / kPoseBlockWarps;
+    ProfScope prof(mdl, st, SMPLK_PROF_POSE_FWD);
+    if (d.J <= 32)
+      pose_forward_block_kernel<1><<<blocks, kPoseBlockWarps * 32, smem, st>>>(d, pa);
+    else
+      pose_forward_block_kernel<2><<<blocks, kPoseBlockWarps * 32, smem, st>>>(d, pa);
+    LAUNCH_CHECK("pose_forward_block_kernel");
+    return 0;
+  }
   const int blocks = (pa.B + kPoseWarps - 1) / kPoseWarps;
   const size_t smem = (size_t)kPoseWarps * (std::max(d.Kpad, 32) + d.J * 12) * sizeof(float);
   ProfScope prof(mdl, st, SMPLK_PROF_POSE_FWD);
@@ -840,7 +865,7 @@ static int launch_fused(const smplk_model* mdl, int rows, float* F_hi, float* F_
   const ModelDev& d = mdl->d;
   const int JC = d.J * 12;
   const int rows_pad = round_up(rows, 2 * kBlendBM);
-  {
+  if (A != nullptr) {                        // null: the pose kernel already wrote At
     ProfScope prof(mdl, st, SMPLK_PROF_TRANSPOSE);
     dim3 grid((JC + 31) / 32, rows_pad / 32);
     transpose_transforms_kernel<<<grid, 256, 0, st>>>(rows, JC, A, transl, At);
@@ -998,11 +1023,14 @@ extern "C" int smplk_forward(const smplk_model* model, const smplk_forward_args*
     pa.H_hi = f16 ? reinterpret_cast<__half*>(F_hi) : nullptr;   // fp16 rows alias the fp32 regions
     pa.H_lo = f16 ? reinterpret_cast<__half*>(F_lo) : nullptr;
     pa.A = A;
+    pa.At = nullptr;
     pa.joints = a->joints ? a->joints + (size_t)c0 * joints_ld : nullptr;
     pa.joints_ld = joints_ld;
     pa.full_pose = a->full_pose ? a->full_pose + (size_t)c0 * 3 * d.J : nullptr;
-    if (int r = launch_pose_forward(model, pa, st)) return r;
     const bool fused = fused_applies(model, rows, path, a->flags, a->verts != nullptr);
+    const bool at_from_pose = fused && pose_block_applies(model);
+    if (at_from_pose) pa.At = At;            // the block pose kernel writes the transposed transforms itself
+    if (int r = launch_pose_forward(model, pa, st)) return r;
     if (a->flags & SMPLK_FLAG_TRANSFORMS_ONLY) continue;    // pose / FK kernel only: A, joints, full_pose
     if (!fused && !d.lbs_only && (a->verts || (a->flags & SMPLK_FLAG_SAVE_FOR_BACKWARD))) {
       if (int r = launch_blend(model, rows, path, F_hi, F_lo, v_posed, st)) return r;
@@ -1010,7 +1038,7 @@ extern "C" int smplk_forward(const smplk_model* model, const smplk_forward_args*
     if (a->verts) {
       float* vout = a->verts + (size_t)c0 * d.V * 3;
       if (fused) {
-        if (int r = launch_fused(model, rows, F_hi, F_lo, A, At, pa.transl, vout, st)) return r;
+        if (int r = launch_fused(model, rows, F_hi, F_lo, at_from_pose ? nullptr : A, At, pa.transl, vout, st)) return r;
       } else {
         if (int r = launch_skin(model, rows, d.lbs_only ? d.bias : v_posed,
                                 d.lbs_only ? 0 : (size_t)d.Npad, A, pa.transl, vout, st)) return r;
