@@ -41,6 +41,33 @@ def test_ctypes_struct_sizes_match_header_layout():
     assert _lib.ModelInfo._fields_[0][0] == "num_verts" and len(_lib.ModelInfo._fields_) == 11
 
 
+def test_ctypes_structs_match_the_compiled_header_layout():
+    """sizeof / offsetof of every argument struct as gcc lays out include/smplk.h == the ctypes mirror."""
+    import subprocess, tempfile
+    pairs = [("smplk_model_desc", _lib.ModelDesc), ("smplk_forward_args", _lib.ForwardArgs),
+             ("smplk_backward_args", _lib.BackwardArgs), ("smplk_reprojection_args", _lib.ReprojArgs),
+             ("smplk_prior_args", _lib.PriorArgs), ("smplk_model_info", _lib.ModelInfo)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "smplk.h"', 'int main(void){']
+    for cname, cls in pairs:
+        lines.append('printf("%s %%zu", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf(" %%zu", offsetof(%s, %s));' % (cname, fname))
+        lines.append('printf("\\n");')
+    lines.append('return 0;}')
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "t.c")
+        open(p, "w").write("\n".join(lines))
+        exe = os.path.join(d, "t")
+        r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), p, "-o", exe],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        out = subprocess.run([exe], capture_output=True, text=True).stdout.strip().splitlines()
+    for (cname, cls), line in zip(pairs, out):
+        nums = [int(x) for x in line.split()[1:]]
+        assert nums[0] == ctypes.sizeof(cls), cname
+        assert nums[1:] == [getattr(cls, f).offset for f, _ in cls._fields_], cname
+
+
 def test_no_gpu_means_loud_failure_not_fallback():
     import torch
     if torch.cuda.is_available():
