@@ -293,7 +293,9 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
           ptx::cp_async_16(bias_warp + i * 16, bias_t + c_lo * kFzChunkCols + i * 4);
         ptx::cp_async_commit();
       }
-      float p[kFzChunkCols], o[kFzChunkCols];
+      // packed pairs: p2[3k + d] = coordinate d of vertices (2k, 2k+1) of the chunk (the tile's columns
+      // are packed in that order), o2 likewise -> the skinning math runs on FFMA2 (fma.rn.f32x2)
+      uint64_t p2[kFzChunkCols / 2], o2[kFzChunkCols / 2];
 
       // (chunk, joint) entry ee -> ring slot: the joint's 12 transform lines of the warp's 32 bodies
       // (128 bytes each, lane = body) + the entry's 64-byte weight line, as 16-byte cp.async pieces
@@ -332,16 +334,20 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
 #pragma unroll
         for (int i = 0; i < kFzChunkVerts / 4; ++i)
           ptx::ld_shared_v4(src + 12 * 128 + i * 16, wv[4 * i], wv[4 * i + 1], wv[4 * i + 2], wv[4 * i + 3]);
+        // two vertices per instruction: the transform components are scalar (broadcast) operands
+        uint64_t a2[12];
 #pragma unroll
-        for (int v = 0; v < kFzChunkVerts; ++v) {
-          const float w = wv[v];
-          const float x = p[3 * v], y = p[3 * v + 1], z = p[3 * v + 2];
-          const float qx = fmaf(a[0], x, fmaf(a[1], y, fmaf(a[2], z, a[3])));
-          const float qy = fmaf(a[4], x, fmaf(a[5], y, fmaf(a[6], z, a[7])));
-          const float qz = fmaf(a[8], x, fmaf(a[9], y, fmaf(a[10], z, a[11])));
-          o[3 * v] = fmaf(w, qx, o[3 * v]);
-          o[3 * v + 1] = fmaf(w, qy, o[3 * v + 1]);
-          o[3 * v + 2] = fmaf(w, qz, o[3 * v + 2]);
+        for (int i = 0; i < 12; ++i) a2[i] = ptx::pack_f32x2(a[i], a[i]);
+#pragma unroll
+        for (int k = 0; k < kFzChunkVerts / 2; ++k) {
+          const uint64_t w2 = ptx::pack_f32x2(wv[2 * k], wv[2 * k + 1]);
+          const uint64_t x = p2[3 * k], y = p2[3 * k + 1], z = p2[3 * k + 2];
+          const uint64_t qx = ptx::fma_f32x2(a2[0], x, ptx::fma_f32x2(a2[1], y, ptx::fma_f32x2(a2[2], z, a2[3])));
+          const uint64_t qy = ptx::fma_f32x2(a2[4], x, ptx::fma_f32x2(a2[5], y, ptx::fma_f32x2(a2[6], z, a2[7])));
+          const uint64_t qz = ptx::fma_f32x2(a2[8], x, ptx::fma_f32x2(a2[9], y, ptx::fma_f32x2(a2[10], z, a2[11])));
+          o2[3 * k] = ptx::fma_f32x2(w2, qx, o2[3 * k]);
+          o2[3 * k + 1] = ptx::fma_f32x2(w2, qy, o2[3 * k + 1]);
+          o2[3 * k + 2] = ptx::fma_f32x2(w2, qz, o2[3 * k + 2]);
         }
       };
       // 32 staged columns (one 128-byte segment per body row) -> global
@@ -399,15 +405,14 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
             FZ_STAMP(dbg_on, &args.dbg[(warp * kFzDbgTiles + it) * 4 + 2]);
           }
           const uint32_t bsrc = bias_warp + (c - c_lo) * (kFzChunkCols * 4);
+          const uint64_t os2 = ptx::pack_f32x2(oscale, oscale);
 #pragma unroll
           for (int i = 0; i < kFzChunkCols; i += 4) {
             float b0, b1, b2, b3;
             ptx::ld_shared_v4(bsrc + i * 4, b0, b1, b2, b3);      // warp-uniform address: broadcast
-            p[i] = fmaf(__uint_as_float(pr[i]), oscale, b0);
-            p[i + 1] = fmaf(__uint_as_float(pr[i + 1]), oscale, b1);
-            p[i + 2] = fmaf(__uint_as_float(pr[i + 2]), oscale, b2);
-            p[i + 3] = fmaf(__uint_as_float(pr[i + 3]), oscale, b3);
-            o[i] = o[i + 1] = o[i + 2] = o[i + 3] = 0.f;
+            p2[i / 2] = ptx::fma_f32x2(ptx::pack_b32x2(pr[i], pr[i + 1]), os2, ptx::pack_f32x2(b0, b1));
+            p2[i / 2 + 1] = ptx::fma_f32x2(ptx::pack_b32x2(pr[i + 2], pr[i + 3]), os2, ptx::pack_f32x2(b2, b3));
+            o2[i / 2] = o2[i / 2 + 1] = 0ull;
           }
         }
         // ---- the chunk's (joint, weights) entries: entry e is applied from its ring slot while
@@ -418,6 +423,12 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
         FZ_STAMP(dbg_c, &dbg_p[1]);
         // ---- o (32 bodies x 36 columns) -> rolling 32-column staging window -> global.  Chunk c
         // starts at window column w0 = 36 c mod 32; its first 32 - w0 columns complete the window.
+        // unpack: output column 6k + 3h + d of the chunk = half h of o2[3k + d]
+        float o[kFzChunkCols];
+#pragma unroll
+        for (int k = 0; k < kFzChunkVerts / 2; ++k)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) ptx::unpack_f32x2(o2[3 * k + d], o[6 * k + d], o[6 * k + 3 + d]);
         const int w0 = (c * kFzChunkCols) & 31;
         const int g0 = w0 >> 2;                  // window position of the chunk's first 4-column group
         __syncwarp();

@@ -357,6 +357,29 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
       : "memory");
 }
 
+// ------------------------------------------------------------------ packed fp32x2 (FFMA2)
+// sm_100 executes fma.rn.f32x2 as one FFMA2: two fp32 FMAs per lane per instruction (a 3-register
+// FFMA issues every other cycle per scheduler, so this doubles the FP32 FMA rate); a {x, x} operand
+// becomes a scalar-broadcast source, no extra move.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack_b32x2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 // ------------------------------------------------------------------ misc
 __device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");

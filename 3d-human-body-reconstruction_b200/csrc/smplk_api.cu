@@ -316,11 +316,15 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
       const size_t nf = (size_t)d.fz_tiles * kBlendBN;
       std::vector<__half> fh(nf * d.Kpad, __float2half(0.f)), fl(nf * d.Kpad, __float2half(0.f));
       std::vector<float> bf(nf + 64, 0.f);
+      // within every 12-vertex chunk (36 columns) the columns are ordered as vertex PAIRS,
+      // [x_2k x_2k+1 y_2k y_2k+1 z_2k z_2k+1], so that the epilogue's TMEM loads land as packed
+      // fp32x2 operands: output column 6k + 3h + d of a chunk sits in GEMM column 6k + 2d + h
       for (int t = 0; t < d.fz_tiles; ++t)
         for (int c = 0; c < kFzTileCols; ++c) {
           const int n = t * kFzTileCols + c;
           if (n >= d.N) break;
-          const size_t row = (size_t)t * kBlendBN + c;
+          const int cc = c % kFzChunkCols, k6 = cc / 6, h = (cc % 6) / 3, dd = cc % 3;
+          const size_t row = (size_t)t * kBlendBN + (c - cc) + 6 * k6 + 2 * dd + h;
           memcpy(&fh[row * d.Kpad], &hh[(size_t)n * d.Kpad], (size_t)d.Kpad * sizeof(__half));
           memcpy(&fl[row * d.Kpad], &hl[(size_t)n * d.Kpad], (size_t)d.Kpad * sizeof(__half));
           bf[row] = (float)desc->v_template[n];
