@@ -232,6 +232,28 @@ def test_smplh_module_pca_mean_mapper_and_wrapper_extras(dev, smplh_model):
     assert _maxerr(out2.vertices, ref2.vertices) <= TOL and _maxerr(out2.joints, ref2.joints) <= TOL
 
 
+@pytest.mark.parametrize("B", [300, 33])
+def test_smplh_module_inference_batches_with_pca_hands_and_pose_mean(dev, smplh_model, B):
+    """The module under torch.no_grad() at a GEMM-sized batch: block pose kernel (PCA hands through
+    warp broadcasts, pose mean from smem) -> fused blend+skinning; and at a batch below the tcgen05
+    threshold of 128 rows.  One betas row broadcast, only the left hand given as PCA input."""
+    m = smplh_model
+    mod = SMPLH(model=m, use_pca=True, num_pca_comps=6, flat_hand_mean=False, create_transl=True,
+                batch_size=B).to(dev)
+    rng = np.random.default_rng(B)
+    kw = dict(betas=rng.standard_normal((1, 16)), global_orient=rng.standard_normal((B, 3)) * 0.4,
+              body_pose=rng.standard_normal((B, 63)) * 0.3, left_hand_pose=rng.standard_normal((B, 6)),
+              right_hand_pose=rng.standard_normal((B, 6)) * 0.0, transl=rng.standard_normal((B, 3)))
+    with torch.no_grad():
+        out = mod(**{k: _t(v, dev) for k, v in kw.items()}, return_full_pose=True)
+    om = O.TorchOracleModel(m, dtype=torch.float64, num_pca_comps=6)
+    ref = om.forward(torch.tensor(kw["betas"]).expand(B, -1), torch.tensor(kw["global_orient"]),
+                     torch.tensor(kw["body_pose"]), torch.tensor(kw["left_hand_pose"]),
+                     torch.tensor(kw["right_hand_pose"]), transl=torch.tensor(kw["transl"]))
+    assert _maxerr(out.vertices, ref.vertices) <= TOL and _maxerr(out.joints, ref.joints) <= TOL
+    assert _maxerr(out.full_pose, ref.full_pose) <= 1e-6
+
+
 def test_dense_weights_take_the_generic_path(dev):
     m = synthetic.make_model("smplh", seed=5, dense_weights=True, dense_regressor=True)
     dm = smplk.DeviceModel(m, device=0)
