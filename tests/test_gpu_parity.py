@@ -142,6 +142,43 @@ def test_fused_path_other_vertex_counts(dev, V, B):
     assert _maxerr(v, ref.vertices) <= TOL and _maxerr(j, ref.joints) <= TOL
 
 
+def test_fused_forward_is_deterministic_and_agrees_with_two_kernel_path_on_random_batches(dev, smplh_model, monkeypatch):
+    """Race / hazard screen for the fused kernel (cp.async ring, rolling staging window, shared
+    accumulators): repeated runs must be BIT-identical, and every batch size must agree with the
+    two-kernel forward.  Sizes straddle the 32-body pose blocks, the 256-body GEMM blocks and the
+    8192-body chunks; outputs are pre-filled with NaN to expose unwritten elements."""
+    m = smplh_model
+    dm_f = smplk.DeviceModel(m, device=0)
+    monkeypatch.setenv("SMPLK_FUSED", "0")
+    dm_u = smplk.DeviceModel(m, device=0)
+    monkeypatch.delenv("SMPLK_FUSED")
+    rng = np.random.default_rng(77)
+    sizes = [129, 255, 256, 288, 1023, 4097, 8192 + 130] + [int(x) for x in rng.integers(130, 3000, size=4)]
+    for B in sizes:
+        betas, pose, transl = synthetic.make_inputs(m, B, seed=B)
+        args = (_t(betas, dev), _t(pose, dev))
+        tr = _t(transl, dev)
+        runs = []
+        for _ in range(3):
+            v = torch.full((B, dm_f.V, 3), float("nan"), device=dev)
+            j = torch.full((B, dm_f.J, 3), float("nan"), device=dev)
+            ws = torch.empty(dm_f.workspace_bytes(B, 0), device=dev, dtype=torch.uint8)
+            a = _lib.ForwardArgs()
+            a.batch, a.flags = B, 0
+            a.betas, a.betas_batch = ctypes.c_void_p(args[0].data_ptr()), B
+            a.pose, a.transl = ctypes.c_void_p(args[1].data_ptr()), ctypes.c_void_p(tr.data_ptr())
+            a.verts, a.joints = ctypes.c_void_p(v.data_ptr()), ctypes.c_void_p(j.data_ptr())
+            a.workspace, a.workspace_bytes = ctypes.c_void_p(ws.data_ptr()), ws.numel()
+            a.stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            dm_f.forward(a)
+            torch.cuda.synchronize()
+            runs.append((v, j))
+        assert all(torch.equal(runs[0][0], r[0]) and torch.equal(runs[0][1], r[1]) for r in runs[1:]), B
+        assert torch.isfinite(runs[0][0]).all()
+        vu, ju, _, _ = body_model_apply(dm_u, *args, transl=tr)
+        assert _maxerr(runs[0][0], vu) <= 3e-6 and _maxerr(runs[0][1], ju) == 0.0, B
+
+
 def test_fused_path_smpl_24_joints_and_broadcast_betas(dev, smpl_model):
     m = smpl_model
     B = 513
