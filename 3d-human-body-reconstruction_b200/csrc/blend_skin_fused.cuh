@@ -19,8 +19,8 @@
 //     per-tile time is max(T_mma, (T_mma + T_hold) / 2).
 //   * Per chunk (36 TMEM columns -> 36 registers + v_template from smem): the chunk's distinct
 //     joints come from a table built at model-create time.  For each (chunk, joint) entry the body's
-//     3x4 transform is read from the TRANSPOSED transform array At[128-body block][joint][12][128]
-//     (lane = body: every component is one coalesced 128-byte line) and applied to the 12 vertices
+//     3x4 transform is read from the joint-major transform array At[128-body block][joint][128][12]
+//     (the 32 bodies of a warp are 1,536 contiguous bytes per joint) and applied to the 12 vertices
 //     with the entry's weights (0 where a vertex does not use the joint; branch-free).
 //   * Transforms and weights travel through a per-warp cp.async ring in shared memory (kFzRing
 //     entries of 13 lines): ptxas tracks ALL global loads of a warp with ONE scoreboard, so a
@@ -81,7 +81,7 @@ struct FusedArgs {
   const int* ch_off;       // [num_n_blocks * 7 + 1] first entry of every 12-vertex chunk
   const int* ch_joint;     // [entries] joint id
   const float4* ch_w;      // [entries][4] weight of that joint for the chunk's 12 vertices (+ 4 zeros)
-  const float* At;         // [ceil(rows/128)][J*12][128] transposed transforms (transl folded in)
+  const float* At;         // [ceil(rows/256)*2][J][128][12] joint-major transforms per 128-body block (transl folded in)
   int J;
   float* out;              // (rows, N) posed vertices
   int rows;
@@ -98,28 +98,21 @@ constexpr int kFzDbgTiles = 32;
 #define FZ_STAMP(cond, ptr_expr) do { } while (0)
 #endif
 
-// A [rows][J*12] -> At [ceil(rows/128)][J*12][128] (+ transl on the translation column), so that the
-// fused epilogue (lane = body) reads every transform component as one 128-byte line.
+// A [rows][J][12] -> At [ceil(rows/128)][J][128][12] (+ transl on the translation column): joint-major
+// within every 128-body block, so that the 32 bodies of a fused-kernel warp are 1,536 contiguous bytes
+// per joint.  Only used with the warp-per-body pose kernel; the block pose kernel writes At itself.
 __global__ void __launch_bounds__(256)
-transpose_transforms_kernel(int rows, int JC, const float* __restrict__ A,
+transpose_transforms_kernel(int rows, int rows_pad, int J, const float* __restrict__ A,
                             const float* __restrict__ transl, float* __restrict__ At) {
-  __shared__ float tile[32][33];
-  const int b0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 32; r += 8) {
-    const int b = b0 + r, c = c0 + tx;
-    float v = 0.f;
-    if (b < rows && c < JC) {
-      v = A[(size_t)b * JC + c];
-      if (transl != nullptr && (c & 3) == 3) v += transl[3 * b + ((c % 12) >> 2)];
-    }
-    tile[r][tx] = v;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;          // one float4 (transform row) each
+  if (i >= rows_pad * J * 3) return;
+  const int r = i % 3, j = (i / 3) % J, b = i / (3 * J);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (b < rows) {
+    v = *reinterpret_cast<const float4*>(A + ((size_t)b * J + j) * 12 + 4 * r);
+    if (transl != nullptr) v.w += transl[3 * b + r];
   }
-  __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const int c = c0 + r, b = b0 + tx;
-    if (c < JC) At[((size_t)(b >> 7) * JC + c) * 128 + (b & 127)] = tile[tx][r];
-  }
+  *reinterpret_cast<float4*>(At + (((size_t)(b >> 7) * J + j) * 128 + (b & 127)) * 12 + 4 * r) = v;
 }
 
 // kN > 0: floats per output row known at compile time (3 * 6890 for SMPL / SMPL-H), so the 32 row
@@ -272,8 +265,9 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
       // with 2 accumulators the per-tile time is max(T_mma, (T_mma + T_hold) / 2).
       const int cb = 3 + (it & 1);
       const int c_lo = half ? cb : 0, c_hi = half ? kFzChunks : cb;
-      // this lane's 16-byte piece (lane & 7) of transform line (lane >> 3) of the warp's 32 bodies
-      const float* At_w = args.At + (size_t)(m0 >> 7) * JC128 + q * 32 + (lane >> 3) * 128 + (lane & 7) * 4;
+      // joint-major per 128-body block: a joint's transforms of this warp's 32 bodies are 96 contiguous
+      // 16-byte pieces; lane l copies pieces l, l + 32, l + 64
+      const float* At_w = args.At + (size_t)(m0 >> 7) * JC128 + q * 32 * 12 + lane * 4;
       const float* bias_t = args.bias + nb * kBlendBN;
       const int row0 = m0 + q * 32;
       const int nrows = min(32, args.rows - row0);
@@ -312,7 +306,7 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
           const float* ap = At_w + (size_t)jj * (12 * 128);
           const uint32_t dst = ring_piece + ps * kFzRingEntryBytes;
 #pragma unroll
-          for (int k = 0; k < 3; ++k) ptx::cp_async_16(dst + k * 512, ap + k * 512);
+          for (int k = 0; k < 3; ++k) ptx::cp_async_16(dst + k * 512, ap + k * 128);
           if (lane < 4) ptx::cp_async_16(dst + 12 * 128, wflat + (size_t)ee * 16 + lane * 4);
         }
         ptx::cp_async_commit();                 // one group per entry, empty past the tile's end
@@ -327,9 +321,10 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
         issue_entry(ee + kFzRing - 1);
         const uint32_t src = ring_warp + cs * kFzRingEntryBytes;
         cs = (cs + 1 == kFzRing) ? 0 : cs + 1;
-        float a[12];
+        float a[12];                              // this body's 3x4 transform: 48 contiguous bytes
 #pragma unroll
-        for (int i = 0; i < 12; ++i) a[i] = ptx::ld_shared_f32(src + i * 128 + lane * 4);
+        for (int i = 0; i < 3; ++i)
+          ptx::ld_shared_v4(src + lane * 48 + i * 16, a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
         float wv[kFzChunkVerts];
 #pragma unroll
         for (int i = 0; i < kFzChunkVerts / 4; ++i)

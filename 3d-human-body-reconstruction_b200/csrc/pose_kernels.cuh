@@ -19,7 +19,7 @@ constexpr int kPoseWarps = 4;
 
 struct PoseFwdArgs {
   int B;
-  float* At;             // [ceil(B/256)*2][J*12][128] transposed transforms (+ transl), or null (block kernel only)
+  float* At;             // [ceil(B/256)*2][J][128][12] joint-major transforms per 128-body block (+ transl), or null (block kernel only)
   const float* betas;
   int betas_B;
   const float* pose;     // (B,3J)
@@ -359,9 +359,9 @@ pose_forward_kernel(const ModelDev m, const PoseFwdArgs a) {
 // long scoreboard at an IPC of 0.03 per warp: every table access (parents / order / level_start /
 // J_template / J_shapedirs / pose_mean / PCA components) is a dependent global load (L1 hit, ~35
 // cycles each, a few hundred of them on the critical path).  Here the block stages those tables in
-// shared memory once, the warps read them with LDS, and because a block now holds 32 bodies it
-// also writes the TRANSPOSED transforms At[128-body block][J*12][128] that the fused blend+skinning
-// kernel reads (lane = body -> one 128-byte line per component), so no separate transposition pass.
+// shared memory once and the warps read them with LDS.  It also writes the joint-major transform
+// copy At[128-body block][J][128][12] that the fused blend+skinning kernel reads (a warp's 32 bodies
+// are 1,536 contiguous bytes per joint), so there is no separate re-blocking pass.
 // ------------------------------------------------------------------------------------------
 constexpr int kPoseBlockWarps = 32;
 
@@ -580,29 +580,28 @@ pose_forward_block_kernel(const ModelDev m, const PoseFwdArgs a) {
       g1.w -= g1.x * Jr[s][0] + g1.y * Jr[s][1] + g1.z * Jr[s][2];
       g2.w -= g2.x * Jr[s][0] + g2.y * Jr[s][1] + g2.z * Jr[s][2];
       if (!live) g0 = g1 = g2 = make_float4(0.f, 0.f, 0.f, 0.f);
-      G4[0] = g0; G4[1] = g1; G4[2] = g2;
       if (a.A && live) {
         float4* dst = reinterpret_cast<float4*>(a.A + ((size_t)b * m.J + j) * 12);
         dst[0] = g0; dst[1] = g1; dst[2] = g2;
       }
+      G4[0] = g0; G4[1] = g1; G4[2] = g2;
     }
   }
-  // ---- transposed transforms for the fused kernel: warp w writes rows w, w+32, ... ; lane = body
+  // ---- joint-major copy for the fused kernel: warp w writes joints w, w + 32; lane = body, so a
+  // joint's 32 x 48 bytes leave as one contiguous 1,536-byte run (transl folded into the translation
+  // column; bodies past the batch, up to the 256-body block, are zero transforms)
   if (a.At != nullptr) {
     __syncthreads();
-    const int JC = m.J * 12;
-    const int bb = blockIdx.x * kPoseBlockWarps + lane;            // body this lane writes
+    const int bb = blockIdx.x * kPoseBlockWarps + lane;
     const float* Gl = pose_smem + lane * L.per_warp + max(m.Kpad, 32);
     float ttx = 0.f, tty = 0.f, ttz = 0.f;
     if (a.transl && bb < a.B) { ttx = a.transl[3 * bb]; tty = a.transl[3 * bb + 1]; ttz = a.transl[3 * bb + 2]; }
-    float* dst = a.At + (size_t)(bb >> 7) * JC * 128 + (bb & 127);
-    for (int row = warp; row < JC; row += kPoseBlockWarps) {
-      float v = Gl[row];
-      if ((row & 3) == 3 && bb < a.B) {
-        const int ax = (row % 12) >> 2;
-        v += ax == 0 ? ttx : (ax == 1 ? tty : ttz);
-      }
-      dst[(size_t)row * 128] = v;
+    for (int j = warp; j < m.J; j += kPoseBlockWarps) {
+      const float4* G4 = reinterpret_cast<const float4*>(Gl + j * 12);
+      float4 g0 = G4[0], g1 = G4[1], g2 = G4[2];
+      g0.w += ttx; g1.w += tty; g2.w += ttz;
+      float4* dst = reinterpret_cast<float4*>(a.At + (((size_t)(bb >> 7) * m.J + j) * 128 + (bb & 127)) * 12);
+      dst[0] = g0; dst[1] = g1; dst[2] = g2;
     }
   }
 }

@@ -871,8 +871,8 @@ static int launch_fused(const smplk_model* mdl, int rows, float* F_hi, float* F_
   const int rows_pad = round_up(rows, 2 * kBlendBM);
   if (A != nullptr) {                        // null: the pose kernel already wrote At
     ProfScope prof(mdl, st, SMPLK_PROF_TRANSPOSE);
-    dim3 grid((JC + 31) / 32, rows_pad / 32);
-    transpose_transforms_kernel<<<grid, 256, 0, st>>>(rows, JC, A, transl, At);
+    const int n4 = rows_pad * d.J * 3;
+    transpose_transforms_kernel<<<(n4 + 255) / 256, 256, 0, st>>>(rows, rows_pad, d.J, A, transl, At);
     LAUNCH_CHECK("transpose_transforms_kernel");
   }
   CUtensorMap tm_fhi, tm_flo;
