@@ -449,7 +449,28 @@ struct PoseBwdArgs {
 };
 
 // smem floats per warp of pose_backward_kernel: world G, local L, dG (12 each), dR (9), dJ, dfull (3 each)
-__host__ __device__ inline int pose_bwd_smem_floats(int J) { return J * 51; }
+// + the summed blend-GEMM gradient row (Kpad)
+__host__ __device__ inline int pose_bwd_smem_floats(int J, int Kpad) { return J * 51 + Kpad; }
+
+// Split-K partials of the backward blend GEMM, d_feat[sp][row][k], summed into split 0 (in place).
+// One thread per (row, k): the loads of a thread are independent and coalesced across the warp, so
+// the up-to-74 partials of a small batch cost a few L2 round trips instead of 74 dependent ones in
+// the pose kernel's single warp per body.
+__global__ void __launch_bounds__(256)
+reduce_splits_kernel(int n, int splits, size_t stride, float* __restrict__ d_feat) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int sp = 0;
+  for (; sp + 4 <= splits; sp += 4) {
+    a0 += d_feat[(size_t)sp * stride + i];
+    a1 += d_feat[(size_t)(sp + 1) * stride + i];
+    a2 += d_feat[(size_t)(sp + 2) * stride + i];
+    a3 += d_feat[(size_t)(sp + 3) * stride + i];
+  }
+  for (; sp < splits; ++sp) a0 += d_feat[(size_t)sp * stride + i];
+  d_feat[i] = (a0 + a1) + (a2 + a3);
+}
 
 template <int SLOTS>
 __global__ void __launch_bounds__(kPoseWarps * 32)
@@ -458,7 +479,7 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kPoseWarps + warp;
   if (b >= a.B) return;
-  float* Gw = pb_smem + warp * pose_bwd_smem_floats(m.J);   // [J][12] world transforms
+  float* Gw = pb_smem + warp * pose_bwd_smem_floats(m.J, m.Kpad);   // [J][12] world transforms
   float* Lc = Gw + m.J * 12;                                // [J][12] local [R | Jrel]
   float* dG = Lc + m.J * 12;                                // [J][12]
   float* dRs = dG + m.J * 12;                               // [J][9]
@@ -610,17 +631,27 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
     for (int q = 0; q < 9; ++q) dRl[s][q] = (j < m.J) ? dRs[j * 9 + q] : 0.f;
   }
 
-  // ---- pose-feature gradient from the blend GEMM, Rodrigues backward
+  // ---- pose-feature gradient from the blend GEMM (split-K partials already summed into the first
+  // split's rows by reduce_splits_kernel): stage the body's row in smem with coalesced loads
+  float* dfeat_sum = dfull + 3 * m.J;
+  if (a.d_feat != nullptr) {
+    __syncwarp();
+    const float* f = a.d_feat + (size_t)b * m.Kpad;
+    for (int k = lane; k < m.P + m.NB; k += 32) {
+      float acc = f[k];
+      for (int sp = 1; sp < a.feat_splits; ++sp) acc += f[(size_t)sp * a.feat_split_stride + k];
+      dfeat_sum[k] = acc;
+    }
+    __syncwarp();
+  }
+  // ---- Rodrigues backward
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
     const int j = lane + 32 * s;
     if (j < m.J) {
       if (a.d_feat != nullptr && j >= 1) {
-        for (int sp = 0; sp < a.feat_splits; ++sp) {
-          const float* f = a.d_feat + (size_t)sp * a.feat_split_stride + (size_t)b * m.Kpad + 9 * (j - 1);
 #pragma unroll
-          for (int i = 0; i < 9; ++i) dRl[s][i] += f[i];
-        }
+        for (int i = 0; i < 9; ++i) dRl[s][i] += dfeat_sum[9 * (j - 1) + i];
       }
       float dr[3];
       rodrigues_backward(rv[s], dRl[s], dr);
@@ -656,9 +687,7 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
     for (int i = lane; i < m.NB; i += 32) {
       float acc = 0.f;
       for (int q = 0; q < 3 * m.J; ++q) acc = fmaf(dJ[q], m.J_shapedirs[(size_t)q * m.NB + i], acc);
-      if (a.d_feat != nullptr)
-        for (int sp = 0; sp < a.feat_splits; ++sp)
-          acc += a.d_feat[(size_t)sp * a.feat_split_stride + (size_t)b * m.Kpad + m.P + i];
+      if (a.d_feat != nullptr) acc += dfeat_sum[m.P + i];
       if (a.betas_B == 1) atomicAdd(&a.d_betas[i], acc);
       else a.d_betas[(size_t)b * m.NB + i] = acc;
     }

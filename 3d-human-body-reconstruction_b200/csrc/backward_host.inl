@@ -172,6 +172,12 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
   pb.dA = dA; pb.d_joints = a->d_joints; pb.joints_ld = joints_ld;
   pb.d_feat = blend_bwd ? dfeat : nullptr;
   pb.feat_splits = L.splits; pb.feat_split_stride = (size_t)L.mpad * d.Kpad;
+  if (pb.d_feat != nullptr && L.splits > 1) {      // sum the split-K partials in parallel, in place
+    const int n = B * d.Kpad;
+    reduce_splits_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, L.splits, pb.feat_split_stride, dfeat);
+    LAUNCH_CHECK("reduce_splits_kernel");
+    pb.feat_splits = 1;
+  }
   pb.dtr_verts = dtr;
   pb.d_betas = d.NB > 0 ? a->d_betas : nullptr;
   pb.d_pose = a->d_pose; pb.d_pca_l = a->d_hand_pca_l; pb.d_pca_r = a->d_hand_pca_r;
@@ -179,7 +185,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
   if (pb.d_betas && pb.betas_B == 1)
     CUDA_TRY(cudaMemsetAsync(a->d_betas, 0, (size_t)d.NB * sizeof(float), st));
   const int blocks = (B + kPoseWarps - 1) / kPoseWarps;
-  const size_t smem = (size_t)kPoseWarps * pose_bwd_smem_floats(d.J) * sizeof(float);
+  const size_t smem = (size_t)kPoseWarps * pose_bwd_smem_floats(d.J, d.Kpad) * sizeof(float);
   { ProfScope prof(model, st, SMPLK_PROF_POSE_BWD);
   if (d.J <= 32) pose_backward_kernel<1><<<blocks, kPoseWarps * 32, smem, st>>>(d, pb);
   else pose_backward_kernel<2><<<blocks, kPoseWarps * 32, smem, st>>>(d, pb); }

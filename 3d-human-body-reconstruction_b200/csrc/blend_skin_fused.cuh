@@ -39,6 +39,9 @@ namespace smplk {
 #ifndef SMPLK_FZ_BACKOFF_NS
 #define SMPLK_FZ_BACKOFF_NS 40
 #endif
+#ifndef SMPLK_FZ_EPI_BACKOFF_NS
+#define SMPLK_FZ_EPI_BACKOFF_NS 20
+#endif
 #ifndef SMPLK_FZ_ROW_BYTES
 #define SMPLK_FZ_ROW_BYTES 64
 #endif
@@ -376,7 +379,7 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
       __syncwarp();
       [[maybe_unused]] const bool dbg_on = args.dbg && blockIdx.x == 0 && lane == 0 && it < kFzDbgTiles;
       FZ_STAMP(dbg_on, &args.dbg[(warp * kFzDbgTiles + it) * 4 + 0]);
-      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::mbar_wait_backoff(&tmem_full[acc], acc_phase, SMPLK_FZ_EPI_BACKOFF_NS);
       ptx::tcgen05_fence_after();
       FZ_STAMP(dbg_on, &args.dbg[(warp * kFzDbgTiles + it) * 4 + 1]);
 

@@ -628,8 +628,8 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
       CUDA_TRY(cudaFuncSetAttribute(pose_forward_block_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
       CUDA_TRY(cudaFuncSetAttribute(pose_forward_block_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
     }
-    CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(skin_backward_grouped_kernel<kSkinBwdStages>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   }
@@ -777,7 +777,11 @@ static BlendPath choose_blend(const smplk_model* mdl, int rows, uint32_t flags) 
   if (flags & SMPLK_FLAG_BLEND_SIMT) return BLEND_SIMT;
   if (flags & SMPLK_FLAG_BLEND_TF32) return BLEND_TF32;
   if (flags & SMPLK_FLAG_BLEND_TCGEN05) return mdl->default_tc;
-  return rows >= 32 ? mdl->default_tc : BLEND_SIMT;
+  // Tensor cores at every batch size: even a single body (127 of 128 tile rows are padding) takes
+  // 19 us on the tcgen05 kernel against 60-135 us for the SIMT kernel, whose 81 blocks cannot pull the
+  // 40 MB operand fast enough -- and batch 1 is what the reference's fitting loop runs
+  // (lib/Gen_SMPLH/fit_single_frame.py:97).  SMPLK_FLAG_BLEND_SIMT still selects the exact-fp32 kernel.
+  return mdl->has_tma ? mdl->default_tc : BLEND_SIMT;
 }
 
 static int launch_blend(const smplk_model* mdl, int rows, BlendPath path, float* F_hi, float* F_lo,
@@ -867,7 +871,6 @@ static bool fused_applies(const smplk_model* mdl, int rows, BlendPath path, uint
 static int launch_fused(const smplk_model* mdl, int rows, float* F_hi, float* F_lo, const float* A,
                         float* At, const float* transl, float* out, cudaStream_t st) {
   const ModelDev& d = mdl->d;
-  const int JC = d.J * 12;
   const int rows_pad = round_up(rows, 2 * kBlendBM);
   if (A != nullptr) {                        // null: the pose kernel already wrote At
     ProfScope prof(mdl, st, SMPLK_PROF_TRANSPOSE);

@@ -368,12 +368,42 @@ def main():
             torch.cuda.synchronize(dev)
             return f0.elapsed_time(f1) / nfb
         fb_ms, fb_torch_ms = time_fb(True), time_fb(False)
+        # the same step captured once into a CUDA graph and replayed (the ~10 short kernels of a
+        # batch-1024 step are launch-bound from Python)
+        fb_graph_ms = None
+        try:
+            gstream = torch.cuda.Stream(dev)
+            gstream.wait_stream(stream)
+            with torch.cuda.stream(gstream):
+                for _ in range(3):
+                    fb_step(True)
+            stream.wait_stream(gstream)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                fb_step(True)
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize(dev)
+            nfb = max(5, min(args.steps, 30))
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            for _ in range(nfb):
+                graph.replay()
+            f1.record(stream)
+            torch.cuda.synchronize(dev)
+            fb_graph_ms = f0.elapsed_time(f1) / nfb
+        except Exception as e:   # graph capture is an optimisation of the harness, not of the path
+            fb_graph_ms = None
+            sys.stderr.write("fwd+bwd CUDA-graph variant skipped: %r\n" % (e,))
         extras["fwd_bwd"] = {"metric": "smplh_fitting_steps_meshes_per_sec_fwd_bwd", "batch": Bb,
                              "value": world * Bb / (fb_ms * 1e-3), "unit": UNIT, "ms_per_step": fb_ms,
                              "loss": "sum ||V - V*||^2 with the fused loss+gradient kernel (smplk.vertex_l2_loss), "
                                      "grads w.r.t. betas, pose, transl through the SMPLH autograd.Function",
                              "ms_per_step_torch_loss": fb_torch_ms,
-                             "value_torch_loss": world * Bb / (fb_torch_ms * 1e-3)}
+                             "value_torch_loss": world * Bb / (fb_torch_ms * 1e-3),
+                             "ms_per_step_cuda_graph": fb_graph_ms,
+                             "value_cuda_graph": (world * Bb / (fb_graph_ms * 1e-3)) if fb_graph_ms else None}
 
         # ---- e2e: C-ABI host-buffer call (pinned host memory, H2D + D2H inside the timed region)
         lib = smplk.load()
