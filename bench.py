@@ -405,6 +405,49 @@ def main():
                              "ms_per_step_cuda_graph": fb_graph_ms,
                              "value_cuda_graph": (world * Bb / (fb_graph_ms * 1e-3)) if fb_graph_ms else None}
 
+        # ---- batch-1 fitting closure (what lib/Gen_SMPLH/fit_single_frame.py runs: batch_size == 1)
+        try:
+            b1, p1, t1 = (torch.tensor(x, device=dev, requires_grad=True) for x in synthetic.make_inputs(model, 1, seed=5))
+            tgt1 = torch.randn(1, dm.V, 3, device=dev)
+
+            def closure():
+                for t_ in (b1, p1, t1):
+                    t_.grad = None
+                v, _, _, _ = body_model_apply(dm, b1, p1, transl=t1)
+                vertex_l2_loss(v, tgt1).sum().backward()
+
+            def timeit(fn, n=50):
+                for _ in range(5):
+                    fn()
+                torch.cuda.synchronize(dev)
+                q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                q0.record(stream)
+                for _ in range(n):
+                    fn()
+                q1.record(stream)
+                torch.cuda.synchronize(dev)
+                return q0.elapsed_time(q1) / n
+            with torch.no_grad():
+                fwd1 = timeit(lambda: body_model_apply(dm, b1.detach(), p1.detach(), transl=t1.detach()))
+            eager1 = timeit(closure)
+            gs = torch.cuda.Stream(dev)
+            gs.wait_stream(stream)
+            with torch.cuda.stream(gs):
+                for _ in range(3):
+                    closure()
+            stream.wait_stream(gs)
+            torch.cuda.synchronize(dev)
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                closure()
+            graph1 = timeit(g1.replay)
+            extras["batch1_fitting_closure"] = {
+                "forward_ms": fwd1, "fwd_bwd_ms_eager": eager1, "fwd_bwd_ms_cuda_graph": graph1,
+                "note": "one body: forward, vertex-L2 loss, backward w.r.t. betas / pose / transl; eager = "
+                        "launched from Python (launch-bound), cuda_graph = the same closure captured once and replayed"}
+        except Exception as e:
+            sys.stderr.write("batch-1 closure timing skipped: %r\n" % (e,))
+
         # ---- e2e: C-ABI host-buffer call (pinned host memory, H2D + D2H inside the timed region)
         lib = smplk.load()
         hb, hp, ht = (torch.tensor(x).pin_memory() for x in synthetic.make_inputs(model, B, seed=7))
