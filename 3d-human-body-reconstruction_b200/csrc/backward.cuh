@@ -75,6 +75,10 @@ struct SkinBwdArgs {
   const float* A;        // (B,J,12)
   float* dvp_hi;         // (B,Npad) tf32-rounded d_v_posed
   float* dvp_lo;         // (B,Npad) residual
+  // fp16 two-term split output (grouped kernel): rows scaled per body by the power of two row_scale[b]
+  __half* h_hi;          // (B,Npad) or null
+  __half* h_lo;
+  const float* row_scale;   // (B) written by dA_kernel
 };
 
 template <bool kReg4>
@@ -178,7 +182,7 @@ skin_backward_kernel(const ModelDev m, const SkinBwdArgs a) {
 // padding of the backward GEMM).
 constexpr int kSkinBwdStages = 3;
 
-template <int kStages>
+template <int kStages, bool kHalfOut>
 __global__ void __launch_bounds__(kGrpThreads, 2)
 skin_backward_grouped_kernel(const ModelDev m, const SkinBwdArgs a) {
   extern __shared__ __align__(16) float sbg_smem[];
@@ -280,6 +284,39 @@ skin_backward_grouped_kernel(const ModelDev m, const SkinBwdArgs a) {
       }
     }
     float o[12] = {ox[0], oy[0], oz[0], ox[1], oy[1], oz[1], ox[2], oy[2], oz[2], ox[3], oy[3], oz[3]};
+    if (kHalfOut) {
+      // fp16 two-term split of the row scaled into the fp16 range (|d_v_posed| <= sqrt(3) max|g|);
+      // a thread's 12 outputs are 24 contiguous bytes per term and the warp's 768 bytes are
+      // contiguous, so they leave straight from registers as 8-byte stores
+      const float sc = a.row_scale[b];
+      uint2 hq[3], lq[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        __half hh[4], ll[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int idx = 4 * i + k;
+          const bool ok = 4 * g + idx / 3 < m.V;
+          const float x = ok ? o[idx] * sc : 0.f;
+          hh[k] = __float2half_rn(x);
+          ll[k] = __float2half_rn(x - __half2float(hh[k]));
+        }
+        const __half2 h01 = __halves2half2(hh[0], hh[1]), h23 = __halves2half2(hh[2], hh[3]);
+        const __half2 l01 = __halves2half2(ll[0], ll[1]), l23 = __halves2half2(ll[2], ll[3]);
+        hq[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        lq[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+      }
+      __syncwarp();                                  // everyone has read its inputs from the slot
+      uint2* gh = reinterpret_cast<uint2*>(a.h_hi + (size_t)b * m.Npad + wf0) + 3 * lane;
+      uint2* gl = reinterpret_cast<uint2*>(a.h_lo + (size_t)b * m.Npad + wf0) + 3 * lane;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (12 * lane + 4 * i + 4 <= n_out) {
+          gh[i] = hq[i];
+          gl[i] = lq[i];
+        }
+      }
+    } else {
     float h[12], l[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
@@ -309,6 +346,7 @@ skin_backward_grouped_kernel(const ModelDev m, const SkinBwdArgs a) {
       }
     }
     __syncwarp();
+    }   // !kHalfOut
   }
 }
 
@@ -321,6 +359,8 @@ struct DAArgs {
   size_t vsrc_stride;
   float* dA;              // (B,J,12)
   float* dtr;             // (B,3)
+  float* row_scale;       // (B) or null: power of two s with sqrt(3) max|g[b]| * s in [2^12, 2^13] (fp16 backward GEMM)
+  float* row_scale_inv;   // (B) or null: 1 / s
 };
 
 #ifndef SMPLK_DA_THREADS
@@ -329,7 +369,7 @@ struct DAArgs {
 constexpr int kDAThreads = SMPLK_DA_THREADS;   // one body per block; fewer, fatter blocks keep a body's rows in L1
 
 __global__ void __launch_bounds__(kDAThreads) dA_kernel(const ModelDev m, const DAArgs a) {
-  __shared__ float red[3][kDAThreads / 32];
+  __shared__ float red[4][kDAThreads / 32];
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* g = a.dverts + (size_t)b * m.V * 3;
@@ -382,9 +422,15 @@ __global__ void __launch_bounds__(kDAThreads) dA_kernel(const ModelDev m, const 
   }
   // translation gradient: plain sum of the vertex gradients
   float s[3] = {0.f, 0.f, 0.f};
+  float gmax = 0.f;
   for (int v = threadIdx.x; v < m.V; v += kDAThreads) {
-    s[0] += g[3 * v + 0]; s[1] += g[3 * v + 1]; s[2] += g[3 * v + 2];
+    const float g0 = g[3 * v + 0], g1 = g[3 * v + 1], g2 = g[3 * v + 2];
+    s[0] += g0; s[1] += g1; s[2] += g2;
+    gmax = fmaxf(gmax, fmaxf(fabsf(g0), fmaxf(fabsf(g1), fabsf(g2))));
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+  if (lane == 0) red[3][warp] = gmax;
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
 #pragma unroll
@@ -396,6 +442,18 @@ __global__ void __launch_bounds__(kDAThreads) dA_kernel(const ModelDev m, const 
     float t = 0.f;
     for (int w = 0; w < kDAThreads / 32; ++w) t += red[threadIdx.x][w];
     a.dtr[3 * b + threadIdx.x] = t;
+  }
+  if (threadIdx.x == 3 && a.row_scale != nullptr) {
+    float mx = 0.f;
+    for (int w = 0; w < kDAThreads / 32; ++w) mx = fmaxf(mx, red[3][w]);
+    float sc = 1.f;
+    if (mx > 0.f && isfinite(mx)) {
+      int e;
+      frexpf(mx * 1.7320508f, &e);          // mx * sqrt(3) in [2^(e-1), 2^e)
+      sc = ldexpf(1.f, max(-100, min(100, 13 - e)));
+    }
+    a.row_scale[b] = sc;
+    a.row_scale_inv[b] = 1.f / sc;
   }
 }
 

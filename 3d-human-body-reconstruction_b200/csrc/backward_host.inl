@@ -2,8 +2,15 @@
 
 struct BwdLayout {
   int m_blocks, n_blocks, k_blocks, splits, kbps, mpad;
-  size_t off_dverts, off_dvp_hi, off_dvp_lo, off_dA, off_dtr, off_dfeat, total;
+  bool f16;           // backward GEMM on fp16 two-term-split operands (else 3xTF32)
+  size_t off_dverts, off_dvp_hi, off_dvp_lo, off_dA, off_dtr, off_scale, off_dfeat, total;
 };
+
+// fp16 operands need the grouped skinning-backward kernel (it writes the scaled half rows)
+static bool bwd_uses_f16(const smplk_model* mdl) {
+  const ModelDev& d = mdl->d;
+  return mdl->bwd_f16 && !d.lbs_only && d.grp_ok && !mdl->force_skin_v1 && ((d.V * 3) % 2 == 0);
+}
 
 static BwdLayout bwd_layout(const smplk_model* mdl, int batch) {
   const ModelDev& d = mdl->d;
@@ -17,9 +24,11 @@ static BwdLayout bwd_layout(const smplk_model* mdl, int batch) {
   L.off_dverts = off; off += align_up((size_t)batch * d.V * 3 * sizeof(float), 1024);
   L.off_dA = off;     off += align_up((size_t)batch * d.J * 12 * sizeof(float), 1024);
   L.off_dtr = off;    off += align_up((size_t)batch * 3 * sizeof(float), 1024);
+  L.off_scale = off;  off += align_up((size_t)batch * 2 * sizeof(float), 1024);
+  L.f16 = bwd_uses_f16(mdl);
   if (!d.lbs_only) {
     L.n_blocks = (d.Kpad + kBlendBN - 1) / kBlendBN;
-    L.k_blocks = d.Npad / ((pair ? 128 : kRowBytes) / 4);
+    L.k_blocks = d.Npad / ((pair ? 128 : kRowBytes) / (L.f16 ? 2 : 4));
     int splits = std::max(1, (pair ? mdl->num_sms / 2 : mdl->num_sms) / (L.m_blocks * L.n_blocks));
     splits = std::min(splits, L.k_blocks);
     L.kbps = (L.k_blocks + splits - 1) / splits;
@@ -63,6 +72,8 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
   float* dverts_eff = reinterpret_cast<float*>(sc + L.off_dverts);
   float* dA = reinterpret_cast<float*>(sc + L.off_dA);
   float* dtr = reinterpret_cast<float*>(sc + L.off_dtr);
+  float* row_scale = reinterpret_cast<float*>(sc + L.off_scale);
+  float* row_scale_inv = row_scale + B;
   float* dvp_hi = reinterpret_cast<float*>(sc + L.off_dvp_hi);
   float* dvp_lo = reinterpret_cast<float*>(sc + L.off_dvp_lo);
   float* dfeat = reinterpret_cast<float*>(sc + L.off_dfeat);
@@ -91,6 +102,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     da.vsrc = d.lbs_only ? d.bias : v_posed;
     da.vsrc_stride = d.lbs_only ? 0 : (size_t)d.Npad;
     da.dA = dA; da.dtr = dtr;
+    da.row_scale = L.f16 ? row_scale : nullptr; da.row_scale_inv = L.f16 ? row_scale_inv : nullptr;
     { ProfScope prof(model, st, SMPLK_PROF_DA);
     dA_kernel<<<B, kDAThreads, 0, st>>>(d, da); }
     LAUNCH_CHECK("dA_kernel");
@@ -104,6 +116,9 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     if (!model->has_tma) return fail(SMPLK_E_DEVICE, "tcgen05 path unavailable");
     SkinBwdArgs sb;
     sb.B = B; sb.dverts = dverts; sb.A = A; sb.dvp_hi = dvp_hi; sb.dvp_lo = dvp_lo;
+    sb.h_hi = reinterpret_cast<__half*>(dvp_hi); sb.h_lo = reinterpret_cast<__half*>(dvp_lo);
+    sb.row_scale = row_scale;
+    const bool f16 = L.f16;
     const int tiles = (d.V + kSkinTileVerts - 1) / kSkinTileVerts;
     const bool grouped = d.grp_ok && !model->force_skin_v1 && ((d.V * 3) % 2 == 0);
     if (grouped) {
@@ -114,7 +129,8 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
       dim3 grid(tiles, (B + bpb - 1) / bpb);
       const size_t smem = (size_t)((kS + 1) * kSkinTileVerts * 3 + 2 * kGrpABodies * grp_a_pad(d.J)) * sizeof(float);
       ProfScope prof(model, st, SMPLK_PROF_SKIN_BWD);
-      skin_backward_grouped_kernel<kS><<<grid, kGrpThreads, smem, st>>>(d, sb);
+      if (f16) skin_backward_grouped_kernel<kS, true><<<grid, kGrpThreads, smem, st>>>(d, sb);
+      else skin_backward_grouped_kernel<kS, false><<<grid, kGrpThreads, smem, st>>>(d, sb);
       LAUNCH_CHECK("skin_backward_grouped_kernel");
     } else {
       int bpb = 16;
@@ -131,36 +147,46 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     CUtensorMap tm_ahi, tm_alo, tm_out;
     const bool pair = model->use_2cta && B > kBlendBM;
     if (pair) {
-      if (int r = make_operand_tmap_2cta(model, &tm_ahi, dvp_hi, d.Npad, B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, false)) return r;
-      if (int r = make_operand_tmap_2cta(model, &tm_alo, dvp_lo, d.Npad, B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, false)) return r;
+      if (int r = make_operand_tmap_2cta(model, &tm_ahi, dvp_hi, d.Npad, B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, f16)) return r;
+      if (int r = make_operand_tmap_2cta(model, &tm_alo, dvp_lo, d.Npad, B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, f16)) return r;
       if (int r = make_tmap_2d(model, &tm_out, dfeat, d.Kpad, (uint64_t)L.splits * L.mpad, kEpiCols, kBlendBM,
                                CU_TENSOR_MAP_L2_PROMOTION_NONE)) return r;
       BlendGemmArgs ga;
       ga.num_m_blocks = L.m_blocks; ga.num_n_blocks = L.n_blocks; ga.num_k_blocks = L.k_blocks;
       ga.num_splits = L.splits; ga.k_blocks_per_split = L.kbps; ga.out_rows_per_split = L.mpad;
-      ga.k_elems = d.Npad; ga.out_scale = 1.0f;
+      ga.k_elems = d.Npad; ga.out_scale = f16 ? 1.0f / d.pd_scale : 1.0f;
       ga.bias = nullptr;
+      ga.row_scale = f16 ? row_scale_inv : nullptr; ga.row_scale_rows = B;
       ga.out = dfeat; ga.out_ld = d.Kpad; ga.out_rows = L.splits * L.mpad; ga.out_cols = d.Kpad;
       const int tiles_g = L.m_blocks * L.n_blocks * L.splits;
       ProfScope prof(model, st, SMPLK_PROF_BLEND_BWD);
-      blend_tcgen05_2cta_kernel<false><<<2 * std::min(tiles_g, model->num_sms / 2), kGemmThreads, k2SmemAlloc, st>>>(
-          tm_ahi, tm_alo, model->tmap2_pdkn_hi, model->tmap2_pdkn_lo, tm_out, ga);
+      if (f16)
+        blend_tcgen05_2cta_kernel<true><<<2 * std::min(tiles_g, model->num_sms / 2), kGemmThreads, k2SmemAlloc, st>>>(
+            tm_ahi, tm_alo, model->tmap2_pdknh_hi, model->tmap2_pdknh_lo, tm_out, ga);
+      else
+        blend_tcgen05_2cta_kernel<false><<<2 * std::min(tiles_g, model->num_sms / 2), kGemmThreads, k2SmemAlloc, st>>>(
+            tm_ahi, tm_alo, model->tmap2_pdkn_hi, model->tmap2_pdkn_lo, tm_out, ga);
       LAUNCH_CHECK("blend_tcgen05_2cta_kernel(backward)");
     } else {
-    if (int r = make_operand_tmap(model, &tm_ahi, dvp_hi, d.Npad, B, kBlendBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, false)) return r;
-    if (int r = make_operand_tmap(model, &tm_alo, dvp_lo, d.Npad, B, kBlendBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, false)) return r;
+    if (int r = make_operand_tmap(model, &tm_ahi, dvp_hi, d.Npad, B, kBlendBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, f16)) return r;
+    if (int r = make_operand_tmap(model, &tm_alo, dvp_lo, d.Npad, B, kBlendBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, f16)) return r;
     if (int r = make_tmap_2d(model, &tm_out, dfeat, d.Kpad, (uint64_t)L.splits * L.mpad, kEpiCols, kBlendBM,
                              CU_TENSOR_MAP_L2_PROMOTION_NONE)) return r;
     BlendGemmArgs ga;
     ga.num_m_blocks = L.m_blocks; ga.num_n_blocks = L.n_blocks; ga.num_k_blocks = L.k_blocks;
     ga.num_splits = L.splits; ga.k_blocks_per_split = L.kbps; ga.out_rows_per_split = L.mpad;
-    ga.k_elems = d.Npad; ga.out_scale = 1.0f;
+    ga.k_elems = d.Npad; ga.out_scale = f16 ? 1.0f / d.pd_scale : 1.0f;
     ga.bias = nullptr;
+    ga.row_scale = f16 ? row_scale_inv : nullptr; ga.row_scale_rows = B;
     ga.out = dfeat; ga.out_ld = d.Kpad; ga.out_rows = L.splits * L.mpad; ga.out_cols = d.Kpad;
     const int tiles_g = L.m_blocks * L.n_blocks * L.splits;
     { ProfScope prof(model, st, SMPLK_PROF_BLEND_BWD);
-    blend_tcgen05_kernel<false><<<std::min(tiles_g, model->num_sms), kGemmThreads, kGemmSmemAlloc, st>>>(
-        tm_ahi, tm_alo, model->tmap_pdkn_hi, model->tmap_pdkn_lo, tm_out, ga); }
+    if (f16)
+      blend_tcgen05_kernel<true><<<std::min(tiles_g, model->num_sms), kGemmThreads, kGemmSmemAlloc, st>>>(
+          tm_ahi, tm_alo, model->tmap_pdknh_hi, model->tmap_pdknh_lo, tm_out, ga);
+    else
+      blend_tcgen05_kernel<false><<<std::min(tiles_g, model->num_sms), kGemmThreads, kGemmSmemAlloc, st>>>(
+          tm_ahi, tm_alo, model->tmap_pdkn_hi, model->tmap_pdkn_lo, tm_out, ga); }
     LAUNCH_CHECK("blend_tcgen05_kernel(backward)");
     }
   }

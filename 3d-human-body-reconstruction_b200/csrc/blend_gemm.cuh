@@ -54,6 +54,8 @@ struct BlendGemmArgs {
   int out_rows_per_split;  // output row offset per split (partials stacked along rows)
   int k_elems;             // contraction length in elements (multiple of the MMA K: 8 tf32 / 16 f16)
   float out_scale;         // accumulator scale applied in the epilogue (1/posedirs scale for f16)
+  const float* row_scale;  // [row_scale_rows] extra per-row scale (row = m block row, split independent), or null
+  int row_scale_rows;
   const float* bias;       // [num_n_blocks * 256] added in the epilogue, or null
   float* out;              // output matrix for the direct (register -> global) epilogue
   int out_ld;              // floats per output row
@@ -197,13 +199,14 @@ blend_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
     const int row = ewarp * 32 + lane;             // row of the 128-row tile == TMEM lane
     const int etid = threadIdx.x - 64;             // 0..127
     const bool store_thread = (etid == 0);
-    const float oscale = args.out_scale;
     int acc = 0;
     uint32_t acc_phase = 0;
     int ebuf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord tc = tile_coord(args, tile);
       const int m0 = tc.out_row0, n0 = tc.n0;
+      float oscale = args.out_scale;
+      if (args.row_scale != nullptr) oscale *= (tc.m0 + row < args.row_scale_rows) ? args.row_scale[tc.m0 + row] : 0.f;
       ptx::named_bar_sync(1, 128);                 // previous tile finished reading bias_s
       bias_s[etid] = args.bias ? args.bias[n0 + etid] : 0.f;
       bias_s[etid + 128] = args.bias ? args.bias[n0 + etid + 128] : 0.f;

@@ -171,13 +171,14 @@ blend_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
     const int row = ewarp * 32 + lane;
     const int etid = threadIdx.x - 64;
     const bool store_thread = (etid == 0);
-    const float oscale = args.out_scale;
     int acc = 0;
     uint32_t acc_phase = 0;
     int ebuf = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       int m0, n0, kb0, kb1, orow;
       coord(tile, m0, n0, kb0, kb1, orow);
+      float oscale = args.out_scale;
+      if (args.row_scale != nullptr) oscale *= (m0 + row < args.row_scale_rows) ? args.row_scale[m0 + row] : 0.f;
       ptx::named_bar_sync(1, 128);
       bias_s[etid] = args.bias ? args.bias[n0 + etid] : 0.f;
       bias_s[etid + 128] = args.bias ? args.bias[n0 + etid + 128] : 0.f;

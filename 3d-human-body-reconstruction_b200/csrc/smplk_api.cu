@@ -90,6 +90,8 @@ struct smplk_model {
   bool use_fused;       // SMPLK_FUSED=0 in the environment selects the two-kernel forward (A/B runs)
   bool use_pose_block;  // SMPLK_POSE_V1=1 selects the warp-per-body pose kernel + transposition pass
   CUtensorMap tmap_pdkn_hi, tmap_pdkn_lo;  // backward: B operand rows = blend features
+  CUtensorMap tmap_pdknh_hi, tmap_pdknh_lo, tmap2_pdknh_hi, tmap2_pdknh_lo;   // same, fp16 two-term split
+  bool bwd_f16;         // backward GEMM on fp16-split operands (SMPLK_BWD_TF32=1 keeps 3xTF32)
   // host staging for smplk_forward_host
   void* stage_dev;
   size_t stage_bytes;
@@ -310,6 +312,16 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
         }
       if (int r = upload(mdl, hh, &d.pd_nk_h_hi)) return r;
       if (int r = upload(mdl, hl, &d.pd_nk_h_lo)) return r;
+      {   // the same split, feature-major [Kpad][Npad]: B operand of the fp16 backward GEMM
+        std::vector<__half> th(nk, __float2half(0.f)), tl(nk, __float2half(0.f));
+        for (int n = 0; n < d.N; ++n)
+          for (int k = 0; k < d.K; ++k) {
+            th[(size_t)k * d.Npad + n] = hh[(size_t)n * d.Kpad + k];
+            tl[(size_t)k * d.Npad + n] = hl[(size_t)n * d.Kpad + k];
+          }
+        if (int r = upload(mdl, th, &d.pd_kn_h_hi)) return r;
+        if (int r = upload(mdl, tl, &d.pd_kn_h_lo)) return r;
+      }
       // same operand in the fused kernel's column layout: tile t = vertices [84 t, 84 t + 84),
       // row 256 t + c <-> flat coordinate 252 t + c (c < 252), rows 256 t + 252.. = 0
       d.fz_tiles = (V + kFzTileVerts - 1) / kFzTileVerts;
@@ -341,6 +353,7 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
   } else {
     d.pd_nk_hi = d.pd_nk_lo = d.pd_kn = d.pd_kn_hi = d.pd_kn_lo = nullptr;
     d.pd_nk_h_hi = d.pd_nk_h_lo = nullptr;
+    d.pd_kn_h_hi = d.pd_kn_h_lo = nullptr;
     d.pdf_h_hi = d.pdf_h_lo = nullptr;
     d.bias_f = nullptr;
     d.fz_tiles = 0;
@@ -599,6 +612,10 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdh_lo, d.pd_nk_h_lo, d.Kpad, d.Npad, p256, true)) return r;
     if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdkn_hi, d.pd_kn_hi, d.Npad, d.Kpad, p256, false)) return r;
     if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdkn_lo, d.pd_kn_lo, d.Npad, d.Kpad, p256, false)) return r;
+    if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdknh_hi, d.pd_kn_h_hi, d.Npad, d.Kpad, p256, true)) return r;
+    if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdknh_lo, d.pd_kn_h_lo, d.Npad, d.Kpad, p256, true)) return r;
+    if (int r = make_operand_tmap(mdl, &mdl->tmap_pdknh_hi, d.pd_kn_h_hi, d.Npad, d.Kpad, kBlendBN, p256, true)) return r;
+    if (int r = make_operand_tmap(mdl, &mdl->tmap_pdknh_lo, d.pd_kn_h_lo, d.Npad, d.Kpad, kBlendBN, p256, true)) return r;
     if (int r = make_operand_tmap_fused(mdl, &mdl->tmapf_pdh_hi, d.pdf_h_hi, d.Kpad, (uint64_t)d.fz_tiles * kBlendBN, p256)) return r;
     if (int r = make_operand_tmap_fused(mdl, &mdl->tmapf_pdh_lo, d.pdf_h_lo, d.Kpad, (uint64_t)d.fz_tiles * kBlendBN, p256)) return r;
     CUDA_TRY(cudaFuncSetAttribute(blend_skin_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFzSmemAlloc));
@@ -630,7 +647,9 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     }
     CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(skin_backward_grouped_kernel<kSkinBwdStages>,
+    CUDA_TRY(cudaFuncSetAttribute(skin_backward_grouped_kernel<kSkinBwdStages, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(skin_backward_grouped_kernel<kSkinBwdStages, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   }
   return 0;
@@ -672,6 +691,7 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   { const char* e = getenv("SMPLK_GEMM_1CTA"); mdl->use_2cta = !(e && e[0] == '1'); }
   { const char* e = getenv("SMPLK_FUSED"); mdl->use_fused = !(e && e[0] == '0'); }
   { const char* e = getenv("SMPLK_POSE_V1"); mdl->use_pose_block = !(e && e[0] == '1'); }
+  { const char* e = getenv("SMPLK_BWD_TF32"); mdl->bwd_f16 = !(e && e[0] == '1'); }
   { const char* e = getenv("SMPLK_BLEND"); mdl->default_tc = (e && strcmp(e, "tf32") == 0) ? BLEND_TF32 : BLEND_F16; }
   for (int i = 0; i < SMPLK_PROF_SLOTS; ++i) { mdl->prof_ms[i] = 0.0; mdl->prof_n[i] = 0; }
   if (prop.major != 10) {
@@ -808,6 +828,7 @@ static int launch_blend(const smplk_model* mdl, int rows, BlendPath path, float*
       ga.k_elems = d.Kpad;
       ga.out_scale = f16 ? 1.0f / d.pd_scale : 1.0f;
       ga.bias = d.bias;
+      ga.row_scale = nullptr; ga.row_scale_rows = 0;
       ga.out = v_posed; ga.out_ld = d.Npad; ga.out_rows = rows; ga.out_cols = d.Npad;
       const int tiles = ga.num_m_blocks * ga.num_n_blocks;
       const int grid = 2 * std::min(tiles, mdl->num_sms / 2);
@@ -838,6 +859,7 @@ static int launch_blend(const smplk_model* mdl, int rows, BlendPath path, float*
     ga.k_elems = d.Kpad;
     ga.out_scale = f16 ? 1.0f / d.pd_scale : 1.0f;
     ga.bias = d.bias;
+    ga.row_scale = nullptr; ga.row_scale_rows = 0;
     ga.out = v_posed; ga.out_ld = d.Npad; ga.out_rows = rows; ga.out_cols = d.Npad;
     const int tiles = ga.num_m_blocks * ga.num_n_blocks;
     const int grid = std::min(tiles, mdl->num_sms);

@@ -433,6 +433,37 @@ def test_backward_matches_autograd_oracle(dev, kind, B, pca, joint_w):
         assert rel <= GRAD_RTOL, (name, rel)
 
 
+def test_backward_is_safe_for_any_gradient_range(dev, smplh_model):
+    """The backward GEMM runs on fp16 two-term-split operands; every body's d_v_posed row is scaled
+    into the fp16 range by its own power of two (from max|d_verts| of that body).  Upstream gradients
+    spanning 16 decades across the batch, a body with zero gradient and one with a single non-zero
+    entry must all keep the 1e-4 relative bound PER BODY."""
+    m = smplh_model
+    dm = smplk.DeviceModel(m, device=0)
+    B = 140
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=31)
+    rng = np.random.default_rng(5)
+    scale = 10.0 ** rng.uniform(-8, 8, size=B)
+    scale[3] = 0.0
+    cot = rng.standard_normal((B, 6890, 3)) * scale[:, None, None]
+    cot[7] = 0.0
+    cot[7, 1234, 1] = 3e-5
+    tb, tp, tt = (_t(x, dev, True) for x in (betas, pose, transl))
+    v = body_model_apply(dm, tb, tp, transl=tt)[0]
+    (v * _t(cot, dev)).sum().backward()
+    ob, op_, ot = (torch.tensor(x, dtype=torch.float64, requires_grad=True) for x in (betas, pose, transl))
+    ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(ob, op_, ot)
+    (ref.vertices * torch.tensor(cot)).sum().backward()
+    for got, want, name in ((tb.grad, ob.grad, "betas"), (tp.grad, op_.grad, "pose"), (tt.grad, ot.grad, "transl")):
+        g = got.double().cpu()
+        assert torch.isfinite(g).all(), name
+        den = want.abs().amax(dim=1).clamp_min(1e-300)
+        rel = ((g - want).abs().amax(dim=1) / den)
+        rel[want.abs().amax(dim=1) == 0] = g.abs().amax(dim=1)[want.abs().amax(dim=1) == 0]
+        # fp32 cotangents: bodies whose scale underflows float32 are exactly zero on both sides
+        assert float(rel.max()) <= GRAD_RTOL, (name, int(rel.argmax()), float(rel.max()))
+
+
 def test_backward_broadcast_betas_and_module_autograd(dev, smplh_model):
     m = smplh_model
     mod = SMPLH(model=m, use_pca=True, num_pca_comps=12, batch_size=1, create_transl=False).to(dev)
