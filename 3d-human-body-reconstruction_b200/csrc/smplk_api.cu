@@ -631,26 +631,24 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     mdl->has_tma = true;
   }
   {
-    const int smem_g = (int)skin_grouped_smem_bytes(d.J);
-    CUDA_TRY(cudaFuncSetAttribute(skin_grouped_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g));
-    CUDA_TRY(cudaFuncSetAttribute(skin_grouped_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g));
-    CUDA_TRY(cudaFuncSetAttribute(skin_grouped8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)skin_grouped8_smem_bytes(d.J)));
-    CUDA_TRY(cudaFuncSetAttribute(skin_grouped8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)skin_grouped8_smem_bytes(d.J)));
-    CUDA_TRY(cudaFuncSetAttribute(skin_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)skin_tma_smem_bytes(d.J)));
-    if ((size_t)pose_block_layout(d).total * sizeof(float) <= 200 * 1024) {
-      const int pb = (int)(pose_block_layout(d).total * sizeof(float));
-      CUDA_TRY(cudaFuncSetAttribute(pose_forward_block_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
-      CUDA_TRY(cudaFuncSetAttribute(pose_forward_block_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
-    }
-    CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(skin_backward_grouped_kernel<kSkinBwdStages, false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(skin_backward_grouped_kernel<kSkinBwdStages, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    // Dynamic shared-memory limits are attributes of the KERNEL, not of a model handle: they are
+    // raised to the device's opt-in maximum once, so that a handle created later for a smaller
+    // skeleton cannot lower the limit a larger model's launches rely on.
+    int max_optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, mdl->device));
+    const cudaFuncAttribute attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    CUDA_TRY(cudaFuncSetAttribute(skin_grouped_kernel<true>, attr, max_optin));
+    CUDA_TRY(cudaFuncSetAttribute(skin_grouped_kernel<false>, attr, max_optin));
+    CUDA_TRY(cudaFuncSetAttribute(skin_grouped8_kernel<true>, attr, max_optin));
+    CUDA_TRY(cudaFuncSetAttribute(skin_grouped8_kernel<false>, attr, max_optin));
+    CUDA_TRY(cudaFuncSetAttribute(skin_tma_kernel, attr, max_optin));
+    CUDA_TRY(cudaFuncSetAttribute(pose_forward_block_kernel<1>, attr, max_optin));
+    CUDA_TRY(cudaFuncSetAttribute(pose_forward_block_kernel<2>, attr, max_optin));
+    CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<1>, attr, max_optin));
+    CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<2>, attr, max_optin));
+    CUDA_TRY(cudaFuncSetAttribute(skin_backward_grouped_kernel<kSkinBwdStages, false>, attr, max_optin));
+    CUDA_TRY(cudaFuncSetAttribute(skin_backward_grouped_kernel<kSkinBwdStages, true>, attr, max_optin));
+    CUDA_TRY(cudaFuncSetAttribute(divide_faces_kernel, attr, max_optin));
   }
   return 0;
 }
@@ -1249,7 +1247,11 @@ extern "C" int smplk_divide_faces(int32_t batch, int32_t num_verts, int32_t num_
   const size_t smem = ((size_t)2 * num_verts + 32) * sizeof(int);
   if (smem > 200 * 1024) return fail(SMPLK_E_SHAPE, "divide_faces: %d vertices exceed the shared-memory table", num_verts);
   CUDA_TRY(cudaSetDevice(device));
-  CUDA_TRY(cudaFuncSetAttribute(divide_faces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {   // smplk_divide_faces needs no model handle: raise the kernel's limit here (idempotent)
+    int max_optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CUDA_TRY(cudaFuncSetAttribute(divide_faces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+  }
   divide_faces_kernel<<<2 * batch, kDivThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       batch, num_verts, num_faces, faces, verts, faces_out, vidx_out, counts);
   LAUNCH_CHECK("divide_faces_kernel");

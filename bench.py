@@ -448,6 +448,26 @@ def main():
         except Exception as e:
             sys.stderr.write("batch-1 closure timing skipped: %r\n" % (e,))
 
+        # ---- BASELINE configs[0]: the numpy twin, one body per call, host numpy in / out (drop-in for
+        # models/smpl_np.py SMPLModel.set_params, which takes 16 ms per call on the build container's
+        # CPU: profiles/r01_reference_cpu_timing.json)
+        try:
+            from smplk import SMPLModel
+            twin = SMPLModel(synthetic.make_model("smpl", num_betas=10, seed=8), device=local)
+            rng1 = np.random.default_rng(0)
+            tp_, tb_, tt_ = rng1.standard_normal((24, 3)) * 0.3, rng1.standard_normal(10), rng1.standard_normal(3)
+            for _ in range(5):
+                twin.set_params(pose=tp_.copy(), beta=tb_.copy(), trans=tt_.copy())
+            t0 = time.perf_counter()
+            for _ in range(200):
+                twin.set_params(pose=tp_.copy(), beta=tb_.copy(), trans=tt_.copy())
+            extras["config1_numpy_twin_batch1"] = {
+                "ms_per_call": (time.perf_counter() - t0) / 200 * 1e3,
+                "note": "smplk.SMPLModel.set_params(pose, beta, trans) -> (6890,3) numpy array: H2D, pose kernel, "
+                        "tcgen05 blend, skinning, D2H, host wall clock"}
+        except Exception as e:
+            sys.stderr.write("config-1 twin timing skipped: %r\n" % (e,))
+
         # ---- e2e: C-ABI host-buffer call (pinned host memory, H2D + D2H inside the timed region)
         lib = smplk.load()
         hb, hp, ht = (torch.tensor(x).pin_memory() for x in synthetic.make_inputs(model, B, seed=7))

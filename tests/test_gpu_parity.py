@@ -433,6 +433,25 @@ def test_backward_matches_autograd_oracle(dev, kind, B, pca, joint_w):
         assert rel <= GRAD_RTOL, (name, rel)
 
 
+def test_handles_of_different_skeletons_coexist(dev, smplh_model, smpl_model):
+    """Dynamic shared-memory limits belong to the kernels, not to a handle: creating a handle for a
+    smaller skeleton (24 joints, 10 betas) after a larger one (52 joints, 16 betas) must not break
+    the larger model's launches (pose block kernel, grouped skinning, backward kernels)."""
+    dm_h = smplk.DeviceModel(smplh_model, device=0)
+    dm_s = smplk.DeviceModel(smpl_model, device=0)          # created second: smaller tables
+    rig = smplk.DeviceModel(synthetic.make_rigged_mesh(3000, seed=1), device=0, lbs_only=True)
+    for dm, m in ((dm_h, smplh_model), (dm_s, smpl_model), (dm_h, smplh_model)):
+        B = 200
+        betas, pose, transl = synthetic.make_inputs(m, B, seed=3)
+        tb, tp, tt = (_t(x, dev, True) for x in (betas, pose, transl))
+        v = body_model_apply(dm, tb, tp, transl=tt)[0]        # SAVE_FOR_BACKWARD: two-kernel forward
+        (v ** 2).sum().backward()
+        with torch.no_grad():
+            v2 = body_model_apply(dm, tb, tp, transl=tt)[0]   # fused forward
+        assert torch.isfinite(tp.grad).all() and _maxerr(v, v2) <= 3e-6
+    del rig
+
+
 def test_backward_is_safe_for_any_gradient_range(dev, smplh_model):
     """The backward GEMM runs on fp16 two-term-split operands; every body's d_v_posed row is scaled
     into the fp16 range by its own power of two (from max|d_verts| of that body).  Upstream gradients
