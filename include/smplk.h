@@ -67,8 +67,10 @@ typedef struct {
 /* Replaces: SMPLHModel.__init__ (models/smplh_np.py:7-37), SMPLModel.__init__
  * (models/smpl_np.py:123-156), RecoverModel.__init__ (lib/model2video.py:14-40) and the buffer
  * registration of upstream smplx.SMPL/SMPLH.__init__ behind models/smplh.py:16-24.
- * Packs the constants on `device`: posedirs|shapedirs as TF32 hi/lo operand pairs with their TMA
- * descriptors, sparse LBS weights, J_template / J_shapedirs, tree depth tables. */
+ * Packs the constants on `device`: posedirs|shapedirs as two-term-split GEMM operands (fp16 hi/lo,
+ * TF32 hi/lo; vertex-major and feature-major; also in the 84-vertex column tiling of the fused
+ * blend+skinning kernel) with their TMA descriptors, sparse LBS weights and the per-chunk joint
+ * tables of the fused epilogue, J_template / J_shapedirs, tree depth tables. */
 int smplk_model_create(const smplk_model_desc* desc, int device, smplk_model** out);
 int smplk_model_destroy(smplk_model* model);
 
