@@ -638,49 +638,64 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
   }
   __syncwarp();
 
-  // ---- chain backward, deepest level first:  G_j = G_p [R_j | Jrel_j]
-  for (int d = m.max_depth; d >= 1; --d) {
+  // ---- chain backward, deepest level first:  G_j = G_p [R_j | Jrel_j].  No atomics: a joint first
+  // gathers what its children (one level down, already final) send up, then derives its own dR and
+  // dJrel from the now-final dG_j (the shared-memory float atomics this replaces were CAS loops and
+  // 45 % of the kernel's stall samples).
+  for (int d = m.max_depth; d >= 0; --d) {
     const int l0 = m.level_start[d], l1 = m.level_start[d + 1];
     for (int i = l0 + lane; i < l1; i += 32) {
       const int j = m.order[i];
-      const int p = m.parents[j];
-      const float* Pm = Gw + p * 12;
-      const float* L = Lc + j * 12;
-      float dg[12];
+      const float* G = Gw + j * 12;
+      float dg[12], dj[3];
 #pragma unroll
       for (int q = 0; q < 12; ++q) dg[q] = dG[j * 12 + q];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
+      for (int r = 0; r < 3; ++r) dj[r] = dJ[j * 3 + r];
+      const int c0 = m.child_ptr[j], c1 = m.child_ptr[j + 1];
+      for (int n = c0; n < c1; ++n) {
+        const int c = m.child_idx[n];
+        const float* L = Lc + c * 12;
+        float cg[12];
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-          dRs[j * 9 + r * 3 + c] = Pm[0 * 4 + r] * dg[0 * 4 + c] + Pm[1 * 4 + r] * dg[1 * 4 + c] +
-                                   Pm[2 * 4 + r] * dg[2 * 4 + c];
-        const float djrel = Pm[0 * 4 + r] * dg[3] + Pm[1 * 4 + r] * dg[7] + Pm[2 * 4 + r] * dg[11];
-        dJ[j * 3 + r] += djrel;
-        atomicAdd(&dJ[p * 3 + r], -djrel);
-      }
+        for (int q = 0; q < 12; ++q) cg[q] = dG[c * 12 + q];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
+        for (int r = 0; r < 3; ++r) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const float v = dg[r * 4 + 0] * L[k * 4 + 0] + dg[r * 4 + 1] * L[k * 4 + 1] +
-                          dg[r * 4 + 2] * L[k * 4 + 2] + dg[r * 4 + 3] * L[k * 4 + 3];
-          atomicAdd(&dG[p * 12 + r * 4 + k], v);
+          for (int k = 0; k < 3; ++k)
+            dg[r * 4 + k] += cg[r * 4 + 0] * L[k * 4 + 0] + cg[r * 4 + 1] * L[k * 4 + 1] +
+                             cg[r * 4 + 2] * L[k * 4 + 2] + cg[r * 4 + 3] * L[k * 4 + 3];
+          dg[r * 4 + 3] += cg[r * 4 + 3];
+          dj[r] -= G[0 * 4 + r] * cg[3] + G[1 * 4 + r] * cg[7] + G[2 * 4 + r] * cg[11];   // Jrel_c = J_c - J_j
         }
-        atomicAdd(&dG[p * 12 + r * 4 + 3], dg[r * 4 + 3]);
       }
+      if (c1 > c0) {
+#pragma unroll
+        for (int q = 0; q < 12; ++q) dG[j * 12 + q] = dg[q];
+      }
+      if (d >= 1) {
+        const float* Pm = Gw + m.parents[j] * 12;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            dRs[j * 9 + r * 3 + c] = Pm[0 * 4 + r] * dg[0 * 4 + c] + Pm[1 * 4 + r] * dg[1 * 4 + c] +
+                                     Pm[2 * 4 + r] * dg[2 * 4 + c];
+          dj[r] += Pm[0 * 4 + r] * dg[3] + Pm[1 * 4 + r] * dg[7] + Pm[2 * 4 + r] * dg[11];
+        }
+      } else {          // root: L_0 = [R_0 | J_0]
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) dRs[j * 9 + r * 3 + c] = dg[r * 4 + c];
+          dj[r] += dg[r * 4 + 3];
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) dJ[j * 3 + r] = dj[r];
     }
     __syncwarp();
   }
-  if (lane == 0) {  // root: L_0 = [R_0 | J_0]
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) dRs[r * 3 + c] = dG[r * 4 + c];
-      dJ[r] += dG[r * 4 + 3];
-    }
-  }
-  __syncwarp();
   float dRl[SLOTS][9];
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
@@ -742,12 +757,24 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
   }
   // ---- d_betas = J_shapedirs^T dJ + (blend GEMM columns P..P+NB)
   if (a.d_betas) {
-    for (int i = lane; i < m.NB; i += 32) {
-      float acc = 0.f;
-      for (int q = 0; q < 3 * m.J; ++q) acc = fmaf(dJ[q], m.J_shapedirs[(size_t)q * m.NB + i], acc);
-      if (a.d_feat != nullptr) acc += dfeat_sum[m.P + i];
-      if (a.betas_B == 1) atomicAdd(&a.d_betas[i], acc);
-      else a.d_betas[(size_t)b * m.NB + i] = acc;
+    // 16 betas a round, the 3J joint coordinates split over the two half-warps, two sums per lane
+    const int nq = 3 * m.J;
+    for (int i0 = 0; i0 < m.NB; i0 += 16) {
+      const int i = i0 + (lane & 15), h = lane >> 4;
+      float acc0 = 0.f, acc1 = 0.f;
+      if (i < m.NB) {
+        for (int q = h; q < nq; q += 4) {
+          acc0 = fmaf(dJ[q], m.J_shapedirs[(size_t)q * m.NB + i], acc0);
+          if (q + 2 < nq) acc1 = fmaf(dJ[q + 2], m.J_shapedirs[(size_t)(q + 2) * m.NB + i], acc1);
+        }
+      }
+      float acc = acc0 + acc1;
+      acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+      if (h == 0 && i < m.NB) {
+        if (a.d_feat != nullptr) acc += dfeat_sum[m.P + i];
+        if (a.betas_B == 1) atomicAdd(&a.d_betas[i], acc);
+        else a.d_betas[(size_t)b * m.NB + i] = acc;
+      }
     }
   }
   if (a.d_transl && lane < 3) {

@@ -38,6 +38,8 @@ struct ModelDev {
   const float* J_shapedirs;   // [J][3][NB]
   const int* parents;         // [J]
   const int* depth;           // [J]
+  const int* child_ptr;       // [J+1] children of joint j: child_idx[child_ptr[j] .. child_ptr[j+1])
+  const int* child_idx;       // [J-1]
   const int* order;           // [J] joints sorted by depth (level-major)
   const int* level_start;     // [max_depth+2] offsets into `order`
   const uint32_t* skin_idx4;  // [V] four u8 joint ids (ell_k <= 4)

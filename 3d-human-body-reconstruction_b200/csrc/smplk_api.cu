@@ -231,6 +231,15 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
   if (int r = upload(mdl, parents, &d.parents)) return r;
   if (int r = upload(mdl, depth, &d.depth)) return r;
   {
+    std::vector<int> cptr(J + 1, 0), cidx(std::max(J - 1, 1), 0);
+    for (int j = 1; j < J; ++j) cptr[parents[j] + 1]++;
+    for (int j = 0; j < J; ++j) cptr[j + 1] += cptr[j];
+    std::vector<int> fill(cptr.begin(), cptr.end() - 1);
+    for (int j = 1; j < J; ++j) cidx[fill[parents[j]]++] = j;
+    if (int r = upload(mdl, cptr, &d.child_ptr)) return r;
+    if (int r = upload(mdl, cidx, &d.child_idx)) return r;
+  }
+  {
     std::vector<int> order, lstart(max_depth + 2, 0);
     for (int dd = 0; dd <= max_depth; ++dd) {
       lstart[dd] = (int)order.size();
