@@ -17,6 +17,9 @@ def __getattr__(name):  # torch-dependent modules load lazily
     if name in ("MeshTopology", "inverse_lbs", "inverse_joints", "transforms"):
         from . import mesh_ops
         return getattr(mesh_ops, name)
+    if name in ("SMPLifyLoss", "PerspectiveCamera", "GraphedClosure", "reprojection_loss", "fit_priors"):
+        from . import fitting
+        return getattr(fitting, name)
     if name in ("SMPLModel", "SMPLHModel", "RecoverModel"):
         from . import np_twins
         return getattr(np_twins, name)

@@ -160,3 +160,53 @@ class SMPLifyLoss(torch.nn.Module):
                          bending_prior_weight=self.bending_prior_weight,
                          hand_prior_weight=self.hand_prior_weight if self.use_hands else 0.0)
         return data.sum() + pri.sum()
+
+
+class GraphedClosure:
+    """A fitting closure captured once into a CUDA graph and replayed.
+
+    The reference's closure (lib/Gen_SMPLH/fitting.py:230-262, `create_fitting_closure`: zero_grad ->
+    body_model(...) -> loss -> backward, called by the optimiser at batch size 1,
+    fit_single_frame.py:97) is launch-bound on this path: ~15 short kernels, 0.24 ms from Python
+    against 0.13 ms of device time.  `GraphedClosure(fn, params)` runs `fn()` (which must build the
+    scalar loss from `params` and whatever static tensors it closes over) a few times eagerly,
+    captures `loss = fn(); loss.backward()` and afterwards replays that graph on every call:
+
+        closure = GraphedClosure(lambda: loss_fn(model(return_verts=True, return_full_pose=True), cam, gt, conf,
+                                                 joint_weights=jw), model.parameters())
+        for _ in range(n):
+            optimiser.step(closure)
+
+    Parameters are updated in place by the optimiser, so the replay sees their new values; the
+    gradients land in the same `.grad` tensors every time (re-attached on each call, so
+    `zero_grad(set_to_none=True)` between calls is harmless).  Inputs other than the parameters must be
+    changed in place (`tensor.copy_`), never rebound.  Shapes are frozen at capture."""
+
+    def __init__(self, fn, params, warmup=3):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("GraphedClosure needs at least one parameter that requires grad")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedClosure needs CUDA parameters (smplk has no CPU path)")
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, int(warmup))):
+                for p in self.params:
+                    p.grad = None
+                fn().backward()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for p in self.params:
+            p.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = fn()
+            self.loss.backward()
+        self.grads = [p.grad for p in self.params]
+
+    def __call__(self):
+        self.graph.replay()
+        for p, g in zip(self.params, self.grads):
+            p.grad = g
+        return self.loss
