@@ -374,7 +374,8 @@ __global__ void __launch_bounds__(kDAThreads) dA_kernel(const ModelDev m, const 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* g = a.dverts + (size_t)b * m.V * 3;
   const float* vp = a.vsrc + (size_t)b * a.vsrc_stride;
-  for (int j = warp; j < m.J; j += kDAThreads / 32) {
+  // gridDim.y blocks share a body's joints (small batches: one block per body leaves the GPU empty)
+  for (int j = warp + (kDAThreads / 32) * blockIdx.y; j < m.J; j += (kDAThreads / 32) * gridDim.y) {
     float acc[12];
 #pragma unroll
     for (int q = 0; q < 12; ++q) acc[q] = 0.f;
@@ -420,6 +421,7 @@ __global__ void __launch_bounds__(kDAThreads) dA_kernel(const ModelDev m, const 
       for (int q = 0; q < 12; ++q) o[q] = acc[q];
     }
   }
+  if (blockIdx.y != 0) return;
   // translation gradient: plain sum of the vertex gradients
   float s[3] = {0.f, 0.f, 0.f};
   float gmax = 0.f;

@@ -104,7 +104,9 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     da.dA = dA; da.dtr = dtr;
     da.row_scale = L.f16 ? row_scale : nullptr; da.row_scale_inv = L.f16 ? row_scale_inv : nullptr;
     { ProfScope prof(model, st, SMPLK_PROF_DA);
-    dA_kernel<<<B, kDAThreads, 0, st>>>(d, da); }
+    int jsplit = 1;
+    while (jsplit < 8 && (long)B * jsplit * 2 <= 4L * model->num_sms && jsplit * (kDAThreads / 32) < d.J) jsplit *= 2;
+    dA_kernel<<<dim3(B, jsplit), kDAThreads, 0, st>>>(d, da); }
     LAUNCH_CHECK("dA_kernel");
   } else {
     CUDA_TRY(cudaMemsetAsync(dA, 0, (size_t)B * d.J * 12 * sizeof(float), st));
