@@ -11,7 +11,8 @@ from ._lib import DeviceModel, build, load  # noqa: F401
 
 
 def __getattr__(name):  # torch-dependent modules load lazily
-    if name in ("SMPL", "SMPLH", "ModelOutput", "create", "body_model_apply", "load_model_file", "vertex_l2_loss"):
+    if name in ("SMPL", "SMPLH", "ModelOutput", "create", "body_model_apply", "load_model_file", "vertex_l2_loss",
+                "fit_vertex_l2"):
         from . import body_models
         return getattr(body_models, name)
     if name in ("MeshTopology", "inverse_lbs", "inverse_joints", "transforms"):

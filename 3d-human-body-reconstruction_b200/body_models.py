@@ -81,6 +81,9 @@ class _BodyModelFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             dm.forward(a)
         ctx.dm, ctx.flags = dm, flags
+        # outputs the loss never touched arrive as None in backward instead of zero tensors: a zero
+        # d_joints would send the backward through the vertex-pick scatter (a copy of d_verts)
+        ctx.set_materialize_grads(False)
         if needs_grad:
             ctx.ws = ws
             ctx.inputs = (betas_c, pose_c, pl, pr, tr)
@@ -157,6 +160,97 @@ def vertex_l2_loss(verts, target, scale=1.0):
     """Per-body squared-L2 vertex (or joint) data term, fused loss + gradient kernel.
     `vertex_l2_loss(v, t).sum().backward()` is the fitting step of BASELINE config 3."""
     return _VertexL2Fn.apply(verts, target, scale)
+
+
+class _FitVertexL2Fn(torch.autograd.Function):
+    """loss (B,) = scale * sum ||V(betas, pose, ...) - V*||^2 in one autograd node (BASELINE config 3).
+
+    Forward: body model with SAVE_FOR_BACKWARD, then the fused loss+gradient kernel; the vertices and
+    their gradient stay internal.  Backward: the body-model backward on the stored gradient; the
+    chain is linear in d_loss, so d_loss[b] scales the small per-body parameter gradients instead of
+    the (B,V,3) vertex gradient (the separate vertex_l2_loss node pays one more pass over it)."""
+
+    @staticmethod
+    def forward(ctx, dm, flags, scale, target, betas, pose, pca_l, pca_r, transl):
+        B = pose.shape[0]
+        dev = pose.device
+        flags |= _lib.FLAG_SAVE_FOR_BACKWARD
+        betas_c, pose_c = _prep(betas, dev), _prep(pose, dev)
+        pl, pr, tr = _prep(pca_l, dev), _prep(pca_r, dev), _prep(transl, dev)
+        tgt = _prep(target, dev)
+        if tuple(tgt.shape) != (B, dm.V, 3):
+            raise ValueError("target must be (%d, %d, 3), got %s" % (B, dm.V, tuple(tgt.shape)))
+        verts = torch.empty(B, dm.V, 3, device=dev, dtype=torch.float32)
+        ws_bytes = dm.workspace_bytes(B, flags)
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        a = _lib.ForwardArgs()
+        a.batch, a.flags = B, flags
+        a.betas, a.betas_batch = _ptr(betas_c), (betas_c.shape[0] if betas_c is not None else 1)
+        a.pose, a.hand_pca_l, a.hand_pca_r, a.transl = _ptr(pose_c), _ptr(pl), _ptr(pr), _ptr(tr)
+        a.verts = _ptr(verts)
+        a.workspace, a.workspace_bytes = _ptr(ws), ws_bytes
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        a.stream = stream
+        loss = torch.empty(B, device=dev, dtype=torch.float32)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            dm.forward(a)
+            # the gradient overwrites the vertices in place (element-wise kernel)
+            _lib.check(lib.smplk_vertex_l2(B, dm.V * 3, _ptr(verts), _ptr(tgt), float(scale), _ptr(verts),
+                                           _ptr(loss), dev.index or 0, stream))
+        ctx.dm, ctx.flags = dm, flags
+        ctx.ws, ctx.g = ws, verts
+        ctx.inputs = (betas_c, pose_c, pl, pr, tr)
+        return loss
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        if d_loss is None:
+            return (None,) * 9
+        dm = ctx.dm
+        betas, pose, pl, pr, tr = ctx.inputs
+        B = pose.shape[0]
+        dev = pose.device
+        need = ctx.needs_input_grad   # (dm, flags, scale, target, betas, pose, pca_l, pca_r, transl)
+        d_loss = d_loss.contiguous().float()
+        g = ctx.g
+        shared_betas = betas is not None and need[4] and betas.shape[0] == 1 and B > 1
+        if shared_betas:        # d_betas sums over bodies inside the kernel: scale before the sum
+            g = g * d_loss.view(-1, 1, 1)
+        d_betas = torch.empty_like(betas) if (betas is not None and need[4]) else None
+        d_pose = torch.empty_like(pose) if need[5] else None
+        d_pl = torch.empty_like(pl) if (pl is not None and need[6]) else None
+        d_pr = torch.empty_like(pr) if (pr is not None and need[7]) else None
+        d_tr = torch.empty_like(tr) if (tr is not None and need[8]) else None
+        sc_bytes = dm.backward_scratch_bytes(B)
+        sc = torch.empty(sc_bytes, device=dev, dtype=torch.uint8)
+        a = _lib.BackwardArgs()
+        a.batch, a.flags = B, ctx.flags
+        a.betas, a.betas_batch = _ptr(betas), (betas.shape[0] if betas is not None else 1)
+        a.pose, a.hand_pca_l, a.hand_pca_r = _ptr(pose), _ptr(pl), _ptr(pr)
+        a.d_verts = _ptr(g)
+        a.d_betas, a.d_pose = _ptr(d_betas), _ptr(d_pose)
+        a.d_hand_pca_l, a.d_hand_pca_r, a.d_transl = _ptr(d_pl), _ptr(d_pr), _ptr(d_tr)
+        a.workspace, a.workspace_bytes = _ptr(ctx.ws), ctx.ws.numel()
+        a.scratch, a.scratch_bytes = _ptr(sc), sc_bytes
+        a.stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            dm.backward(a)
+        if not shared_betas:
+            s = d_loss.view(-1, 1)
+            d_betas, d_pose, d_pl, d_pr, d_tr = (None if t is None else t * s for t in (d_betas, d_pose, d_pl, d_pr, d_tr))
+        return None, None, None, None, d_betas, d_pose, d_pl, d_pr, d_tr
+
+
+def fit_vertex_l2(dm, betas, pose, target, pca_l=None, pca_r=None, transl=None, add_pose_mean=False,
+                  scale=1.0, flags=0):
+    """Per-body loss (B,) = scale * sum ||V - target||^2 of the posed vertices against target meshes,
+    as ONE autograd node: body-model forward + fused loss/gradient kernel forward, body-model backward
+    on the stored vertex gradient.  `fit_vertex_l2(...).sum().backward()` is the fitting step of
+    BASELINE config 3; it equals `vertex_l2_loss(body_model_apply(...)[0], target)`."""
+    if add_pose_mean:
+        flags |= _lib.FLAG_ADD_POSE_MEAN
+    return _FitVertexL2Fn.apply(dm, flags, scale, target, betas, pose, pca_l, pca_r, transl)
 
 
 def body_model_apply(dm, betas, pose, pca_l=None, pca_r=None, transl=None, add_pose_mean=False,
@@ -286,10 +380,7 @@ class SMPL(_BodyModelBase):
     NUM_BODY_JOINTS = 23
     KIND = "smpl"
 
-    def forward(self, betas=None, body_pose=None, global_orient=None, transl=None,
-                return_verts=True, return_full_pose=False, pose2rot=True, **kwargs):
-        if not pose2rot:
-            raise NotImplementedError("pose2rot=False (rotation-matrix input) is not supported")
+    def _assemble(self, betas, body_pose, global_orient, transl):
         dev = self.v_template.device
         go = self._default(global_orient, "global_orient", self.batch_size, 3, dev)
         bp = self._default(body_pose, "body_pose", self.batch_size, 69, dev)
@@ -299,7 +390,18 @@ class SMPL(_BodyModelBase):
         pose = torch.cat([self._expand(go, B), self._expand(bp, B)], dim=1)
         if tr is not None:
             tr = self._expand(tr, B)
-        dm = self.device_model(dev)
+        return self.device_model(dev), go, bp, be, tr, pose
+
+    def vertex_l2(self, target, scale=1.0, betas=None, body_pose=None, global_orient=None, transl=None):
+        """Per-body scale * sum ||vertices - target||^2 as one autograd node (see fit_vertex_l2)."""
+        dm, go, bp, be, tr, pose = self._assemble(betas, body_pose, global_orient, transl)
+        return fit_vertex_l2(dm, be, pose, target, transl=tr, scale=scale)
+
+    def forward(self, betas=None, body_pose=None, global_orient=None, transl=None,
+                return_verts=True, return_full_pose=False, pose2rot=True, **kwargs):
+        if not pose2rot:
+            raise NotImplementedError("pose2rot=False (rotation-matrix input) is not supported")
+        dm, go, bp, be, tr, pose = self._assemble(betas, body_pose, global_orient, transl)
         verts, joints, jreg, full_pose = body_model_apply(
             dm, be, pose, transl=tr, want_regressed=self._regressor_extra is not None)
         self._verts_cache = verts
@@ -353,11 +455,7 @@ class SMPLH(_BodyModelBase):
         if dev is not None:
             self.to(dev)
 
-    def forward(self, betas=None, global_orient=None, body_pose=None, left_hand_pose=None,
-                right_hand_pose=None, transl=None, return_verts=True, return_full_pose=False,
-                pose2rot=True, get_skin=True, **kwargs):
-        if not pose2rot:
-            raise NotImplementedError("pose2rot=False (rotation-matrix input) is not supported")
+    def _assemble(self, betas, global_orient, body_pose, left_hand_pose, right_hand_pose, transl):
         dev = self.v_template.device
         hand_dim = self.num_pca_comps if self.use_pca else 45
         go = self._default(global_orient, "global_orient", self.batch_size, 3, dev)
@@ -379,6 +477,23 @@ class SMPLH(_BodyModelBase):
         else:
             pose = torch.cat([go_e, bp_e, lh_e, rh_e], dim=1)
             pca_l = pca_r = None
+        return dm, go, bp, be, lh, rh, tr, pose, pca_l, pca_r, (go_e, bp_e, lh_e, rh_e)
+
+    def vertex_l2(self, target, scale=1.0, betas=None, global_orient=None, body_pose=None,
+                  left_hand_pose=None, right_hand_pose=None, transl=None):
+        """Per-body scale * sum ||vertices - target||^2 as one autograd node (see fit_vertex_l2)."""
+        dm, _, _, be, _, _, tr, pose, pca_l, pca_r, _ = self._assemble(
+            betas, global_orient, body_pose, left_hand_pose, right_hand_pose, transl)
+        return fit_vertex_l2(dm, be, pose, target, pca_l=pca_l, pca_r=pca_r, transl=tr, add_pose_mean=True,
+                             scale=scale)
+
+    def forward(self, betas=None, global_orient=None, body_pose=None, left_hand_pose=None,
+                right_hand_pose=None, transl=None, return_verts=True, return_full_pose=False,
+                pose2rot=True, get_skin=True, **kwargs):
+        if not pose2rot:
+            raise NotImplementedError("pose2rot=False (rotation-matrix input) is not supported")
+        dm, go, bp, be, lh, rh, tr, pose, pca_l, pca_r, (go_e, bp_e, lh_e, rh_e) = self._assemble(
+            betas, global_orient, body_pose, left_hand_pose, right_hand_pose, transl)
         verts, joints, jreg, full_pose = body_model_apply(
             dm, be, pose, pca_l=pca_l, pca_r=pca_r, transl=tr, add_pose_mean=True,
             want_regressed=self._regressor_extra is not None)

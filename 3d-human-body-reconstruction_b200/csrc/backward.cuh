@@ -43,19 +43,36 @@ __global__ void scatter_joint_grads_kernel(const ModelDev m, int B, const float*
 // lib/Gen_SMPLH/fitting.py:491-495 applied to vertices):  loss[b] = scale * sum ||V - V*||^2,
 // grad = 2 * scale * (V - V*).  One pass over V and V* instead of ~6 elementwise torch kernels.
 __global__ void __launch_bounds__(256)
-vertex_l2_kernel(int n_per_body, const float* __restrict__ verts, const float* __restrict__ target,
-                 float scale, float* __restrict__ grad, float* __restrict__ loss) {
+vertex_l2_kernel(int n_per_body, const float* verts, const float* __restrict__ target,
+                 float scale, float* grad, float* __restrict__ loss, int vec2) {
+  // `grad` may alias `verts` (the fused fitting node overwrites the vertices with their gradient):
+  // every element is read and written by the same thread, and neither pointer is __restrict__
   __shared__ float red[8];
   const int b = blockIdx.y;
   const size_t base = (size_t)b * n_per_body;
-  const int chunk = (n_per_body + gridDim.x - 1) / gridDim.x;
-  const int i0 = blockIdx.x * chunk, i1 = min(n_per_body, i0 + chunk);
   float acc = 0.f;
   const float s2 = 2.f * scale;
-  for (int i = i0 + threadIdx.x; i < i1; i += 256) {
-    const float d = verts[base + i] - __ldcs(target + base + i);
-    acc = fmaf(d, d, acc);
-    if (grad) grad[base + i] = s2 * d;
+  if (vec2) {             // rows are 8-byte aligned: two floats per access
+    const int n2 = n_per_body >> 1;
+    const int chunk = (n2 + gridDim.x - 1) / gridDim.x;
+    const int i0 = blockIdx.x * chunk, i1 = min(n2, i0 + chunk);
+    const float2* v2 = reinterpret_cast<const float2*>(verts + base);
+    const float2* t2 = reinterpret_cast<const float2*>(target + base);
+    float2* g2 = reinterpret_cast<float2*>(grad ? grad + base : nullptr);
+    for (int i = i0 + threadIdx.x; i < i1; i += 256) {
+      const float2 v = v2[i], t = __ldcs(t2 + i);
+      const float dx = v.x - t.x, dy = v.y - t.y;
+      acc = fmaf(dx, dx, fmaf(dy, dy, acc));
+      if (grad) g2[i] = make_float2(s2 * dx, s2 * dy);
+    }
+  } else {
+    const int chunk = (n_per_body + gridDim.x - 1) / gridDim.x;
+    const int i0 = blockIdx.x * chunk, i1 = min(n_per_body, i0 + chunk);
+    for (int i = i0 + threadIdx.x; i < i1; i += 256) {
+      const float d = verts[base + i] - __ldcs(target + base + i);
+      acc = fmaf(d, d, acc);
+      if (grad) grad[base + i] = s2 * d;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

@@ -1174,7 +1174,9 @@ extern "C" int smplk_vertex_l2(int32_t batch, int32_t floats_per_body, const flo
   CUDA_TRY(cudaMemsetAsync(loss, 0, (size_t)batch * sizeof(float), st));
   int gx = 8;
   while (gx > 1 && (long)gx * batch > 16384) gx >>= 1;
-  vertex_l2_kernel<<<dim3(gx, batch), 256, 0, st>>>(floats_per_body, verts, target, scale, grad, loss);
+  const int vec2 = (floats_per_body % 2 == 0) && ((reinterpret_cast<uintptr_t>(verts) | reinterpret_cast<uintptr_t>(target) |
+                                                   reinterpret_cast<uintptr_t>(grad)) & 7) == 0;
+  vertex_l2_kernel<<<dim3(gx, batch), 256, 0, st>>>(floats_per_body, verts, target, scale, grad, loss, vec2);
   LAUNCH_CHECK("vertex_l2_kernel");
   return 0;
 }

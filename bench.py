@@ -347,11 +347,16 @@ def main():
 
         from smplk.body_models import vertex_l2_loss
 
+        from smplk.body_models import fit_vertex_l2
+
         def fb_step(fused):
             for t_ in (bb, pb, tb_):
                 t_.grad = None
-            v, _, _, _ = body_model_apply(dm, bb, pb, transl=tb_)
-            loss = vertex_l2_loss(v, target).sum() if fused else ((v - target) ** 2).sum()
+            if fused == "node":       # body model + loss as one autograd node (smplk.fit_vertex_l2)
+                loss = fit_vertex_l2(dm, bb, pb, target, transl=tb_).sum()
+            else:
+                v, _, _, _ = body_model_apply(dm, bb, pb, transl=tb_)
+                loss = vertex_l2_loss(v, target).sum() if fused else ((v - target) ** 2).sum()
             loss.backward()
             return loss
 
@@ -367,7 +372,7 @@ def main():
             f1.record(stream)
             torch.cuda.synchronize(dev)
             return f0.elapsed_time(f1) / nfb
-        fb_ms, fb_torch_ms = time_fb(True), time_fb(False)
+        fb_ms, fb_torch_ms, fb_two_ms = time_fb("node"), time_fb(False), time_fb(True)
         # the same step captured once into a CUDA graph and replayed (the ~10 short kernels of a
         # batch-1024 step are launch-bound from Python)
         fb_graph_ms = None
@@ -376,12 +381,12 @@ def main():
             gstream.wait_stream(stream)
             with torch.cuda.stream(gstream):
                 for _ in range(3):
-                    fb_step(True)
+                    fb_step("node")
             stream.wait_stream(gstream)
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                fb_step(True)
+                fb_step("node")
             for _ in range(3):
                 graph.replay()
             torch.cuda.synchronize(dev)
@@ -398,8 +403,11 @@ def main():
             sys.stderr.write("fwd+bwd CUDA-graph variant skipped: %r\n" % (e,))
         extras["fwd_bwd"] = {"metric": "smplh_fitting_steps_meshes_per_sec_fwd_bwd", "batch": Bb,
                              "value": world * Bb / (fb_ms * 1e-3), "unit": UNIT, "ms_per_step": fb_ms,
-                             "loss": "sum ||V - V*||^2 with the fused loss+gradient kernel (smplk.vertex_l2_loss), "
-                                     "grads w.r.t. betas, pose, transl through the SMPLH autograd.Function",
+                             "loss": "sum ||V - V*||^2, body model + fused loss/gradient kernel as one autograd node "
+                                     "(smplk.fit_vertex_l2), grads w.r.t. betas, pose, transl",
+                             "ms_per_step_two_nodes": fb_two_ms,
+                             "value_two_nodes": world * Bb / (fb_two_ms * 1e-3),
+                             "two_nodes": "body_model_apply(...) then smplk.vertex_l2_loss(v, target) as separate autograd nodes",
                              "ms_per_step_torch_loss": fb_torch_ms,
                              "value_torch_loss": world * Bb / (fb_torch_ms * 1e-3),
                              "ms_per_step_cuda_graph": fb_graph_ms,

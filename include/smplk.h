@@ -168,7 +168,8 @@ int smplk_batch_rodrigues(int32_t n, const float* axis_angle, float* rotmats, in
 /* Fused vertex data term of a fitting step (the squared-L2 loss of
  * lib/Gen_SMPLH/fitting.py:491-495 on vertices; BASELINE config 3): loss[b] = scale * sum over
  * the body's floats of (verts - target)^2 and, if `grad` is given, grad = 2 * scale * (verts -
- * target), in one pass.  Feed `grad` to smplk_backward as d_verts. */
+ * target), in one pass.  Feed `grad` to smplk_backward as d_verts.  `grad` may be the same buffer
+ * as `verts` (the gradient then replaces the vertices). */
 int smplk_vertex_l2(int32_t batch, int32_t floats_per_body, const float* verts, const float* target,
                     float scale, float* grad, float* loss, int device, smplk_stream stream);
 

@@ -606,6 +606,52 @@ def test_fused_vertex_l2_loss_matches_torch(dev, smpl_model):
     assert no_grad.shape == (B,) and not no_grad.requires_grad
 
 
+def test_one_node_fitting_step_matches_two_nodes(dev, smplh_model, smpl_model):
+    """smplk.fit_vertex_l2 (body model + loss as one autograd node, BASELINE config 3) against the
+    torch loss on the differentiable vertices: per-body weights on the loss, per-body and shared
+    betas, hand PCA through the module method."""
+    from smplk.body_models import fit_vertex_l2, SMPLH
+    m = smpl_model
+    dm = smplk.DeviceModel(m, device=0)
+    for B, shared in ((37, False), (5, True), (1, False)):
+        betas, pose, transl = synthetic.make_inputs(m, B, seed=4)
+        if shared:
+            betas = betas[:1]
+        tgt = torch.randn(B, 6890, 3, device=dev)
+        wts = torch.arange(1, B + 1, device=dev, dtype=torch.float32)
+        res = []
+        for node in (True, False):
+            tb, tp, tt = (_t(x, dev, True) for x in (betas, pose, transl))
+            if node:
+                per_body = fit_vertex_l2(dm, tb, tp, tgt, transl=tt, scale=0.5)
+            else:
+                v = body_model_apply(dm, tb, tp, transl=tt)[0]
+                per_body = 0.5 * ((v - tgt) ** 2).sum(dim=(1, 2))
+            (per_body * wts).sum().backward()
+            res.append((per_body.detach(), tb.grad, tp.grad, tt.grad))
+        for a, b in zip(*res):
+            assert a.shape == b.shape
+            assert _maxerr(a, b) <= 2e-5 * float(b.abs().max()), (B, shared)
+    # module method, SMPL-H with PCA hands and pose mean
+    B = 9
+    mod = SMPLH(model=smplh_model, use_pca=True, num_pca_comps=12, batch_size=B).to(dev)
+    rng = np.random.default_rng(3)
+    vals = dict(betas=rng.standard_normal((B, 16)), global_orient=rng.standard_normal((B, 3)) * 0.3,
+                body_pose=rng.standard_normal((B, 63)) * 0.3, left_hand_pose=rng.standard_normal((B, 12)),
+                right_hand_pose=rng.standard_normal((B, 12)), transl=rng.standard_normal((B, 3)))
+    tgt = torch.randn(B, 6890, 3, device=dev)
+    grads = []
+    for node in (True, False):
+        mod.reset_params(**vals)
+        mod.zero_grad()
+        loss = mod.vertex_l2(tgt).sum() if node else ((mod(return_verts=True).vertices - tgt) ** 2).sum()
+        loss.backward()
+        grads.append([float(loss)] + [p.grad.clone() for _, p in sorted(mod.named_parameters())])
+    assert abs(grads[0][0] - grads[1][0]) <= 1e-5 * abs(grads[1][0])
+    for a, b in zip(grads[0][1:], grads[1][1:]):
+        assert _maxerr(a, b) <= 2e-5 * float(b.abs().max())
+
+
 def test_errors_are_loud(dev, smpl_model):
     dm = smplk.DeviceModel(smpl_model, device=0)
     b, p, t = synthetic.make_inputs(smpl_model, 2)
