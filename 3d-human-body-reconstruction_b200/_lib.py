@@ -21,6 +21,7 @@ FLAG_BLEND_SIMT = 4
 FLAG_BLEND_TCGEN05 = 8
 FLAG_BLEND_TF32 = 16
 FLAG_TRANSFORMS_ONLY = 32
+FLAG_FIT_VERTEX_L2 = 64
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -114,7 +115,7 @@ EXPORTED_SYMBOLS = [
     "smplk_batch_rodrigues", "smplk_forward_host", "smplk_last_error_string", "smplk_version",
     "smplk_launch_count", "smplk_workspace_layout", "smplk_profile_enable", "smplk_profile_read", "smplk_vertex_l2",
     "smplk_inverse_lbs", "smplk_inverse_joints", "smplk_vertex_normals", "smplk_divide_faces",
-    "smplk_reprojection_loss", "smplk_fit_priors",
+    "smplk_reprojection_loss", "smplk_fit_priors", "smplk_fit_vertex_l2",
 ]
 PROF_SLOTS = ["pose_fwd", "blend_tcgen05", "blend_simt", "skin", "dA", "skin_bwd", "blend_bwd",
               "pose_bwd", "blend_skin_fused", "transpose"]
@@ -198,6 +199,9 @@ def load():
                                     ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                     ctypes.c_void_p]
     lib.smplk_vertex_l2.restype = ctypes.c_int
+    lib.smplk_fit_vertex_l2.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float,
+                                        ctypes.c_void_p]
+    lib.smplk_fit_vertex_l2.restype = ctypes.c_int
     lib.smplk_profile_enable.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.smplk_profile_enable.restype = ctypes.c_int
     lib.smplk_profile_read.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
@@ -342,3 +346,6 @@ class DeviceModel:
 
     def backward(self, args):
         check(self._lib.smplk_backward(self.handle, ctypes.byref(args)))
+
+    def fit_vertex_l2(self, args, target_ptr, scale, loss_ptr):
+        check(self._lib.smplk_fit_vertex_l2(self.handle, ctypes.byref(args), target_ptr, float(scale), loss_ptr))

@@ -165,8 +165,8 @@ def vertex_l2_loss(verts, target, scale=1.0):
 class _FitVertexL2Fn(torch.autograd.Function):
     """loss (B,) = scale * sum ||V(betas, pose, ...) - V*||^2 in one autograd node (BASELINE config 3).
 
-    Forward: body model with SAVE_FOR_BACKWARD, then the fused loss+gradient kernel; the vertices and
-    their gradient stay internal.  Backward: the body-model backward on the stored gradient; the
+    Forward: smplk_fit_vertex_l2 (pose kernel, blend GEMM, then skinning + loss + gradient +
+    skinning backward as one kernel); the vertices never reach HBM, their gradient stays internal.  Backward: the body-model backward on the stored gradient; the
     chain is linear in d_loss, so d_loss[b] scales the small per-body parameter gradients instead of
     the (B,V,3) vertex gradient (the separate vertex_l2_loss node pays one more pass over it)."""
 
@@ -174,8 +174,13 @@ class _FitVertexL2Fn(torch.autograd.Function):
     def forward(ctx, dm, flags, scale, target, betas, pose, pca_l, pca_r, transl):
         B = pose.shape[0]
         dev = pose.device
-        flags |= _lib.FLAG_SAVE_FOR_BACKWARD
+        flags |= _lib.FLAG_SAVE_FOR_BACKWARD | _lib.FLAG_FIT_VERTEX_L2
         betas_c, pose_c = _prep(betas, dev), _prep(pose, dev)
+        # one betas row shared by all bodies: run it per body, so that backward can weight every
+        # body's d_betas by d_loss[b] before summing them
+        ctx.shared_betas = betas_c is not None and betas_c.shape[0] == 1 and B > 1
+        if ctx.shared_betas:
+            betas_c = betas_c.expand(B, -1).contiguous()
         pl, pr, tr = _prep(pca_l, dev), _prep(pca_r, dev), _prep(transl, dev)
         tgt = _prep(target, dev)
         if tuple(tgt.shape) != (B, dm.V, 3):
@@ -192,12 +197,9 @@ class _FitVertexL2Fn(torch.autograd.Function):
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         a.stream = stream
         loss = torch.empty(B, device=dev, dtype=torch.float32)
-        lib = _lib.load()
         with torch.cuda.device(dev):
-            dm.forward(a)
-            # the gradient overwrites the vertices in place (element-wise kernel)
-            _lib.check(lib.smplk_vertex_l2(B, dm.V * 3, _ptr(verts), _ptr(tgt), float(scale), _ptr(verts),
-                                           _ptr(loss), dev.index or 0, stream))
+            # `verts` comes back holding the vertex gradient 2 scale (V - V*), not the vertices
+            dm.fit_vertex_l2(a, _ptr(tgt), scale, _ptr(loss))
         ctx.dm, ctx.flags = dm, flags
         ctx.ws, ctx.g = ws, verts
         ctx.inputs = (betas_c, pose_c, pl, pr, tr)
@@ -214,9 +216,6 @@ class _FitVertexL2Fn(torch.autograd.Function):
         need = ctx.needs_input_grad   # (dm, flags, scale, target, betas, pose, pca_l, pca_r, transl)
         d_loss = d_loss.contiguous().float()
         g = ctx.g
-        shared_betas = betas is not None and need[4] and betas.shape[0] == 1 and B > 1
-        if shared_betas:        # d_betas sums over bodies inside the kernel: scale before the sum
-            g = g * d_loss.view(-1, 1, 1)
         d_betas = torch.empty_like(betas) if (betas is not None and need[4]) else None
         d_pose = torch.empty_like(pose) if need[5] else None
         d_pl = torch.empty_like(pl) if (pl is not None and need[6]) else None
@@ -236,9 +235,10 @@ class _FitVertexL2Fn(torch.autograd.Function):
         a.stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         with torch.cuda.device(dev):
             dm.backward(a)
-        if not shared_betas:
-            s = d_loss.view(-1, 1)
-            d_betas, d_pose, d_pl, d_pr, d_tr = (None if t is None else t * s for t in (d_betas, d_pose, d_pl, d_pr, d_tr))
+        s = d_loss.view(-1, 1)
+        d_betas, d_pose, d_pl, d_pr, d_tr = (None if t is None else t * s for t in (d_betas, d_pose, d_pl, d_pr, d_tr))
+        if ctx.shared_betas and d_betas is not None:
+            d_betas = d_betas.sum(dim=0, keepdim=True)
         return None, None, None, None, d_betas, d_pose, d_pl, d_pr, d_tr
 
 

@@ -50,8 +50,12 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
   if (!model || !a) return fail(SMPLK_E_ARG, "null argument");
   const ModelDev& d = model->d;
   if (a->batch < 1 || !a->pose) return fail(SMPLK_E_ARG, "batch and pose are required");
-  if (!(a->flags & SMPLK_FLAG_SAVE_FOR_BACKWARD))
+  if (!(a->flags & (SMPLK_FLAG_SAVE_FOR_BACKWARD | SMPLK_FLAG_FIT_VERTEX_L2)))
     return fail(SMPLK_E_ARG, "backward needs the workspace of a forward run with SMPLK_FLAG_SAVE_FOR_BACKWARD");
+  // after smplk_fit_vertex_l2's fused kernel d_v_posed already sits in the workspace (bf16 split rows)
+  const bool dvp_ready = (a->flags & SMPLK_FLAG_FIT_VERTEX_L2) && fit_fused_applies(model);
+  if (dvp_ready && (a->d_joints || a->d_joints_regressed))
+    return fail(SMPLK_E_ARG, "smplk_fit_vertex_l2's backward takes d_verts only");
   if (a->betas && a->betas_batch != 1 && a->betas_batch != a->batch)
     return fail(SMPLK_E_SHAPE, "betas_batch must be 1 or batch");
   const WsLayout w = ws_layout(d, a->batch, a->flags);
@@ -102,7 +106,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     da.vsrc = d.lbs_only ? d.bias : v_posed;
     da.vsrc_stride = d.lbs_only ? 0 : (size_t)d.Npad;
     da.dA = dA; da.dtr = dtr;
-    da.row_scale = L.f16 ? row_scale : nullptr; da.row_scale_inv = L.f16 ? row_scale_inv : nullptr;
+    da.row_scale = (L.f16 && !dvp_ready) ? row_scale : nullptr; da.row_scale_inv = (L.f16 && !dvp_ready) ? row_scale_inv : nullptr;
     { ProfScope prof(model, st, SMPLK_PROF_DA);
     int jsplit = 1;
     while (jsplit < 8 && (long)B * jsplit * 2 <= 4L * model->num_sms && jsplit * (kDAThreads / 32) < d.J) jsplit *= 2;
@@ -123,7 +127,10 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     const bool f16 = L.f16;
     const int tiles = (d.V + kSkinTileVerts - 1) / kSkinTileVerts;
     const bool grouped = d.grp_ok && !model->force_skin_v1 && ((d.V * 3) % 2 == 0);
-    if (grouped) {
+    if (dvp_ready) {
+      dvp_hi = reinterpret_cast<float*>(ws + w.off_dvp);
+      dvp_lo = reinterpret_cast<float*>(ws + w.off_dvp + (size_t)w.chunk * d.Npad * sizeof(uint16_t));
+    } else if (grouped) {
       constexpr int kS = kSkinBwdStages;
       int bpb = 32;
       while (bpb > 8 && (long)tiles * ((B + bpb - 1) / bpb) < 3L * 2 * model->num_sms) bpb >>= 1;
@@ -158,13 +165,15 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
       ga.num_splits = L.splits; ga.k_blocks_per_split = L.kbps; ga.out_rows_per_split = L.mpad;
       ga.k_elems = d.Npad; ga.out_scale = f16 ? 1.0f / d.pd_scale : 1.0f;
       ga.bias = nullptr;
-      ga.row_scale = f16 ? row_scale_inv : nullptr; ga.row_scale_rows = B;
+      ga.row_scale = (f16 && !dvp_ready) ? row_scale_inv : nullptr; ga.row_scale_rows = B;
+      ga.a_bf16 = dvp_ready ? 1 : 0;
       ga.out = dfeat; ga.out_ld = d.Kpad; ga.out_rows = L.splits * L.mpad; ga.out_cols = d.Kpad;
       const int tiles_g = L.m_blocks * L.n_blocks * L.splits;
       ProfScope prof(model, st, SMPLK_PROF_BLEND_BWD);
       if (f16)
         blend_tcgen05_2cta_kernel<true><<<2 * std::min(tiles_g, model->num_sms / 2), kGemmThreads, k2SmemAlloc, st>>>(
-            tm_ahi, tm_alo, model->tmap2_pdknh_hi, model->tmap2_pdknh_lo, tm_out, ga);
+            tm_ahi, tm_alo, dvp_ready ? model->tmap2_pdknb_hi : model->tmap2_pdknh_hi,
+            dvp_ready ? model->tmap2_pdknb_lo : model->tmap2_pdknh_lo, tm_out, ga);
       else
         blend_tcgen05_2cta_kernel<false><<<2 * std::min(tiles_g, model->num_sms / 2), kGemmThreads, k2SmemAlloc, st>>>(
             tm_ahi, tm_alo, model->tmap2_pdkn_hi, model->tmap2_pdkn_lo, tm_out, ga);
@@ -179,13 +188,15 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     ga.num_splits = L.splits; ga.k_blocks_per_split = L.kbps; ga.out_rows_per_split = L.mpad;
     ga.k_elems = d.Npad; ga.out_scale = f16 ? 1.0f / d.pd_scale : 1.0f;
     ga.bias = nullptr;
-    ga.row_scale = f16 ? row_scale_inv : nullptr; ga.row_scale_rows = B;
+    ga.row_scale = (f16 && !dvp_ready) ? row_scale_inv : nullptr; ga.row_scale_rows = B;
+    ga.a_bf16 = dvp_ready ? 1 : 0;
     ga.out = dfeat; ga.out_ld = d.Kpad; ga.out_rows = L.splits * L.mpad; ga.out_cols = d.Kpad;
     const int tiles_g = L.m_blocks * L.n_blocks * L.splits;
     { ProfScope prof(model, st, SMPLK_PROF_BLEND_BWD);
     if (f16)
       blend_tcgen05_kernel<true><<<std::min(tiles_g, model->num_sms), kGemmThreads, kGemmSmemAlloc, st>>>(
-          tm_ahi, tm_alo, model->tmap_pdknh_hi, model->tmap_pdknh_lo, tm_out, ga);
+          tm_ahi, tm_alo, dvp_ready ? model->tmap_pdknb_hi : model->tmap_pdknh_hi,
+          dvp_ready ? model->tmap_pdknb_lo : model->tmap_pdknh_lo, tm_out, ga);
     else
       blend_tcgen05_kernel<false><<<std::min(tiles_g, model->num_sms), kGemmThreads, kGemmSmemAlloc, st>>>(
           tm_ahi, tm_alo, model->tmap_pdkn_hi, model->tmap_pdkn_lo, tm_out, ga); }

@@ -60,6 +60,7 @@ struct BlendGemmArgs {
   float* out;              // output matrix for the direct (register -> global) epilogue
   int out_ld;              // floats per output row
   int out_rows, out_cols;  // valid extent (rows / columns beyond it are not written)
+  int a_bf16 = 0;          // f16 kernels: both operands hold bf16 (instruction descriptor a_format = b_format = 1)
 };
 
 // tile -> (m block, n block, k range); m fastest so CTAs running together share the B operand
@@ -153,8 +154,8 @@ blend_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = kF16 ? ptx::make_idesc_f16(kBlendBM, kBlendBN)
-                                      : ptx::make_idesc_tf32(kBlendBM, kBlendBN);
+      const uint32_t idesc = (kF16 ? ptx::make_idesc_f16(kBlendBM, kBlendBN)
+                                   : ptx::make_idesc_tf32(kBlendBM, kBlendBN)) | ((kF16 && args.a_bf16) ? ((1u << 7) | (1u << 10)) : 0u);
       constexpr int kElemsPerBlock = kRowBytes / (kF16 ? 2 : 4);
       constexpr int kUmmaK = kF16 ? 16 : 8;
       int stage = 0;

@@ -127,8 +127,8 @@ blend_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = kF16 ? ptx::make_idesc_f16(2 * kBlendBM, kBlendBN)
-                                      : ptx::make_idesc_tf32(2 * kBlendBM, kBlendBN);
+      const uint32_t idesc = (kF16 ? ptx::make_idesc_f16(2 * kBlendBM, kBlendBN)
+                                   : ptx::make_idesc_tf32(2 * kBlendBM, kBlendBN)) | ((kF16 && args.a_bf16) ? ((1u << 7) | (1u << 10)) : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;

@@ -30,6 +30,8 @@ struct ModelDev {
   const __half* pd_nk_h_lo;   // [Npad][Kpad] fp16 lo term
   const __half* pd_kn_h_hi;   // [Kpad][Npad] fp16 hi term, feature-major (backward GEMM operand)
   const __half* pd_kn_h_lo;   // [Kpad][Npad] fp16 lo term
+  const uint16_t* pd_kn_b_hi; // [Kpad][Npad] bf16 hi term of the same scaled operand (fitting-step backward)
+  const uint16_t* pd_kn_b_lo; // [Kpad][Npad] bf16 lo term
   float pd_scale;             // power of two; the f16 GEMM epilogue multiplies by 1/pd_scale
   const float* pd_kn;         // [Kpad][Npad] exact fp32, N contiguous
   const float* pd_kn_hi;      // [Kpad][Npad] tf32-rounded (backward GEMM operand)

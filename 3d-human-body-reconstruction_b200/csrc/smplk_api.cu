@@ -20,6 +20,7 @@
 #include "pose_kernels.cuh"
 #include "skinning.cuh"
 #include "skinning8.cuh"
+#include "skin_fit.cuh"
 #include "mesh_ops.cuh"
 #include "fit_loss.cuh"
 
@@ -91,6 +92,7 @@ struct smplk_model {
   bool use_pose_block;  // SMPLK_POSE_V1=1 selects the warp-per-body pose kernel + transposition pass
   CUtensorMap tmap_pdkn_hi, tmap_pdkn_lo;  // backward: B operand rows = blend features
   CUtensorMap tmap_pdknh_hi, tmap_pdknh_lo, tmap2_pdknh_hi, tmap2_pdknh_lo;   // same, fp16 two-term split
+  CUtensorMap tmap_pdknb_hi, tmap_pdknb_lo, tmap2_pdknb_hi, tmap2_pdknb_lo;   // same, bf16 two-term split
   bool bwd_f16;         // backward GEMM on fp16-split operands (SMPLK_BWD_TF32=1 keeps 3xTF32)
   // host staging for smplk_forward_host
   void* stage_dev;
@@ -101,6 +103,7 @@ struct smplk_model {
   bool skin_g8;         // 8 vertices per thread (default; SMPLK_SKIN_G8=0 selects the 4-vertex kernel)
   bool skin_tma;        // SMPLK_SKIN_TMA=1: per-warp cp.async.bulk pipeline (measured slower: 0.210 vs 0.182 ms)
   bool force_skin_v1;   // SMPLK_SKIN_V1=1 in the environment: per-vertex gather kernel (A/B testing)
+  bool fit_fused;       // fused skinning + loss + skinning-backward kernel of smplk_fit_vertex_l2 (SMPLK_FIT_FUSED=0: off)
   mutable bool prof_on;
   mutable std::vector<ProfRec> prof_pending;
   mutable double prof_ms[SMPLK_PROF_SLOTS];
@@ -331,6 +334,21 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
         if (int r = upload(mdl, th, &d.pd_kn_h_hi)) return r;
         if (int r = upload(mdl, tl, &d.pd_kn_h_lo)) return r;
       }
+      {   // bf16 two-term split of the same scaled operand: B of the backward GEMM after
+          // smplk_fit_vertex_l2, whose d_v_posed rows are bf16 (tcgen05 kind::f16 faults on mixed
+          // fp16 x bf16 operands)
+        std::vector<uint16_t> bh(nk, 0), bl(nk, 0);
+        for (int n = 0; n < d.N; ++n)
+          for (int k = 0; k < d.K; ++k) {
+            const float x = kn[(size_t)k * d.Npad + n] * d.pd_scale;
+            const __nv_bfloat16 h = __float2bfloat16_rn(x);
+            const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+            memcpy(&bh[(size_t)k * d.Npad + n], &h, 2);
+            memcpy(&bl[(size_t)k * d.Npad + n], &l, 2);
+          }
+        if (int r = upload(mdl, bh, &d.pd_kn_b_hi)) return r;
+        if (int r = upload(mdl, bl, &d.pd_kn_b_lo)) return r;
+      }
       // same operand in the fused kernel's column layout: tile t = vertices [84 t, 84 t + 84),
       // row 256 t + c <-> flat coordinate 252 t + c (c < 252), rows 256 t + 252.. = 0
       d.fz_tiles = (V + kFzTileVerts - 1) / kFzTileVerts;
@@ -363,6 +381,7 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     d.pd_nk_hi = d.pd_nk_lo = d.pd_kn = d.pd_kn_hi = d.pd_kn_lo = nullptr;
     d.pd_nk_h_hi = d.pd_nk_h_lo = nullptr;
     d.pd_kn_h_hi = d.pd_kn_h_lo = nullptr;
+    d.pd_kn_b_hi = d.pd_kn_b_lo = nullptr;
     d.pdf_h_hi = d.pdf_h_lo = nullptr;
     d.bias_f = nullptr;
     d.fz_tiles = 0;
@@ -625,6 +644,10 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdknh_lo, d.pd_kn_h_lo, d.Npad, d.Kpad, p256, true)) return r;
     if (int r = make_operand_tmap(mdl, &mdl->tmap_pdknh_hi, d.pd_kn_h_hi, d.Npad, d.Kpad, kBlendBN, p256, true)) return r;
     if (int r = make_operand_tmap(mdl, &mdl->tmap_pdknh_lo, d.pd_kn_h_lo, d.Npad, d.Kpad, kBlendBN, p256, true)) return r;
+    if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdknb_hi, d.pd_kn_b_hi, d.Npad, d.Kpad, p256, true)) return r;
+    if (int r = make_operand_tmap_2cta(mdl, &mdl->tmap2_pdknb_lo, d.pd_kn_b_lo, d.Npad, d.Kpad, p256, true)) return r;
+    if (int r = make_operand_tmap(mdl, &mdl->tmap_pdknb_hi, d.pd_kn_b_hi, d.Npad, d.Kpad, kBlendBN, p256, true)) return r;
+    if (int r = make_operand_tmap(mdl, &mdl->tmap_pdknb_lo, d.pd_kn_b_lo, d.Npad, d.Kpad, kBlendBN, p256, true)) return r;
     if (int r = make_operand_tmap_fused(mdl, &mdl->tmapf_pdh_hi, d.pdf_h_hi, d.Kpad, (uint64_t)d.fz_tiles * kBlendBN, p256)) return r;
     if (int r = make_operand_tmap_fused(mdl, &mdl->tmapf_pdh_lo, d.pdf_h_lo, d.Kpad, (uint64_t)d.fz_tiles * kBlendBN, p256)) return r;
     CUDA_TRY(cudaFuncSetAttribute(blend_skin_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFzSmemAlloc));
@@ -658,6 +681,7 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     CUDA_TRY(cudaFuncSetAttribute(skin_backward_grouped_kernel<kSkinBwdStages, false>, attr, max_optin));
     CUDA_TRY(cudaFuncSetAttribute(skin_backward_grouped_kernel<kSkinBwdStages, true>, attr, max_optin));
     CUDA_TRY(cudaFuncSetAttribute(divide_faces_kernel, attr, max_optin));
+    CUDA_TRY(cudaFuncSetAttribute(skin_fit_l2_kernel, attr, max_optin));
   }
   return 0;
 }
@@ -695,6 +719,7 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   { const char* e = getenv("SMPLK_SKIN_G8"); mdl->skin_g8 = !(e && e[0] == '0'); }
   { const char* e = getenv("SMPLK_SKIN_TMA"); mdl->skin_tma = (e && e[0] == '1'); }
   { const char* e = getenv("SMPLK_SKIN_V1"); mdl->force_skin_v1 = e && e[0] == '1'; }
+  { const char* e = getenv("SMPLK_FIT_FUSED"); mdl->fit_fused = !(e && e[0] == '0'); }
   { const char* e = getenv("SMPLK_GEMM_1CTA"); mdl->use_2cta = !(e && e[0] == '1'); }
   { const char* e = getenv("SMPLK_FUSED"); mdl->use_fused = !(e && e[0] == '0'); }
   { const char* e = getenv("SMPLK_POSE_V1"); mdl->use_pose_block = !(e && e[0] == '1'); }
@@ -732,11 +757,12 @@ constexpr int kDefaultChunk = 8192;
 
 struct WsLayout {
   int chunk;
-  size_t off_fhi, off_flo, off_A, off_At, off_vposed, total;
+  size_t off_fhi, off_flo, off_A, off_At, off_vposed, off_dvp, total;
 };
 
 static WsLayout ws_layout(const ModelDev& d, int batch, uint32_t flags) {
   WsLayout w;
+  if (flags & SMPLK_FLAG_FIT_VERTEX_L2) flags |= SMPLK_FLAG_SAVE_FOR_BACKWARD;
   w.chunk = (flags & SMPLK_FLAG_SAVE_FOR_BACKWARD) ? batch : std::min(batch, kDefaultChunk);
   if (w.chunk < 1) w.chunk = 1;
   const size_t rows_pad = (size_t)round_up(w.chunk, kBlendBM);
@@ -748,6 +774,9 @@ static WsLayout ws_layout(const ModelDev& d, int batch, uint32_t flags) {
   w.off_At = off;  if (!d.lbs_only) off += align_up((size_t)round_up(w.chunk, 2 * kBlendBM) * d.J * 12 * sizeof(float), 1024);
   w.off_vposed = off;
   if (!d.lbs_only) off += align_up((size_t)w.chunk * d.Npad * sizeof(float), 1024);
+  // d_v_posed of the fused fitting step: bf16 hi rows, then bf16 lo rows
+  w.off_dvp = off;
+  if ((flags & SMPLK_FLAG_FIT_VERTEX_L2) && !d.lbs_only) off += align_up((size_t)2 * w.chunk * d.Npad * sizeof(uint16_t), 1024);
   w.total = off;
   return w;
 }
@@ -1007,8 +1036,43 @@ static int launch_skin(const smplk_model* mdl, int rows, const float* vsrc, size
   return 0;
 }
 
+// smplk_fit_vertex_l2: what replaces the plain skinning launch
+struct FitL2 {
+  const float* target;
+  float scale;
+  float* loss;
+};
+
+// the fused skinning + loss + skinning-backward kernel needs the 4-vertex group tables, 8-byte
+// aligned (B,V,3) rows and the fp16-class backward GEMM
+static bool fit_fused_applies(const smplk_model* mdl) {
+  const ModelDev& d = mdl->d;
+  return !d.lbs_only && d.grp_ok && !mdl->force_skin_v1 && mdl->has_tma && mdl->bwd_f16 && mdl->fit_fused &&
+         ((d.V * 3) % 2 == 0);
+}
+
+static int forward_impl(const smplk_model* model, const smplk_forward_args* a, uint32_t flags, const FitL2* fit);
+
 extern "C" int smplk_forward(const smplk_model* model, const smplk_forward_args* a) {
   if (!model || !a) return fail(SMPLK_E_ARG, "null argument");
+  if (a->flags & SMPLK_FLAG_FIT_VERTEX_L2)
+    return fail(SMPLK_E_ARG, "SMPLK_FLAG_FIT_VERTEX_L2 belongs to smplk_fit_vertex_l2");
+  return forward_impl(model, a, a->flags, nullptr);
+}
+
+extern "C" int smplk_fit_vertex_l2(const smplk_model* model, const smplk_forward_args* a, const float* target,
+                                   float scale, float* loss) {
+  if (!model || !a || !target || !loss) return fail(SMPLK_E_ARG, "null argument");
+  if (!a->verts) return fail(SMPLK_E_ARG, "the verts buffer (it receives the vertex gradient) is required");
+  if (a->joints_regressed || (a->joints && model->d.E > 0))
+    return fail(SMPLK_E_ARG, "vertex-pick / regressed joints are not available from smplk_fit_vertex_l2");
+  if (a->flags & SMPLK_FLAG_TRANSFORMS_ONLY) return fail(SMPLK_E_ARG, "SMPLK_FLAG_TRANSFORMS_ONLY excludes the loss");
+  FitL2 fit;
+  fit.target = target; fit.scale = scale; fit.loss = loss;
+  return forward_impl(model, a, a->flags | SMPLK_FLAG_FIT_VERTEX_L2 | SMPLK_FLAG_SAVE_FOR_BACKWARD, &fit);
+}
+
+static int forward_impl(const smplk_model* model, const smplk_forward_args* a, const uint32_t flags, const FitL2* fit) {
   const ModelDev& d = model->d;
   if (a->batch < 1) return fail(SMPLK_E_ARG, "batch must be >= 1");
   if (!a->pose) return fail(SMPLK_E_ARG, "pose is required");
@@ -1017,14 +1081,14 @@ extern "C" int smplk_forward(const smplk_model* model, const smplk_forward_args*
                 a->betas_batch, a->batch);
   if ((a->hand_pca_l || a->hand_pca_r) && d.C == 0)
     return fail(SMPLK_E_ARG, "hand PCA coefficients given but the model has no PCA components");
-  if ((a->flags & SMPLK_FLAG_TRANSFORMS_ONLY) && (a->verts || a->joints_regressed))
+  if ((flags & SMPLK_FLAG_TRANSFORMS_ONLY) && (a->verts || a->joints_regressed))
     return fail(SMPLK_E_ARG, "SMPLK_FLAG_TRANSFORMS_ONLY excludes the verts / joints_regressed outputs");
-  if (!(a->flags & SMPLK_FLAG_TRANSFORMS_ONLY) &&
+  if (!(flags & SMPLK_FLAG_TRANSFORMS_ONLY) &&
       ((a->joints && d.E > 0 && !a->verts) || (a->joints_regressed && !a->verts)))
     return fail(SMPLK_E_ARG, "vertex picks / regressed joints need the verts output buffer");
   if (a->joints_regressed && d.R == 0)
     return fail(SMPLK_E_ARG, "joints_regressed requested but the model has no regressor_posed");
-  const WsLayout w = ws_layout(d, a->batch, a->flags);
+  const WsLayout w = ws_layout(d, a->batch, flags);
   if (!a->workspace || a->workspace_bytes < w.total)
     return fail(SMPLK_E_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
                 a->workspace_bytes);
@@ -1051,9 +1115,9 @@ extern "C" int smplk_forward(const smplk_model* model, const smplk_forward_args*
     pa.pose = a->pose + (size_t)c0 * 3 * d.J;
     pa.pca_l = a->hand_pca_l ? a->hand_pca_l + (size_t)c0 * d.C : nullptr;
     pa.pca_r = a->hand_pca_r ? a->hand_pca_r + (size_t)c0 * d.C : nullptr;
-    pa.add_mean = (a->flags & SMPLK_FLAG_ADD_POSE_MEAN) ? 1 : 0;
+    pa.add_mean = (flags & SMPLK_FLAG_ADD_POSE_MEAN) ? 1 : 0;
     pa.transl = a->transl ? a->transl + (size_t)c0 * 3 : nullptr;
-    const BlendPath path = d.lbs_only ? BLEND_SIMT : choose_blend(model, rows, a->flags);
+    const BlendPath path = d.lbs_only ? BLEND_SIMT : choose_blend(model, rows, flags);
     const bool f16 = !d.lbs_only && path == BLEND_F16;
     pa.F_hi = (d.lbs_only || f16) ? nullptr : F_hi;
     pa.F_lo = (d.lbs_only || f16) ? nullptr : F_lo;
@@ -1064,12 +1128,12 @@ extern "C" int smplk_forward(const smplk_model* model, const smplk_forward_args*
     pa.joints = a->joints ? a->joints + (size_t)c0 * joints_ld : nullptr;
     pa.joints_ld = joints_ld;
     pa.full_pose = a->full_pose ? a->full_pose + (size_t)c0 * 3 * d.J : nullptr;
-    const bool fused = fused_applies(model, rows, path, a->flags, a->verts != nullptr);
+    const bool fused = fused_applies(model, rows, path, flags, a->verts != nullptr);
     const bool at_from_pose = fused && pose_block_applies(model);
     if (at_from_pose) pa.At = At;            // the block pose kernel writes the transposed transforms itself
     if (int r = launch_pose_forward(model, pa, st)) return r;
-    if (a->flags & SMPLK_FLAG_TRANSFORMS_ONLY) continue;    // pose / FK kernel only: A, joints, full_pose
-    if (!fused && !d.lbs_only && (a->verts || (a->flags & SMPLK_FLAG_SAVE_FOR_BACKWARD))) {
+    if (flags & SMPLK_FLAG_TRANSFORMS_ONLY) continue;    // pose / FK kernel only: A, joints, full_pose
+    if (!fused && !d.lbs_only && (a->verts || (flags & SMPLK_FLAG_SAVE_FOR_BACKWARD))) {
       if (int r = launch_blend(model, rows, path, F_hi, F_lo, v_posed, st)) return r;
     }
     if (a->verts) {
@@ -1077,8 +1141,32 @@ extern "C" int smplk_forward(const smplk_model* model, const smplk_forward_args*
       if (fused) {
         if (int r = launch_fused(model, rows, F_hi, F_lo, at_from_pose ? nullptr : A, At, pa.transl, vout, st)) return r;
       } else {
-        if (int r = launch_skin(model, rows, d.lbs_only ? d.bias : v_posed,
-                                d.lbs_only ? 0 : (size_t)d.Npad, A, pa.transl, vout, st)) return r;
+        if (fit != nullptr && fit_fused_applies(model)) {
+          // skinning + loss + gradient + skinning backward in one kernel; vout receives the gradient
+          CUDA_TRY(cudaMemsetAsync(fit->loss + c0, 0, (size_t)rows * sizeof(float), st));
+          SkinFitArgs fa;
+          fa.B = rows;
+          fa.vposed = v_posed; fa.vposed_stride = (size_t)d.Npad; fa.A = A; fa.transl = pa.transl;
+          fa.target = fit->target + (size_t)c0 * d.V * 3; fa.scale = fit->scale;
+          fa.grad = vout; fa.loss = fit->loss + c0;
+          fa.dvp_hi = reinterpret_cast<__nv_bfloat16*>(ws + w.off_dvp);
+          fa.dvp_lo = fa.dvp_hi + (size_t)w.chunk * d.Npad;
+          const int tiles = (d.V + kSkinTileVerts - 1) / kSkinTileVerts;
+          int bpb = 32;
+          while (bpb > 8 && (long)tiles * ((rows + bpb - 1) / bpb) < 3L * 2 * model->num_sms) bpb >>= 1;
+          while (bpb > 1 && (long)tiles * ((rows + bpb - 1) / bpb) < 2L * model->num_sms) bpb >>= 1;
+          fa.bodies_per_block = bpb;
+          ProfScope prof(model, st, SMPLK_PROF_SKIN);
+          skin_fit_l2_kernel<<<dim3(tiles, (rows + bpb - 1) / bpb), kGrpThreads, skin_grouped_smem_bytes(d.J), st>>>(d, fa);
+          LAUNCH_CHECK("skin_fit_l2_kernel");
+        } else {
+          if (int r = launch_skin(model, rows, d.lbs_only ? d.bias : v_posed,
+                                  d.lbs_only ? 0 : (size_t)d.Npad, A, pa.transl, vout, st)) return r;
+          if (fit != nullptr) {   // generic weights: stand-alone loss kernel, gradient in place
+            if (int r = smplk_vertex_l2(rows, d.V * 3, vout, fit->target + (size_t)c0 * d.V * 3, fit->scale, vout,
+                                        fit->loss + c0, model->device, a->stream)) return r;
+          }
+        }
       }
       if (a->joints && d.E > 0) {
         const int n = rows * d.E;

@@ -92,6 +92,7 @@ int smplk_model_get_info(const smplk_model* model, smplk_model_info* info);
 #define SMPLK_FLAG_BLEND_TF32 16u       /* force the 3xTF32 operand format (default: fp16 two-term split) */
 #define SMPLK_FLAG_TRANSFORMS_ONLY 32u  /* run the pose / FK kernel only: skinning transforms A (workspace), FK
                                            joints, full_pose; with E > 0 the vertex-pick joints are left unwritten */
+#define SMPLK_FLAG_FIT_VERTEX_L2 64u    /* workspace / backward of smplk_fit_vertex_l2 (implies SAVE_FOR_BACKWARD) */
 
 /* Bytes of device workspace `smplk_forward` needs for `batch` bodies (256-byte aligned base). */
 size_t smplk_workspace_bytes(const smplk_model* model, int32_t batch, uint32_t flags);
@@ -180,6 +181,18 @@ int smplk_vertex_l2(int32_t batch, int32_t floats_per_body, const float* verts, 
 int smplk_forward_host(smplk_model* model, int32_t batch, uint32_t flags, const float* betas,
                        int32_t betas_batch, const float* pose, const float* transl, float* verts,
                        float* joints, smplk_stream stream);
+
+/* The forward half of a vertex-L2 fitting step (BASELINE config 3; the squared-L2 data term of
+ * lib/Gen_SMPLH/fitting.py:491-495 on vertices) in one call: body-model forward as smplk_forward
+ * with SMPLK_FLAG_SAVE_FOR_BACKWARD | SMPLK_FLAG_FIT_VERTEX_L2 in a->flags, then
+ *   loss[b] = scale * sum ||verts[b] - target[b]||^2,   a->verts <- 2 scale (verts - target)
+ * i.e. a->verts (B,V,3) receives the vertex GRADIENT, not the vertices.  Skinning, loss, gradient
+ * and the skinning backward run as one kernel where the model allows (sparse weights, 3V even);
+ * d_v_posed is then kept in the workspace and smplk_backward, called with the same flags and
+ * d_verts = a->verts, skips its own skinning backward.  a->joints may be given only when the model
+ * has no vertex-pick joints; a->joints_regressed must be null.  `target` (B,V,3), `loss` (B). */
+int smplk_fit_vertex_l2(const smplk_model* model, const smplk_forward_args* a, const float* target,
+                        float scale, float* loss);
 
 /* ---- mesh operations either side of the forward (SURVEY.md 8f "next" rows 2 and 4) ----------- */
 

@@ -9,7 +9,8 @@ from smplk import _lib, synthetic
 from smplk.body_models import body_model_apply
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-bwd = len(sys.argv) > 2 and sys.argv[2] == "bwd"
+bwd = len(sys.argv) > 2 and sys.argv[2] in ("bwd", "fit")
+fit = len(sys.argv) > 2 and sys.argv[2] == "fit"     # body model + vertex-L2 loss as one autograd node
 kind = os.environ.get("KIND", "smplh")
 dev = torch.device("cuda:0")
 model = synthetic.make_model(kind, seed=0)
@@ -19,6 +20,10 @@ if bwd:
     b.requires_grad_(True); p.requires_grad_(True); t.requires_grad_(True)
 tgt = torch.randn(B, dm.V, 3, device=dev) if bwd else None
 def step():
+    if fit:
+        from smplk.body_models import fit_vertex_l2
+        fit_vertex_l2(dm, b, p, tgt, transl=t).sum().backward()
+        return
     v = body_model_apply(dm, b, p, transl=t)[0]
     if bwd:
         ((v - tgt) ** 2).sum().backward()
