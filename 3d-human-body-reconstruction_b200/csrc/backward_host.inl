@@ -132,8 +132,8 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
       dvp_lo = reinterpret_cast<float*>(ws + w.off_dvp + (size_t)w.chunk * d.Npad * sizeof(uint16_t));
     } else if (grouped) {
       constexpr int kS = kSkinBwdStages;
-      int bpb = 32;
-      while (bpb > 8 && (long)tiles * ((B + bpb - 1) / bpb) < 3L * 2 * model->num_sms) bpb >>= 1;
+      int bpb = pick_bpb(B, tiles, 2 * model->num_sms, 32);
+      if (model->skin_bpb > 0) bpb = model->skin_bpb;
       sb.bodies_per_block = bpb;
       dim3 grid(tiles, (B + bpb - 1) / bpb);
       const size_t smem = (size_t)((kS + 1) * kSkinTileVerts * 3 + 2 * kGrpABodies * grp_a_pad(d.J)) * sizeof(float);

@@ -992,6 +992,20 @@ static int launch_fused(const smplk_model* mdl, int rows, float* F_hi, float* F_
   return 0;
 }
 
+// Bodies per block of the streaming skinning kernels: the grid (tiles x body groups) should fill a
+// whole number of waves of `resident` co-resident blocks -- measured on the fitting-step kernel at
+// 1,024 bodies: 0.095 ms at 25 bodies per block (287 blocks, one wave of 296) against 0.106 ms at
+// 8 (3.03 waves), 0.118-0.121 ms at 21 / 32 (1.16 / 0.76 waves).  Fewest waves with <= max_bpb bodies.
+static int pick_bpb(int rows, int tiles, int resident, int max_bpb) {
+  for (int k = 1; k <= 32; ++k) {
+    const int groups = (resident * k) / tiles;
+    if (groups < 1) continue;
+    const int bpb = (rows + groups - 1) / groups;
+    if (bpb <= max_bpb) return std::max(bpb, 1);
+  }
+  return max_bpb;
+}
+
 static int launch_skin(const smplk_model* mdl, int rows, const float* vsrc, size_t vstride,
                        const float* A, const float* transl, float* out, cudaStream_t st) {
   const ModelDev& d = mdl->d;
@@ -1003,20 +1017,22 @@ static int launch_skin(const smplk_model* mdl, int rows, const float* vsrc, size
   const bool grouped = d.grp_ok && !mdl->force_skin_v1;
   const size_t smem = grouped ? skin_grouped_smem_bytes(d.J)
                               : (size_t)(2 * kSkinTileVerts * 3 + 2 * ((d.J * 12 + 3) & ~3)) * sizeof(float);
-  // bodies per block: measured sweep at B=4096 (0.220/0.187/0.177/0.183/0.204 ms for 4/8/16/32/64):
-  // long enough to amortise the weight load and pipeline fill, short enough for >= ~6 waves
+  // bodies per block: see pick_bpb (whole waves; 0.177 -> 0.169 ms at B=4096, 0.056 -> 0.049 ms at 1024)
   const int resident = (grouped ? 2 : 4) * mdl->num_sms;
   int bpb = 32;
-  while (bpb > 8 && (long)tiles * ((rows + bpb - 1) / bpb) < 6L * resident) bpb >>= 1;
-  while (bpb > 1 && (long)tiles * ((rows + bpb - 1) / bpb) < resident) bpb >>= 1;
+  if (grouped) {
+    bpb = pick_bpb(rows, tiles, resident, 32);
+  } else {
+    while (bpb > 8 && (long)tiles * ((rows + bpb - 1) / bpb) < 6L * resident) bpb >>= 1;
+    while (bpb > 1 && (long)tiles * ((rows + bpb - 1) / bpb) < resident) bpb >>= 1;
+  }
   if (mdl->skin_bpb > 0) bpb = mdl->skin_bpb;
   sa.bodies_per_block = bpb;
   dim3 grid(tiles, (rows + bpb - 1) / bpb);
   ProfScope prof(mdl, st, SMPLK_PROF_SKIN);
   if (grouped && d.grp8_ok && mdl->skin_g8) {
     const int res8 = 3 * mdl->num_sms;
-    int bpb8 = 32;
-    while (bpb8 > 4 && (long)tiles * ((rows + bpb8 - 1) / bpb8) < 3L * res8) bpb8 >>= 1;
+    int bpb8 = pick_bpb(rows, tiles, res8, 32);
     if (mdl->skin_bpb > 0) bpb8 = mdl->skin_bpb;
     sa.bodies_per_block = bpb8;
     dim3 grid8(tiles, (rows + bpb8 - 1) / bpb8);
@@ -1152,9 +1168,8 @@ static int forward_impl(const smplk_model* model, const smplk_forward_args* a, c
           fa.dvp_hi = reinterpret_cast<__nv_bfloat16*>(ws + w.off_dvp);
           fa.dvp_lo = fa.dvp_hi + (size_t)w.chunk * d.Npad;
           const int tiles = (d.V + kSkinTileVerts - 1) / kSkinTileVerts;
-          int bpb = 32;
-          while (bpb > 8 && (long)tiles * ((rows + bpb - 1) / bpb) < 3L * 2 * model->num_sms) bpb >>= 1;
-          while (bpb > 1 && (long)tiles * ((rows + bpb - 1) / bpb) < 2L * model->num_sms) bpb >>= 1;
+          int bpb = pick_bpb(rows, tiles, 2 * model->num_sms, 32);
+          if (model->skin_bpb > 0) bpb = model->skin_bpb;
           fa.bodies_per_block = bpb;
           ProfScope prof(model, st, SMPLK_PROF_SKIN);
           skin_fit_l2_kernel<<<dim3(tiles, (rows + bpb - 1) / bpb), kGrpThreads, skin_grouped_smem_bytes(d.J), st>>>(d, fa);

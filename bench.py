@@ -333,7 +333,7 @@ def main():
         if "skin" in kern:
             s_ms = kern["skin"]
             gbs = FWD_BYTES_SKIN * B / (s_ms * 1e-3) / 1e9
-            extras["roofline_skinning"] = {"kernel": "skin_grouped8_kernel (two-kernel forward: SAVE_FOR_BACKWARD / SMPLK_FUSED=0)",
+            extras["roofline_skinning"] = {"kernel": "skin_grouped_kernel (two-kernel forward: SAVE_FOR_BACKWARD / SMPLK_FUSED=0)",
                                            "bound": "hbm", "achieved": gbs,
                                            "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                                            "traffic": None, "ms_per_launch": s_ms,
