@@ -166,9 +166,10 @@ class _FitVertexL2Fn(torch.autograd.Function):
     """loss (B,) = scale * sum ||V(betas, pose, ...) - V*||^2 in one autograd node (BASELINE config 3).
 
     Forward: smplk_fit_vertex_l2 (pose kernel, blend GEMM, then skinning + loss + gradient +
-    skinning backward as one kernel); the vertices never reach HBM, their gradient stays internal.  Backward: the body-model backward on the stored gradient; the
-    chain is linear in d_loss, so d_loss[b] scales the small per-body parameter gradients instead of
-    the (B,V,3) vertex gradient (the separate vertex_l2_loss node pays one more pass over it)."""
+    skinning backward as one kernel); the vertices never reach HBM, their gradient stays internal.
+    Backward: the body-model backward on the stored gradient; the chain is linear in d_loss, so the
+    pose backward kernel scales body b's parameter gradients by d_loss[b] (smplk_backward_args.d_loss)
+    instead of a pass over the (B,V,3) vertex gradient, which the separate vertex_l2_loss node pays."""
 
     @staticmethod
     def forward(ctx, dm, flags, scale, target, betas, pose, pca_l, pca_r, transl):
@@ -176,11 +177,6 @@ class _FitVertexL2Fn(torch.autograd.Function):
         dev = pose.device
         flags |= _lib.FLAG_SAVE_FOR_BACKWARD | _lib.FLAG_FIT_VERTEX_L2
         betas_c, pose_c = _prep(betas, dev), _prep(pose, dev)
-        # one betas row shared by all bodies: run it per body, so that backward can weight every
-        # body's d_betas by d_loss[b] before summing them
-        ctx.shared_betas = betas_c is not None and betas_c.shape[0] == 1 and B > 1
-        if ctx.shared_betas:
-            betas_c = betas_c.expand(B, -1).contiguous()
         pl, pr, tr = _prep(pca_l, dev), _prep(pca_r, dev), _prep(transl, dev)
         tgt = _prep(target, dev)
         if tuple(tgt.shape) != (B, dm.V, 3):
@@ -233,12 +229,9 @@ class _FitVertexL2Fn(torch.autograd.Function):
         a.workspace, a.workspace_bytes = _ptr(ctx.ws), ctx.ws.numel()
         a.scratch, a.scratch_bytes = _ptr(sc), sc_bytes
         a.stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        a.d_loss = _ptr(d_loss)      # the pose backward kernel scales body b's gradients by d_loss[b]
         with torch.cuda.device(dev):
             dm.backward(a)
-        s = d_loss.view(-1, 1)
-        d_betas, d_pose, d_pl, d_pr, d_tr = (None if t is None else t * s for t in (d_betas, d_pose, d_pl, d_pr, d_tr))
-        if ctx.shared_betas and d_betas is not None:
-            d_betas = d_betas.sum(dim=0, keepdim=True)
         return None, None, None, None, d_betas, d_pose, d_pl, d_pr, d_tr
 
 

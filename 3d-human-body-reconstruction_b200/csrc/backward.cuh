@@ -523,6 +523,7 @@ struct PoseBwdArgs {
   float* d_pca_l;            // (B,C) or null
   float* d_pca_r;
   float* d_transl;           // (B,3) or null
+  const float* d_loss;       // (B) or null: scale of body b's parameter gradients
 };
 
 // smem floats per warp of pose_backward_kernel: world G, local L, dG (12 each), dR (9), dJ, dfull (3 each)
@@ -752,26 +753,27 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
   }
   __syncwarp();
 
+  const float gs = a.d_loss ? a.d_loss[b] : 1.f;        // upstream gradient of this body's loss
   const int hand0 = m.J - 30;
   if (a.d_pose) {
     for (int i = lane; i < 3 * m.J; i += 32) {
       const int j = i / 3;
       const bool from_pca = (a.pca_l && j >= hand0 && j < hand0 + 15) || (a.pca_r && j >= hand0 + 15);
-      a.d_pose[(size_t)b * 3 * m.J + i] = from_pca ? 0.f : dfull[i];
+      a.d_pose[(size_t)b * 3 * m.J + i] = from_pca ? 0.f : gs * dfull[i];
     }
   }
   if (a.d_pca_l && a.pca_l) {
     for (int c = lane; c < m.C; c += 32) {
       float acc = 0.f;
       for (int i = 0; i < 45; ++i) acc = fmaf(m.comp_l[c * 45 + i], dfull[3 * hand0 + i], acc);
-      a.d_pca_l[(size_t)b * m.C + c] = acc;
+      a.d_pca_l[(size_t)b * m.C + c] = gs * acc;
     }
   }
   if (a.d_pca_r && a.pca_r) {
     for (int c = lane; c < m.C; c += 32) {
       float acc = 0.f;
       for (int i = 0; i < 45; ++i) acc = fmaf(m.comp_r[c * 45 + i], dfull[3 * (hand0 + 15) + i], acc);
-      a.d_pca_r[(size_t)b * m.C + c] = acc;
+      a.d_pca_r[(size_t)b * m.C + c] = gs * acc;
     }
   }
   // ---- d_betas = J_shapedirs^T dJ + (blend GEMM columns P..P+NB)
@@ -791,6 +793,7 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
       acc += __shfl_xor_sync(0xffffffffu, acc, 16);
       if (h == 0 && i < m.NB) {
         if (a.d_feat != nullptr) acc += dfeat_sum[m.P + i];
+        acc *= gs;
         if (a.betas_B == 1) atomicAdd(&a.d_betas[i], acc);
         else a.d_betas[(size_t)b * m.NB + i] = acc;
       }
@@ -800,7 +803,7 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
     float t = a.dtr_verts ? a.dtr_verts[3 * b + lane] : 0.f;
     if (a.d_joints)
       for (int j = 0; j < m.J; ++j) t += a.d_joints[(size_t)b * a.joints_ld + 3 * j + lane];
-    a.d_transl[3 * b + lane] = t;
+    a.d_transl[3 * b + lane] = gs * t;
   }
 }
 

@@ -421,8 +421,7 @@ def main():
             def closure():
                 for t_ in (b1, p1, t1):
                     t_.grad = None
-                v, _, _, _ = body_model_apply(dm, b1, p1, transl=t1)
-                vertex_l2_loss(v, tgt1).sum().backward()
+                fit_vertex_l2(dm, b1, p1, tgt1, transl=t1).sum().backward()
 
             def timeit(fn, n=50):
                 for _ in range(5):

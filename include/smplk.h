@@ -148,6 +148,10 @@ typedef struct {
   void* scratch;              /* smplk_backward_scratch_bytes() bytes                              */
   size_t scratch_bytes;
   smplk_stream stream;
+  const float* d_loss;        /* (B) or NULL: every parameter gradient of body b is multiplied by d_loss[b]
+                                 (the upstream gradient of a per-body loss whose d_verts was formed for
+                                 d_loss = 1, e.g. after smplk_fit_vertex_l2); a shared betas row receives
+                                 sum_b d_loss[b] d_betas_b */
 } smplk_backward_args;
 
 size_t smplk_backward_scratch_bytes(const smplk_model* model, int32_t batch);
