@@ -140,24 +140,35 @@ skin_fit_l2_kernel(const ModelDev m, const SkinFitArgs a) {
       vy[0] = c0.y; vy[1] = c1.x; vy[2] = c1.w; vy[3] = c2.z;
       vz[0] = c0.z; vz[1] = c1.y; vz[2] = c2.x; vz[3] = c2.w;
     }
-    float ox[4] = {0.f, 0.f, 0.f, 0.f}, oy[4] = {0.f, 0.f, 0.f, 0.f}, oz[4] = {0.f, 0.f, 0.f, 0.f};
+    // blended transforms of the 4 vertices, T_i = sum_u w_ui A_u: applied to v_posed now and,
+    // transposed, to the gradient below (one pass over the joints instead of two)
+    float T[4][12];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int q = 0; q < 12; ++q) T[i][q] = 0.f;
+    }
 #pragma unroll
     for (int u = 0; u < kGrpJoints; ++u) {
       if (used & (1u << u)) {
         const int j = ((u < 4 ? jid.x : jid.y) >> (8 * (u & 3))) & 0xff;
         const float4* Aj = reinterpret_cast<const float4*>(Ab + j * 12);
         const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+        const float Aq[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
         const float wu[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float px = fmaf(r0.x, vx[i], fmaf(r0.y, vy[i], fmaf(r0.z, vz[i], r0.w)));
-          const float py = fmaf(r1.x, vx[i], fmaf(r1.y, vy[i], fmaf(r1.z, vz[i], r1.w)));
-          const float pz = fmaf(r2.x, vx[i], fmaf(r2.y, vy[i], fmaf(r2.z, vz[i], r2.w)));
-          ox[i] = fmaf(wu[i], px, ox[i]);
-          oy[i] = fmaf(wu[i], py, oy[i]);
-          oz[i] = fmaf(wu[i], pz, oz[i]);
+#pragma unroll
+          for (int q = 0; q < 12; ++q) T[i][q] = fmaf(wu[i], Aq[q], T[i][q]);
         }
       }
+    }
+    float ox[4], oy[4], oz[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ox[i] = fmaf(T[i][0], vx[i], fmaf(T[i][1], vy[i], fmaf(T[i][2], vz[i], T[i][3])));
+      oy[i] = fmaf(T[i][4], vx[i], fmaf(T[i][5], vy[i], fmaf(T[i][6], vz[i], T[i][7])));
+      oz[i] = fmaf(T[i][8], vx[i], fmaf(T[i][9], vy[i], fmaf(T[i][10], vz[i], T[i][11])));
     }
     mine[0] = make_float4(ox[0] + tx, oy[0] + ty, oz[0] + tz, ox[1] + tx);
     mine[1] = make_float4(oy[1] + ty, oz[1] + tz, ox[2] + tx, oy[2] + ty);
@@ -191,24 +202,10 @@ skin_fit_l2_kernel(const ModelDev m, const SkinFitArgs a) {
     }
     __syncwarp();                                        // the slot is free for the copy of body b + stages
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ox[i] = oy[i] = oz[i] = 0.f;
-#pragma unroll
-    for (int u = 0; u < kGrpJoints; ++u) {
-      if (used & (1u << u)) {
-        const int j = ((u < 4 ? jid.x : jid.y) >> (8 * (u & 3))) & 0xff;
-        const float4* Aj = reinterpret_cast<const float4*>(Ab + j * 12);
-        const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
-        const float wu[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {   // R_u^T g
-          const float px = fmaf(r0.x, vx[i], fmaf(r1.x, vy[i], r2.x * vz[i]));
-          const float py = fmaf(r0.y, vx[i], fmaf(r1.y, vy[i], r2.y * vz[i]));
-          const float pz = fmaf(r0.z, vx[i], fmaf(r1.z, vy[i], r2.z * vz[i]));
-          ox[i] = fmaf(wu[i], px, ox[i]);
-          oy[i] = fmaf(wu[i], py, oy[i]);
-          oz[i] = fmaf(wu[i], pz, oz[i]);
-        }
-      }
+    for (int i = 0; i < 4; ++i) {   // d_v_posed = T_R^T g
+      ox[i] = fmaf(T[i][0], vx[i], fmaf(T[i][4], vy[i], T[i][8] * vz[i]));
+      oy[i] = fmaf(T[i][1], vx[i], fmaf(T[i][5], vy[i], T[i][9] * vz[i]));
+      oz[i] = fmaf(T[i][2], vx[i], fmaf(T[i][6], vy[i], T[i][10] * vz[i]));
     }
     // bf16 two-term split; a thread's 12 columns are 24 contiguous bytes per term
     const float o[12] = {ox[0], oy[0], oz[0], ox[1], oy[1], oz[1], ox[2], oy[2], oz[2], ox[3], oy[3], oz[3]};
