@@ -397,7 +397,7 @@ class SMPL(_BodyModelBase):
         dm, go, bp, be, tr, pose = self._assemble(betas, body_pose, global_orient, transl)
         verts, joints, jreg, full_pose = body_model_apply(
             dm, be, pose, transl=tr, want_regressed=self._regressor_extra is not None)
-        self._verts_cache = verts
+        self._verts_cache = verts.detach()   # never keeps the autograd graph alive
         joints = self._finish(verts, joints, jreg, tr)
         if return_full_pose:  # differentiable view of the assembled pose (cheap torch glue)
             full_pose = pose
@@ -490,7 +490,7 @@ class SMPLH(_BodyModelBase):
         verts, joints, jreg, full_pose = body_model_apply(
             dm, be, pose, pca_l=pca_l, pca_r=pca_r, transl=tr, add_pose_mean=True,
             want_regressed=self._regressor_extra is not None)
-        self._verts_cache = verts
+        self._verts_cache = verts.detach()   # never keeps the autograd graph alive
         joints = self._finish(verts, joints, jreg, tr)
         if return_full_pose:  # differentiable assembly (upstream: cat + PCA einsum + pose_mean)
             if self.use_pca:

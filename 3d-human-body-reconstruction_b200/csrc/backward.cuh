@@ -39,6 +39,88 @@ __global__ void scatter_joint_grads_kernel(const ModelDev m, int B, const float*
   }
 }
 
+// Keypoint fitting (the reference's actual closure: the data term of lib/Gen_SMPLH/fitting.py:369-381
+// reads only joints): the vertex gradient is non-zero at the E vertex-pick joints alone (nose, eyes,
+// ears, toes, heels, finger tips), so the dense backward -- a (B,V,3) gradient buffer, dA over every
+// vertex, the skinning backward and a 20,736-deep GEMM -- collapses to one small exact-fp32 kernel:
+//   per pick e (vertex v_e, gradient g_e = d_joints[J + e]):
+//     dA[b, j]   += w g_e (x) [v_posed[b, v_e]; 1]              over the <= ell_k joints of v_e
+//     d_e         = sum_k w_k R_{j_k}^T g_e                       (d_v_posed at the pick)
+//   d_feat[b, k]  = sum_{e,c} d_e[c] * pd[k, 3 v_e + c]           (ModelDev::pick_pd, gathered at create)
+//   dtr[b]        = sum_e g_e
+// One block per body.
+struct PickBwdArgs {
+  int B;
+  const float* d_joints;    // (B, joints_ld); picks start at column 3J
+  int joints_ld;
+  const float* A;           // (B,J,12)
+  const float* vsrc;        // v_posed rows or the shared template
+  size_t vsrc_stride;
+  float* dA;                // (B,J,12)
+  float* dtr;               // (B,3)
+  float* d_feat;            // (B,Kpad) or null
+};
+
+constexpr int kPickThreads = 128;
+__host__ __device__ inline size_t pick_bwd_smem_bytes(int J, int E) {
+  return (size_t)(2 * J * 12 + 3 * E + 4) * sizeof(float);
+}
+
+__global__ void __launch_bounds__(kPickThreads) pick_backward_kernel(const ModelDev m, const PickBwdArgs a) {
+  extern __shared__ __align__(16) float pk_smem[];
+  float* sA = pk_smem;                    // [J][12] transforms of this body
+  float* sdA = sA + m.J * 12;             // [J][12]
+  float* sd = sdA + m.J * 12;             // [3E] d_v_posed at the picks
+  float* sdtr = sd + 3 * m.E;             // [3]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < m.J * 12; i += kPickThreads) {
+    sA[i] = a.A[(size_t)b * m.J * 12 + i];
+    sdA[i] = 0.f;
+  }
+  if (tid < 3) sdtr[tid] = 0.f;
+  __syncthreads();
+  for (int e = tid; e < m.E; e += kPickThreads) {
+    const int v = m.extra_vids[e];
+    const float* gp = a.d_joints + (size_t)b * a.joints_ld + 3 * (m.J + e);
+    const float* xp = a.vsrc + (size_t)b * a.vsrc_stride + 3 * (size_t)v;
+    const float g[3] = {gp[0], gp[1], gp[2]};
+    const float x[4] = {xp[0], xp[1], xp[2], 1.f};
+    float d[3] = {0.f, 0.f, 0.f};
+    for (int k = 0; k < m.ell_k; ++k) {
+      const float w = m.ell_w[(size_t)k * m.V + v];
+      if (w == 0.f) continue;
+      const int j = m.ell_idx[(size_t)k * m.V + v];
+      const float* Aj = sA + j * 12;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float wg = w * g[r];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) atomicAdd(&sdA[j * 12 + r * 4 + c], wg * x[c]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) d[c] = fmaf(wg, Aj[r * 4 + c], d[c]);
+      }
+    }
+    sd[3 * e + 0] = d[0]; sd[3 * e + 1] = d[1]; sd[3 * e + 2] = d[2];
+    atomicAdd(&sdtr[0], g[0]); atomicAdd(&sdtr[1], g[1]); atomicAdd(&sdtr[2], g[2]);
+  }
+  __syncthreads();
+  for (int i = tid; i < m.J * 12; i += kPickThreads) a.dA[(size_t)b * m.J * 12 + i] = sdA[i];
+  if (tid < 3) a.dtr[3 * b + tid] = sdtr[tid];
+  if (a.d_feat != nullptr) {
+    const int n = 3 * m.E;
+    for (int k = tid; k < m.Kpad; k += kPickThreads) {
+      float a0 = 0.f, a1 = 0.f;
+      int i = 0;
+      for (; i + 2 <= n; i += 2) {
+        a0 = fmaf(sd[i], m.pick_pd[(size_t)i * m.Kpad + k], a0);
+        a1 = fmaf(sd[i + 1], m.pick_pd[(size_t)(i + 1) * m.Kpad + k], a1);
+      }
+      if (i < n) a0 = fmaf(sd[i], m.pick_pd[(size_t)i * m.Kpad + k], a0);
+      a.d_feat[(size_t)b * m.Kpad + k] = a0 + a1;
+    }
+  }
+}
+
 // Fused vertex L2 data term of the fitting step (config 3; squared-L2 form of
 // lib/Gen_SMPLH/fitting.py:491-495 applied to vertices):  loss[b] = scale * sum ||V - V*||^2,
 // grad = 2 * scale * (V - V*).  One pass over V and V* instead of ~6 elementwise torch kernels.

@@ -83,8 +83,22 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
   float* dfeat = reinterpret_cast<float*>(sc + L.off_dfeat);
   const int joints_ld = 3 * (d.J + d.E);
 
+  // ---- keypoint fitting: only vertex-pick joints carry a vertex gradient -> one sparse kernel
+  const bool want_blend_grads = !d.lbs_only && (a->d_pose || a->d_betas || a->d_hand_pca_l || a->d_hand_pca_r);
+  const bool picks_only = model->sparse_picks && !a->d_verts && !(a->d_joints_regressed && d.R > 0) && a->d_joints &&
+                          d.E > 0 && !dvp_ready && (d.lbs_only || d.pick_pd != nullptr);
+  if (picks_only) {
+    PickBwdArgs pk;
+    pk.B = B; pk.d_joints = a->d_joints; pk.joints_ld = joints_ld; pk.A = A;
+    pk.vsrc = d.lbs_only ? d.bias : v_posed; pk.vsrc_stride = d.lbs_only ? 0 : (size_t)d.Npad;
+    pk.dA = dA; pk.dtr = dtr; pk.d_feat = want_blend_grads ? dfeat : nullptr;
+    { ProfScope prof(model, st, SMPLK_PROF_DA);
+    pick_backward_kernel<<<B, kPickThreads, pick_bwd_smem_bytes(d.J, d.E), st>>>(d, pk); }
+    LAUNCH_CHECK("pick_backward_kernel");
+  }
+
   // ---- effective vertex gradient (vertex picks and posed-vertex regressors fold into it)
-  const bool scatter = (a->d_joints && d.E > 0) || (a->d_joints_regressed && d.R > 0);
+  const bool scatter = !picks_only && ((a->d_joints && d.E > 0) || (a->d_joints_regressed && d.R > 0));
   const float* dverts = a->d_verts;
   if (scatter) {
     const size_t bytes = (size_t)B * d.V * 3 * sizeof(float);
@@ -100,7 +114,9 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
   }
 
   const bool have_dv = dverts != nullptr;
-  if (have_dv) {
+  if (picks_only) {
+    // dA, dtr and d_feat are already there
+  } else if (have_dv) {
     DAArgs da;
     da.B = B; da.dverts = dverts;
     da.vsrc = d.lbs_only ? d.bias : v_posed;
@@ -209,9 +225,9 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
   pb.pose = a->pose; pb.pca_l = a->hand_pca_l; pb.pca_r = a->hand_pca_r;
   pb.add_mean = (a->flags & SMPLK_FLAG_ADD_POSE_MEAN) ? 1 : 0;
   pb.dA = dA; pb.d_joints = a->d_joints; pb.joints_ld = joints_ld;
-  pb.d_feat = blend_bwd ? dfeat : nullptr;
-  pb.feat_splits = L.splits; pb.feat_split_stride = (size_t)L.mpad * d.Kpad;
-  if (pb.d_feat != nullptr && L.splits > 1) {      // sum the split-K partials in parallel, in place
+  pb.d_feat = (blend_bwd || (picks_only && want_blend_grads)) ? dfeat : nullptr;
+  pb.feat_splits = picks_only ? 1 : L.splits; pb.feat_split_stride = (size_t)L.mpad * d.Kpad;
+  if (pb.d_feat != nullptr && L.splits > 1 && !picks_only) {      // sum the split-K partials in parallel, in place
     const int n = B * d.Kpad;
     reduce_splits_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, L.splits, pb.feat_split_stride, dfeat);
     LAUNCH_CHECK("reduce_splits_kernel");

@@ -61,6 +61,7 @@ struct ModelDev {
   const float* comp_r;        // [C][45]
   const float* pose_mean;     // [3J]
   const int* extra_vids;      // [E]
+  const float* pick_pd;       // [3E][Kpad] exact fp32 rows of [posedirs | shapedirs] at the picked vertices' coordinates (or null)
   const int* reg_ptr;         // [R+1] CSR of regressor_posed
   const int* reg_col;         // [nnzR]
   const float* reg_val;       // [nnzR]

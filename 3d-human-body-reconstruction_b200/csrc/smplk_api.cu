@@ -103,6 +103,7 @@ struct smplk_model {
   bool skin_g8;         // 8 vertices per thread (default; SMPLK_SKIN_G8=0 selects the 4-vertex kernel)
   bool skin_tma;        // SMPLK_SKIN_TMA=1: per-warp cp.async.bulk pipeline (measured slower: 0.210 vs 0.182 ms)
   bool force_skin_v1;   // SMPLK_SKIN_V1=1 in the environment: per-vertex gather kernel (A/B testing)
+  bool sparse_picks;    // SMPLK_SPARSE_PICKS=0: keypoint-only gradients take the dense backward (A/B testing)
   bool fit_fused;       // fused skinning + loss + skinning-backward kernel of smplk_fit_vertex_l2 (SMPLK_FIT_FUSED=0: off)
   mutable bool prof_on;
   mutable std::vector<ProfRec> prof_pending;
@@ -595,6 +596,19 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
       if (ev[e] < 0 || ev[e] >= V) return fail(SMPLK_E_ARG, "extra_vertex_ids[%d] out of range", e);
     }
     if (int r = upload(mdl, ev, &d.extra_vids)) return r;
+    d.pick_pd = nullptr;
+    if (!lbs_only && d.E > 0) {   // rows of the blend operand at the picked coordinates (sparse keypoint backward)
+      std::vector<float> pp((size_t)3 * d.E * d.Kpad, 0.f);
+      for (int e = 0; e < d.E; ++e)
+        for (int c = 0; c < 3; ++c) {
+          const int n = 3 * ev[e] + c;
+          const double* pdrow = desc->posedirs + (size_t)n * d.P;
+          const double* sdrow = desc->shapedirs + (size_t)n * NB;
+          for (int k = 0; k < d.K; ++k)
+            pp[(size_t)(3 * e + c) * d.Kpad + k] = (float)(k < d.P ? pdrow[k] : sdrow[k - d.P]);
+        }
+      if (int r = upload(mdl, pp, &d.pick_pd)) return r;
+    }
     std::vector<int> rptr(d.R + 1, 0), rcol;
     std::vector<float> rval;
     for (int r = 0; r < d.R; ++r) {
@@ -682,6 +696,7 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     CUDA_TRY(cudaFuncSetAttribute(skin_backward_grouped_kernel<kSkinBwdStages, true>, attr, max_optin));
     CUDA_TRY(cudaFuncSetAttribute(divide_faces_kernel, attr, max_optin));
     CUDA_TRY(cudaFuncSetAttribute(skin_fit_l2_kernel, attr, max_optin));
+    CUDA_TRY(cudaFuncSetAttribute(pick_backward_kernel, attr, max_optin));
   }
   return 0;
 }
@@ -720,6 +735,7 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   { const char* e = getenv("SMPLK_SKIN_TMA"); mdl->skin_tma = (e && e[0] == '1'); }
   { const char* e = getenv("SMPLK_SKIN_V1"); mdl->force_skin_v1 = e && e[0] == '1'; }
   { const char* e = getenv("SMPLK_FIT_FUSED"); mdl->fit_fused = !(e && e[0] == '0'); }
+  { const char* e = getenv("SMPLK_SPARSE_PICKS"); mdl->sparse_picks = !(e && e[0] == '0'); }
   { const char* e = getenv("SMPLK_GEMM_1CTA"); mdl->use_2cta = !(e && e[0] == '1'); }
   { const char* e = getenv("SMPLK_FUSED"); mdl->use_fused = !(e && e[0] == '0'); }
   { const char* e = getenv("SMPLK_POSE_V1"); mdl->use_pose_block = !(e && e[0] == '1'); }

@@ -433,6 +433,61 @@ def test_backward_matches_autograd_oracle(dev, kind, B, pca, joint_w):
         assert rel <= GRAD_RTOL, (name, rel)
 
 
+@pytest.mark.parametrize("kind,B,pca", [("smplh", 6, True), ("smpl", 33, False)])
+def test_keypoint_only_backward_takes_the_sparse_path_and_matches_oracle(dev, kind, B, pca, monkeypatch):
+    """A loss on joints alone (FK joints + vertex picks: the data term of lib/Gen_SMPLH/fitting.py:369-381)
+    runs the sparse pick kernel instead of the dense vertex backward: same gradients as the float64
+    autograd oracle and as the dense path (SMPLK_SPARSE_PICKS=0), fewer launches."""
+    from smplk import _lib
+    m = synthetic.make_model(kind, seed=17)
+    J = 52 if kind == "smplh" else 24
+    om = O.TorchOracleModel(m, dtype=torch.float64, num_pca_comps=12)
+    rng = np.random.default_rng(5)
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=12)
+    lh, rh = rng.standard_normal((B, 12)), rng.standard_normal((B, 12))
+    tgt_j = rng.standard_normal((B, J + 21, 3))
+    wj = rng.uniform(0.2, 2.0, size=(1, J + 21, 1))
+
+    def loss_fn(j):
+        t = torch.as_tensor(tgt_j, dtype=j.dtype, device=j.device)
+        w = torch.as_tensor(wj, dtype=j.dtype, device=j.device)
+        return (w * (j - t) ** 2).sum()
+
+    ob, op, ot = (torch.tensor(x, dtype=torch.float64, requires_grad=True) for x in (betas, pose, transl))
+    ol, orr = (torch.tensor(x, dtype=torch.float64, requires_grad=True) for x in (lh, rh))
+    if pca:
+        o = om.forward(ob, op[:, :3], op[:, 3:66], ol, orr, transl=ot)
+        oj = o.joints[:, :J + 21]
+    else:
+        o = om.forward_full_pose(ob, op, ot)
+        oj = torch.cat([o.joints, o.vertices[:, torch.as_tensor(m["extra_vertex_ids"], dtype=torch.long)]], 1)
+    loss_fn(oj).backward()
+
+    results = {}
+    for mode in ("sparse", "dense"):
+        if mode == "dense":
+            monkeypatch.setenv("SMPLK_SPARSE_PICKS", "0")
+        dm = smplk.DeviceModel(m, device=0, num_pca_comps=12 if pca else 0, extra_vertex_ids=m["extra_vertex_ids"])
+        gb, gp, gt = (_t(x, dev, True) for x in (betas, pose, transl))
+        gl, gr = (_t(x, dev, True) for x in (lh, rh))
+        v, j, _, _ = body_model_apply(dm, gb, gp, pca_l=gl if pca else None, pca_r=gr if pca else None, transl=gt,
+                                      add_pose_mean=pca)
+        loss = loss_fn(j)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        loss.backward()
+        torch.cuda.synchronize()
+        launches = _lib.launch_count() - n0
+        grads = [gb.grad, gt.grad, gp.grad[:, :66] if pca else gp.grad] + ([gl.grad, gr.grad] if pca else [])
+        results[mode] = (launches, grads)
+    refs = [ob.grad, ot.grad, op.grad[:, :66] if pca else op.grad] + ([ol.grad, orr.grad] if pca else [])
+    for got, ref in zip(results["sparse"][1], refs):
+        assert _maxerr(got, ref) / float(ref.abs().max()) <= GRAD_RTOL
+    for got, ref in zip(results["sparse"][1], results["dense"][1]):
+        assert _maxerr(got, ref) <= 1e-5 * float(ref.abs().max())
+    assert results["sparse"][0] == 2 and results["dense"][0] > results["sparse"][0], (results["sparse"][0], results["dense"][0])
+
+
 def test_handles_of_different_skeletons_coexist(dev, smplh_model, smpl_model):
     """Dynamic shared-memory limits belong to the kernels, not to a handle: creating a handle for a
     smaller skeleton (24 joints, 10 betas) after a larger one (52 joints, 16 betas) must not break
