@@ -54,7 +54,7 @@ class _BodyModelFn(torch.autograd.Function):
     """verts, joints, joints_regressed, full_pose = f(betas, pose, pca_l, pca_r, transl)."""
 
     @staticmethod
-    def forward(ctx, dm, flags, want_regressed, betas, pose, pca_l, pca_r, transl):
+    def forward(ctx, dm, flags, want_regressed, want_verts, betas, pose, pca_l, pca_r, transl):
         B = pose.shape[0]
         dev = pose.device
         needs_grad = any(t is not None and t.requires_grad
@@ -63,10 +63,12 @@ class _BodyModelFn(torch.autograd.Function):
             flags |= _lib.FLAG_SAVE_FOR_BACKWARD
         betas_c, pose_c = _prep(betas, dev), _prep(pose, dev)
         pl, pr, tr = _prep(pca_l, dev), _prep(pca_r, dev), _prep(transl, dev)
-        verts = torch.empty(B, dm.V, 3, device=dev, dtype=torch.float32)
-        joints = torch.empty(B, dm.J + dm.E, 3, device=dev, dtype=torch.float32)
         jreg = (torch.empty(B, dm.R, 3, device=dev, dtype=torch.float32)
                 if (want_regressed and dm.R > 0) else None)
+        # joints only (return_verts=False): the library blends and skins the picked vertices alone
+        want_verts = want_verts or jreg is not None
+        verts = torch.empty(B, dm.V, 3, device=dev, dtype=torch.float32) if want_verts else None
+        joints = torch.empty(B, dm.J + dm.E, 3, device=dev, dtype=torch.float32)
         full_pose = torch.empty(B, 3 * dm.J, device=dev, dtype=torch.float32)
         ws_bytes = dm.workspace_bytes(B, flags)
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
@@ -91,6 +93,9 @@ class _BodyModelFn(torch.autograd.Function):
         if jreg is None:
             jreg = torch.empty(0, device=dev)
             ctx.mark_non_differentiable(jreg)
+        if verts is None:
+            verts = torch.empty(0, device=dev)
+            ctx.mark_non_differentiable(verts)
         return verts, joints, jreg, full_pose
 
     @staticmethod
@@ -99,14 +104,15 @@ class _BodyModelFn(torch.autograd.Function):
         betas, pose, pl, pr, tr = ctx.inputs
         B = pose.shape[0]
         dev = pose.device
-        need = ctx.needs_input_grad  # (dm, flags, want_reg, betas, pose, pca_l, pca_r, transl)
+        need = ctx.needs_input_grad[1:]  # (flags, want_reg, want_verts, betas, pose, pca_l, pca_r, transl)
 
         def grad_in(g):
             if g is None:
                 return None
             return g.contiguous().float()
 
-        d_verts, d_joints = grad_in(d_verts), grad_in(d_joints)
+        d_verts = grad_in(d_verts) if (d_verts is not None and d_verts.numel() > 0) else None
+        d_joints = grad_in(d_joints)
         d_jreg = grad_in(d_jreg) if (d_jreg is not None and d_jreg.numel() > 0) else None
         d_betas = torch.empty_like(betas) if (betas is not None and need[3]) else None
         d_pose = torch.empty_like(pose) if need[4] else None
@@ -127,7 +133,7 @@ class _BodyModelFn(torch.autograd.Function):
         a.stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         with torch.cuda.device(dev):
             dm.backward(a)
-        return None, None, None, d_betas, d_pose, d_pl, d_pr, d_tr
+        return None, None, None, None, d_betas, d_pose, d_pl, d_pr, d_tr
 
 
 class _VertexL2Fn(torch.autograd.Function):
@@ -247,12 +253,14 @@ def fit_vertex_l2(dm, betas, pose, target, pca_l=None, pca_r=None, transl=None, 
 
 
 def body_model_apply(dm, betas, pose, pca_l=None, pca_r=None, transl=None, add_pose_mean=False,
-                     want_regressed=False, flags=0):
-    """Functional entry point: (verts, joints_fk_plus_picks, joints_regressed|None, full_pose)."""
+                     want_regressed=False, flags=0, want_verts=True):
+    """Functional entry point: (verts|None, joints_fk_plus_picks, joints_regressed|None, full_pose).
+    want_verts=False (and no regressed joints): only the vertex-pick joints' vertices are blended
+    and skinned (pick_forward_kernel), verts is None."""
     if add_pose_mean:
         flags |= _lib.FLAG_ADD_POSE_MEAN
-    v, j, r, fp = _BodyModelFn.apply(dm, flags, want_regressed, betas, pose, pca_l, pca_r, transl)
-    return v, j, (r if r.numel() > 0 else None), fp
+    v, j, r, fp = _BodyModelFn.apply(dm, flags, want_regressed, want_verts, betas, pose, pca_l, pca_r, transl)
+    return (v if v.numel() > 0 else None), j, (r if r.numel() > 0 else None), fp
 
 
 class _BodyModelBase(nn.Module):
@@ -396,8 +404,8 @@ class SMPL(_BodyModelBase):
             raise NotImplementedError("pose2rot=False (rotation-matrix input) is not supported")
         dm, go, bp, be, tr, pose = self._assemble(betas, body_pose, global_orient, transl)
         verts, joints, jreg, full_pose = body_model_apply(
-            dm, be, pose, transl=tr, want_regressed=self._regressor_extra is not None)
-        self._verts_cache = verts.detach()   # never keeps the autograd graph alive
+            dm, be, pose, transl=tr, want_regressed=self._regressor_extra is not None, want_verts=return_verts)
+        self._verts_cache = None if verts is None else verts.detach()   # never keeps the autograd graph alive
         joints = self._finish(verts, joints, jreg, tr)
         if return_full_pose:  # differentiable view of the assembled pose (cheap torch glue)
             full_pose = pose
@@ -489,8 +497,8 @@ class SMPLH(_BodyModelBase):
             betas, global_orient, body_pose, left_hand_pose, right_hand_pose, transl)
         verts, joints, jreg, full_pose = body_model_apply(
             dm, be, pose, pca_l=pca_l, pca_r=pca_r, transl=tr, add_pose_mean=True,
-            want_regressed=self._regressor_extra is not None)
-        self._verts_cache = verts.detach()   # never keeps the autograd graph alive
+            want_regressed=self._regressor_extra is not None, want_verts=return_verts)
+        self._verts_cache = None if verts is None else verts.detach()   # never keeps the autograd graph alive
         joints = self._finish(verts, joints, jreg, tr)
         if return_full_pose:  # differentiable assembly (upstream: cat + PCA einsum + pose_mean)
             if self.use_pca:

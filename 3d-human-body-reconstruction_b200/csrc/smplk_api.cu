@@ -21,6 +21,7 @@
 #include "skinning.cuh"
 #include "skinning8.cuh"
 #include "skin_fit.cuh"
+#include "picks.cuh"
 #include "mesh_ops.cuh"
 #include "fit_loss.cuh"
 
@@ -697,6 +698,7 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     CUDA_TRY(cudaFuncSetAttribute(divide_faces_kernel, attr, max_optin));
     CUDA_TRY(cudaFuncSetAttribute(skin_fit_l2_kernel, attr, max_optin));
     CUDA_TRY(cudaFuncSetAttribute(pick_backward_kernel, attr, max_optin));
+    CUDA_TRY(cudaFuncSetAttribute(pick_forward_kernel, attr, max_optin));
   }
   return 0;
 }
@@ -1115,9 +1117,12 @@ static int forward_impl(const smplk_model* model, const smplk_forward_args* a, c
     return fail(SMPLK_E_ARG, "hand PCA coefficients given but the model has no PCA components");
   if ((flags & SMPLK_FLAG_TRANSFORMS_ONLY) && (a->verts || a->joints_regressed))
     return fail(SMPLK_E_ARG, "SMPLK_FLAG_TRANSFORMS_ONLY excludes the verts / joints_regressed outputs");
-  if (!(flags & SMPLK_FLAG_TRANSFORMS_ONLY) &&
+  // joints without vertices: the E picked vertices alone are blended and skinned (pick_forward_kernel)
+  const bool picks_fwd = !(flags & SMPLK_FLAG_TRANSFORMS_ONLY) && !a->verts && a->joints && d.E > 0 &&
+                         !a->joints_regressed && (d.lbs_only || d.pick_pd != nullptr) && fit == nullptr;
+  if (!(flags & SMPLK_FLAG_TRANSFORMS_ONLY) && !picks_fwd &&
       ((a->joints && d.E > 0 && !a->verts) || (a->joints_regressed && !a->verts)))
-    return fail(SMPLK_E_ARG, "vertex picks / regressed joints need the verts output buffer");
+    return fail(SMPLK_E_ARG, "regressed joints need the verts output buffer");
   if (a->joints_regressed && d.R == 0)
     return fail(SMPLK_E_ARG, "joints_regressed requested but the model has no regressor_posed");
   const WsLayout w = ws_layout(d, a->batch, flags);
@@ -1165,6 +1170,17 @@ static int forward_impl(const smplk_model* model, const smplk_forward_args* a, c
     if (at_from_pose) pa.At = At;            // the block pose kernel writes the transposed transforms itself
     if (int r = launch_pose_forward(model, pa, st)) return r;
     if (flags & SMPLK_FLAG_TRANSFORMS_ONLY) continue;    // pose / FK kernel only: A, joints, full_pose
+    if (picks_fwd) {
+      PickFwdArgs pf;
+      pf.B = rows; pf.H_hi = pa.H_hi; pf.H_lo = pa.H_lo; pf.F_hi = pa.F_hi; pf.F_lo = pa.F_lo;
+      pf.A = A; pf.transl = pa.transl;
+      pf.vposed = d.lbs_only ? nullptr : v_posed;     // the picked entries are what the sparse backward reads
+      pf.joints = pa.joints; pf.joints_ld = joints_ld;
+      ProfScope prof(model, st, SMPLK_PROF_SKIN);
+      pick_forward_kernel<<<rows, kPickFwdThreads, pick_fwd_smem_bytes(d.J, d.E, std::max(d.Kpad, 1)), st>>>(d, pf);
+      LAUNCH_CHECK("pick_forward_kernel");
+      continue;
+    }
     if (!fused && !d.lbs_only && (a->verts || (flags & SMPLK_FLAG_SAVE_FOR_BACKWARD))) {
       if (int r = launch_blend(model, rows, path, F_hi, F_lo, v_posed, st)) return r;
     }

@@ -488,6 +488,48 @@ def test_keypoint_only_backward_takes_the_sparse_path_and_matches_oracle(dev, ki
     assert results["sparse"][0] == 2 and results["dense"][0] > results["sparse"][0], (results["sparse"][0], results["dense"][0])
 
 
+def test_joints_only_forward_matches_dense_forward_and_backward(dev, smplh_model):
+    """return_verts=False (fit_single_frame.py:313, fitting.py:82): only the 21 picked vertices are
+    blended and skinned.  Joints agree with the full forward to 1e-6 m, gradients of a joints loss with
+    the dense route, 3 launches forward+backward... and the oracle."""
+    from smplk import _lib
+    from smplk.body_models import SMPLH
+    B = 11
+    mod = SMPLH(model=smplh_model, use_pca=True, num_pca_comps=12, batch_size=B).to(dev)
+    rng = np.random.default_rng(8)
+    vals = dict(betas=rng.standard_normal((B, 16)), global_orient=rng.standard_normal((B, 3)) * 0.3,
+                body_pose=rng.standard_normal((B, 63)) * 0.3, left_hand_pose=rng.standard_normal((B, 12)),
+                right_hand_pose=rng.standard_normal((B, 12)), transl=rng.standard_normal((B, 3)))
+    mod.reset_params(**vals)
+    tgt = _t(rng.standard_normal((B, 73, 3)), dev)
+    grads, joints, launches = [], [], []
+    for rv in (False, True):
+        mod.zero_grad()
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        out = mod(return_verts=rv)
+        ((out.joints - tgt) ** 2).sum().backward()
+        torch.cuda.synchronize()
+        launches.append(_lib.launch_count() - n0)
+        assert (out.vertices is None) == (not rv)
+        joints.append(out.joints.detach().clone())
+        grads.append({n: p.grad.clone() for n, p in mod.named_parameters()})
+    assert _maxerr(joints[0], joints[1]) <= 1e-6
+    for n in grads[0]:
+        assert _maxerr(grads[0][n], grads[1][n]) <= 1e-5 * float(grads[1][n].abs().max()), n
+    assert launches[0] == 4 and launches[1] > launches[0], launches      # pose, picks | picks backward, pose backward
+    # oracle joints
+    om = O.TorchOracleModel(smplh_model, dtype=torch.float64, num_pca_comps=12)
+    t = {k: torch.tensor(v) for k, v in vals.items()}
+    ref = om.forward(t["betas"], t["global_orient"], t["body_pose"], t["left_hand_pose"], t["right_hand_pose"],
+                     transl=t["transl"])
+    assert _maxerr(joints[0].double().cpu(), ref.joints[:, :73]) <= TOL
+    # no-grad inference and the rigged-mesh-free SMPL case
+    with torch.no_grad():
+        j2 = mod(return_verts=False).joints
+    assert _maxerr(j2, joints[0]) <= 1e-6
+
+
 def test_handles_of_different_skeletons_coexist(dev, smplh_model, smpl_model):
     """Dynamic shared-memory limits belong to the kernels, not to a handle: creating a handle for a
     smaller skeleton (24 joints, 10 betas) after a larger one (52 joints, 16 betas) must not break
