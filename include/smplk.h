@@ -124,7 +124,11 @@ typedef struct {
 /* Replaces, per batch of bodies: upstream smplx.SMPLH.forward / SMPL.forward + lbs() as called at
  * models/smplh.py:26-31 and lib/Gen_SMPLH/fitting.py:243-245, and the numpy twins
  * SMPLHModel.set_params/update/compute_R_G/do_skinning (models/smplh_np.py:39-86),
- * SMPLModel (models/smpl_np.py:158-206), RecoverModel.set_params (lib/model2video.py:42-81). */
+ * SMPLModel (models/smpl_np.py:158-206), RecoverModel.set_params (lib/model2video.py:42-81).
+ * verts == NULL with joints != NULL (return_verts=False, fit_single_frame.py:313): only the E
+ * vertex-pick joints' vertices are blended and skinned.  With SMPLK_FLAG_SAVE_FOR_BACKWARD the
+ * workspace then holds v_posed at those vertices only, i.e. a later smplk_backward may be given
+ * d_joints (FK joints and picks) but not d_verts / d_joints_regressed. */
 int smplk_forward(const smplk_model* model, const smplk_forward_args* args);
 
 typedef struct {

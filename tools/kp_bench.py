@@ -1,6 +1,6 @@
 """Keypoint-fitting closure (the reference's fit_single_frame closure: SMPL-H forward, camera
 projection + GMoF data term + priors, backward) timed eager and as a replayed CUDA graph.
-Usage: [SMPLK_SPARSE_PICKS=0] python tools/kp_bench.py [B ...]"""
+Usage: [SMPLK_SPARSE_PICKS=0] [RETURN_VERTS=0] python tools/kp_bench.py [B ...]"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -21,7 +21,8 @@ for B in [int(x) for x in sys.argv[1:]] or [1, 64, 1024]:
     gt2d = torch.rand(B, nj, 2, device=dev) * 1024
     conf = torch.ones(B, nj, device=dev)
     loss_fn = SMPLifyLoss(rho=100.0, data_weight=1.0, shape_weight=0.5, hand_prior_weight=0.1)
-    fn = lambda: loss_fn(mod(return_verts=True, return_full_pose=True), cam, gt2d, conf, joint_weights=conf)
+    rv = os.environ.get("RETURN_VERTS", "1") != "0"
+    fn = lambda: loss_fn(mod(return_verts=rv, return_full_pose=True), cam, gt2d, conf, joint_weights=conf)
 
     def eager():
         mod.zero_grad()
@@ -41,5 +42,5 @@ for B in [int(x) for x in sys.argv[1:]] or [1, 64, 1024]:
     t_e = timeit(eager)
     g = GraphedClosure(fn, mod.parameters())
     t_g = timeit(g)
-    print("keypoint closure B=%d sparse_picks=%s: eager %.4f ms, graph %.4f ms" % (
-        B, os.environ.get("SMPLK_SPARSE_PICKS", "1"), t_e, t_g))
+    print("keypoint closure B=%d sparse_picks=%s return_verts=%s: eager %.4f ms, graph %.4f ms" % (
+        B, os.environ.get("SMPLK_SPARSE_PICKS", "1"), rv, t_e, t_g))
