@@ -76,7 +76,7 @@ class BackwardArgs(ctypes.Structure):
         ("d_transl", ctypes.c_void_p),
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
         ("scratch", ctypes.c_void_p), ("scratch_bytes", ctypes.c_size_t),
-        ("stream", ctypes.c_void_p), ("d_loss", ctypes.c_void_p),
+        ("stream", ctypes.c_void_p), ("d_loss", ctypes.c_void_p), ("d_full_pose", ctypes.c_void_p),
     ]
 
 

@@ -89,7 +89,6 @@ class _BodyModelFn(torch.autograd.Function):
         if needs_grad:
             ctx.ws = ws
             ctx.inputs = (betas_c, pose_c, pl, pr, tr)
-        ctx.mark_non_differentiable(full_pose)
         if jreg is None:
             jreg = torch.empty(0, device=dev)
             ctx.mark_non_differentiable(jreg)
@@ -114,6 +113,7 @@ class _BodyModelFn(torch.autograd.Function):
         d_verts = grad_in(d_verts) if (d_verts is not None and d_verts.numel() > 0) else None
         d_joints = grad_in(d_joints)
         d_jreg = grad_in(d_jreg) if (d_jreg is not None and d_jreg.numel() > 0) else None
+        d_full_pose = grad_in(d_full_pose)
         d_betas = torch.empty_like(betas) if (betas is not None and need[3]) else None
         d_pose = torch.empty_like(pose) if need[4] else None
         d_pl = torch.empty_like(pl) if (pl is not None and need[5]) else None
@@ -126,6 +126,7 @@ class _BodyModelFn(torch.autograd.Function):
         a.betas, a.betas_batch = _ptr(betas), (betas.shape[0] if betas is not None else 1)
         a.pose, a.hand_pca_l, a.hand_pca_r = _ptr(pose), _ptr(pl), _ptr(pr)
         a.d_verts, a.d_joints, a.d_joints_regressed = _ptr(d_verts), _ptr(d_joints), _ptr(d_jreg)
+        a.d_full_pose = _ptr(d_full_pose)
         a.d_betas, a.d_pose = _ptr(d_betas), _ptr(d_pose)
         a.d_hand_pca_l, a.d_hand_pca_r, a.d_transl = _ptr(d_pl), _ptr(d_pr), _ptr(d_tr)
         a.workspace, a.workspace_bytes = _ptr(ctx.ws), ctx.ws.numel()
@@ -407,8 +408,6 @@ class SMPL(_BodyModelBase):
             dm, be, pose, transl=tr, want_regressed=self._regressor_extra is not None, want_verts=return_verts)
         self._verts_cache = None if verts is None else verts.detach()   # never keeps the autograd graph alive
         joints = self._finish(verts, joints, jreg, tr)
-        if return_full_pose:  # differentiable view of the assembled pose (cheap torch glue)
-            full_pose = pose
         return ModelOutput(vertices=verts if return_verts else None, joints=joints,
                            full_pose=full_pose if return_full_pose else None, betas=be,
                            global_orient=go, body_pose=bp)
@@ -428,6 +427,7 @@ class SMPLH(_BodyModelBase):
         batch_size = kwargs.get("batch_size", 1)
         super().__init__(model_path=model_path, model=model, **kwargs)
         self.use_pca = use_pca
+        self._pad_cache = {}
         self.num_pca_comps = num_pca_comps
         self.flat_hand_mean = flat_hand_mean
         m = self._model_dict
@@ -472,7 +472,9 @@ class SMPLH(_BodyModelBase):
             tr = self._expand(tr, B)
         dm = self.device_model(dev)
         if self.use_pca:
-            pad = torch.zeros(B, 90, dtype=torch.float32, device=dev)
+            pad = self._pad_cache.get((B, str(dev)))
+            if pad is None:       # hand slots of the axis-angle row (filled from the PCA coefficients in the kernel)
+                pad = self._pad_cache[(B, str(dev))] = torch.zeros(B, 90, dtype=torch.float32, device=dev)
             pose = torch.cat([go_e, bp_e, pad], dim=1)
             pca_l, pca_r = lh_e, rh_e
         else:
@@ -500,13 +502,8 @@ class SMPLH(_BodyModelBase):
             want_regressed=self._regressor_extra is not None, want_verts=return_verts)
         self._verts_cache = None if verts is None else verts.detach()   # never keeps the autograd graph alive
         joints = self._finish(verts, joints, jreg, tr)
-        if return_full_pose:  # differentiable assembly (upstream: cat + PCA einsum + pose_mean)
-            if self.use_pca:
-                lh_aa = lh_e @ self.left_hand_components
-                rh_aa = rh_e @ self.right_hand_components
-            else:
-                lh_aa, rh_aa = lh_e, rh_e
-            full_pose = torch.cat([go_e, bp_e, lh_aa, rh_aa], dim=1) + self.pose_mean
+        # full_pose (PCA hands + pose mean applied) is an output of the pose kernel, differentiable through
+        # the same autograd node (upstream assembles it with cat + einsum + add)
         return ModelOutput(vertices=verts if return_verts else None, joints=joints,
                            full_pose=full_pose if return_full_pose else None, betas=be,
                            global_orient=go, body_pose=bp, left_hand_pose=lh, right_hand_pose=rh)

@@ -606,6 +606,7 @@ struct PoseBwdArgs {
   float* d_pca_r;
   float* d_transl;           // (B,3) or null
   const float* d_loss;       // (B) or null: scale of body b's parameter gradients
+  const float* d_full_pose;  // (B,3J) or null: gradient w.r.t. the assembled pose output
 };
 
 // smem floats per warp of pose_backward_kernel: world G, local L, dG (12 each), dR (9), dJ, dfull (3 each)
@@ -830,6 +831,10 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
       }
       float dr[3];
       rodrigues_backward(rv[s], dRl[s], dr);
+      if (a.d_full_pose != nullptr) {
+        const float* dfp = a.d_full_pose + (size_t)b * 3 * m.J + 3 * j;
+        dr[0] += dfp[0]; dr[1] += dfp[1]; dr[2] += dfp[2];
+      }
       dfull[3 * j + 0] = dr[0]; dfull[3 * j + 1] = dr[1]; dfull[3 * j + 2] = dr[2];
     }
   }

@@ -156,6 +156,8 @@ typedef struct {
                                  (the upstream gradient of a per-body loss whose d_verts was formed for
                                  d_loss = 1, e.g. after smplk_fit_vertex_l2); a shared betas row receives
                                  sum_b d_loss[b] d_betas_b */
+  const float* d_full_pose;   /* (B,3J) or NULL: gradient w.r.t. the forward's full_pose output (pose priors
+                                 read it, lib/Gen_SMPLH/fitting.py:383-413); flows to d_pose / d_hand_pca_* */
 } smplk_backward_args;
 
 size_t smplk_backward_scratch_bytes(const smplk_model* model, int32_t batch);
