@@ -61,7 +61,7 @@ struct PickBwdArgs {
   float* d_feat;            // (B,Kpad) or null
 };
 
-constexpr int kPickThreads = 128;
+constexpr int kPickThreads = 256;
 __host__ __device__ inline size_t pick_bwd_smem_bytes(int J, int E) {
   return (size_t)(2 * J * 12 + 3 * E + 4) * sizeof(float);
 }
@@ -637,6 +637,16 @@ template <int SLOTS>
 __global__ void __launch_bounds__(kPoseWarps * 32)
 pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
   extern __shared__ __align__(16) float pb_smem[];
+  // the skeleton's index tables, staged once per block: the level walks otherwise chain three or
+  // four dependent global loads per level (L2 latency each when a single body is fitted)
+  __shared__ int s_par[kMaxJoints], s_ord[kMaxJoints], s_lvl[kMaxJoints + 2], s_cptr[kMaxJoints + 1], s_cidx[kMaxJoints];
+  for (int i = threadIdx.x; i < m.J; i += blockDim.x) {
+    s_par[i] = m.parents[i]; s_ord[i] = m.order[i]; s_cptr[i] = m.child_ptr[i];
+    if (i < m.J - 1) s_cidx[i] = m.child_idx[i];
+  }
+  if (threadIdx.x == 0) s_cptr[m.J] = m.child_ptr[m.J];
+  for (int i = threadIdx.x; i < m.max_depth + 2; i += blockDim.x) s_lvl[i] = m.level_start[i];
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kPoseWarps + warp;
   if (b >= a.B) return;
@@ -659,15 +669,7 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
       float R[9];
       load_joint_pose(m, a.pose, a.pca_l, a.pca_r, a.add_mean, b, j, rv[s]);
       rodrigues(rv[s][0], rv[s][1], rv[s][2], R);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float v = m.J_template[3 * j + c];
-        if (betas_row != nullptr) {
-          const float* sd = m.J_shapedirs + (size_t)(3 * j + c) * m.NB;
-          for (int i = 0; i < m.NB; ++i) v = fmaf(sd[i], betas_row[i], v);
-        }
-        Jr[s][c] = v;
-      }
+      rest_joint(m, betas_row, j, Jr[s]);
       float4* l4 = reinterpret_cast<float4*>(Lc + j * 12);
       l4[0] = make_float4(R[0], R[1], R[2], Jr[s][0]);
       l4[1] = make_float4(R[3], R[4], R[5], Jr[s][1]);
@@ -681,7 +683,7 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
     const int j = lane + 32 * s;
     pj[s][0] = pj[s][1] = pj[s][2] = 0.f;
     if (j >= 1 && j < m.J) {
-      const float* lp = Lc + m.parents[j] * 12;
+      const float* lp = Lc + s_par[j] * 12;
       pj[s][0] = lp[3]; pj[s][1] = lp[7]; pj[s][2] = lp[11];
     }
   }
@@ -702,10 +704,10 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
   }
   __syncwarp();
   for (int d = 1; d <= m.max_depth; ++d) {
-    const int l0 = m.level_start[d], l1 = m.level_start[d + 1];
+    const int l0 = s_lvl[d], l1 = s_lvl[d + 1];
     for (int i = l0 + lane; i < l1; i += 32) {
-      const int j = m.order[i];
-      const float* Pm = Gw + m.parents[j] * 12;
+      const int j = s_ord[i];
+      const float* Pm = Gw + s_par[j] * 12;
       float out[12];
       affine_mul(Pm, Lc + j * 12, out);
 #pragma unroll
@@ -746,18 +748,18 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
   // dJrel from the now-final dG_j (the shared-memory float atomics this replaces were CAS loops and
   // 45 % of the kernel's stall samples).
   for (int d = m.max_depth; d >= 0; --d) {
-    const int l0 = m.level_start[d], l1 = m.level_start[d + 1];
+    const int l0 = s_lvl[d], l1 = s_lvl[d + 1];
     for (int i = l0 + lane; i < l1; i += 32) {
-      const int j = m.order[i];
+      const int j = s_ord[i];
       const float* G = Gw + j * 12;
       float dg[12], dj[3];
 #pragma unroll
       for (int q = 0; q < 12; ++q) dg[q] = dG[j * 12 + q];
 #pragma unroll
       for (int r = 0; r < 3; ++r) dj[r] = dJ[j * 3 + r];
-      const int c0 = m.child_ptr[j], c1 = m.child_ptr[j + 1];
+      const int c0 = s_cptr[j], c1 = s_cptr[j + 1];
       for (int n = c0; n < c1; ++n) {
-        const int c = m.child_idx[n];
+        const int c = s_cidx[n];
         const float* L = Lc + c * 12;
         float cg[12];
 #pragma unroll
@@ -777,7 +779,7 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
         for (int q = 0; q < 12; ++q) dG[j * 12 + q] = dg[q];
       }
       if (d >= 1) {
-        const float* Pm = Gw + m.parents[j] * 12;
+        const float* Pm = Gw + s_par[j] * 12;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
 #pragma unroll
@@ -852,6 +854,7 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
   if (a.d_pca_l && a.pca_l) {
     for (int c = lane; c < m.C; c += 32) {
       float acc = 0.f;
+#pragma unroll 9
       for (int i = 0; i < 45; ++i) acc = fmaf(m.comp_l[c * 45 + i], dfull[3 * hand0 + i], acc);
       a.d_pca_l[(size_t)b * m.C + c] = gs * acc;
     }
@@ -859,6 +862,7 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
   if (a.d_pca_r && a.pca_r) {
     for (int c = lane; c < m.C; c += 32) {
       float acc = 0.f;
+#pragma unroll 9
       for (int i = 0; i < 45; ++i) acc = fmaf(m.comp_r[c * 45 + i], dfull[3 * (hand0 + 15) + i], acc);
       a.d_pca_r[(size_t)b * m.C + c] = gs * acc;
     }
@@ -871,6 +875,7 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
       const int i = i0 + (lane & 15), h = lane >> 4;
       float acc0 = 0.f, acc1 = 0.f;
       if (i < m.NB) {
+#pragma unroll 4
         for (int q = h; q < nq; q += 4) {
           acc0 = fmaf(dJ[q], m.J_shapedirs[(size_t)q * m.NB + i], acc0);
           if (q + 2 < nq) acc1 = fmaf(dJ[q + 2], m.J_shapedirs[(size_t)(q + 2) * m.NB + i], acc1);

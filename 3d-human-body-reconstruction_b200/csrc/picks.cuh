@@ -25,7 +25,7 @@ struct PickFwdArgs {
   int joints_ld;
 };
 
-constexpr int kPickFwdThreads = 128;
+constexpr int kPickFwdThreads = 512;
 __host__ __device__ inline size_t pick_fwd_smem_bytes(int J, int E, int Kpad) {
   return (size_t)(Kpad + J * 12 + 3 * E + 4) * sizeof(float);
 }

@@ -62,6 +62,32 @@ __device__ __forceinline__ void rodrigues(float rx, float ry, float rz, float* R
 }
 
 // Assembled axis-angle of joint j for body b: `pose` columns, hand PCA override, pose mean.
+// Rest joint j = J_template[j] + J_shapedirs[j] . betas, four betas a round with every load issued
+// before the first use: for a single cold body the plain loop serialises one L2 round trip per beta.
+__device__ __forceinline__ void rest_joint(const ModelDev& m, const float* betas_row, int j, float* out) {
+  float v0 = m.J_template[3 * j], v1 = m.J_template[3 * j + 1], v2 = m.J_template[3 * j + 2];
+  if (betas_row != nullptr) {
+    const float* s0 = m.J_shapedirs + (size_t)(3 * j) * m.NB;
+    const float* s1 = s0 + m.NB;
+    const float* s2 = s1 + m.NB;
+    int i = 0;
+    for (; i + 4 <= m.NB; i += 4) {
+      const float b0 = betas_row[i], b1 = betas_row[i + 1], b2 = betas_row[i + 2], b3 = betas_row[i + 3];
+      const float x0 = s0[i], x1 = s0[i + 1], x2 = s0[i + 2], x3 = s0[i + 3];
+      const float y0 = s1[i], y1 = s1[i + 1], y2 = s1[i + 2], y3 = s1[i + 3];
+      const float z0 = s2[i], z1 = s2[i + 1], z2 = s2[i + 2], z3 = s2[i + 3];
+      v0 = fmaf(x3, b3, fmaf(x2, b2, fmaf(x1, b1, fmaf(x0, b0, v0))));
+      v1 = fmaf(y3, b3, fmaf(y2, b2, fmaf(y1, b1, fmaf(y0, b0, v1))));
+      v2 = fmaf(z3, b3, fmaf(z2, b2, fmaf(z1, b1, fmaf(z0, b0, v2))));
+    }
+    for (; i < m.NB; ++i) {
+      const float bi = betas_row[i];
+      v0 = fmaf(s0[i], bi, v0); v1 = fmaf(s1[i], bi, v1); v2 = fmaf(s2[i], bi, v2);
+    }
+  }
+  out[0] = v0; out[1] = v1; out[2] = v2;
+}
+
 __device__ __forceinline__ void load_joint_pose(const ModelDev& m, const float* pose,
                                                 const float* pca_l, const float* pca_r,
                                                 int add_mean, int b, int j, float* r) {
@@ -70,6 +96,7 @@ __device__ __forceinline__ void load_joint_pose(const ModelDev& m, const float* 
     const float* comp = m.comp_l + 3 * (j - hand0);
     const float* c = pca_l + (size_t)b * m.C;
     float x = 0.f, y = 0.f, z = 0.f;
+#pragma unroll 4
     for (int i = 0; i < m.C; ++i) {
       float ci = c[i];
       x = fmaf(ci, comp[i * 45 + 0], x);
@@ -81,6 +108,7 @@ __device__ __forceinline__ void load_joint_pose(const ModelDev& m, const float* 
     const float* comp = m.comp_r + 3 * (j - hand0 - 15);
     const float* c = pca_r + (size_t)b * m.C;
     float x = 0.f, y = 0.f, z = 0.f;
+#pragma unroll 4
     for (int i = 0; i < m.C; ++i) {
       float ci = c[i];
       x = fmaf(ci, comp[i * 45 + 0], x);
@@ -209,6 +237,12 @@ template <int SLOTS>
 __global__ void __launch_bounds__(kPoseWarps * 32)
 pose_forward_kernel(const ModelDev m, const PoseFwdArgs a) {
   extern __shared__ __align__(16) float pose_smem[];
+  // the skeleton's index tables, staged once per block: the level walk otherwise chains three
+  // dependent global loads per level (L2 latency each for a single body)
+  __shared__ int s_par[kMaxJoints], s_ord[kMaxJoints], s_lvl[kMaxJoints + 2];
+  for (int i = threadIdx.x; i < m.J; i += blockDim.x) { s_par[i] = m.parents[i]; s_ord[i] = m.order[i]; }
+  for (int i = threadIdx.x; i < m.max_depth + 2; i += blockDim.x) s_lvl[i] = m.level_start[i];
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kPoseWarps + warp;
   if (b >= a.B) return;
@@ -231,15 +265,7 @@ pose_forward_kernel(const ModelDev m, const PoseFwdArgs a) {
         fp[0] = rv[0]; fp[1] = rv[1]; fp[2] = rv[2];
       }
       rodrigues(rv[0], rv[1], rv[2], R);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float v = m.J_template[3 * j + c];
-        if (betas_row != nullptr) {
-          const float* sd = m.J_shapedirs + (size_t)(3 * j + c) * m.NB;
-          for (int i = 0; i < m.NB; ++i) v = fmaf(sd[i], betas_row[i], v);
-        }
-        Jr[s][c] = v;
-      }
+      rest_joint(m, betas_row, j, Jr[s]);
       float4* g = reinterpret_cast<float4*>(Gs + j * 12);
       g[0] = make_float4(R[0], R[1], R[2], Jr[s][0]);
       g[1] = make_float4(R[3], R[4], R[5], Jr[s][1]);
@@ -262,7 +288,7 @@ pose_forward_kernel(const ModelDev m, const PoseFwdArgs a) {
     const int j = lane + 32 * s;
     pj[s][0] = pj[s][1] = pj[s][2] = 0.f;
     if (j >= 1 && j < m.J) {
-      const float* gp = Gs + m.parents[j] * 12;
+      const float* gp = Gs + s_par[j] * 12;
       pj[s][0] = gp[3]; pj[s][1] = gp[7]; pj[s][2] = gp[11];
     }
   }
@@ -303,10 +329,10 @@ pose_forward_kernel(const ModelDev m, const PoseFwdArgs a) {
 
   // ---- walk the tree level by level: G_j = G_parent(j) * L_j
   for (int d = 1; d <= m.max_depth; ++d) {
-    const int l0 = m.level_start[d], l1 = m.level_start[d + 1];
+    const int l0 = s_lvl[d], l1 = s_lvl[d + 1];
     for (int i = l0 + lane; i < l1; i += 32) {
-      const int j = m.order[i];
-      const float4* P4 = reinterpret_cast<const float4*>(Gs + m.parents[j] * 12);
+      const int j = s_ord[i];
+      const float4* P4 = reinterpret_cast<const float4*>(Gs + s_par[j] * 12);
       float4* L4 = reinterpret_cast<float4*>(Gs + j * 12);
       const float4 p0 = P4[0], p1 = P4[1], p2 = P4[2];
       const float4 q0 = L4[0], q1 = L4[1], q2 = L4[2];

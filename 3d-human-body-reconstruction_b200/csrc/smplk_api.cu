@@ -683,22 +683,30 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     // skeleton cannot lower the limit a larger model's launches rely on.
     int max_optin = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, mdl->device));
-    const cudaFuncAttribute attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    CUDA_TRY(cudaFuncSetAttribute(skin_grouped_kernel<true>, attr, max_optin));
-    CUDA_TRY(cudaFuncSetAttribute(skin_grouped_kernel<false>, attr, max_optin));
-    CUDA_TRY(cudaFuncSetAttribute(skin_grouped8_kernel<true>, attr, max_optin));
-    CUDA_TRY(cudaFuncSetAttribute(skin_grouped8_kernel<false>, attr, max_optin));
-    CUDA_TRY(cudaFuncSetAttribute(skin_tma_kernel, attr, max_optin));
-    CUDA_TRY(cudaFuncSetAttribute(pose_forward_block_kernel<1>, attr, max_optin));
-    CUDA_TRY(cudaFuncSetAttribute(pose_forward_block_kernel<2>, attr, max_optin));
-    CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<1>, attr, max_optin));
-    CUDA_TRY(cudaFuncSetAttribute(pose_backward_kernel<2>, attr, max_optin));
-    CUDA_TRY(cudaFuncSetAttribute(skin_backward_grouped_kernel<kSkinBwdStages, false>, attr, max_optin));
-    CUDA_TRY(cudaFuncSetAttribute(skin_backward_grouped_kernel<kSkinBwdStages, true>, attr, max_optin));
-    CUDA_TRY(cudaFuncSetAttribute(divide_faces_kernel, attr, max_optin));
-    CUDA_TRY(cudaFuncSetAttribute(skin_fit_l2_kernel, attr, max_optin));
-    CUDA_TRY(cudaFuncSetAttribute(pick_backward_kernel, attr, max_optin));
-    CUDA_TRY(cudaFuncSetAttribute(pick_forward_kernel, attr, max_optin));
+    // (a kernel's static shared memory counts against the same per-block limit)
+#define SMPLK_MAX_DYN_SMEM(kernel)                                                                        \
+    do {                                                                                                  \
+      cudaFuncAttributes fa_;                                                                             \
+      CUDA_TRY(cudaFuncGetAttributes(&fa_, kernel));                                                      \
+      CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,                  \
+                                    max_optin - (int)fa_.sharedSizeBytes));                               \
+    } while (0)
+    SMPLK_MAX_DYN_SMEM((skin_grouped_kernel<true>));
+    SMPLK_MAX_DYN_SMEM((skin_grouped_kernel<false>));
+    SMPLK_MAX_DYN_SMEM((skin_grouped8_kernel<true>));
+    SMPLK_MAX_DYN_SMEM((skin_grouped8_kernel<false>));
+    SMPLK_MAX_DYN_SMEM((skin_tma_kernel));
+    SMPLK_MAX_DYN_SMEM((pose_forward_block_kernel<1>));
+    SMPLK_MAX_DYN_SMEM((pose_forward_block_kernel<2>));
+    SMPLK_MAX_DYN_SMEM((pose_backward_kernel<1>));
+    SMPLK_MAX_DYN_SMEM((pose_backward_kernel<2>));
+    SMPLK_MAX_DYN_SMEM((skin_backward_grouped_kernel<kSkinBwdStages, false>));
+    SMPLK_MAX_DYN_SMEM((skin_backward_grouped_kernel<kSkinBwdStages, true>));
+    SMPLK_MAX_DYN_SMEM((divide_faces_kernel));
+    SMPLK_MAX_DYN_SMEM((skin_fit_l2_kernel));
+    SMPLK_MAX_DYN_SMEM((pick_backward_kernel));
+    SMPLK_MAX_DYN_SMEM((pick_forward_kernel));
+#undef SMPLK_MAX_DYN_SMEM
   }
   return 0;
 }
