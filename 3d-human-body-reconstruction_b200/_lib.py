@@ -22,6 +22,7 @@ FLAG_BLEND_TCGEN05 = 8
 FLAG_BLEND_TF32 = 16
 FLAG_TRANSFORMS_ONLY = 32
 FLAG_FIT_VERTEX_L2 = 64
+FLAG_LOSS_SUM = 128
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

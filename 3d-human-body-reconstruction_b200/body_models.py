@@ -199,7 +199,7 @@ class _FitVertexL2Fn(torch.autograd.Function):
         a.workspace, a.workspace_bytes = _ptr(ws), ws_bytes
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         a.stream = stream
-        loss = torch.empty(B, device=dev, dtype=torch.float32)
+        loss = torch.empty((() if (flags & _lib.FLAG_LOSS_SUM) else (B,)), device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             # `verts` comes back holding the vertex gradient 2 scale (V - V*), not the vertices
             dm.fit_vertex_l2(a, _ptr(tgt), scale, _ptr(loss))
@@ -243,13 +243,18 @@ class _FitVertexL2Fn(torch.autograd.Function):
 
 
 def fit_vertex_l2(dm, betas, pose, target, pca_l=None, pca_r=None, transl=None, add_pose_mean=False,
-                  scale=1.0, flags=0):
+                  scale=1.0, flags=0, reduce="none"):
     """Per-body loss (B,) = scale * sum ||V - target||^2 of the posed vertices against target meshes,
     as ONE autograd node: body-model forward + fused loss/gradient kernel forward, body-model backward
     on the stored vertex gradient.  `fit_vertex_l2(...).sum().backward()` is the fitting step of
-    BASELINE config 3; it equals `vertex_l2_loss(body_model_apply(...)[0], target)`."""
+    BASELINE config 3; it equals `vertex_l2_loss(body_model_apply(...)[0], target)`.
+    reduce="sum" returns the scalar sum over the bodies (accumulated inside the kernel)."""
     if add_pose_mean:
         flags |= _lib.FLAG_ADD_POSE_MEAN
+    if reduce == "sum":       # the kernel accumulates one scalar: no separate sum / expand kernels around the node
+        flags |= _lib.FLAG_LOSS_SUM
+    elif reduce != "none":
+        raise ValueError("reduce must be 'none' or 'sum'")
     return _FitVertexL2Fn.apply(dm, flags, scale, target, betas, pose, pca_l, pca_r, transl)
 
 
@@ -394,10 +399,10 @@ class SMPL(_BodyModelBase):
             tr = self._expand(tr, B)
         return self.device_model(dev), go, bp, be, tr, pose
 
-    def vertex_l2(self, target, scale=1.0, betas=None, body_pose=None, global_orient=None, transl=None):
+    def vertex_l2(self, target, scale=1.0, betas=None, body_pose=None, global_orient=None, transl=None, reduce="none"):
         """Per-body scale * sum ||vertices - target||^2 as one autograd node (see fit_vertex_l2)."""
         dm, go, bp, be, tr, pose = self._assemble(betas, body_pose, global_orient, transl)
-        return fit_vertex_l2(dm, be, pose, target, transl=tr, scale=scale)
+        return fit_vertex_l2(dm, be, pose, target, transl=tr, scale=scale, reduce=reduce)
 
     def forward(self, betas=None, body_pose=None, global_orient=None, transl=None,
                 return_verts=True, return_full_pose=False, pose2rot=True, **kwargs):
@@ -483,12 +488,12 @@ class SMPLH(_BodyModelBase):
         return dm, go, bp, be, lh, rh, tr, pose, pca_l, pca_r, (go_e, bp_e, lh_e, rh_e)
 
     def vertex_l2(self, target, scale=1.0, betas=None, global_orient=None, body_pose=None,
-                  left_hand_pose=None, right_hand_pose=None, transl=None):
+                  left_hand_pose=None, right_hand_pose=None, transl=None, reduce="none"):
         """Per-body scale * sum ||vertices - target||^2 as one autograd node (see fit_vertex_l2)."""
         dm, _, _, be, _, _, tr, pose, pca_l, pca_r, _ = self._assemble(
             betas, global_orient, body_pose, left_hand_pose, right_hand_pose, transl)
         return fit_vertex_l2(dm, be, pose, target, pca_l=pca_l, pca_r=pca_r, transl=tr, add_pose_mean=True,
-                             scale=scale)
+                             scale=scale, reduce=reduce)
 
     def forward(self, betas=None, global_orient=None, body_pose=None, left_hand_pose=None,
                 right_hand_pose=None, transl=None, return_verts=True, return_full_pose=False,

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kPickThreads) pick_backward_kernel(const Model
 // grad = 2 * scale * (V - V*).  One pass over V and V* instead of ~6 elementwise torch kernels.
 __global__ void __launch_bounds__(256)
 vertex_l2_kernel(int n_per_body, const float* verts, const float* __restrict__ target,
-                 float scale, float* grad, float* __restrict__ loss, int vec2) {
+                 float scale, float* grad, float* __restrict__ loss, int vec2, int loss_stride) {
   // `grad` may alias `verts` (the fused fitting node overwrites the vertices with their gradient):
   // every element is read and written by the same thread, and neither pointer is __restrict__
   __shared__ float red[8];
@@ -163,7 +163,7 @@ vertex_l2_kernel(int n_per_body, const float* verts, const float* __restrict__ t
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += red[w];
-    atomicAdd(loss + b, scale * t);
+    atomicAdd(loss + (size_t)b * loss_stride, scale * t);
   }
 }
 
@@ -606,6 +606,7 @@ struct PoseBwdArgs {
   float* d_pca_r;
   float* d_transl;           // (B,3) or null
   const float* d_loss;       // (B) or null: scale of body b's parameter gradients
+  int d_loss_stride;         // 1, or 0 when d_loss is one float for all bodies
   const float* d_full_pose;  // (B,3J) or null: gradient w.r.t. the assembled pose output
 };
 
@@ -842,7 +843,7 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
   }
   __syncwarp();
 
-  const float gs = a.d_loss ? a.d_loss[b] : 1.f;        // upstream gradient of this body's loss
+  const float gs = a.d_loss ? a.d_loss[(size_t)b * a.d_loss_stride] : 1.f;        // upstream gradient of this body's loss
   const int hand0 = m.J - 30;
   if (a.d_pose) {
     for (int i = lane; i < 3 * m.J; i += 32) {

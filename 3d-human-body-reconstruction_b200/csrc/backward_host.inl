@@ -238,6 +238,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
   pb.d_pose = a->d_pose; pb.d_pca_l = a->d_hand_pca_l; pb.d_pca_r = a->d_hand_pca_r;
   pb.d_transl = a->d_transl;
   pb.d_loss = a->d_loss;
+  pb.d_loss_stride = (a->flags & SMPLK_FLAG_LOSS_SUM) ? 0 : 1;
   pb.d_full_pose = a->d_full_pose;
   if (pb.d_betas && pb.betas_B == 1)
     CUDA_TRY(cudaMemsetAsync(a->d_betas, 0, (size_t)d.NB * sizeof(float), st));

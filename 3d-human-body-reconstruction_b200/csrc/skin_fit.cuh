@@ -27,7 +27,8 @@ struct SkinFitArgs {
   const float* target;        // (B,V,3)
   float scale;
   float* grad;                // (B,V,3)
-  float* loss;                // (B), zeroed by the host, accumulated with atomics
+  float* loss;                // (B) -- or one float with loss_stride 0 --, zeroed by the host, accumulated with atomics
+  int loss_stride;
   __nv_bfloat16* dvp_hi;      // (B,Npad)
   __nv_bfloat16* dvp_lo;
 };
@@ -108,6 +109,7 @@ skin_fit_l2_kernel(const ModelDev m, const SkinFitArgs a) {
   for (int i = 0; i < kGrpStages - 1; ++i) issue_v(b0 + i);
   const float s2 = 2.f * a.scale;
   const int col0 = wf0 + 12 * lane;                       // first d_v_posed column of this thread
+  float loss_run = 0.f;
 
   for (int b = b0; b < b1; ++b) {
     const int rel = b - b0;
@@ -192,7 +194,8 @@ skin_fit_l2_kernel(const ModelDev m, const SkinFitArgs a) {
     }
 #pragma unroll
     for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
-    if (lane == 0 && w_nfloat > 0) atomicAdd(a.loss + b, a.scale * acc);
+    if (a.loss_stride == 0) loss_run += acc;            // one float for all bodies: one atomic per warp, after the loop
+    else if (lane == 0 && w_nfloat > 0) atomicAdd(a.loss + b, a.scale * acc);
     __syncwarp();
     {
       const float4 c0 = mine[0], c1 = mine[1], c2 = mine[2];
@@ -224,6 +227,7 @@ skin_fit_l2_kernel(const ModelDev m, const SkinFitArgs a) {
       }
     }
   }
+  if (a.loss_stride == 0 && lane == 0 && w_nfloat > 0) atomicAdd(a.loss, a.scale * loss_run);
 }
 
 }  // namespace smplk

@@ -1094,6 +1094,8 @@ static bool fit_fused_applies(const smplk_model* mdl) {
 }
 
 static int forward_impl(const smplk_model* model, const smplk_forward_args* a, uint32_t flags, const FitL2* fit);
+static int vertex_l2_impl(int32_t batch, int32_t floats_per_body, const float* verts, const float* target,
+                          float scale, float* grad, float* loss, int loss_stride, int device, smplk_stream stream);
 
 extern "C" int smplk_forward(const smplk_model* model, const smplk_forward_args* a) {
   if (!model || !a) return fail(SMPLK_E_ARG, "null argument");
@@ -1199,12 +1201,13 @@ static int forward_impl(const smplk_model* model, const smplk_forward_args* a, c
       } else {
         if (fit != nullptr && fit_fused_applies(model)) {
           // skinning + loss + gradient + skinning backward in one kernel; vout receives the gradient
-          CUDA_TRY(cudaMemsetAsync(fit->loss + c0, 0, (size_t)rows * sizeof(float), st));
+          const int loss_stride = (flags & SMPLK_FLAG_LOSS_SUM) ? 0 : 1;
+          CUDA_TRY(cudaMemsetAsync(fit->loss + (size_t)c0 * loss_stride, 0, (size_t)(loss_stride ? rows : 1) * sizeof(float), st));
           SkinFitArgs fa;
           fa.B = rows;
           fa.vposed = v_posed; fa.vposed_stride = (size_t)d.Npad; fa.A = A; fa.transl = pa.transl;
           fa.target = fit->target + (size_t)c0 * d.V * 3; fa.scale = fit->scale;
-          fa.grad = vout; fa.loss = fit->loss + c0;
+          fa.grad = vout; fa.loss = fit->loss + (size_t)c0 * loss_stride; fa.loss_stride = loss_stride;
           fa.dvp_hi = reinterpret_cast<__nv_bfloat16*>(ws + w.off_dvp);
           fa.dvp_lo = fa.dvp_hi + (size_t)w.chunk * d.Npad;
           const int tiles = (d.V + kSkinTileVerts - 1) / kSkinTileVerts;
@@ -1218,8 +1221,9 @@ static int forward_impl(const smplk_model* model, const smplk_forward_args* a, c
           if (int r = launch_skin(model, rows, d.lbs_only ? d.bias : v_posed,
                                   d.lbs_only ? 0 : (size_t)d.Npad, A, pa.transl, vout, st)) return r;
           if (fit != nullptr) {   // generic weights: stand-alone loss kernel, gradient in place
-            if (int r = smplk_vertex_l2(rows, d.V * 3, vout, fit->target + (size_t)c0 * d.V * 3, fit->scale, vout,
-                                        fit->loss + c0, model->device, a->stream)) return r;
+            const int ls = (flags & SMPLK_FLAG_LOSS_SUM) ? 0 : 1;
+            if (int r = vertex_l2_impl(rows, d.V * 3, vout, fit->target + (size_t)c0 * d.V * 3, fit->scale, vout,
+                                       fit->loss + (size_t)c0 * ls, ls, model->device, a->stream)) return r;
           }
         }
       }
@@ -1310,16 +1314,21 @@ extern "C" int smplk_forward_host(smplk_model* model, int32_t batch, uint32_t fl
 extern "C" int smplk_vertex_l2(int32_t batch, int32_t floats_per_body, const float* verts,
                                const float* target, float scale, float* grad, float* loss,
                                int device, smplk_stream stream) {
+  return vertex_l2_impl(batch, floats_per_body, verts, target, scale, grad, loss, 1, device, stream);
+}
+
+static int vertex_l2_impl(int32_t batch, int32_t floats_per_body, const float* verts, const float* target,
+                          float scale, float* grad, float* loss, int loss_stride, int device, smplk_stream stream) {
   if (batch < 1 || floats_per_body < 1 || !verts || !target || !loss)
     return fail(SMPLK_E_ARG, "bad argument");
   CUDA_TRY(cudaSetDevice(device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  CUDA_TRY(cudaMemsetAsync(loss, 0, (size_t)batch * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(loss, 0, (size_t)(loss_stride ? batch : 1) * sizeof(float), st));
   int gx = 8;
   while (gx > 1 && (long)gx * batch > 16384) gx >>= 1;
   const int vec2 = (floats_per_body % 2 == 0) && ((reinterpret_cast<uintptr_t>(verts) | reinterpret_cast<uintptr_t>(target) |
                                                    reinterpret_cast<uintptr_t>(grad)) & 7) == 0;
-  vertex_l2_kernel<<<dim3(gx, batch), 256, 0, st>>>(floats_per_body, verts, target, scale, grad, loss, vec2);
+  vertex_l2_kernel<<<dim3(gx, batch), 256, 0, st>>>(floats_per_body, verts, target, scale, grad, loss, vec2, loss_stride);
   LAUNCH_CHECK("vertex_l2_kernel");
   return 0;
 }

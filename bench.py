@@ -356,7 +356,7 @@ def main():
             for t_ in (bb, pb, tb_):
                 t_.grad = None
             if fused == "node":       # body model + loss as one autograd node (smplk.fit_vertex_l2)
-                loss = fit_vertex_l2(dm, bb, pb, target, transl=tb_).sum()
+                loss = fit_vertex_l2(dm, bb, pb, target, transl=tb_, reduce="sum")
             else:
                 v, _, _, _ = body_model_apply(dm, bb, pb, transl=tb_)
                 loss = vertex_l2_loss(v, target).sum() if fused else ((v - target) ** 2).sum()
@@ -424,7 +424,7 @@ def main():
             def closure():
                 for t_ in (b1, p1, t1):
                     t_.grad = None
-                fit_vertex_l2(dm, b1, p1, tgt1, transl=t1).sum().backward()
+                fit_vertex_l2(dm, b1, p1, tgt1, transl=t1, reduce="sum").backward()
 
             def timeit(fn, n=50):
                 for _ in range(5):

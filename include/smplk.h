@@ -93,6 +93,8 @@ int smplk_model_get_info(const smplk_model* model, smplk_model_info* info);
 #define SMPLK_FLAG_TRANSFORMS_ONLY 32u  /* run the pose / FK kernel only: skinning transforms A (workspace), FK
                                            joints, full_pose; with E > 0 the vertex-pick joints are left unwritten */
 #define SMPLK_FLAG_FIT_VERTEX_L2 64u    /* workspace / backward of smplk_fit_vertex_l2 (implies SAVE_FOR_BACKWARD) */
+#define SMPLK_FLAG_LOSS_SUM 128u        /* smplk_fit_vertex_l2: `loss` is ONE float, the sum over the bodies;
+                                           smplk_backward: `d_loss` is one float (the gradient of that sum) */
 
 /* Bytes of device workspace `smplk_forward` needs for `batch` bodies (256-byte aligned base). */
 size_t smplk_workspace_bytes(const smplk_model* model, int32_t batch, uint32_t flags);

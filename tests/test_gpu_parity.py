@@ -747,6 +747,15 @@ def test_one_node_fitting_step_matches_two_nodes(dev, smplh_model, smpl_model):
     assert abs(grads[0][0] - grads[1][0]) <= 1e-5 * abs(grads[1][0])
     for a, b in zip(grads[0][1:], grads[1][1:]):
         assert _maxerr(a, b) <= 2e-5 * float(b.abs().max())
+    # reduce="sum": the scalar accumulated in the kernel, scaled by an upstream factor in backward
+    mod.reset_params(**vals)
+    mod.zero_grad()
+    total = mod.vertex_l2(tgt, reduce="sum")
+    assert total.dim() == 0
+    (0.5 * total).backward()
+    assert abs(float(total) - grads[1][0]) <= 1e-5 * abs(grads[1][0])
+    for (_, p), b in zip(sorted(mod.named_parameters()), grads[1][1:]):
+        assert _maxerr(p.grad, 0.5 * b) <= 2e-5 * float(b.abs().max())
 
 
 def test_errors_are_loud(dev, smpl_model):
