@@ -113,6 +113,86 @@ def fit_priors(betas=None, pose_embedding=None, body_pose=None, left_hand_pose=N
                          shape_weight, body_pose_weight, bending_prior_weight, hand_prior_weight)
 
 
+def _launch_reproj(joints, translation, rotation, focal, center, gt, weights, rho, data_weight, loss):
+    """Runs smplk_reprojection_loss into `loss` (B,); returns (d_joints, d_translation) for d_loss = 1."""
+    B, Jn = joints.shape[0], joints.shape[1]
+    dev = joints.device
+    dj = torch.empty_like(joints)
+    dt = torch.empty(B, 3, device=dev)
+    a = _lib.ReprojArgs()
+    a.batch, a.num_joints = B, Jn
+    a.joints, a.rotation, a.translation = _ptr(joints), _ptr(rotation), _ptr(translation)
+    a.focal, a.center, a.camera_batch = _ptr(focal), _ptr(center), translation.shape[0]
+    a.gt_joints, a.weights = _ptr(gt), _ptr(weights)
+    a.weights_batch = weights.shape[0] if weights is not None else 1
+    a.rho, a.data_weight = float(rho), float(data_weight)
+    a.loss, a.d_joints, a.d_translation = _ptr(loss), _ptr(dj), _ptr(dt)
+    a.device = dev.index or 0
+    a.stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(_lib.load().smplk_reprojection_loss(ctypes.byref(a)))
+    return dj, dt
+
+
+def _launch_priors(ts, shape_w, pose_w, bend_w, hand_w, loss):
+    """Runs smplk_fit_priors into `loss` (B,); returns the gradient list (None where the input is None)."""
+    ref = next(t for t in ts if t is not None)
+    B, dev = ref.shape[0], ref.device
+    grads = [None if t is None else torch.empty_like(t) for t in ts]
+    a = _lib.PriorArgs()
+    a.batch = B
+    a.betas, a.num_betas = _ptr(ts[0]), (ts[0].shape[1] if ts[0] is not None else 0)
+    a.pose_embedding, a.num_embedding = _ptr(ts[1]), (ts[1].shape[1] if ts[1] is not None else 0)
+    a.body_pose, a.num_body_pose = _ptr(ts[2]), (ts[2].shape[1] if ts[2] is not None else 0)
+    a.left_hand_pose, a.right_hand_pose = _ptr(ts[3]), _ptr(ts[4])
+    a.num_hand = ts[3].shape[1] if ts[3] is not None else (ts[4].shape[1] if ts[4] is not None else 0)
+    a.shape_weight, a.body_pose_weight = float(shape_w), float(pose_w)
+    a.bending_prior_weight, a.hand_prior_weight = float(bend_w), float(hand_w)
+    a.loss = _ptr(loss)
+    a.d_betas, a.d_pose_embedding, a.d_body_pose = _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2])
+    a.d_left_hand_pose, a.d_right_hand_pose = _ptr(grads[3]), _ptr(grads[4])
+    a.device = dev.index or 0
+    a.stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(_lib.load().smplk_fit_priors(ctypes.byref(a)))
+    return grads
+
+
+class _SMPLifyTotal(torch.autograd.Function):
+    """Scalar total of SMPLifyLoss (data term + priors, lib/Gen_SMPLH/fitting.py:365-449) as ONE autograd
+    node: the two loss kernels write into one (2,B) buffer summed by a single reduction, and backward
+    scales every stored gradient by the upstream scalar with one multi-tensor kernel -- instead of two
+    nodes, three reductions / adds and six element-wise kernels (the closure at batch 1 is made of such
+    2-3 us kernels)."""
+
+    @staticmethod
+    def forward(ctx, joints, translation, betas, emb, body_pose, lh, rh, rotation, focal, center, gt, weights,
+                rho, data_weight, shape_w, pose_w, bend_w, hand_w):
+        if not joints.is_cuda:
+            raise RuntimeError("smplk fitting losses need CUDA tensors (no CPU fallback)")
+        joints, translation, rotation = _f(joints), _f(translation), _f(rotation)
+        focal, center, gt, weights = _f(focal), _f(center), _f(gt), _f(weights)
+        ts = [_f(t) for t in (betas, emb, body_pose, lh, rh)]
+        B, dev = joints.shape[0], joints.device
+        both = torch.empty(2, B, device=dev)
+        dj, dt = _launch_reproj(joints, translation, rotation, focal, center, gt, weights, rho, data_weight, both[0])
+        if any(t is not None for t in ts):
+            pg = _launch_priors(ts, shape_w, pose_w, bend_w, hand_w, both[1])
+        else:
+            pg = [None] * 5
+            both[1].zero_()
+        ctx.cam_batch = translation.shape[0]
+        ctx.grads = [dj, dt] + pg
+        return both.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        live = [t for t in ctx.grads if t is not None]
+        scaled = iter(torch._foreach_mul(live, g))
+        out = [None if t is None else next(scaled) for t in ctx.grads]
+        if ctx.cam_batch == 1 and out[1].shape[0] != 1:
+            out[1] = out[1].sum(0, keepdim=True)
+        return tuple(out) + (None,) * 11
+
+
 class PerspectiveCamera(torch.nn.Module):
     """Parameter holder with the attributes of lib/Gen_SMPLH/camera.py:52-117."""
 
@@ -148,18 +228,15 @@ class SMPLifyLoss(torch.nn.Module):
     def forward(self, body_model_output, camera, gt_joints, joints_conf, body_model_faces=None,
                 joint_weights=None, use_vposer=False, pose_embedding=None, **kwargs):
         w = joint_weights * joints_conf if self.use_joints_conf else joint_weights
-        data = reprojection_loss(body_model_output.joints, camera.rotation, camera.translation, camera.focal,
-                                 camera.center, gt_joints, w, self.rho, self.data_weight)
         body_pose = body_model_output.full_pose[:, 3:66]
-        pri = fit_priors(betas=body_model_output.betas,
-                         pose_embedding=pose_embedding if use_vposer else None,
-                         body_pose=body_pose,
-                         left_hand_pose=body_model_output.left_hand_pose if self.use_hands else None,
-                         right_hand_pose=body_model_output.right_hand_pose if self.use_hands else None,
-                         shape_weight=self.shape_weight, body_pose_weight=self.body_pose_weight,
-                         bending_prior_weight=self.bending_prior_weight,
-                         hand_prior_weight=self.hand_prior_weight if self.use_hands else 0.0)
-        return data.sum() + pri.sum()
+        return _SMPLifyTotal.apply(
+            body_model_output.joints, camera.translation, body_model_output.betas,
+            pose_embedding if use_vposer else None, body_pose,
+            body_model_output.left_hand_pose if self.use_hands else None,
+            body_model_output.right_hand_pose if self.use_hands else None,
+            camera.rotation, camera.focal, camera.center, gt_joints, w, self.rho, self.data_weight,
+            self.shape_weight, self.body_pose_weight, self.bending_prior_weight,
+            self.hand_prior_weight if self.use_hands else 0.0)
 
 
 class GraphedClosure:
