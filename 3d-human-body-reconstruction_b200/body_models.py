@@ -188,6 +188,8 @@ class _FitVertexL2Fn(torch.autograd.Function):
         tgt = _prep(target, dev)
         if tuple(tgt.shape) != (B, dm.V, 3):
             raise ValueError("target must be (%d, %d, 3), got %s" % (B, dm.V, tuple(tgt.shape)))
+        if tgt.data_ptr() % 8:       # a view at an odd float offset: the kernel reads 8-byte pairs
+            tgt = tgt.clone()
         verts = torch.empty(B, dm.V, 3, device=dev, dtype=torch.float32)
         ws_bytes = dm.workspace_bytes(B, flags)
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)

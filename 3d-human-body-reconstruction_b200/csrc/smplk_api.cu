@@ -1111,6 +1111,8 @@ extern "C" int smplk_fit_vertex_l2(const smplk_model* model, const smplk_forward
   if (a->joints_regressed || (a->joints && model->d.E > 0))
     return fail(SMPLK_E_ARG, "vertex-pick / regressed joints are not available from smplk_fit_vertex_l2");
   if (a->flags & SMPLK_FLAG_TRANSFORMS_ONLY) return fail(SMPLK_E_ARG, "SMPLK_FLAG_TRANSFORMS_ONLY excludes the loss");
+  if (fit_fused_applies(model) && ((reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(a->verts)) & 7))
+    return fail(SMPLK_E_ARG, "target and verts must be 8-byte aligned");
   FitL2 fit;
   fit.target = target; fit.scale = scale; fit.loss = loss;
   return forward_impl(model, a, a->flags | SMPLK_FLAG_FIT_VERTEX_L2 | SMPLK_FLAG_SAVE_FOR_BACKWARD, &fit);

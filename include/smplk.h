@@ -202,7 +202,8 @@ int smplk_forward_host(smplk_model* model, int32_t batch, uint32_t flags, const 
  * and the skinning backward run as one kernel where the model allows (sparse weights, 3V even);
  * d_v_posed is then kept in the workspace and smplk_backward, called with the same flags and
  * d_verts = a->verts, skips its own skinning backward.  a->joints may be given only when the model
- * has no vertex-pick joints; a->joints_regressed must be null.  `target` (B,V,3), `loss` (B). */
+ * has no vertex-pick joints; a->joints_regressed must be null.  `target` (B,V,3) and a->verts must be
+ * 8-byte aligned; `loss` (B), or one float with SMPLK_FLAG_LOSS_SUM. */
 int smplk_fit_vertex_l2(const smplk_model* model, const smplk_forward_args* a, const float* target,
                         float scale, float* loss);
 

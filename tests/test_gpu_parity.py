@@ -747,6 +747,13 @@ def test_one_node_fitting_step_matches_two_nodes(dev, smplh_model, smpl_model):
     assert abs(grads[0][0] - grads[1][0]) <= 1e-5 * abs(grads[1][0])
     for a, b in zip(grads[0][1:], grads[1][1:]):
         assert _maxerr(a, b) <= 2e-5 * float(b.abs().max())
+    # a target view at an odd float offset (4-byte aligned only) is copied, not read misaligned
+    flat = torch.zeros(B * 6890 * 3 + 1, device=dev)
+    flat[1:] = tgt.reshape(-1)
+    odd = flat[1:].view(B, 6890, 3)
+    assert odd.data_ptr() % 8 == 4
+    mod.reset_params(**vals)
+    assert abs(float(mod.vertex_l2(odd).sum()) - grads[1][0]) <= 1e-5 * abs(grads[1][0])
     # reduce="sum": the scalar accumulated in the kernel, scaled by an upstream factor in backward
     mod.reset_params(**vals)
     mod.zero_grad()
