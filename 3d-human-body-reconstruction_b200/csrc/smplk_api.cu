@@ -1143,6 +1143,8 @@ static int forward_impl(const smplk_model* model, const smplk_forward_args* a, c
                 a->workspace_bytes);
   if (reinterpret_cast<uintptr_t>(a->workspace) & 255)
     return fail(SMPLK_E_WORKSPACE, "workspace must be 256-byte aligned");
+  if (reinterpret_cast<uintptr_t>(a->verts) & 7)     // the skinning kernels store 8-byte pairs
+    return fail(SMPLK_E_ARG, "verts must be 8-byte aligned");
   int cur = -1;
   CUDA_TRY(cudaGetDevice(&cur));
   if (cur != model->device) CUDA_TRY(cudaSetDevice(model->device));

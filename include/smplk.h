@@ -114,7 +114,7 @@ typedef struct {
   const float* hand_pca_l;    /* (B, C) or NULL: if given, joints 22..36 = hand_pca_l @ comp_l     */
   const float* hand_pca_r;    /* (B, C) or NULL: joints 37..51                                     */
   const float* transl;        /* (B,3) or NULL                                                     */
-  float* verts;               /* out (B,V,3) or NULL                                               */
+  float* verts;               /* out (B,V,3), 8-byte aligned, or NULL                              */
   float* joints;              /* out (B, J+E, 3): FK joints then vertex picks, + transl; or NULL   */
   float* joints_regressed;    /* out (B, R, 3): regressor_posed @ verts; or NULL                   */
   float* full_pose;           /* out (B, 3J) assembled pose (PCA + mean applied); or NULL          */
