@@ -147,3 +147,28 @@ def test_module_signatures_mirror_reference():
     from smplk import np_twins
     for cls in (np_twins.SMPLHModel, np_twins.SMPLModel, np_twins.RecoverModel):
         assert list(inspect.signature(cls.set_params).parameters)[1:] == ["pose", "beta", "trans"]
+
+
+def test_flag_constants_match_the_header():
+    """Every SMPLK_FLAG_* of include/smplk.h has the same value in the ctypes mirror, and vice versa."""
+    import re
+    text = open(os.path.join(ROOT, "include", "smplk.h")).read()
+    header = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+SMPLK_FLAG_(\w+)\s+(\d+)u", text)}
+    mirror = {k[len("FLAG_"):]: v for k, v in vars(_lib).items() if k.startswith("FLAG_")}
+    assert header == mirror, (header, mirror)
+    vals = sorted(header.values())
+    assert vals == [1 << i for i in range(len(vals))]          # distinct single bits
+    slots = int(re.search(r"#define\s+SMPLK_PROF_SLOTS\s+(\d+)", text).group(1))
+    assert slots == len(_lib.PROF_SLOTS)
+
+
+def test_graphed_closure_refuses_cpu_parameters():
+    """No CPU path anywhere: the graph wrapper fails loudly on CPU parameters instead of running eagerly."""
+    import pytest
+    import torch
+    from smplk.fitting import GraphedClosure
+    p = torch.nn.Parameter(torch.zeros(3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GraphedClosure(lambda: (p ** 2).sum(), [p])
+    with pytest.raises(ValueError):
+        GraphedClosure(lambda: None, [torch.zeros(3)])
