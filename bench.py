@@ -150,6 +150,23 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def _stdout_to_stderr():
+    """Point file descriptor 1 at stderr for the duration (covers native writes, not just sys.stdout)."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    try:
+        os.dup2(2, 1)
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -180,10 +197,15 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its version banner to stdout at NCCL_DEBUG=VERSION; stdout carries the one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries the one JSON line: whatever the communicator set-up prints there (NCCL's
+        # "NCCL version ..." banner is written to file descriptor 1 by native code) goes to stderr
+        with _stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=dev)
+            try:                                      # the communicator is created here, inside the redirection
+                dist.barrier()
+                torch.cuda.synchronize(dev)
+            except Exception as e:                    # only the banner's destination depends on it
+                sys.stderr.write("early barrier skipped: %r\n" % (e,))
 
     B = args.batch
     model = synthetic.make_model("smplh", seed=0)
