@@ -121,6 +121,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # all the host threads this process may use (torchrun sets OMP_NUM_THREADS=1 for its children)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     from smplk import synthetic
     model = synthetic.make_model("smplh", seed=0)
     from oracle import smpl_oracle as O
