@@ -116,25 +116,29 @@ EXPORTED_SYMBOLS = [
     "smplk_batch_rodrigues", "smplk_forward_host", "smplk_last_error_string", "smplk_version",
     "smplk_launch_count", "smplk_workspace_layout", "smplk_profile_enable", "smplk_profile_read", "smplk_vertex_l2",
     "smplk_inverse_lbs", "smplk_inverse_joints", "smplk_vertex_normals", "smplk_divide_faces",
-    "smplk_reprojection_loss", "smplk_fit_priors", "smplk_fit_vertex_l2",
+    "smplk_reprojection_loss", "smplk_fit_priors", "smplk_fit_vertex_l2", "smplk_skin_transforms",
 ]
 PROF_SLOTS = ["pose_fwd", "blend_tcgen05", "blend_simt", "skin", "dA", "skin_bwd", "blend_bwd",
               "pose_bwd", "blend_skin_fused", "transpose"]
 
 
-def build(force=False, verbose=False):
-    """Compile csrc/ into libsmplk.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+def build(force=False, verbose=False, ab=False):
+    """Compile csrc/ into libsmplk.so for sm_100a with nvcc (cross-compiles without a GPU).
+    ab=True builds libsmplk_ab.so with -DSMPLK_AB: the product library plus the A/B kernels that are
+    on no default path (exact-fp32 SIMT blend, bulk-copy skinning) and their tuning switches; select
+    it with SMPLK_LIB=<path> (tools/, the SIMT cross-checks of the parity tests)."""
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
-    if not force and os.path.exists(LIB_PATH):
-        if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in srcs):
-            return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "smplk_api.cu")]
+    out = os.path.join(_HERE, "libsmplk_ab.so") if ab else LIB_PATH
+    if not force and os.path.exists(out):
+        if os.path.getmtime(out) >= max(os.path.getmtime(s) for s in srcs):
+            return out
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-DSMPLK_AB"] if ab else []) + ["-o", out, os.path.join(CSRC, "smplk_api.cu")]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    return LIB_PATH
+    return out
 
 
 _lib = None
@@ -203,6 +207,8 @@ def load():
     lib.smplk_fit_vertex_l2.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float,
                                         ctypes.c_void_p]
     lib.smplk_fit_vertex_l2.restype = ctypes.c_int
+    lib.smplk_skin_transforms.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]
+    lib.smplk_skin_transforms.restype = ctypes.c_int
     lib.smplk_profile_enable.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.smplk_profile_enable.restype = ctypes.c_int
     lib.smplk_profile_read.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),

@@ -12,6 +12,7 @@ body_pose, hand poses (axis-angle or PCA) and transl.  torch only provides devic
 current stream and the autograd glue.
 """
 import ctypes
+import os
 import pickle
 from collections import namedtuple
 
@@ -25,6 +26,20 @@ ModelOutput = namedtuple("ModelOutput", ["vertices", "joints", "full_pose", "bet
                                          "global_orient", "body_pose", "expression",
                                          "left_hand_pose", "right_hand_pose", "jaw_pose"])
 ModelOutput.__new__.__defaults__ = (None,) * len(ModelOutput._fields)
+
+
+def resolve_model_path(model_path, kind, gender="neutral", ext="pkl"):
+    """Upstream smplx path rule (lib/gen_smplh.py:75-90 passes a FOLDER): a directory holds
+    `<KIND>_<GENDER>.<ext>` (SMPLH_MALE.pkl, SMPL_NEUTRAL.pkl ...); a file path is taken as is."""
+    if os.path.isdir(model_path):
+        fn = "%s_%s.%s" % (kind.upper(), str(gender).upper(), ext)
+        cand = os.path.join(model_path, fn)
+        if not os.path.exists(cand) and ext == "pkl" and os.path.exists(cand[:-3] + "npz"):
+            cand = cand[:-3] + "npz"
+        if not os.path.exists(cand):
+            raise FileNotFoundError("Path %s does not exist!" % cand)
+        return cand
+    return model_path
 
 
 def load_model_file(path):
@@ -50,6 +65,27 @@ def _prep(t, device):
     return t.contiguous()
 
 
+def _check_inputs(dm, B, betas, pose, pca_l, pca_r, transl):
+    """Shapes the C side strides over with fixed widths; upstream raises on these from its cat / matmul."""
+    if pose.dim() != 2 or pose.shape[1] != 3 * dm.J:
+        raise ValueError("pose must be (B, %d) axis-angle for this %d-joint model, got %s"
+                         % (3 * dm.J, dm.J, tuple(pose.shape)))
+    if betas is not None and (betas.dim() != 2 or betas.shape[1] != dm.NB or betas.shape[0] not in (1, B)):
+        raise ValueError("betas must be (1|%d, %d), got %s" % (B, dm.NB, tuple(betas.shape)))
+    for name, t in (("left_hand_pose", pca_l), ("right_hand_pose", pca_r)):
+        if t is not None and (t.dim() != 2 or tuple(t.shape) != (B, dm.C)):
+            raise ValueError("%s PCA coefficients must be (%d, %d), got %s" % (name, B, dm.C, tuple(t.shape)))
+    if transl is not None and tuple(transl.shape) != (B, 3):
+        raise ValueError("transl must be (%d, 3), got %s" % (B, tuple(transl.shape)))
+
+
+def _grad_flows(*ts):
+    """True when autograd will record the node: grad mode on and an input that requires grad.  Under
+    torch.no_grad() module Parameters still report requires_grad, and the inference forward must not
+    keep the whole batch's v_posed (it takes the fused blend+skinning kernel and 8192-body chunks)."""
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+
+
 class _BodyModelFn(torch.autograd.Function):
     """verts, joints, joints_regressed, full_pose = f(betas, pose, pca_l, pca_r, transl)."""
 
@@ -57,12 +93,11 @@ class _BodyModelFn(torch.autograd.Function):
     def forward(ctx, dm, flags, want_regressed, want_verts, betas, pose, pca_l, pca_r, transl):
         B = pose.shape[0]
         dev = pose.device
-        needs_grad = any(t is not None and t.requires_grad
-                         for t in (betas, pose, pca_l, pca_r, transl))
-        if needs_grad:
-            flags |= _lib.FLAG_SAVE_FOR_BACKWARD
+        # body_model_apply sets SAVE_FOR_BACKWARD when a gradient can flow (grad mode is always off in here)
+        needs_grad = bool(flags & _lib.FLAG_SAVE_FOR_BACKWARD)
         betas_c, pose_c = _prep(betas, dev), _prep(pose, dev)
         pl, pr, tr = _prep(pca_l, dev), _prep(pca_r, dev), _prep(transl, dev)
+        _check_inputs(dm, B, betas_c, pose_c, pl, pr, tr)
         jreg = (torch.empty(B, dm.R, 3, device=dev, dtype=torch.float32)
                 if (want_regressed and dm.R > 0) else None)
         # joints only (return_verts=False): the library blends and skins the picked vertices alone
@@ -142,7 +177,9 @@ class _VertexL2Fn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, verts, target, scale):
-        v, t = verts.contiguous(), target.contiguous()
+        if tuple(target.shape) != tuple(verts.shape):
+            raise ValueError("target %s must have the shape of verts %s" % (tuple(target.shape), tuple(verts.shape)))
+        v, t = _prep(verts, verts.device), _prep(target, verts.device)
         B = v.shape[0]
         n = v[0].numel()
         loss = torch.empty(B, device=v.device, dtype=torch.float32)
@@ -186,6 +223,7 @@ class _FitVertexL2Fn(torch.autograd.Function):
         betas_c, pose_c = _prep(betas, dev), _prep(pose, dev)
         pl, pr, tr = _prep(pca_l, dev), _prep(pca_r, dev), _prep(transl, dev)
         tgt = _prep(target, dev)
+        _check_inputs(dm, B, betas_c, pose_c, pl, pr, tr)
         if tuple(tgt.shape) != (B, dm.V, 3):
             raise ValueError("target must be (%d, %d, 3), got %s" % (B, dm.V, tuple(tgt.shape)))
         if tgt.data_ptr() % 8:       # a view at an odd float offset: the kernel reads 8-byte pairs
@@ -267,6 +305,8 @@ def body_model_apply(dm, betas, pose, pca_l=None, pca_r=None, transl=None, add_p
     and skinned (pick_forward_kernel), verts is None."""
     if add_pose_mean:
         flags |= _lib.FLAG_ADD_POSE_MEAN
+    if _grad_flows(betas, pose, pca_l, pca_r, transl):
+        flags |= _lib.FLAG_SAVE_FOR_BACKWARD
     v, j, r, fp = _BodyModelFn.apply(dm, flags, want_regressed, want_verts, betas, pose, pca_l, pca_r, transl)
     return (v if v.numel() > 0 else None), j, (r if r.numel() > 0 else None), fp
 
@@ -280,14 +320,14 @@ class _BodyModelBase(nn.Module):
                  betas=None, num_betas=None, create_global_orient=True, global_orient=None,
                  create_body_pose=True, body_pose=None, create_transl=True, transl=None,
                  dtype=torch.float32, batch_size=1, gender="neutral", J_regressor_extra=None,
-                 joint_map=None, vertex_ids=None, device=None, **kwargs):
+                 joint_map=None, vertex_ids=None, device=None, ext="pkl", **kwargs):
         super().__init__()
         if dtype != torch.float32:
             raise ValueError("smplk computes in float32 (got dtype %s)" % dtype)
         if model is None:
             if model_path is None:
                 raise ValueError("give `model` (dict) or `model_path`")
-            model = load_model_file(model_path)
+            model = load_model_file(resolve_model_path(model_path, self.KIND, gender, ext))
         self.batch_size = batch_size
         self.gender = gender
         self.dtype = dtype
@@ -314,7 +354,9 @@ class _BodyModelBase(nn.Module):
         if J_regressor_extra is not None:
             self._regressor_extra = np.asarray(J_regressor_extra, np.float64)
             self.register_buffer("J_regressor_extra", torch.tensor(self._regressor_extra, dtype=dtype))
-        self.joint_map = None if joint_map is None else torch.as_tensor(np.asarray(joint_map), dtype=torch.long)
+        # a buffer: follows .to(device) (a per-call H2D copy is illegal during CUDA-graph capture)
+        self.register_buffer("joint_map", None if joint_map is None else
+                             torch.as_tensor(np.asarray(joint_map), dtype=torch.long))
 
         def param(flag, value, shape, name):
             if not flag:
@@ -380,7 +422,7 @@ class _BodyModelBase(nn.Module):
         if jreg is not None:
             joints = torch.cat([joints, jreg], dim=1)
         if self.joint_map is not None:
-            joints = joints[:, self.joint_map.to(joints.device)]
+            joints = joints[:, self.joint_map]
         return joints
 
 
@@ -511,6 +553,11 @@ class SMPLH(_BodyModelBase):
         joints = self._finish(verts, joints, jreg, tr)
         # full_pose (PCA hands + pose mean applied) is an output of the pose kernel, differentiable through
         # the same autograd node (upstream assembles it with cat + einsum + add)
+        if self.use_pca:
+            # upstream returns the PROJECTED 45-D hand poses (einsum with the components, before the mean
+            # is added); here they are the hand slots of full_pose minus the mean, one kernel for both hands
+            hands = full_pose[:, 66:156] - self.pose_mean[66:156]
+            lh, rh = hands[:, :45], hands[:, 45:]
         return ModelOutput(vertices=verts if return_verts else None, joints=joints,
                            full_pose=full_pose if return_full_pose else None, betas=be,
                            global_orient=go, body_pose=bp, left_hand_pose=lh, right_hand_pose=rh)
@@ -522,6 +569,9 @@ def create(model_path=None, model_type="smplh", **kwargs):
     kwargs.pop("create_jaw_pose", None)
     kwargs.pop("create_leye_pose", None)
     kwargs.pop("create_reye_pose", None)
+    # upstream: a folder holds one sub-folder per model type (<dir>/smplh/SMPLH_MALE.pkl)
+    if model_path is not None and os.path.isdir(model_path) and os.path.isdir(os.path.join(model_path, model_type)):
+        model_path = os.path.join(model_path, model_type)
     if model_type.lower() == "smpl":
         return SMPL(model_path=model_path, **kwargs)
     if model_type.lower() == "smplh":

@@ -13,30 +13,30 @@
 
 namespace smplk {
 
-// d_verts_eff[b, vid[e]] += d_joints[b, J+e];  d_verts_eff[b, col[n]] += val[n] d_jreg[b, r]
+// d_verts_eff[b, v] += sum over the picks / regressor rows that read vertex v (ModelDev::sc_*): one
+// thread per (body, touched vertex), terms added in table order -> no atomics, bit-reproducible.
 __global__ void scatter_joint_grads_kernel(const ModelDev m, int B, const float* __restrict__ d_joints,
                                            int joints_ld, const float* __restrict__ d_jreg,
                                            float* __restrict__ dverts) {
   const int b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  float* dvb = dverts + (size_t)b * m.V * 3;
-  if (d_joints != nullptr && i < m.E) {
-    const float* g = d_joints + (size_t)b * joints_ld + 3 * (m.J + i);
-    float* o = dvb + (size_t)m.extra_vids[i] * 3;
-    atomicAdd(o + 0, g[0]); atomicAdd(o + 1, g[1]); atomicAdd(o + 2, g[2]);
-  }
-  if (d_jreg != nullptr) {
-    const int nnz = m.reg_ptr[m.R];
-    for (int n = i; n < nnz; n += gridDim.x * blockDim.x) {
-      int r = 0;
-      while (n >= m.reg_ptr[r + 1]) ++r;
-      const float w = m.reg_val[n];
-      const float* g = d_jreg + ((size_t)b * m.R + r) * 3;
-      float* o = dvb + (size_t)m.reg_col[n] * 3;
-      atomicAdd(o + 0, w * g[0]); atomicAdd(o + 1, w * g[1]); atomicAdd(o + 2, w * g[2]);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B || t >= m.sc_T) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int n = m.sc_ptr[t]; n < m.sc_ptr[t + 1]; ++n) {
+    const int src = m.sc_src[n];
+    const float* g;
+    if (src < m.E) {
+      if (d_joints == nullptr) continue;
+      g = d_joints + (size_t)b * joints_ld + 3 * (m.J + src);
+    } else {
+      if (d_jreg == nullptr) continue;
+      g = d_jreg + ((size_t)b * m.R + (src - m.E)) * 3;
     }
+    const float w = m.sc_w[n];
+    s0 = fmaf(w, g[0], s0); s1 = fmaf(w, g[1], s1); s2 = fmaf(w, g[2], s2);
   }
+  float* o = dverts + ((size_t)b * m.V + m.sc_vert[t]) * 3;
+  o[0] += s0; o[1] += s1; o[2] += s2;
 }
 
 // Keypoint fitting (the reference's actual closure: the data term of lib/Gen_SMPLH/fitting.py:369-381

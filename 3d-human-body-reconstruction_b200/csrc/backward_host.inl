@@ -66,7 +66,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     return fail(SMPLK_E_WORKSPACE, "scratch too small: need %zu bytes, got %zu", L.total, a->scratch_bytes);
   if ((reinterpret_cast<uintptr_t>(a->scratch) & 255) || (reinterpret_cast<uintptr_t>(a->workspace) & 255))
     return fail(SMPLK_E_WORKSPACE, "workspace and scratch must be 256-byte aligned");
-  CUDA_TRY(cudaSetDevice(model->device));
+  DEVICE_GUARD(model->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(a->stream);
   const int B = a->batch;
   uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
@@ -104,8 +104,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     const size_t bytes = (size_t)B * d.V * 3 * sizeof(float);
     if (a->d_verts) CUDA_TRY(cudaMemcpyAsync(dverts_eff, a->d_verts, bytes, cudaMemcpyDeviceToDevice, st));
     else CUDA_TRY(cudaMemsetAsync(dverts_eff, 0, bytes, st));
-    const int work = std::max(d.E, a->d_joints_regressed ? 1024 : 0);
-    dim3 grid((work + 127) / 128, B);
+    dim3 grid((d.sc_T + 127) / 128, B);
     scatter_joint_grads_kernel<<<grid, 128, 0, st>>>(d, B, (d.E > 0) ? a->d_joints : nullptr, joints_ld,
                                                      (d.R > 0) ? a->d_joints_regressed : nullptr,
                                                      dverts_eff);

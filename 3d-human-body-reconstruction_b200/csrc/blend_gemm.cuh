@@ -256,6 +256,7 @@ blend_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
   }
 }
 
+#ifdef SMPLK_AB   // validation kernel (SMPLK_FLAG_BLEND_SIMT): built only with -DSMPLK_AB
 // ------------------------------------------------------------------------------------------
 // exact-fp32 SIMT path (tiny batches, validation)
 // ------------------------------------------------------------------------------------------
@@ -306,5 +307,6 @@ blend_simt_kernel(const ModelDev m, const BlendSimtArgs a) {
     if (b < a.M) *reinterpret_cast<float4*>(a.out + (size_t)b * m.Npad + n) = acc[bb];
   }
 }
+#endif  // SMPLK_AB
 
 }  // namespace smplk

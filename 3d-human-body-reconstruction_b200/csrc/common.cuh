@@ -65,6 +65,14 @@ struct ModelDev {
   const int* reg_ptr;         // [R+1] CSR of regressor_posed
   const int* reg_col;         // [nnzR]
   const float* reg_val;       // [nnzR]
+  // backward of the vertex picks + posed-vertex regressors as a GATHER per touched vertex (deterministic):
+  // vertex sc_vert[t] receives sum_n sc_w[n] * g(sc_src[n]),  n in [sc_ptr[t], sc_ptr[t+1]);
+  // sc_src < E: d_joints row J + src (a pick);  sc_src >= E: d_joints_regressed row src - E
+  int sc_T;
+  const int* sc_vert;         // [T]
+  const int* sc_ptr;          // [T+1]
+  const int* sc_src;          // [nnz]
+  const float* sc_w;          // [nnz]
   // fused blend+skinning kernel (blend_skin_fused.cuh): 84 whole vertices per 256-column tile
   int fz_ok;                  // 1 when the per-chunk joint lists are short enough for the fused epilogue
   int fz_tiles;               // ceil(V / 84)

@@ -310,6 +310,7 @@ skin_grouped_kernel(const ModelDev m, const SkinArgs a) {
   }
 }
 
+#ifdef SMPLK_AB   // A/B variant, not on any default path: built only with -DSMPLK_AB
 // ------------------------------------------------------------------------------------------
 // skin_tma_kernel -- skin_grouped_kernel with the streaming data moved off the LSU pipe.
 //
@@ -501,6 +502,7 @@ skin_tma_kernel(const ModelDev m, const SkinArgs a) {
   }
   if (lane == 0) ptx::tma_store_wait<0>();
 }
+#endif  // SMPLK_AB
 
 // joints[b, J + e] = verts[b, extra_vids[e]]  (upstream VertexJointSelector; verts already + transl)
 __global__ void gather_extra_joints_kernel(const ModelDev m, int B, const float* __restrict__ verts,

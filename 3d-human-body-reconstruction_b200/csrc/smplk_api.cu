@@ -57,6 +57,27 @@ static int fail(int code, const char* fmt, ...) {
       return fail((int)e_, "launch of %s failed: %s", name, cudaGetErrorString(e_));     \
   } while (0)
 
+// Every entry point works on its model's (or the named) device and leaves the caller's current device
+// as it found it (a single process may drive several GPUs).
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) {
+      err = cudaSetDevice(dev);
+      changed = err == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+#define DEVICE_GUARD(dev)                                                                \
+  DeviceGuard device_guard_(dev);                                                        \
+  if (device_guard_.err != cudaSuccess)                                                  \
+    return fail((int)device_guard_.err, "cudaSetDevice(%d) failed: %s", (int)(dev),      \
+                cudaGetErrorString(device_guard_.err))
+
 extern "C" const char* smplk_last_error_string(void) { return g_err; }
 extern "C" int smplk_version(void) { return SMPLK_VERSION; }
 extern "C" uint64_t smplk_launch_count(void) { return g_launches.load(); }
@@ -196,7 +217,7 @@ static int make_operand_tmap_fused(const smplk_model* mdl, CUtensorMap* map, con
 
 extern "C" int smplk_model_destroy(smplk_model* model) {
   if (!model) return 0;
-  cudaSetDevice(model->device);
+  DeviceGuard device_guard_(model->device);
   for (void* p : model->allocs) cudaFree(p);
   if (model->stage_dev) cudaFree(model->stage_dev);
   delete model;
@@ -625,6 +646,26 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     if (int r = upload(mdl, rptr, &d.reg_ptr)) return r;
     if (int r = upload(mdl, rcol, &d.reg_col)) return r;
     if (int r = upload(mdl, rval, &d.reg_val)) return r;
+    // the same picks / regressor entries, grouped by the vertex they read (gather form of the backward)
+    {
+      std::vector<std::vector<std::pair<int, float>>> by_vert(V);
+      for (int e = 0; e < d.E; ++e) by_vert[ev[e]].push_back({e, 1.0f});
+      for (int r = 0; r < d.R; ++r)
+        for (int n = rptr[r]; n < rptr[r + 1]; ++n) by_vert[rcol[n]].push_back({d.E + r, rval[n]});
+      std::vector<int> sv, sp(1, 0), ss;
+      std::vector<float> sw;
+      for (int v = 0; v < V; ++v) {
+        if (by_vert[v].empty()) continue;
+        sv.push_back(v);
+        for (auto& e : by_vert[v]) { ss.push_back(e.first); sw.push_back(e.second); }
+        sp.push_back((int)ss.size());
+      }
+      d.sc_T = (int)sv.size();
+      if (int r = upload(mdl, sv, &d.sc_vert)) return r;
+      if (int r = upload(mdl, sp, &d.sc_ptr)) return r;
+      if (int r = upload(mdl, ss, &d.sc_src)) return r;
+      if (int r = upload(mdl, sw, &d.sc_w)) return r;
+    }
   }
 
   // ---- TMA descriptors of the constant GEMM operand
@@ -695,7 +736,9 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     SMPLK_MAX_DYN_SMEM((skin_grouped_kernel<false>));
     SMPLK_MAX_DYN_SMEM((skin_grouped8_kernel<true>));
     SMPLK_MAX_DYN_SMEM((skin_grouped8_kernel<false>));
+#ifdef SMPLK_AB
     SMPLK_MAX_DYN_SMEM((skin_tma_kernel));
+#endif
     SMPLK_MAX_DYN_SMEM((pose_forward_block_kernel<1>));
     SMPLK_MAX_DYN_SMEM((pose_forward_block_kernel<2>));
     SMPLK_MAX_DYN_SMEM((pose_backward_kernel<1>));
@@ -727,7 +770,7 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
     return fail(SMPLK_E_DEVICE, "no CUDA device available (%s); smplk has no CPU fallback",
                 e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
   if (device < 0 || device >= ndev) return fail(SMPLK_E_DEVICE, "device %d out of range", device);
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   smplk_model* mdl = new (std::nothrow) smplk_model();
@@ -740,10 +783,13 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   mdl->stage_bytes = 0;
   mdl->encode = nullptr;
   mdl->prof_on = false;
+  mdl->skin_bpb = 0; mdl->skin_g8 = true; mdl->skin_tma = false; mdl->force_skin_v1 = false;
+#ifdef SMPLK_AB   // tuning switches of kernels that are not on a default path
   { const char* e = getenv("SMPLK_SKIN_BPB"); mdl->skin_bpb = e ? atoi(e) : 0; }
   { const char* e = getenv("SMPLK_SKIN_G8"); mdl->skin_g8 = !(e && e[0] == '0'); }
   { const char* e = getenv("SMPLK_SKIN_TMA"); mdl->skin_tma = (e && e[0] == '1'); }
   { const char* e = getenv("SMPLK_SKIN_V1"); mdl->force_skin_v1 = e && e[0] == '1'; }
+#endif
   { const char* e = getenv("SMPLK_FIT_FUSED"); mdl->fit_fused = !(e && e[0] == '0'); }
   { const char* e = getenv("SMPLK_SPARSE_PICKS"); mdl->sparse_picks = !(e && e[0] == '0'); }
   { const char* e = getenv("SMPLK_GEMM_1CTA"); mdl->use_2cta = !(e && e[0] == '1'); }
@@ -935,6 +981,7 @@ static int launch_blend(const smplk_model* mdl, int rows, BlendPath path, float*
           tm_fhi, tm_flo, mdl->tmap_pd_hi, mdl->tmap_pd_lo, tm_out, ga);
     LAUNCH_CHECK("blend_tcgen05_kernel");
   } else {
+#ifdef SMPLK_AB
     BlendSimtArgs sa;
     sa.M = rows; sa.F_hi = F_hi; sa.F_lo = F_lo; sa.out = v_posed;
     dim3 grid((d.Npad / 4 + kSimtThreads - 1) / kSimtThreads, (rows + kSimtBodies - 1) / kSimtBodies);
@@ -942,6 +989,10 @@ static int launch_blend(const smplk_model* mdl, int rows, BlendPath path, float*
     ProfScope prof(mdl, st, SMPLK_PROF_BLEND_SIMT);
     blend_simt_kernel<<<grid, kSimtThreads, smem, st>>>(d, sa);
     LAUNCH_CHECK("blend_simt_kernel");
+#else
+    return fail(SMPLK_E_UNSUPPORTED, "the exact-fp32 SIMT blend kernel (SMPLK_FLAG_BLEND_SIMT) is an A/B variant: "
+                                      "build the library with -DSMPLK_AB");
+#endif
   }
   return 0;
 }
@@ -1039,7 +1090,10 @@ static int launch_skin(const smplk_model* mdl, int rows, const float* vsrc, size
   sa.B = rows;
   const int tiles = (d.V + kSkinTileVerts - 1) / kSkinTileVerts;
   sa.vsrc = vsrc; sa.vsrc_stride = vstride; sa.A = A; sa.transl = transl; sa.out = out;
+  sa.debug_copy_only = 0;
+#ifdef SMPLK_AB
   { const char* e = getenv("SMPLK_SKIN_COPYONLY"); sa.debug_copy_only = (e && e[0] == '1') ? 1 : 0; }
+#endif
   const bool grouped = d.grp_ok && !mdl->force_skin_v1;
   const size_t smem = grouped ? skin_grouped_smem_bytes(d.J)
                               : (size_t)(2 * kSkinTileVerts * 3 + 2 * ((d.J * 12 + 3) & ~3)) * sizeof(float);
@@ -1064,8 +1118,10 @@ static int launch_skin(const smplk_model* mdl, int rows, const float* vsrc, size
     dim3 grid8(tiles, (rows + bpb8 - 1) / bpb8);
     if (vstride == 0) skin_grouped8_kernel<true><<<grid8, k8Threads, skin_grouped8_smem_bytes(d.J), st>>>(d, sa);
     else skin_grouped8_kernel<false><<<grid8, k8Threads, skin_grouped8_smem_bytes(d.J), st>>>(d, sa);
+#ifdef SMPLK_AB
   } else if (grouped && vstride != 0 && mdl->skin_tma) {
     skin_tma_kernel<<<grid, kGrpThreads, skin_tma_smem_bytes(d.J), st>>>(d, sa);
+#endif
   } else if (grouped) {
     if (vstride == 0) skin_grouped_kernel<true><<<grid, kGrpThreads, smem, st>>>(d, sa);
     else skin_grouped_kernel<false><<<grid, kGrpThreads, smem, st>>>(d, sa);
@@ -1145,9 +1201,7 @@ static int forward_impl(const smplk_model* model, const smplk_forward_args* a, c
     return fail(SMPLK_E_WORKSPACE, "workspace must be 256-byte aligned");
   if (reinterpret_cast<uintptr_t>(a->verts) & 7)     // the skinning kernels store 8-byte pairs
     return fail(SMPLK_E_ARG, "verts must be 8-byte aligned");
-  int cur = -1;
-  CUDA_TRY(cudaGetDevice(&cur));
-  if (cur != model->device) CUDA_TRY(cudaSetDevice(model->device));
+  DEVICE_GUARD(model->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(a->stream);
   uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
   float* F_hi = reinterpret_cast<float*>(ws + w.off_fhi);
@@ -1252,7 +1306,7 @@ extern "C" int smplk_regress_joints(const smplk_model* model, int32_t batch, con
   if (!model || !verts || !out || batch < 1) return fail(SMPLK_E_ARG, "bad argument");
   const ModelDev& d = model->d;
   if (d.R == 0) return fail(SMPLK_E_ARG, "model has no regressor_posed");
-  CUDA_TRY(cudaSetDevice(model->device));
+  DEVICE_GUARD(model->device);
   const long nthreads = (long)batch * d.R * 32;
   regress_joints_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0,
                           reinterpret_cast<cudaStream_t>(stream)>>>(d, batch, verts, out);
@@ -1260,10 +1314,43 @@ extern "C" int smplk_regress_joints(const smplk_model* model, int32_t batch, con
   return 0;
 }
 
+// A[b,j] = [G_R | G_t - G_R J_j]: the rest-pose removal of do_skinning (models/smplh_np.py:73-78)
+__global__ void rest_removal_kernel(int n, const float* __restrict__ G, const float* __restrict__ Jr,
+                                    float* __restrict__ A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* g = G + (size_t)i * 16;
+  const float* j = Jr + (size_t)i * 3;
+  float* o = A + (size_t)i * 12;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float r0 = g[4 * r], r1 = g[4 * r + 1], r2 = g[4 * r + 2];
+    o[4 * r] = r0; o[4 * r + 1] = r1; o[4 * r + 2] = r2;
+    o[4 * r + 3] = g[4 * r + 3] - (r0 * j[0] + r1 * j[1] + r2 * j[2]);
+  }
+}
+
+extern "C" int smplk_skin_transforms(const smplk_model* model, int32_t batch, const float* G,
+                                     const float* joints_rest, const float* v_posed, int32_t v_posed_ld,
+                                     const float* transl, float* A, float* verts, smplk_stream stream) {
+  if (!model || batch < 1 || !G || !joints_rest || !A || !verts) return fail(SMPLK_E_ARG, "bad argument");
+  const ModelDev& d = model->d;
+  if (v_posed && (v_posed_ld < 3 * d.V || (v_posed_ld & 3) || (reinterpret_cast<uintptr_t>(v_posed) & 15)))
+    return fail(SMPLK_E_ARG, "v_posed rows must be 16-byte aligned: v_posed_ld a multiple of 4 floats >= 3V");
+  if (!v_posed && !d.lbs_only) return fail(SMPLK_E_ARG, "v_posed is required for a blendshape model");
+  if (reinterpret_cast<uintptr_t>(verts) & 7) return fail(SMPLK_E_ARG, "verts must be 8-byte aligned");
+  DEVICE_GUARD(model->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int n = batch * d.J;
+  rest_removal_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, G, joints_rest, A);
+  LAUNCH_CHECK("rest_removal_kernel");
+  return launch_skin(model, batch, v_posed ? v_posed : d.bias, v_posed ? (size_t)v_posed_ld : 0, A, transl, verts, st);
+}
+
 extern "C" int smplk_batch_rodrigues(int32_t n, const float* axis_angle, float* rotmats, int device,
                                      smplk_stream stream) {
   if (n < 1 || !axis_angle || !rotmats) return fail(SMPLK_E_ARG, "bad argument");
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   rodrigues_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       n, axis_angle, rotmats);
   LAUNCH_CHECK("rodrigues_kernel");
@@ -1276,7 +1363,7 @@ extern "C" int smplk_forward_host(smplk_model* model, int32_t batch, uint32_t fl
                                   smplk_stream stream) {
   if (!model || !pose || batch < 1) return fail(SMPLK_E_ARG, "bad argument");
   const ModelDev& d = model->d;
-  CUDA_TRY(cudaSetDevice(model->device));
+  DEVICE_GUARD(model->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   flags &= ~SMPLK_FLAG_SAVE_FOR_BACKWARD;
   const size_t ws_bytes = smplk_workspace_bytes(model, batch, flags);
@@ -1325,7 +1412,7 @@ static int vertex_l2_impl(int32_t batch, int32_t floats_per_body, const float* v
                           float scale, float* grad, float* loss, int loss_stride, int device, smplk_stream stream) {
   if (batch < 1 || floats_per_body < 1 || !verts || !target || !loss)
     return fail(SMPLK_E_ARG, "bad argument");
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaMemsetAsync(loss, 0, (size_t)(loss_stride ? batch : 1) * sizeof(float), st));
   int gx = 8;
@@ -1346,7 +1433,7 @@ extern "C" int smplk_profile_enable(smplk_model* model, int enable) {
 extern "C" int smplk_profile_read(smplk_model* model, double ms[SMPLK_PROF_SLOTS],
                                   int64_t counts[SMPLK_PROF_SLOTS], int reset) {
   if (!model || !ms || !counts) return fail(SMPLK_E_ARG, "null argument");
-  CUDA_TRY(cudaSetDevice(model->device));
+  DEVICE_GUARD(model->device);
   for (ProfRec& r : model->prof_pending) {
     CUDA_TRY(cudaEventSynchronize(r.e1));
     float t = 0.f;
@@ -1373,7 +1460,7 @@ extern "C" int smplk_inverse_lbs(const smplk_model* model, int32_t batch, const 
                                  smplk_stream stream) {
   if (!model || batch < 1 || !A || !verts || !v_rest) return fail(SMPLK_E_ARG, "bad argument");
   const ModelDev& d = model->d;
-  CUDA_TRY(cudaSetDevice(model->device));
+  DEVICE_GUARD(model->device);
   dim3 grid((d.V + 255) / 256, batch);
   inverse_lbs_kernel<<<grid, 256, (size_t)d.J * 12 * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
       d, batch, A, verts, transl, v_rest);
@@ -1386,7 +1473,7 @@ extern "C" int smplk_inverse_joints(int32_t batch, int32_t num_joints, const flo
                                     smplk_stream stream) {
   if (batch < 1 || num_joints < 1 || !A || !joints || !out || joints_ld < 3 * num_joints)
     return fail(SMPLK_E_ARG, "bad argument");
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   const int n = batch * num_joints;
   inverse_joints_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       batch, num_joints, A, joints, joints_ld, transl, out);
@@ -1399,7 +1486,7 @@ extern "C" int smplk_vertex_normals(int32_t batch, int32_t num_verts, const int3
                                     float* normals, int device, smplk_stream stream) {
   if (batch < 1 || num_verts < 1 || !faces || !vf_ptr || !vf_face || !verts || !normals)
     return fail(SMPLK_E_ARG, "bad argument");
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   dim3 grid((num_verts + 255) / 256, batch);
   vertex_normals_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       batch, num_verts, faces, vf_ptr, vf_face, verts, normals);
@@ -1414,7 +1501,7 @@ extern "C" int smplk_divide_faces(int32_t batch, int32_t num_verts, int32_t num_
     return fail(SMPLK_E_ARG, "bad argument");
   const size_t smem = ((size_t)2 * num_verts + 32) * sizeof(int);
   if (smem > 200 * 1024) return fail(SMPLK_E_SHAPE, "divide_faces: %d vertices exceed the shared-memory table", num_verts);
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   {   // smplk_divide_faces needs no model handle: raise the kernel's limit here (idempotent)
     int max_optin = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
@@ -1436,7 +1523,7 @@ extern "C" int smplk_reprojection_loss(const smplk_reprojection_args* a) {
   if ((a->camera_batch != 1 && a->camera_batch != a->batch) ||
       (a->weights && a->weights_batch != 1 && a->weights_batch != a->batch))
     return fail(SMPLK_E_SHAPE, "camera_batch / weights_batch must be 1 or batch");
-  CUDA_TRY(cudaSetDevice(a->device));
+  DEVICE_GUARD(a->device);
   ReprojArgs r;
   r.B = a->batch; r.Jn = a->num_joints; r.joints = a->joints; r.rotation = a->rotation;
   r.translation = a->translation; r.focal = a->focal; r.center = a->center; r.cam_batch = a->camera_batch;
@@ -1453,7 +1540,7 @@ extern "C" int smplk_reprojection_loss(const smplk_reprojection_args* a) {
 extern "C" int smplk_fit_priors(const smplk_prior_args* a) {
   if (!a || a->batch < 1 || !a->loss) return fail(SMPLK_E_ARG, "bad argument");
   if (a->body_pose && a->num_body_pose < 56) return fail(SMPLK_E_SHAPE, "body_pose needs >= 56 columns for the angle prior");
-  CUDA_TRY(cudaSetDevice(a->device));
+  DEVICE_GUARD(a->device);
   PriorArgs p;
   p.B = a->batch; p.betas = a->betas; p.nb = a->num_betas; p.pose_embedding = a->pose_embedding;
   p.ne = a->num_embedding; p.body_pose = a->body_pose; p.np = a->num_body_pose; p.lhand = a->left_hand_pose;

@@ -27,6 +27,72 @@ def _f(t):
     return None if t is None else t.contiguous().float()
 
 
+def _launch_reproj(joints, translation, rotation, focal, center, gt, weights, rho, data_weight, loss):
+    """Runs smplk_reprojection_loss into `loss` (B,); returns (d_joints, d_translation) for d_loss = 1."""
+    B, Jn = joints.shape[0], joints.shape[1]
+    dev = joints.device
+    dj = torch.empty_like(joints)
+    dt = torch.empty(B, 3, device=dev)
+    a = _lib.ReprojArgs()
+    a.batch, a.num_joints = B, Jn
+    a.joints, a.rotation, a.translation = _ptr(joints), _ptr(rotation), _ptr(translation)
+    a.focal, a.center, a.camera_batch = _ptr(focal), _ptr(center), translation.shape[0]
+    a.gt_joints, a.weights = _ptr(gt), _ptr(weights)
+    a.weights_batch = weights.shape[0] if weights is not None else 1
+    a.rho, a.data_weight = float(rho), float(data_weight)
+    a.loss, a.d_joints, a.d_translation = _ptr(loss), _ptr(dj), _ptr(dt)
+    a.device = dev.index or 0
+    a.stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(_lib.load().smplk_reprojection_loss(ctypes.byref(a)))
+    return dj, dt
+
+
+def _prior_rows(ts, B=None):
+    """The kernel strides every prior input over B rows.  Inputs with one row (shared betas,
+    upstream lbs batch_size = max(...)) are expanded; anything else must have B rows.
+    Returns (B, expanded inputs, per-input `was broadcast` flags)."""
+    live = [t for t in ts if t is not None]
+    if B is None:
+        B = max(t.shape[0] for t in live)
+    out, bc = [], []
+    for t in ts:
+        if t is None:
+            out.append(None)
+            bc.append(False)
+            continue
+        if t.dim() != 2 or t.shape[0] not in (1, B):
+            raise ValueError("prior inputs must be (1|%d, n), got %s" % (B, tuple(t.shape)))
+        bc.append(t.shape[0] == 1 and B > 1)
+        out.append(t.expand(B, -1).contiguous() if bc[-1] else t)
+    return B, out, bc
+
+
+def _launch_priors(ts, shape_w, pose_w, bend_w, hand_w, loss):
+    """Runs smplk_fit_priors into `loss` (B,) on inputs that all have B rows; returns the gradient
+    list (None where the input is None)."""
+    ref = next(t for t in ts if t is not None)
+    B, dev = ref.shape[0], ref.device
+    grads = [None if t is None else torch.empty_like(t) for t in ts]
+    a = _lib.PriorArgs()
+    a.batch = B
+    a.betas, a.num_betas = _ptr(ts[0]), (ts[0].shape[1] if ts[0] is not None else 0)
+    a.pose_embedding, a.num_embedding = _ptr(ts[1]), (ts[1].shape[1] if ts[1] is not None else 0)
+    a.body_pose, a.num_body_pose = _ptr(ts[2]), (ts[2].shape[1] if ts[2] is not None else 0)
+    a.left_hand_pose, a.right_hand_pose = _ptr(ts[3]), _ptr(ts[4])
+    if ts[3] is not None and ts[4] is not None and ts[3].shape[1] != ts[4].shape[1]:
+        raise ValueError("left / right hand pose widths differ: %d vs %d" % (ts[3].shape[1], ts[4].shape[1]))
+    a.num_hand = ts[3].shape[1] if ts[3] is not None else (ts[4].shape[1] if ts[4] is not None else 0)
+    a.shape_weight, a.body_pose_weight = float(shape_w), float(pose_w)
+    a.bending_prior_weight, a.hand_prior_weight = float(bend_w), float(hand_w)
+    a.loss = _ptr(loss)
+    a.d_betas, a.d_pose_embedding, a.d_body_pose = _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2])
+    a.d_left_hand_pose, a.d_right_hand_pose = _ptr(grads[3]), _ptr(grads[4])
+    a.device = dev.index or 0
+    a.stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(_lib.load().smplk_fit_priors(ctypes.byref(a)))
+    return grads
+
+
 class _Reproj(torch.autograd.Function):
     @staticmethod
     def forward(ctx, joints, translation, rotation, focal, center, gt, weights, rho, data_weight):
@@ -34,22 +100,9 @@ class _Reproj(torch.autograd.Function):
             raise RuntimeError("smplk fitting losses need CUDA tensors (no CPU fallback)")
         joints, translation, rotation = _f(joints), _f(translation), _f(rotation)
         focal, center, gt, weights = _f(focal), _f(center), _f(gt), _f(weights)
-        B, Jn = joints.shape[0], joints.shape[1]
-        dev = joints.device
-        loss = torch.empty(B, device=dev)
-        dj = torch.empty_like(joints)
-        dt = torch.empty(B, 3, device=dev)
-        a = _lib.ReprojArgs()
-        a.batch, a.num_joints = B, Jn
-        a.joints, a.rotation, a.translation = _ptr(joints), _ptr(rotation), _ptr(translation)
-        a.focal, a.center, a.camera_batch = _ptr(focal), _ptr(center), translation.shape[0]
-        a.gt_joints, a.weights = _ptr(gt), _ptr(weights)
-        a.weights_batch = weights.shape[0] if weights is not None else 1
-        a.rho, a.data_weight = float(rho), float(data_weight)
-        a.loss, a.d_joints, a.d_translation = _ptr(loss), _ptr(dj), _ptr(dt)
-        a.device = dev.index or 0
-        a.stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        _lib.check(_lib.load().smplk_reprojection_loss(ctypes.byref(a)))
+        loss = torch.empty(joints.shape[0], device=joints.device)
+        with torch.cuda.device(joints.device):
+            dj, dt = _launch_reproj(joints, translation, rotation, focal, center, gt, weights, rho, data_weight, loss)
         ctx.save_for_backward(dj, dt)
         ctx.cam_batch = translation.shape[0]
         return loss
@@ -78,82 +131,24 @@ class _Priors(torch.autograd.Function):
         ref = next(t for t in ts if t is not None)
         if not ref.is_cuda:
             raise RuntimeError("smplk fitting losses need CUDA tensors (no CPU fallback)")
-        ts = [_f(t) for t in ts]
-        B, dev = ref.shape[0], ref.device
-        loss = torch.empty(B, device=dev)
-        grads = [None if t is None else torch.empty_like(t) for t in ts]
-        a = _lib.PriorArgs()
-        a.batch = B
-        a.betas, a.num_betas = _ptr(ts[0]), (ts[0].shape[1] if ts[0] is not None else 0)
-        a.pose_embedding, a.num_embedding = _ptr(ts[1]), (ts[1].shape[1] if ts[1] is not None else 0)
-        a.body_pose, a.num_body_pose = _ptr(ts[2]), (ts[2].shape[1] if ts[2] is not None else 0)
-        a.left_hand_pose, a.right_hand_pose = _ptr(ts[3]), _ptr(ts[4])
-        a.num_hand = ts[3].shape[1] if ts[3] is not None else (ts[4].shape[1] if ts[4] is not None else 0)
-        a.shape_weight, a.body_pose_weight = float(shape_w), float(pose_w)
-        a.bending_prior_weight, a.hand_prior_weight = float(bend_w), float(hand_w)
-        a.loss = _ptr(loss)
-        a.d_betas, a.d_pose_embedding, a.d_body_pose = _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2])
-        a.d_left_hand_pose, a.d_right_hand_pose = _ptr(grads[3]), _ptr(grads[4])
-        a.device = dev.index or 0
-        a.stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        _lib.check(_lib.load().smplk_fit_priors(ctypes.byref(a)))
-        ctx.grads = grads
+        B, ts, ctx.bc = _prior_rows([_f(t) for t in ts])
+        loss = torch.empty(B, device=ref.device)
+        with torch.cuda.device(ref.device):
+            ctx.grads = _launch_priors(ts, shape_w, pose_w, bend_w, hand_w, loss)
         return loss
 
     @staticmethod
     def backward(ctx, g):
         out = [None if d is None else d * g[:, None] for d in ctx.grads]
+        out = [o.sum(0, keepdim=True) if (o is not None and bc) else o for o, bc in zip(out, ctx.bc)]
         return tuple(out) + (None, None, None, None)
 
 
 def fit_priors(betas=None, pose_embedding=None, body_pose=None, left_hand_pose=None, right_hand_pose=None,
                shape_weight=0.0, body_pose_weight=0.0, bending_prior_weight=0.0, hand_prior_weight=0.0):
-    """(B,) prior loss; `body_pose` is full_pose[:, 3:66]."""
+    """(B,) prior loss; `body_pose` is full_pose[:, 3:66].  One-row inputs (shared betas) broadcast."""
     return _Priors.apply(betas, pose_embedding, body_pose, left_hand_pose, right_hand_pose,
                          shape_weight, body_pose_weight, bending_prior_weight, hand_prior_weight)
-
-
-def _launch_reproj(joints, translation, rotation, focal, center, gt, weights, rho, data_weight, loss):
-    """Runs smplk_reprojection_loss into `loss` (B,); returns (d_joints, d_translation) for d_loss = 1."""
-    B, Jn = joints.shape[0], joints.shape[1]
-    dev = joints.device
-    dj = torch.empty_like(joints)
-    dt = torch.empty(B, 3, device=dev)
-    a = _lib.ReprojArgs()
-    a.batch, a.num_joints = B, Jn
-    a.joints, a.rotation, a.translation = _ptr(joints), _ptr(rotation), _ptr(translation)
-    a.focal, a.center, a.camera_batch = _ptr(focal), _ptr(center), translation.shape[0]
-    a.gt_joints, a.weights = _ptr(gt), _ptr(weights)
-    a.weights_batch = weights.shape[0] if weights is not None else 1
-    a.rho, a.data_weight = float(rho), float(data_weight)
-    a.loss, a.d_joints, a.d_translation = _ptr(loss), _ptr(dj), _ptr(dt)
-    a.device = dev.index or 0
-    a.stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    _lib.check(_lib.load().smplk_reprojection_loss(ctypes.byref(a)))
-    return dj, dt
-
-
-def _launch_priors(ts, shape_w, pose_w, bend_w, hand_w, loss):
-    """Runs smplk_fit_priors into `loss` (B,); returns the gradient list (None where the input is None)."""
-    ref = next(t for t in ts if t is not None)
-    B, dev = ref.shape[0], ref.device
-    grads = [None if t is None else torch.empty_like(t) for t in ts]
-    a = _lib.PriorArgs()
-    a.batch = B
-    a.betas, a.num_betas = _ptr(ts[0]), (ts[0].shape[1] if ts[0] is not None else 0)
-    a.pose_embedding, a.num_embedding = _ptr(ts[1]), (ts[1].shape[1] if ts[1] is not None else 0)
-    a.body_pose, a.num_body_pose = _ptr(ts[2]), (ts[2].shape[1] if ts[2] is not None else 0)
-    a.left_hand_pose, a.right_hand_pose = _ptr(ts[3]), _ptr(ts[4])
-    a.num_hand = ts[3].shape[1] if ts[3] is not None else (ts[4].shape[1] if ts[4] is not None else 0)
-    a.shape_weight, a.body_pose_weight = float(shape_w), float(pose_w)
-    a.bending_prior_weight, a.hand_prior_weight = float(bend_w), float(hand_w)
-    a.loss = _ptr(loss)
-    a.d_betas, a.d_pose_embedding, a.d_body_pose = _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2])
-    a.d_left_hand_pose, a.d_right_hand_pose = _ptr(grads[3]), _ptr(grads[4])
-    a.device = dev.index or 0
-    a.stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    _lib.check(_lib.load().smplk_fit_priors(ctypes.byref(a)))
-    return grads
 
 
 class _SMPLifyTotal(torch.autograd.Function):
@@ -170,15 +165,17 @@ class _SMPLifyTotal(torch.autograd.Function):
             raise RuntimeError("smplk fitting losses need CUDA tensors (no CPU fallback)")
         joints, translation, rotation = _f(joints), _f(translation), _f(rotation)
         focal, center, gt, weights = _f(focal), _f(center), _f(gt), _f(weights)
-        ts = [_f(t) for t in (betas, emb, body_pose, lh, rh)]
         B, dev = joints.shape[0], joints.device
+        # the batch is the joints' (shared betas of shape (1,NB) broadcast over it)
+        _, ts, ctx.bc = _prior_rows([_f(t) for t in (betas, emb, body_pose, lh, rh)], B)
         both = torch.empty(2, B, device=dev)
-        dj, dt = _launch_reproj(joints, translation, rotation, focal, center, gt, weights, rho, data_weight, both[0])
-        if any(t is not None for t in ts):
-            pg = _launch_priors(ts, shape_w, pose_w, bend_w, hand_w, both[1])
-        else:
-            pg = [None] * 5
-            both[1].zero_()
+        with torch.cuda.device(dev):
+            dj, dt = _launch_reproj(joints, translation, rotation, focal, center, gt, weights, rho, data_weight, both[0])
+            if any(t is not None for t in ts):
+                pg = _launch_priors(ts, shape_w, pose_w, bend_w, hand_w, both[1])
+            else:
+                pg = [None] * 5
+                both[1].zero_()
         ctx.cam_batch = translation.shape[0]
         ctx.grads = [dj, dt] + pg
         return both.sum()
@@ -190,6 +187,9 @@ class _SMPLifyTotal(torch.autograd.Function):
         out = [None if t is None else next(scaled) for t in ctx.grads]
         if ctx.cam_batch == 1 and out[1].shape[0] != 1:
             out[1] = out[1].sum(0, keepdim=True)
+        for i, bc in enumerate(ctx.bc):
+            if bc and out[2 + i] is not None:
+                out[2 + i] = out[2 + i].sum(0, keepdim=True)
         return tuple(out) + (None,) * 11
 
 

@@ -174,6 +174,18 @@ int smplk_backward(const smplk_model* model, const smplk_backward_args* args);
 int smplk_regress_joints(const smplk_model* model, int32_t batch, const float* verts, float* out,
                          smplk_stream stream);
 
+/* Replaces do_skinning(G) of the numpy twins (models/smplh_np.py:72-82, models/smpl_np.py:191-202,
+ * lib/model2video.py:66-81): the caller hands in the GLOBAL joint transforms G (B,J,4,4) row-major it got
+ * from compute_R_G (possibly edited), the rest joints (B,J,3) and the blended vertices;
+ *   A[b,j] = [G_R | G_t - G_R J_j]   (written to `A`, (B,J,12), also an output)
+ *   verts[b,v] = (sum_k w[v,k] A[b,j_k]) [v_posed[b,v]; 1] + transl[b]
+ * v_posed: (B, v_posed_ld) rows, 16-byte aligned (v_posed_ld % 4 == 0, >= 3V); NULL for a rigged mesh
+ * (its own v_template is skinned).  All pointers are device pointers. */
+int smplk_skin_transforms(const smplk_model* model, int32_t batch, const float* G,
+                          const float* joints_rest, const float* v_posed, int32_t v_posed_ld,
+                          const float* transl /* (B,3) or NULL */, float* A, float* verts,
+                          smplk_stream stream);
+
 /* Replaces utils/geometry.py:9-23 batch_rodrigues (axis-angle (n,3) -> rotation matrices (n,3,3)). */
 int smplk_batch_rodrigues(int32_t n, const float* axis_angle, float* rotmats, int device,
                           smplk_stream stream);

@@ -73,8 +73,13 @@ def test_smplh_forward_matches_oracle(dev, smplh_model, B, flags):
     args64 = [torch.tensor(x, dtype=torch.float64) for x in (betas, pose, transl)]
     ref32 = om32.forward_full_pose(*[a.float() for a in args64])
     ref64 = om64.forward_full_pose(*args64)
-    v, j, jr, fp = body_model_apply(dm, _t(betas, dev), _t(pose, dev), transl=_t(transl, dev),
-                                    want_regressed=True, flags=flags)
+    try:
+        v, j, jr, fp = body_model_apply(dm, _t(betas, dev), _t(pose, dev), transl=_t(transl, dev),
+                                        want_regressed=True, flags=flags)
+    except RuntimeError as e:
+        if "SMPLK_AB" in str(e):      # the exact-fp32 SIMT kernel ships only in -DSMPLK_AB builds
+            pytest.skip("library built without -DSMPLK_AB")
+        raise
     assert _maxerr(v, ref32.vertices) <= TOL and _maxerr(v, ref64.vertices) <= TOL
     assert _maxerr(j[:, :52], ref32.joints) <= TOL
     picks = ref64.vertices[:, torch.as_tensor(m["extra_vertex_ids"], dtype=torch.long)]
@@ -89,8 +94,14 @@ def test_blend_operand_formats_agree(dev, smplh_model):
     dm = smplk.DeviceModel(smplh_model, device=0)
     betas, pose, transl = synthetic.make_inputs(smplh_model, 200, seed=9)
     run = lambda f: body_model_apply(dm, _t(betas, dev), _t(pose, dev), transl=_t(transl, dev), flags=f)[0]
-    simt, f16, tf32 = run(_lib.FLAG_BLEND_SIMT), run(_lib.FLAG_BLEND_TCGEN05), run(_lib.FLAG_BLEND_TF32)
-    assert _maxerr(simt, f16) <= 5e-6 and _maxerr(simt, tf32) <= 5e-6 and _maxerr(f16, tf32) <= 2e-6
+    f16, tf32 = run(_lib.FLAG_BLEND_TCGEN05), run(_lib.FLAG_BLEND_TF32)
+    assert _maxerr(f16, tf32) <= 2e-6
+    try:
+        simt = run(_lib.FLAG_BLEND_SIMT)
+    except RuntimeError as e:         # A/B kernel: only in -DSMPLK_AB builds
+        assert "SMPLK_AB" in str(e)
+        return
+    assert _maxerr(simt, f16) <= 5e-6 and _maxerr(simt, tf32) <= 5e-6
 
 
 @pytest.mark.parametrize("B", [129, 257, 300, 1000, 2049])
