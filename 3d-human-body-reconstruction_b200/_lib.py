@@ -116,7 +116,7 @@ EXPORTED_SYMBOLS = [
     "smplk_batch_rodrigues", "smplk_forward_host", "smplk_last_error_string", "smplk_version",
     "smplk_launch_count", "smplk_workspace_layout", "smplk_profile_enable", "smplk_profile_read", "smplk_vertex_l2",
     "smplk_inverse_lbs", "smplk_inverse_joints", "smplk_vertex_normals", "smplk_divide_faces",
-    "smplk_reprojection_loss", "smplk_fit_priors", "smplk_fit_vertex_l2", "smplk_skin_transforms",
+    "smplk_reprojection_loss", "smplk_fit_priors", "smplk_fit_vertex_l2", "smplk_skin_transforms", "smplk_remove_rest",
 ]
 PROF_SLOTS = ["pose_fwd", "blend_tcgen05", "blend_simt", "skin", "dA", "skin_bwd", "blend_bwd",
               "pose_bwd", "blend_skin_fused", "transpose"]
@@ -209,6 +209,8 @@ def load():
     lib.smplk_fit_vertex_l2.restype = ctypes.c_int
     lib.smplk_skin_transforms.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]
     lib.smplk_skin_transforms.restype = ctypes.c_int
+    lib.smplk_remove_rest.argtypes = [i32, i32, vp, vp, vp, ctypes.c_int, vp]
+    lib.smplk_remove_rest.restype = ctypes.c_int
     lib.smplk_profile_enable.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.smplk_profile_enable.restype = ctypes.c_int
     lib.smplk_profile_read.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),

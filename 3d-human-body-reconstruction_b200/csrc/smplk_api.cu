@@ -119,6 +119,8 @@ struct smplk_model {
   // host staging for smplk_forward_host
   void* stage_dev;
   size_t stage_bytes;
+  cudaStream_t copy_stream;                 // device->host copies of smplk_forward_host
+  std::vector<cudaEvent_t> chunk_events;    // one per chunk of that call
   // optional per-kernel device timing (smplk_profile_*)
   BlendPath default_tc;  // BLEND_F16 unless SMPLK_BLEND=tf32 in the environment
   int skin_bpb;         // SMPLK_SKIN_BPB: override bodies per block (tuning)
@@ -220,6 +222,8 @@ extern "C" int smplk_model_destroy(smplk_model* model) {
   DeviceGuard device_guard_(model->device);
   for (void* p : model->allocs) cudaFree(p);
   if (model->stage_dev) cudaFree(model->stage_dev);
+  for (cudaEvent_t e : model->chunk_events) cudaEventDestroy(e);
+  if (model->copy_stream) cudaStreamDestroy(model->copy_stream);
   delete model;
   return 0;
 }
@@ -781,6 +785,7 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   mdl->cc_major = prop.major;
   mdl->stage_dev = nullptr;
   mdl->stage_bytes = 0;
+  mdl->copy_stream = nullptr;
   mdl->encode = nullptr;
   mdl->prof_on = false;
   mdl->skin_bpb = 0; mdl->skin_g8 = true; mdl->skin_tma = false; mdl->force_skin_v1 = false;
@@ -1330,6 +1335,16 @@ __global__ void rest_removal_kernel(int n, const float* __restrict__ G, const fl
   }
 }
 
+extern "C" int smplk_remove_rest(int32_t batch, int32_t num_joints, const float* G, const float* joints_rest,
+                                 float* A, int device, smplk_stream stream) {
+  if (batch < 1 || num_joints < 1 || !G || !joints_rest || !A) return fail(SMPLK_E_ARG, "bad argument");
+  DEVICE_GUARD(device);
+  const int n = batch * num_joints;
+  rest_removal_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(n, G, joints_rest, A);
+  LAUNCH_CHECK("rest_removal_kernel");
+  return 0;
+}
+
 extern "C" int smplk_skin_transforms(const smplk_model* model, int32_t batch, const float* G,
                                      const float* joints_rest, const float* v_posed, int32_t v_posed_ld,
                                      const float* transl, float* A, float* verts, smplk_stream stream) {
@@ -1357,16 +1372,26 @@ extern "C" int smplk_batch_rodrigues(int32_t n, const float* axis_angle, float* 
   return 0;
 }
 
+// Host-buffer forward.  The device->host copy of the vertices (82,680 B per body) is ~25x the kernel
+// time, so the batch is cut into chunks: chunk c is computed on the caller's stream while chunk c-1
+// drains over PCIe on a second (model-owned) stream, ordered by one event per chunk.  The device
+// staging buffer holds the whole batch, so a chunk's copy never blocks a later chunk's kernels.
+constexpr int kHostChunk = 1024;
+
 extern "C" int smplk_forward_host(smplk_model* model, int32_t batch, uint32_t flags,
                                   const float* betas, int32_t betas_batch, const float* pose,
                                   const float* transl, float* verts, float* joints,
                                   smplk_stream stream) {
   if (!model || !pose || batch < 1) return fail(SMPLK_E_ARG, "bad argument");
+  if (betas && betas_batch != 1 && betas_batch != batch)
+    return fail(SMPLK_E_SHAPE, "betas_batch must be 1 or batch (got %d for batch %d)", betas_batch, batch);
   const ModelDev& d = model->d;
   DEVICE_GUARD(model->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   flags &= ~SMPLK_FLAG_SAVE_FOR_BACKWARD;
-  const size_t ws_bytes = smplk_workspace_bytes(model, batch, flags);
+  const int chunk = std::min<int>(batch, kHostChunk);
+  const int nchunks = (batch + chunk - 1) / chunk;
+  const size_t ws_bytes = smplk_workspace_bytes(model, chunk, flags);
   const size_t nb_betas = betas ? align_up((size_t)betas_batch * d.NB * 4, 256) : 0;
   const size_t nb_pose = align_up((size_t)batch * 3 * d.J * 4, 256);
   const size_t nb_tr = transl ? align_up((size_t)batch * 12, 256) : 0;
@@ -1380,6 +1405,12 @@ extern "C" int smplk_forward_host(smplk_model* model, int32_t batch, uint32_t fl
     CUDA_TRY(cudaMalloc(&model->stage_dev, total));
     model->stage_bytes = total;
   }
+  if (!model->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&model->copy_stream, cudaStreamNonBlocking));
+  while ((int)model->chunk_events.size() < nchunks) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    model->chunk_events.push_back(e);
+  }
   uint8_t* p = reinterpret_cast<uint8_t*>(model->stage_dev);
   void* ws = p; p += align_up(ws_bytes, 256);
   float* d_betas = betas ? reinterpret_cast<float*>(p) : nullptr; p += nb_betas;
@@ -1390,14 +1421,30 @@ extern "C" int smplk_forward_host(smplk_model* model, int32_t batch, uint32_t fl
   if (betas) CUDA_TRY(cudaMemcpyAsync(d_betas, betas, (size_t)betas_batch * d.NB * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(d_pose, pose, (size_t)batch * 3 * d.J * 4, cudaMemcpyHostToDevice, st));
   if (transl) CUDA_TRY(cudaMemcpyAsync(d_tr, transl, (size_t)batch * 12, cudaMemcpyHostToDevice, st));
-  smplk_forward_args fa;
-  memset(&fa, 0, sizeof(fa));
-  fa.batch = batch; fa.flags = flags; fa.betas = d_betas; fa.betas_batch = betas ? betas_batch : 1;
-  fa.pose = d_pose; fa.transl = d_tr; fa.verts = d_verts; fa.joints = d_joints;
-  fa.workspace = ws; fa.workspace_bytes = ws_bytes; fa.stream = stream;
-  if (int r = smplk_forward(model, &fa)) return r;
-  if (verts) CUDA_TRY(cudaMemcpyAsync(verts, d_verts, (size_t)batch * d.V * 12, cudaMemcpyDeviceToHost, st));
-  if (joints) CUDA_TRY(cudaMemcpyAsync(joints, d_joints, (size_t)batch * (d.J + d.E) * 12, cudaMemcpyDeviceToHost, st));
+  const size_t jl = (size_t)(d.J + d.E) * 3;
+  for (int c = 0; c < nchunks; ++c) {
+    const int c0 = c * chunk, rows = std::min(chunk, batch - c0);
+    smplk_forward_args fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.batch = rows; fa.flags = flags;
+    fa.betas = d_betas ? (betas_batch == 1 ? d_betas : d_betas + (size_t)c0 * d.NB) : nullptr;
+    fa.betas_batch = (betas && betas_batch != 1) ? rows : 1;
+    fa.pose = d_pose + (size_t)c0 * 3 * d.J;
+    fa.transl = d_tr ? d_tr + (size_t)c0 * 3 : nullptr;
+    fa.verts = d_verts + (size_t)c0 * d.V * 3;
+    fa.joints = d_joints ? d_joints + (size_t)c0 * jl : nullptr;
+    fa.workspace = ws; fa.workspace_bytes = ws_bytes; fa.stream = stream;
+    if (int r = smplk_forward(model, &fa)) return r;
+    CUDA_TRY(cudaEventRecord(model->chunk_events[c], st));
+    CUDA_TRY(cudaStreamWaitEvent(model->copy_stream, model->chunk_events[c], 0));
+    if (verts)
+      CUDA_TRY(cudaMemcpyAsync(verts + (size_t)c0 * d.V * 3, fa.verts, (size_t)rows * d.V * 12, cudaMemcpyDeviceToHost,
+                               model->copy_stream));
+    if (joints)
+      CUDA_TRY(cudaMemcpyAsync(joints + (size_t)c0 * jl, fa.joints, (size_t)rows * jl * 4, cudaMemcpyDeviceToHost,
+                               model->copy_stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(model->copy_stream));
   CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
 }

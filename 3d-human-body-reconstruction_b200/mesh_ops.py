@@ -60,6 +60,21 @@ def transforms(dm, betas, pose, transl=None):
     return A, joints[:, :dm.J]
 
 
+def remove_rest(G, joints_rest):
+    """A (B,J,3,4) = [G_R | G_t - G_R J] from global transforms G (B,J,4,4) and rest joints (B,J,3): the
+    `G - pack(G . [J;0])` step of lib/mesh2smpl_model.py:194-199 / models/smplh_np.py:73-78."""
+    _check_cuda(G, joints_rest)
+    B, J = G.shape[0], G.shape[1]
+    if tuple(G.shape) != (B, J, 4, 4) or tuple(joints_rest.shape) != (B, J, 3):
+        raise ValueError("G must be (B,J,4,4) and joints_rest (B,J,3)")
+    G = G.contiguous().float()
+    joints_rest = joints_rest.contiguous().float()
+    A = torch.empty(B, J, 3, 4, device=G.device)
+    _lib.check(_lib.load().smplk_remove_rest(B, J, _ptr(G), _ptr(joints_rest), _ptr(A), G.device.index or 0,
+                                             _stream(G.device)))
+    return A
+
+
 def inverse_lbs(dm, A, verts, transl=None):
     """v_rest = (W.A)^-1 [verts - transl; 1] per vertex, with the skin weights of `dm`."""
     _check_cuda(A, verts, transl)

@@ -20,3 +20,30 @@ def max_over_ranks_ms(local_ms, dist=None, device=None):
     t = torch.tensor([float(local_ms)], dtype=torch.float64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def forward_shard(dm, betas, pose, transl=None, world_size=1, rank=0, **kwargs):
+    """This rank's part of a batched forward over `world_size` GPUs: the contiguous slice
+    [lo, hi) of the bodies, evaluated by the rank's own DeviceModel (`dm`, one handle per GPU) through
+    smplk_forward.  `betas` / `pose` / `transl` describe the WHOLE batch (numpy or torch, any device; a
+    one-row betas is shared); only the slice is copied to the device.  Returns (lo, hi, verts, joints)
+    with the outputs left on the rank's GPU -- results stay sharded, no collective."""
+    import numpy as np
+    import torch
+    from .body_models import body_model_apply
+    total = pose.shape[0]
+    lo, hi = shard_bounds(total, world_size, rank)
+    dev = torch.device("cuda", dm.device)
+
+    def take(a, rows):
+        if a is None:
+            return None
+        a = a[rows] if a.shape[0] != 1 else a
+        t = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)) if not torch.is_tensor(a) else a.float()
+        return t.to(dev, non_blocking=True).contiguous()
+    rows = slice(lo, hi)
+    if hi == lo:
+        return lo, hi, None, None
+    with torch.cuda.device(dev):
+        v, j, _, _ = body_model_apply(dm, take(betas, rows), take(pose, rows), transl=take(transl, rows), **kwargs)
+    return lo, hi, v, j

@@ -92,12 +92,39 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_baseline(model, sample_bodies=256, budget_s=12.0):
-    """Oracle port of the reference torch path (upstream smplx lbs restatement) on the host cores,
-    fp32, all threads, on a bounded sample of the same synthetic workload."""
+def _host_threads():
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its children)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return max(1, os.cpu_count() or 1)
+
+
+def _median_ms(fn, n):
+    fn()
+    ts = []
+    for _ in range(n):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    return float(np.median(ts)) * 1e3
+
+
+def cpu_baseline(model, sample_bodies, budget_s=12.0):
+    """The reference's CPU path restated (oracle/) and timed on this box's host cores, bounded samples:
+
+      value (C4)  torch-CPU fp32 restatement of upstream smplx.lbs, all host threads, passes of the SAME
+                  step as the GPU arm
+      c1 / c2     numpy float64 restatement of models/smpl_np.py / models/smplh_np.py set_params, one body
+                  per call, median of 20 calls (BASELINE config 1; C1 / C2)
+      c3          the per-frame replay loop of lib/model2video.py:514-518 over 1,000 frames of the AMASS
+                  clip fixture: LBS-only rigged mesh (RecoverModel math, 24 joints, 6,890 vertices), and the
+                  full SMPL-H forward over 200 frames (C3)
+    """
     import torch
     from oracle import smpl_oracle as O
-    from smplk import synthetic
+    from smplk import clips, synthetic
+    torch.set_num_threads(_host_threads())
     om = O.TorchOracleModel(model, dtype=torch.float32)
     betas, pose, transl = synthetic.make_inputs(model, sample_bodies, seed=123)
     tb, tp, tt = torch.tensor(betas), torch.tensor(pose), torch.tensor(transl)
@@ -110,49 +137,124 @@ def cpu_baseline(model, sample_bodies=256, budget_s=12.0):
             el = time.perf_counter() - t0
             if el > budget_s or n >= 200:
                 break
-    return {"value": sample_bodies * n / el, "unit": UNIT, "cores": torch.get_num_threads(),
-            "kind": "port",
-            "sample": "%d passes of %d bodies (torch-CPU fp32 restatement of smplx.lbs, oracle/smpl_oracle.py), %.1f s"
-                      % (n, sample_bodies, el)}
+    out = {"value": sample_bodies * n / el, "unit": UNIT, "cores": torch.get_num_threads(),
+           "kind": "port",
+           "sample": "%d passes of %d bodies (torch-CPU fp32 restatement of smplx.lbs, oracle/smpl_oracle.py), %.1f s"
+                     % (n, sample_bodies, el)}
+    try:
+        rng = np.random.default_rng(0)
+        ms_ = synthetic.make_model("smpl", num_betas=10, seed=8)
+        mh_ = synthetic.make_model("smplh", num_betas=10, seed=7)
+        p24, p52 = rng.standard_normal((24, 3)) * 0.3, rng.standard_normal((52, 3)) * 0.3
+        be, tr = rng.standard_normal(10), rng.standard_normal(3)
+        c1 = _median_ms(lambda: O.np_forward(ms_, p24, be, tr), 20)
+        c2 = _median_ms(lambda: O.np_forward(mh_, p52, be, tr), 20)
+        out["c1"] = {"ms_per_body": c1, "value": 1e3 / c1, "unit": UNIT, "cores": "numpy BLAS default",
+                     "what": "SMPL B=1 float64, oracle np_forward (models/smpl_np.py:158-206 set_params), median of 20"}
+        out["c2"] = {"ms_per_body": c2, "value": 1e3 / c2, "unit": UNIT, "cores": "numpy BLAS default",
+                     "what": "SMPL-H B=1 float64, oracle np_forward (models/smplh_np.py:39-86 set_params), median of 20"}
+        clip = clips.read_amsass(os.path.join(ROOT, "tests", "golden", "amass_clip_09_05.npz"), full=True)
+        n0 = clip.poses.shape[0]
+        rig = synthetic.make_rigged_mesh(6890, seed=13)
+        frames = 1000
+        t0 = time.perf_counter()
+        for i in range(frames):                      # lib/model2video.py:514-518: one set_params per frame
+            O.np_lbs_only(rig, clip.poses[i % n0, :72], clip.trans[i % n0])
+        el_rig = time.perf_counter() - t0
+        fh = 200
+        t0 = time.perf_counter()
+        for i in range(fh):
+            O.np_forward(model, clip.poses[i % n0], clip.betas[:model["shapedirs"].shape[2]], clip.trans[i % n0])
+        el_h = time.perf_counter() - t0
+        out["c3"] = {"lbs_only_frames_per_s": frames / el_rig, "lbs_only_sample": "%d frames, 6,890-vertex rig, %.1f s" % (frames, el_rig),
+                     "lbs_only_100k_frames_s": 1e5 * el_rig / frames,
+                     "smplh_frames_per_s": fh / el_h, "smplh_sample": "%d frames, %.1f s" % (fh, el_h),
+                     "smplh_100k_frames_s": 1e5 * el_h / fh,
+                     "what": "per-frame replay loop (lib/model2video.py:514-518) over the tiled AMASS clip, numpy float64 oracle"}
+    except Exception as e:       # the extra baselines never take the bench line down
+        out["c_error"] = repr(e)
+    return out
 
 
 def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (oracle port: the reference is pure
+    Python over un-vendored smplx, and /root/reference does not exist on the GPU box), all host threads,
+    each step one pass over the SAME batch as the GPU arm's step."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # all the host threads this process may use (torchrun sets OMP_NUM_THREADS=1 for its children)
-    try:
-        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    except (AttributeError, OSError):
-        torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.set_num_threads(_host_threads())
     from smplk import synthetic
     model = synthetic.make_model("smplh", seed=0)
     from oracle import smpl_oracle as O
     om = O.TorchOracleModel(model, dtype=torch.float32)
-    sample = 256
-    betas, pose, transl = synthetic.make_inputs(model, sample, seed=1)
+    B = args.batch
+    betas, pose, transl = synthetic.make_inputs(model, B, seed=1)
     tb, tp, tt = torch.tensor(betas), torch.tensor(pose), torch.tensor(transl)
+    sub = 512          # bodies are independent: the step is evaluated in slices to bound host memory (T is B x V x 16 floats)
+
+    def step():
+        for c0 in range(0, B, sub):
+            om.forward_full_pose(tb[c0:c0 + sub], tp[c0:c0 + sub], tt[c0:c0 + sub])
     with torch.no_grad():
-        for _ in range(max(1, min(args.warmup, 3))):
-            om.forward_full_pose(tb, tp, tt)
+        for _ in range(max(1, min(args.warmup, 2))):
+            step()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            om.forward_full_pose(tb, tp, tt)
+            step()
         el = time.perf_counter() - t0
-    val = sample * args.steps / el
+    val = B * args.steps / el
     cores = torch.get_num_threads()
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "SMPL-H forward+LBS batch %d fp32 (52 joints, 16 betas, 459 posedirs)" % args.batch,
-                       "step_sample": "%d bodies per step on the host CPU" % sample},
+            "config": workload_config(B, args.gpus),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d steps x %d bodies, torch-CPU fp32 restatement of the reference torch path" % (args.steps, sample)},
+                             "sample": "%d steps x %d bodies (one GPU's share of a step; in slices of %d), torch-CPU fp32 "
+                                       "restatement of the reference torch path" % (args.steps, B, sub)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+NSETS = 4
+
+
+def workload_config(B, world):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": "SMPL-H forward+LBS batch %d per GPU, fp32, 52 joints, 16 betas, 459 posedirs "
+                        "(BASELINE.json configs[1])" % B,
+            "global_batch": world * B, "parallelism": "batch-sharded x%d, no collective" % world,
+            "l2": "per-step output %.0f MB (verts) > 126 MB L2; %d rotating input sets" % (B * 82680 / 1e6, NSETS),
+            "weights": "canonically sparse LBS weights (<=4 per vertex)"}
+
+
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads (and so its pinned staging buffers, first-touch) to the NUMA node the
+    rank's GPU hangs off: with 8 ranks copying 339 MB per step each, buffers that all sit on one node
+    make that node's memory controllers / the socket interconnect the bottleneck."""
+    info = {"bound": False}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        pci = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % pci).read().strip())
+        info.update(pci=pci, numa_node=node)
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=len(allowed))
+    except Exception as e:
+        info["error"] = repr(e)
+    return info
 
 
 import contextlib
@@ -200,6 +302,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if os.environ.get("SMPLK_BENCH_NUMA", "1") != "0" else {"bound": False}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # stdout carries the one JSON line: whatever the communicator set-up prints there (NCCL's
@@ -215,7 +318,7 @@ def main():
     B = args.batch
     model = synthetic.make_model("smplh", seed=0)
     dm = smplk.DeviceModel(model, device=local)
-    NSETS = 4  # rotate inputs; per-step footprint (v_posed + verts = %d MB) already exceeds the 126 MB L2
+    # NSETS rotating input sets; the per-step output (339 MB of vertices) already exceeds the 126 MB L2
     sets = []
     for s in range(NSETS):
         b, p, t = synthetic.make_inputs(model, B, seed=10 * rank + s)
@@ -297,9 +400,11 @@ def main():
         #   SMPLK_BLEND=tf32: 3xTF32   -> ceiling = TF32 dense peak (cuBLAS, measured here) / 3
         dense_peak = peaks["bf16"] if fmt != "tf32" else (tf32_peak or peaks["bf16"] / 2)
         ncu_traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_ncu_fused_traffic.json")
-        if os.path.exists(tp):
-            ncu_traffic = json.load(open(tp))
+        for name in ("r02_ncu_fused_traffic.json", "r01_ncu_fused_traffic.json"):
+            tp = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tp):
+                ncu_traffic = json.load(open(tp))
+                break
 
         def tensor_roofline(name, g_ms, npad, note_extra=""):
             alg_tflops = GEMM_FLOPS_PER_BODY * B / (g_ms * 1e-3) / 1e12
@@ -443,6 +548,28 @@ def main():
                              "ms_per_step_cuda_graph": fb_graph_ms,
                              "value_cuda_graph": (world * Bb / (fb_graph_ms * 1e-3)) if fb_graph_ms else None}
 
+        dm.profile_enable(True)
+        dm.profile_read()
+        for _ in range(10):
+            fb_step("node")
+        torch.cuda.synchronize(dev)
+        fbk = {k: v[0] / v[1] for k, v in dm.profile_read(reset=True).items() if v[1] > 0}
+        dm.profile_enable(False)
+        extras["fwd_bwd"]["kernel_ms"] = fbk
+        extras["fwd_bwd"]["kernel_ms_note"] = ("CUDA events around each launch of the one-node step: pose_fwd, blend_tcgen05 "
+                                               "(forward GEMM), skin (= skin_fit_l2: skinning + loss + gradient + skinning backward), "
+                                               "dA, blend_bwd (backward GEMM), pose_bwd")
+        best_fb = min(fb_ms, fb_graph_ms) if fb_graph_ms else fb_ms
+        fb_tflops = 2 * GEMM_FLOPS_PER_BODY * Bb / (best_fb * 1e-3) / 1e12
+        fb_gbs = 167384 * Bb / (best_fb * 1e-3) / 1e9
+        extras["roofline_fwd_bwd"] = {
+            "kernel": "fitting step (config 3, batch %d): %d launches" % (Bb, len(fbk)), "bound": "tensor",
+            "achieved": fb_tflops, "peak": dense_peak / 3.0, "unit": "TFLOP/s", "frac": fb_tflops / (dense_peak / 3.0),
+            "traffic": None, "ms_per_step": best_fb,
+            "hbm": {"achieved": fb_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": fb_gbs / peaks["hbm"]},
+            "note": "achieved = 2 GEMMs x 2*B*20670*475 fp32-equivalent FLOPs / step time (CUDA graph replay when captured); "
+                    "peak = dense tensor peak / 3 passes; hbm = 167,384 algorithmic B/body (SURVEY 8d fwd+bwd fused minimum) / step time"}
+
         # ---- batch-1 fitting closure (what lib/Gen_SMPLH/fit_single_frame.py runs: batch_size == 1)
         try:
             b1, p1, t1 = (torch.tensor(x, device=dev, requires_grad=True) for x in synthetic.make_inputs(model, 1, seed=5))
@@ -505,6 +632,128 @@ def main():
         except Exception as e:
             sys.stderr.write("config-1 twin timing skipped: %r\n" % (e,))
 
+        def timed_ms(fn, reps, warm=2):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize(dev)
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record(stream)
+            for _ in range(reps):
+                fn()
+            q1.record(stream)
+            torch.cuda.synchronize(dev)
+            return q0.elapsed_time(q1) / reps
+
+        def fwd_call(m_, b_, p_, t_, v_, ws_, j_=None):
+            a = _lib.ForwardArgs()
+            a.batch, a.flags = p_.shape[0], 0
+            a.betas, a.betas_batch = (ctypes.c_void_p(b_.data_ptr()) if b_ is not None else None), (b_.shape[0] if b_ is not None else 1)
+            a.pose, a.transl = ctypes.c_void_p(p_.data_ptr()), ctypes.c_void_p(t_.data_ptr())
+            a.verts = ctypes.c_void_p(v_.data_ptr())
+            a.joints = ctypes.c_void_p(j_.data_ptr()) if j_ is not None else None
+            a.workspace, a.workspace_bytes = ctypes.c_void_p(ws_.data_ptr()), ws_.numel()
+            a.stream = ctypes.c_void_p(stream.cuda_stream)
+            m_.forward(a)
+
+        # ---- the operand format north_star names (3xTF32) next to the fp16 two-term default
+        if rank == 0:
+            try:
+                os.environ["SMPLK_BLEND"] = "tf32"
+                dm_t = smplk.DeviceModel(model, device=local)
+                del os.environ["SMPLK_BLEND"]
+                wst = torch.empty(dm_t.workspace_bytes(B, 0), device=dev, dtype=torch.uint8)
+                dm_t.profile_enable(True)
+                for i in range(10):
+                    fwd_call(dm_t, *sets[i % NSETS], verts, wst, joints)
+                torch.cuda.synchronize(dev)
+                pt = {k: v[0] / v[1] for k, v in dm_t.profile_read(reset=True).items() if v[1] > 0}
+                dm_t.profile_enable(False)
+                g_ms = pt.get("blend_tcgen05")
+                extras["blend_tf32_variant"] = {
+                    "kernel_ms": pt, "forward_ms": sum(pt.values()),
+                    "blend_gemm_tflops_fp32_equiv": (GEMM_FLOPS_PER_BODY * B / (g_ms * 1e-3) / 1e12) if g_ms else None,
+                    "frac_of_tf32_ceiling": (GEMM_FLOPS_PER_BODY * B / (g_ms * 1e-3) / 1e12) / ((tf32_peak or peaks["bf16"] / 2) / 3.0) if g_ms else None,
+                    "note": "SMPLK_BLEND=tf32: 3xTF32 blend GEMM (tcgen05 kind::tf32) + skinning kernel, same batch; the default is "
+                            "the fp16 hi+lo split fused with the skinning epilogue (equal 11+11 mantissa bits, half the tensor time)"}
+                del dm_t, wst
+            except Exception as e:
+                os.environ.pop("SMPLK_BLEND", None)
+                sys.stderr.write("tf32 variant skipped: %r\n" % (e,))
+
+        # ---- BASELINE config 4: one point of the batch sweep, 64K bodies on this GPU (vertices of the whole
+        # slice resident: 5.4 GB), forward in 8192-body chunks through a bounded workspace
+        try:
+            n4 = 1 << 16
+            gen = torch.Generator(device=dev).manual_seed(100 + rank)
+            b4 = torch.randn(n4, 16, device=dev, generator=gen)
+            p4 = torch.randn(n4, 156, device=dev, generator=gen) * 0.3
+            t4 = torch.randn(n4, 3, device=dev, generator=gen)
+            v4 = torch.empty(n4, dm.V, 3, device=dev)
+            j4 = torch.empty(n4, dm.J, 3, device=dev)
+            ws4 = torch.empty(dm.workspace_bytes(n4, 0), device=dev, dtype=torch.uint8)
+            ms4 = timed_ms(lambda: fwd_call(dm, b4, p4, t4, v4, ws4, j4), 5)
+            if world > 1:
+                t = torch.tensor([ms4], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms4 = float(t.item())
+            extras["config4_64k_per_gpu"] = {"metric": METRIC, "bodies_per_gpu": n4, "n_gpus": world, "ms": ms4,
+                                             "value": world * n4 / (ms4 * 1e-3), "unit": UNIT,
+                                             "note": "BASELINE configs[3], the 64K-bodies-per-GPU point; tools/sweep.py runs the whole sweep"}
+            del b4, p4, t4, v4, j4, ws4
+            torch.cuda.empty_cache()
+        except Exception as e:
+            sys.stderr.write("config-4 point skipped: %r\n" % (e,))
+
+        # ---- BASELINE config 5: 100k-frame sequence tiled from the AMASS clip fixture, one betas row, no render
+        if rank == 0:
+            try:
+                from smplk import clips
+                clip = clips.read_amsass(os.path.join(ROOT, "tests", "golden", "amass_clip_09_05.npz"), full=True)
+                N5, n0 = 100000, clip.poses.shape[0]
+                reps5 = N5 // n0 + 1
+                pose5 = torch.tensor(np.tile(clip.poses, (reps5, 1))[:N5].astype(np.float32), device=dev)
+                tr5 = torch.tensor(np.tile(clip.trans, (reps5, 1))[:N5].astype(np.float32), device=dev)
+                be5 = torch.tensor(clip.betas.reshape(1, 16).astype(np.float32), device=dev)
+                ck = 16384                     # frames whose vertices are resident at once (1.35 GB)
+                v5 = torch.empty(ck, dm.V, 3, device=dev)
+                ws5 = torch.empty(dm.workspace_bytes(ck, 0), device=dev, dtype=torch.uint8)
+
+                def run_smplh():
+                    for f0 in range(0, N5, ck):
+                        f1 = min(N5, f0 + ck)
+                        fwd_call(dm, be5, pose5[f0:f1], tr5[f0:f1], v5, ws5)
+                ms5 = timed_ms(run_smplh, 3, warm=1)
+                c5 = {"frames": N5, "smplh": {"ms": ms5, "value": N5 / (ms5 * 1e-3), "unit": "frames/s",
+                                              "note": "full SMPL-H forward (hands, 16 betas broadcast); each %d-frame chunk overwrites the last" % ck},
+                      "lbs_only": []}
+                del v5, ws5
+                p24 = pose5[:, :72].contiguous()
+                p24.view(N5, 24, 3)[:, [13, 14, 22, 23]] = 0.0           # lib/model2video.py:44-45
+                for nv in (6890, 50000, 200000):
+                    rig = synthetic.make_rigged_mesh(nv, seed=13)
+                    rdm = smplk.DeviceModel(rig, device=local, lbs_only=True)
+                    ckr = max(256, min(16384, int(8e9 // (nv * 12))))
+                    vr = torch.empty(ckr, nv, 3, device=dev)
+                    wsr = torch.empty(rdm.workspace_bytes(ckr, 0), device=dev, dtype=torch.uint8)
+
+                    def run_rig():
+                        for f0 in range(0, N5, ckr):
+                            f1 = min(N5, f0 + ckr)
+                            fwd_call(rdm, None, p24[f0:f1], tr5[f0:f1], vr, wsr)
+                    msr = timed_ms(run_rig, 2, warm=1)
+                    wgbs = N5 * nv * 12 / (msr * 1e-3) / 1e9
+                    c5["lbs_only"].append({"verts": nv, "ms": msr, "value": N5 / (msr * 1e-3), "unit": "frames/s",
+                                           "hbm_write_gbs": wgbs, "frac_of_hbm_peak": wgbs / peaks["hbm"],
+                                           "note": "rigged-mesh replay (RecoverModel, 24 joints): the only HBM stream is the vertex write "
+                                                   "(template + weights are L2-resident); chunks of %d frames" % ckr})
+                    del vr, wsr, rdm
+                    torch.cuda.empty_cache()
+                extras["config5_sequence_100k"] = c5
+                del pose5, tr5, p24
+                torch.cuda.empty_cache()
+            except Exception as e:
+                sys.stderr.write("config-5 timing skipped: %r\n" % (e,))
+
         # ---- e2e: C-ABI host-buffer call (pinned host memory, H2D + D2H inside the timed region)
         lib = smplk.load()
         hb, hp, ht = (torch.tensor(x).pin_memory() for x in synthetic.make_inputs(model, B, seed=7))
@@ -530,29 +779,52 @@ def main():
             t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms = float(t.item())
+        # copy-only ceiling of the same step on this box, all ranks at once: ONE cudaMemcpyAsync per buffer
+        # (inputs H2D, then the vertices D2H from a resident device buffer into the same pinned host buffer)
+        def copy_only():
+            for h_, d_ in ((hb, sets[0][0]), (hp, sets[0][1]), (ht, sets[0][2])):
+                d_.copy_(h_, non_blocking=True)
+            hv.copy_(verts, non_blocking=True)
+        for _ in range(2):
+            copy_only()
+        barrier()
+        c0_, c1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0_.record(stream)
+        for _ in range(ne):
+            copy_only()
+        c1_.record(stream)
+        torch.cuda.synchronize(dev)
+        copy_ms = c0_.elapsed_time(c1_) / ne
+        if world > 1:
+            t = torch.tensor([copy_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            copy_ms = float(t.item())
+        d2h_bytes = int(hv.numel()) * 4
         extras["e2e"] = {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT,
                          "h2d_bytes_per_step": int(hb.numel() + hp.numel() + ht.numel()) * 4,
-                         "d2h_bytes_per_step": int(hv.numel()) * 4, "ms_per_step": e2e_ms,
-                         "api": "smplk_forward_host (C ABI, pinned host buffers; numpy-twin path)"}
+                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
+                         "api": "smplk_forward_host (C ABI, pinned host buffers; numpy-twin path): 1024-body chunks, "
+                                "kernels on the caller's stream overlapped with the D2H of the previous chunk on a copy stream",
+                         "copy_only_ms_per_step": copy_ms,
+                         "copy_only_d2h_gbs_per_gpu": d2h_bytes / (copy_ms * 1e-3) / 1e9,
+                         "frac_of_copy_ceiling": copy_ms / e2e_ms,
+                         "numa": numa,
+                         "note": "copy_only = the same buffers moved by plain cudaMemcpyAsync with no kernels, all ranks concurrently "
+                                 "(max over ranks): the PCIe / host-memory ceiling of this box for the step"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (blend contraction on tensor cores with two-term split operands, %s; fp32 accumulate and fp32 everywhere else)" % ("3xTF32" if os.environ.get("SMPLK_BLEND") == "tf32" else "fp16 hi+lo"),
                 "data": "synthetic",
-                "config": {"workload": "SMPL-H forward+LBS batch %d per GPU, fp32, 52 joints, 16 betas, 459 posedirs "
-                                       "(BASELINE.json configs[1])" % B,
-                           "global_batch": world * B, "parallelism": "batch-sharded x%d, no collective" % world,
-                           "l2": "per-step output %.0f MB (verts) > 126 MB L2; %d rotating input sets"
-                                 % (B * 82680 / 1e6, NSETS),
-                           "weights": "canonically sparse LBS weights (<=4 per vertex)"},
+                "config": workload_config(B, world),
                 "clocks": clocks.summary(), "gpu_launches": int(launches),
                 "hbm_gbs_fused_equiv": FWD_BYTES_FUSED * world * B * args.steps / (ms * 1e-3) / 1e9}
         line.update(extras)
         if "e2e" not in line:
             line["e2e"] = None
         if not args.no_cpu_baseline and not args.no_extras:
-            line["cpu_baseline"] = cpu_baseline(model)
+            line["cpu_baseline"] = cpu_baseline(model, 512)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

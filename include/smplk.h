@@ -186,6 +186,13 @@ int smplk_skin_transforms(const smplk_model* model, int32_t batch, const float* 
                           const float* transl /* (B,3) or NULL */, float* A, float* verts,
                           smplk_stream stream);
 
+/* The rest-pose removal alone: A[b,j] (3x4) = [G_R | G_t - G_R J_j] from global transforms G (B,J,4,4) and
+ * rest joints (B,J,3) -- the `G - pack(G . [J;0])` step of do_skinning (models/smplh_np.py:73-78) and of
+ * RecoverModel.to_T_pose (lib/mesh2smpl_model.py:194-199), whose result feeds smplk_inverse_lbs /
+ * smplk_inverse_joints.  Device pointers. */
+int smplk_remove_rest(int32_t batch, int32_t num_joints, const float* G, const float* joints_rest,
+                      float* A /* out (B,J,12) */, int device, smplk_stream stream);
+
 /* Replaces utils/geometry.py:9-23 batch_rodrigues (axis-angle (n,3) -> rotation matrices (n,3,3)). */
 int smplk_batch_rodrigues(int32_t n, const float* axis_angle, float* rotmats, int device,
                           smplk_stream stream);

@@ -21,6 +21,11 @@ def main():
     n0 = d["poses"].shape[0]
     np.savez_compressed(os.path.join(OUT, "amass_clip_fixture.npz"),
                         **{k: (d[k][keep] if d[k].ndim > 0 and d[k].shape[0] == n0 else d[k]) for k in d.files})
+    # a whole real clip (143 frames, 156-D poses with hands, float32) for the 100k-frame replay of
+    # BASELINE config 5: the tests tile it, exactly as SURVEY 8(d) prescribes
+    np.savez_compressed(os.path.join(OUT, "amass_clip_09_05.npz"), poses=d["poses"].astype(np.float32),
+                        trans=d["trans"].astype(np.float32), betas=d["betas"].astype(np.float32),
+                        mocap_framerate=d["mocap_framerate"])
     m = pickle.load(open(os.path.join(REF, "mixamo/0007/result.pkl"), "rb"), encoding="iso-8859-1")
     n = 4
     mm = {"anim_len": n, "smpl_array": np.asarray(m["smpl_array"])[:n], "cam_array": np.asarray(m["cam_array"])[:n]}

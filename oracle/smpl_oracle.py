@@ -152,8 +152,11 @@ def np_inverse_lbs(rig_weights, A, verts):
 
 def np_inverse_joints(A, joints):
     """lib/mesh2smpl_model.py:205-207: J = inv(G) [or_J; 1] with G the rest-removed transforms."""
+    A = np.asarray(A, np.float64)
+    if A.shape[-2:] == (4, 4):
+        A = A[:, :3, :]
     A4 = np.zeros((A.shape[0], 4, 4))
-    A4[:, :3, :] = np.asarray(A, np.float64).reshape(-1, 3, 4)
+    A4[:, :3, :] = A.reshape(-1, 3, 4)
     A4[:, 3, 3] = 1.0
     jh = np.concatenate([np.asarray(joints, np.float64), np.ones((joints.shape[0], 1))], 1)
     return np.einsum("jab,jb->ja", np.linalg.inv(A4), jh)[:, :3]
@@ -206,7 +209,8 @@ def np_divide_face(verts, faces):
 # ----------------------------------------------------------------------------------------
 
 OracleOutput = namedtuple("OracleOutput", ["vertices", "joints", "full_pose", "v_posed", "A",
-                                           "joints_fk"])
+                                           "joints_fk", "left_hand_pose", "right_hand_pose"])
+OracleOutput.__new__.__defaults__ = (None, None)
 
 
 def torch_rodrigues_quat(theta):
@@ -355,7 +359,8 @@ class TorchOracleModel:
             joints = torch.cat([joints, extra], dim=1)
             if self.joint_map is not None:
                 joints = joints[:, self.joint_map]
-        return OracleOutput(verts, joints, full_pose, v_posed, A, joints_fk)
+        # upstream returns the hand poses AFTER the PCA projection (45-D), before the mean is added
+        return OracleOutput(verts, joints, full_pose, v_posed, A, joints_fk, left_hand_pose, right_hand_pose)
 
     def forward_full_pose(self, betas, full_pose, transl=None):
         """lbs on an already assembled (B,3J) axis-angle pose (numpy-twin style input)."""

@@ -136,8 +136,9 @@ def test_batched_fitting_step_through_body_model_and_loss():
     eye = torch.eye(3, dtype=torch.float64).repeat(B, 1, 1)
     data = FO.data_term(ro.joints, eye, ct, torch.full((B, 2), 5000.0, dtype=torch.float64),
                         torch.full((B, 2), 256.0, dtype=torch.float64), gt.double().cpu(), (jw * conf).double().cpu(), 100.0, 1.0)
-    pri = FO.prior_term(betas=t["betas"], body_pose=ro.full_pose[:, 3:66], lhand=t["left_hand_pose"],
-                        rhand=t["right_hand_pose"], shape_weight=5.0, bending_prior_weight=3.17, hand_prior_weight=4.0)
+    # upstream hands the PROJECTED 45-D hand poses to the prior (lib/Gen_SMPLH/fitting.py:399-413)
+    pri = FO.prior_term(betas=t["betas"], body_pose=ro.full_pose[:, 3:66], lhand=ro.left_hand_pose,
+                        rhand=ro.right_hand_pose, shape_weight=5.0, bending_prior_weight=3.17, hand_prior_weight=4.0)
     ref = data.sum() + pri.sum()
     ref.backward()
     assert abs(float(loss) / float(ref) - 1) <= 1e-5

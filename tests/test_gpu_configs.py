@@ -1,0 +1,181 @@
+"""GPU parity at the BASELINE configurations' own sizes:
+
+  * the inference call of the drop-in module under torch.no_grad() (lib/Gen_SMPLH/fitting.py:82) runs
+    the fused blend+skinning kernel -- asserted through the library's per-kernel launch counters;
+  * config 3: the one-node fitting step `fit_vertex_l2` (skin_fit_l2_kernel + bf16 two-term backward
+    GEMM) against the float64 autograd oracle at B = 1024 and B = 129, with upstream gradients and
+    residuals spanning many decades across the batch; bound 1e-4 relative PER BODY;
+  * config 5: a 100,000-frame SMPL-H sequence tiled from a real AMASS clip (156-D with hands,
+    trans - trans[0], one betas row), spot-checked on both sides of every 8192-frame chunk boundary.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import smplk
+from smplk import _lib, clips, synthetic
+from smplk.body_models import SMPLH, body_model_apply, fit_vertex_l2
+from oracle import smpl_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+GRAD_RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def smplh_model():
+    return synthetic.make_model("smplh", seed=21)
+
+
+def _t(x, dev, grad=False):
+    return torch.tensor(np.asarray(x, dtype=np.float32), device=dev, requires_grad=grad)
+
+
+def test_parameter_driven_module_call_under_no_grad_runs_the_fused_kernel(dev, smplh_model):
+    """nn.Parameters keep requires_grad=True under torch.no_grad(); the inference forward must still
+    take pose_forward_block + blend_skin_fused (2 kernels + the vertex-pick gather) and not the
+    SAVE_FOR_BACKWARD two-kernel path with its whole-batch v_posed workspace."""
+    m = smplh_model
+    B = 300
+    mod = SMPLH(model=m, use_pca=True, num_pca_comps=12, batch_size=B, create_transl=True).to(dev)
+    rng = np.random.default_rng(4)
+    vals = dict(betas=rng.standard_normal((B, 16)), global_orient=rng.standard_normal((B, 3)) * 0.3,
+                body_pose=rng.standard_normal((B, 63)) * 0.3, left_hand_pose=rng.standard_normal((B, 12)),
+                right_hand_pose=rng.standard_normal((B, 12)), transl=rng.standard_normal((B, 3)))
+    mod.reset_params(**vals)
+    assert all(p.requires_grad for p in mod.parameters())
+    dm = mod.device_model(dev)
+    dm.profile_enable(True)
+    dm.profile_read()
+    with torch.no_grad():
+        out = mod(return_verts=True)
+    torch.cuda.synchronize()
+    prof = dm.profile_read()
+    assert prof["blend_skin_fused"][1] == 1 and prof["pose_fwd"][1] == 1
+    assert prof["skin"][1] == 0 and prof["blend_tcgen05"][1] == 0
+    # with gradients enabled the same call keeps v_posed for the backward: two-kernel path
+    out_g = mod(return_verts=True)
+    torch.cuda.synchronize()
+    prof = dm.profile_read()
+    dm.profile_enable(False)
+    assert prof["blend_skin_fused"][1] == 0 and prof["blend_tcgen05"][1] == 1 and prof["skin"][1] == 1
+    assert out_g.vertices.requires_grad and not out.vertices.requires_grad
+    om = O.TorchOracleModel(m, dtype=torch.float64, num_pca_comps=12)
+    t = {k: torch.tensor(v) for k, v in vals.items()}
+    ref = om.forward(t["betas"], t["global_orient"], t["body_pose"], t["left_hand_pose"], t["right_hand_pose"],
+                     transl=t["transl"])
+    for o in (out, out_g):
+        assert float((o.vertices.detach().double().cpu() - ref.vertices).abs().max()) <= TOL
+        assert float((o.joints.detach().double().cpu() - ref.joints).abs().max()) <= TOL
+    # upstream returns the PCA-projected 45-D hand poses
+    assert out.left_hand_pose.shape == (B, 45)
+    assert float((out.left_hand_pose.double().cpu() - ref.left_hand_pose).abs().max()) <= 1e-5
+    assert float((out.right_hand_pose.double().cpu() - ref.right_hand_pose).abs().max()) <= 1e-5
+
+
+def _oracle_fit_grads(m, betas, pose, transl, target, d_loss, chunk=128):
+    """float64 autograd of sum_b d_loss[b] * ||V_b - V*_b||^2, in chunks of bodies (they are independent)."""
+    om = O.TorchOracleModel(m, dtype=torch.float64)
+    B = pose.shape[0]
+    loss = np.zeros(B)
+    gb, gp, gt = np.zeros_like(betas, np.float64), np.zeros_like(pose, np.float64), np.zeros_like(transl, np.float64)
+    for c0 in range(0, B, chunk):
+        s = slice(c0, min(B, c0 + chunk))
+        tb, tp, tt = (torch.tensor(np.asarray(x[s], np.float64), requires_grad=True) for x in (betas, pose, transl))
+        out = om.forward_full_pose(tb, tp, tt)
+        per = ((out.vertices - torch.tensor(np.asarray(target[s], np.float64))) ** 2).sum(dim=(1, 2))
+        (per * torch.tensor(d_loss[s])).sum().backward()
+        loss[s] = per.detach().numpy()
+        gb[s], gp[s], gt[s] = tb.grad.numpy(), tp.grad.numpy(), tt.grad.numpy()
+    return loss, gb, gp, gt
+
+
+@pytest.mark.parametrize("B", [1024, 129])
+def test_fit_vertex_l2_matches_float64_oracle_at_config3_size(dev, smplh_model, B):
+    """BASELINE config 3 at its own batch (1024) and at a ragged one: loss and gradients of the one-node
+    fitting step against float64 autograd.  Residual magnitudes span 6 decades across the bodies
+    (1e-2 .. 1e4 m) and the upstream d_loss 16 decades; one body has d_loss = 0.  The d_v_posed rows of
+    this path are bf16 two-term splits (16 mantissa bits): the bound is 1e-4 relative per body."""
+    m = smplh_model
+    dm = smplk.DeviceModel(m, device=0)
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=300 + B)
+    rng = np.random.default_rng(B)
+    om32 = O.TorchOracleModel(m, dtype=torch.float64)
+    with torch.no_grad():
+        parts = [om32.forward_full_pose(*[torch.tensor(np.asarray(x[c:c + 256], np.float64)) for x in (betas, pose, transl)]).vertices
+                 for c in range(0, B, 256)]
+    v_ref = torch.cat(parts).numpy()
+    res_scale = 10.0 ** rng.uniform(-2, 4, size=B)
+    target = (v_ref + rng.standard_normal(v_ref.shape) * res_scale[:, None, None]).astype(np.float32)
+    d_loss = 10.0 ** rng.uniform(-8, 8, size=B)
+    d_loss[5] = 0.0
+    tb, tp, tt = (_t(x, dev, True) for x in (betas, pose, transl))
+    dm.profile_enable(True)
+    dm.profile_read()
+    loss = fit_vertex_l2(dm, tb, tp, _t(target, dev), transl=tt)
+    (loss * _t(d_loss, dev)).sum().backward()
+    torch.cuda.synchronize()
+    prof = dm.profile_read()
+    dm.profile_enable(False)
+    assert prof["skin"][1] == 1 and prof["skin_bwd"][1] == 0 and prof["blend_bwd"][1] == 1   # the fused fitting kernel ran
+    want_loss, gb, gp, gt = _oracle_fit_grads(m, betas, pose, transl, target, d_loss)
+    rel_loss = np.abs(loss.detach().double().cpu().numpy() - want_loss) / want_loss
+    assert rel_loss.max() <= 1e-5, (int(rel_loss.argmax()), float(rel_loss.max()))
+    for got, want, name in ((tb.grad, gb, "betas"), (tp.grad, gp, "pose"), (tt.grad, gt, "transl")):
+        g = got.double().cpu().numpy()
+        assert np.isfinite(g).all(), name
+        den = np.abs(want).max(axis=1)
+        err = np.abs(g - want).max(axis=1)
+        rel = np.where(den > 0, err / np.where(den > 0, den, 1.0), np.abs(g).max(axis=1))
+        assert rel.max() <= GRAD_RTOL, (name, int(rel.argmax()), float(rel.max()))
+
+
+def test_config5_full_100k_frame_amass_sequence(dev, golden_dir):
+    """BASELINE config 5 at its full length: the real AMASS clip data/amsass/09_05_poses.npz (143 frames,
+    156-D poses with both hands, lib/model2video.py:527-531) tiled to 100,000 frames with its
+    trans - trans[0], the clip's single betas (16,) row broadcast.  8.3 GB of vertices stay on
+    the device; 40 frames -- both sides of every 8192-frame chunk boundary plus the ends and the tile
+    seams -- are checked against the float64 oracle."""
+    c = clips.read_amsass(os.path.join(golden_dir, "amass_clip_09_05.npz"), full=True)
+    n0 = c.poses.shape[0]
+    assert c.poses.shape == (143, 156) and c.betas.shape == (16,) and np.all(c.trans[0] == 0)
+    N = 100000
+    reps = N // n0 + 1
+    poses = np.tile(c.poses, (reps, 1))[:N].astype(np.float32)
+    trans = np.tile(c.trans, (reps, 1))[:N].astype(np.float32)      # the looped clip restarts at its origin
+    m = synthetic.make_model("smplh", seed=0)
+    dm = smplk.DeviceModel(m, device=0)
+    betas = _t(c.betas.reshape(1, 16), dev)
+    dm.profile_enable(True)
+    dm.profile_read()
+    v, j, _, _ = body_model_apply(dm, betas, _t(poses, dev), transl=_t(trans, dev))
+    torch.cuda.synchronize()
+    prof = dm.profile_read()
+    dm.profile_enable(False)
+    chunks = (N + 8191) // 8192
+    assert prof["blend_skin_fused"][1] == chunks and prof["pose_fwd"][1] == chunks
+    assert v.shape == (N, 6890, 3)
+    idx = sorted(set([0, 1, n0 - 1, n0, N - 2, N - 1] + [k * 8192 + d for k in range(1, chunks) for d in (-1, 0)] +
+                     [50000, 77777, 12345, 99000 // n0 * n0, 99000 // n0 * n0 - 1]))
+    assert len(idx) >= 32
+    ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(
+        torch.tensor(np.repeat(c.betas.reshape(1, 16), len(idx), 0), dtype=torch.float64),
+        torch.tensor(poses[idx], dtype=torch.float64), torch.tensor(trans[idx], dtype=torch.float64))
+    ii = torch.as_tensor(idx, device=dev)
+    ev = float((v[ii].double().cpu() - ref.vertices).abs().max())
+    ej = float((j[ii].double().cpu() - ref.joints).abs().max())
+    assert ev <= TOL and ej <= TOL, (ev, ej)
+    # periodicity over the whole sequence: frame i + 143 k repeats frame i, wherever it lands in a chunk
+    fin = torch.isfinite(v.view(N, -1)).all(dim=1)
+    assert bool(fin.all())
+    last = (N // n0 - 1) * n0
+    for off in (n0, 57 * n0, last):
+        assert float((v[off:off + n0] - v[:n0]).abs().max()) <= 1e-6

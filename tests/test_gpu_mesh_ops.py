@@ -119,3 +119,53 @@ def test_divide_face_matches_reference_golden_and_oracle(golden_dir):
         got = res[b]
         for w, gt in zip(want, got):
             assert np.array_equal(np.asarray(w), gt.cpu().numpy())
+
+
+def test_twin_replays_reference_unposing_call_sequence(golden_dir):
+    """The numpy twin offers what lib/mesh2smpl_model.py:146-207 reads from its `smpl` object (`.J`,
+    `compute_R_G()`), and the un-posing kernels reproduce the reference's own outputs
+    (tests/golden/unpose.npz: SMPLModel.inverse and RecoverModel.to_T_pose executed by
+    oracle/make_golden_inverse.py).  fp32 tolerances: 1e-5 m forward, 3e-5 m through the inverse."""
+    from smplk.mesh_ops import remove_rest
+    g = np.load(os.path.join(golden_dir, "unpose.npz"))
+    m = synthetic.make_model("smpl", num_betas=int(g["num_betas"]), seed=int(g["seed"]))
+    smpl = smplk.SMPLModel(m, device=0)
+    for i in range(g["inv_pose"].shape[0]):
+        v = smpl.set_params(pose=g["inv_pose"][i].copy(), beta=g["inv_beta"][i].copy(), trans=g["inv_trans"][i].copy())
+        assert np.abs(v[::53] - g["inv_posed_sub"][i]).max() <= 1e-5
+        assert np.abs(smpl.J - g["inv_J"][i]).max() <= 1e-5           # models/smpl_np.py:169-170
+        assert np.abs(smpl.R - g["inv_R"][i]).max() <= 2e-6
+        assert np.abs(smpl.v_posed[::53] - g["inv_v_posed_sub"][i]).max() <= 1e-5
+        G = smpl.compute_R_G()
+        assert G.shape == (24, 4, 4) and np.abs(G - g["inv_G"][i]).max() <= 1e-5
+        smpl.do_skinning(G)                                             # the second half of update()
+        assert np.abs(smpl.verts[::53] - g["inv_posed_sub"][i]).max() <= 1e-5
+        smpl.inverse()                                                  # models/smpl_np.py:239-246
+        assert np.abs(smpl.verts - g["inv_unposed"][i]).max() <= 3e-5
+    # ---- lib/mesh2smpl_model.py:183-207, line by line on the twin
+    rig = synthetic.make_rigged_mesh(num_verts=int(g["tp_num_verts"]), seed=int(g["tp_rig_seed"]))
+    W = np.asarray(rig["weights"], np.float64)
+    rig["weights"] = W / W.sum(axis=1)[:, None]                         # :153
+    rig_dm = smplk.DeviceModel(rig, device=0, lbs_only=True)
+    smpl.set_params(g["tp_or_pose"].copy(), g["tp_or_shape"].copy())    # :188
+    G = smpl.compute_R_G()                                              # :193
+    assert np.abs(smpl.J - g["tp_smpl_J"]).max() <= 1e-5                # :197 reads smpl.J
+    A = remove_rest(_t(G[None]), _t(smpl.J[None]))                      # :194-199
+    v_template = inverse_lbs(rig_dm, A.reshape(1, 24, 12), _t(g["tp_or_verts"][None]))   # :200-203
+    J = inverse_joints(A.reshape(1, 24, 12), _t(g["tp_or_J"][None]))    # :205-207
+    assert np.abs(v_template[0].double().cpu().numpy() - g["tp_v_template"]).max() <= 3e-5
+    assert np.abs(J[0].double().cpu().numpy() - g["tp_J"]).max() <= 1e-5
+
+
+def test_twin_rejects_wrong_widths():
+    """A 72-value clip row on a 52-joint model must raise, not read past the array."""
+    m = synthetic.make_model("smplh", num_betas=10, seed=3)
+    tw = smplk.SMPLHModel(m, device=0)
+    with pytest.raises(ValueError):
+        tw.forward_batch(np.zeros((4, 72)))
+    with pytest.raises(ValueError):
+        tw.forward_batch(np.zeros((4, 156)), betas=np.zeros((4, 16)).reshape(-1, 10)[:3])
+    with pytest.raises(ValueError):
+        tw.forward_batch(np.zeros((4, 156)), trans=np.zeros((3, 3)))
+    with pytest.raises(ValueError):
+        tw.set_params(pose=np.zeros((24, 3)))

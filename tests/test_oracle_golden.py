@@ -160,3 +160,31 @@ def test_vertex_normals_and_inverse_joints_oracle_properties():
     posed_J = r["G"][:, :3, 3]
     back = O.np_inverse_joints(r["A"][:, :3, :], posed_J)
     assert np.abs(back - r["J"]).max() < 1e-10
+
+
+def test_unposing_oracle_matches_reference_inverse_and_to_T_pose(golden_dir):
+    """SURVEY 8f row 2, pinned by reference execution (oracle/make_golden_inverse.py):
+    models/smpl_np.py SMPLModel.inverse (:239-246) with the compute_R_G by-products (J, R, v_posed, G),
+    and lib/mesh2smpl_model.py RecoverModel.to_T_pose (:183-207)."""
+    g = np.load(os.path.join(golden_dir, "unpose.npz"))
+    m = synthetic.make_model("smpl", num_betas=int(g["num_betas"]), seed=int(g["seed"]))
+    assert abs(model_checksum(m) - float(g["checksum"])) < 1e-9
+    for i in range(g["inv_pose"].shape[0]):
+        r = O.np_forward(m, g["inv_pose"][i], g["inv_beta"][i], g["inv_trans"][i])
+        assert np.abs(r["J"] - g["inv_J"][i]).max() < 1e-12
+        assert np.abs(r["R"] - g["inv_R"][i]).max() < 1e-12
+        assert np.abs(r["G"] - g["inv_G"][i]).max() < 1e-12
+        assert np.abs(r["v_posed"][::53] - g["inv_v_posed_sub"][i]).max() < 1e-12
+        assert np.abs(r["verts"][::53] - g["inv_posed_sub"][i]).max() < 1e-12
+        un = O.np_inverse_lbs(m["weights"], r["A"], r["verts"] - g["inv_trans"][i][None])
+        assert np.abs(un[::53] - g["inv_unposed_sub"][i]).max() < 1e-11
+        assert np.abs(un - g["inv_unposed"][i]).max() < 1e-6          # f32-stored full field
+    # to_T_pose: SMPL transforms of (or_pose, or_shape) blended with the RECOVERED mesh's weights
+    rig = synthetic.make_rigged_mesh(num_verts=int(g["tp_num_verts"]), seed=int(g["tp_rig_seed"]))
+    W = np.asarray(rig["weights"], np.float64)
+    W = W / W.sum(axis=1)[:, None]
+    assert abs(float(np.abs(W).sum()) - float(g["tp_weights_checksum"])) < 1e-9
+    r = O.np_forward(m, g["tp_or_pose"], g["tp_or_shape"])
+    assert np.abs(r["J"] - g["tp_smpl_J"]).max() < 1e-12
+    assert np.abs(O.np_inverse_lbs(W, r["A"], g["tp_or_verts"]) - g["tp_v_template"]).max() < 1e-10
+    assert np.abs(O.np_inverse_joints(r["A"], g["tp_or_J"]) - g["tp_J"]).max() < 1e-10
