@@ -33,8 +33,18 @@
 
 namespace smplk {
 
+// Epilogue warps: 8 (two per TMEM lane quarter; the product configuration) or 12 (three per quarter).
+// ncu on the 8-warp kernel (profiles/r02_ncu_fused.txt) shows stall_wait as the largest stall (29 % of the
+// samples) at 39 % issue-active, which suggested more warps; measured on B200 (profiles/r02_fused_variants.txt)
+// the 12-warp build is SLOWER: 0.236 vs 0.213 ms at 4,096 bodies.  14 warps get only 128 registers each
+// (the launch fails with 136 or 144: the register file is allocated as for 16 warps) and spill, and the
+// extra per-warp buffers cost one GEMM stage (4 -> 3 stages alone: 0.227 ms) and one ring entry; the
+// shared-memory pipe (l1tex 67 %), shared with the GEMM's operand traffic, is the second limiter.
+#ifndef SMPLK_FZ_EPI_WARPS
+#define SMPLK_FZ_EPI_WARPS 8
+#endif
 #ifndef SMPLK_FZ_RING
-#define SMPLK_FZ_RING 4      // transform entries in flight per epilogue warp (cp.async ring in smem)
+#define SMPLK_FZ_RING (SMPLK_FZ_EPI_WARPS == 12 ? 3 : 4)   // transform entries in flight per epilogue warp (cp.async ring in smem)
 #endif
 #ifndef SMPLK_FZ_BACKOFF_NS
 #define SMPLK_FZ_BACKOFF_NS 40
@@ -50,7 +60,10 @@ namespace smplk {
 // leave room for the epilogue's transform ring; 128-byte rows x 3 stages (the stand-alone GEMM's
 // choice) would fill shared memory.
 constexpr int kFzRowBytes = SMPLK_FZ_ROW_BYTES;
-constexpr int kFzStages = kFzRowBytes == 64 ? 4 : 2;
+#ifndef SMPLK_FZ_STAGES
+#define SMPLK_FZ_STAGES (SMPLK_FZ_ROW_BYTES == 64 ? (SMPLK_FZ_EPI_WARPS == 12 ? 3 : 4) : 2)
+#endif
+constexpr int kFzStages = SMPLK_FZ_STAGES;
 constexpr int kFzKSteps = kFzRowBytes / 32;                 // UMMA k-steps (16 fp16 = 32 B) per k-block
 constexpr int kFzElemsPerBlock = kFzRowBytes / 2;           // fp16 elements per k-block
 constexpr int kFzTileABytes = kBlendBM * kFzRowBytes;       // this CTA's 128 feature rows
@@ -58,8 +71,10 @@ constexpr int kFzTileBBytes = (kBlendBN / 2) * kFzRowBytes; // this CTA's half o
 constexpr int kFzStageBytes = 2 * kFzTileABytes + 2 * kFzTileBBytes;
 constexpr int kFzRing = SMPLK_FZ_RING;
 constexpr int kFzRingEntryBytes = 13 * 128;                 // 12 transform lines + 1 weight line per warp
-constexpr int kFzEpiWarps = 8;
-constexpr int kFzThreads = 64 + kFzEpiWarps * 32;   // producer warp, MMA warp, 2 x 4 epilogue warps
+constexpr int kFzEpiWarps = SMPLK_FZ_EPI_WARPS;
+constexpr int kFzParts = kFzEpiWarps / 4;           // epilogue warps per TMEM lane quarter
+static_assert(kFzEpiWarps == 8 || kFzEpiWarps == 12, "two or three epilogue warps per TMEM lane quarter");
+constexpr int kFzThreads = 64 + kFzEpiWarps * 32;   // producer warp, MMA warp, kFzParts x 4 epilogue warps
 constexpr int kFzTileVerts = 84;                    // whole vertices per 256-column tile
 constexpr int kFzTileCols = 3 * kFzTileVerts;       // 252 output coordinates per tile (+ 4 zero columns)
 constexpr int kFzChunkVerts = 12;
@@ -120,8 +135,18 @@ transpose_transforms_kernel(int rows, int rows_pad, int J, const float* __restri
 
 // kN > 0: floats per output row known at compile time (3 * 6890 for SMPL / SMPL-H), so the 32 row
 // addresses of a window store are immediates; kN == 0: row pitch from args.N.
+// 14 warps: __launch_bounds__(448) gives 128 registers per thread; a __maxnreg__ of 136 or 144 compiles
+// without spills but the launch is refused (too many resources), see above.
+#ifndef SMPLK_FZ_MAXNREG
+#define SMPLK_FZ_MAXNREG 0
+#endif
+#if SMPLK_FZ_EPI_WARPS == 12 && SMPLK_FZ_MAXNREG > 0
+#define SMPLK_FZ_BOUNDS __maxnreg__(SMPLK_FZ_MAXNREG)
+#else
+#define SMPLK_FZ_BOUNDS __launch_bounds__(kFzThreads, 1)
+#endif
 template <int kN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFzThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) SMPLK_FZ_BOUNDS
 blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
                         const __grid_constant__ CUtensorMap tmap_f_lo,
                         const __grid_constant__ CUtensorMap tmap_pd_hi,
@@ -161,7 +186,7 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], 512);   // all 8 epilogue warps, in both CTAs
+      ptx::mbar_init(&tmem_empty[s], 2 * 32 * kFzEpiWarps);   // every epilogue thread, in both CTAs
     }
     ptx::fence_barrier_init();
   }
@@ -242,7 +267,7 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
     }
   } else {
     // ===================== skinning epilogue (warps 2..9) =====================
-    const int half = (warp - 2) >> 2;         // which part of every tile's chunk range this warp takes
+    const int part = (warp - 2) >> 2;         // which part of every tile's chunk range this warp takes
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
     const uint32_t stage_u32 = ptx::smem_u32(epi_base + (warp - 2) * kFzStageWords);
     const uint32_t stage_row = stage_u32 + lane * (kFzStageStride * 4);   // this body's staged row
@@ -263,11 +288,21 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
       const int m0 = mb * 2 * kBlendBM + (int)rank * kBlendBM;
       const int acc = it & 1;                   // TMEM accumulator buffer of this tile
       const uint32_t acc_phase = (it >> 1) & 1;
-      // Both warps of a TMEM lane quarter work on EVERY tile, one on chunks [0, cb) and the other on
-      // [cb, 7) (the 4/3 split alternates), so an accumulator is held for about half an epilogue:
-      // with 2 accumulators the per-tile time is max(T_mma, (T_mma + T_hold) / 2).
-      const int cb = 3 + (it & 1);
-      const int c_lo = half ? cb : 0, c_hi = half ? kFzChunks : cb;
+      // All warps of a TMEM lane quarter work on EVERY tile, each on a contiguous range of its 7 chunks
+      // (3/4 for two warps, 2/2/3 for three; the longer share rotates with the tile), so an accumulator is
+      // held for a fraction of an epilogue: with 2 accumulators the per-tile time is
+      // max(T_mma, (T_mma + T_hold) / 2).
+      int c_lo = 0, c_hi = 0;
+      {
+        constexpr int base = kFzChunks / kFzParts, rem = kFzChunks % kFzParts;
+        int acc_c = 0;
+#pragma unroll
+        for (int pp = 0; pp < kFzParts; ++pp) {
+          const int sz = base + ((((pp + it) % kFzParts) < rem) ? 1 : 0);
+          if (pp == part) { c_lo = acc_c; c_hi = acc_c + sz; }
+          acc_c += sz;
+        }
+      }
       // joint-major per 128-body block: a joint's transforms of this warp's 32 bodies are 96 contiguous
       // 16-byte pieces; lane l copies pieces l, l + 32, l + 64
       const float* At_w = args.At + (size_t)(m0 >> 7) * JC128 + q * 32 * 12 + lane * 4;
@@ -385,7 +420,7 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
 
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; ++c) {
-        [[maybe_unused]] const bool dbg_c = dbg_on && (warp == 2 || warp == 6) && it < 4;
+        [[maybe_unused]] const bool dbg_c = dbg_on && (warp & 3) == 2 && it < 4;
         [[maybe_unused]] long long* dbg_p = args.dbg ? args.dbg + (0 * kFzDbgTiles + it * 7 + c) * 4 : nullptr;
         FZ_STAMP(dbg_c, &dbg_p[0]);
         // ---- TMEM accumulator columns of chunk c -> p (+ v_template), o = 0

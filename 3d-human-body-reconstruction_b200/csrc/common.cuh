@@ -54,6 +54,9 @@ struct ModelDev {
   int grp8_ok;                // same for 8-vertex groups
   const uint2* grp8_joints;   // [ceil(V/8)]
   const float4* grp8_w;       // [ceil(V/8)][8 joints][2] weights of the group's 8 vertices
+  const int* grp8_ovf_ptr;    // [ceil(V/8)+1] groups bound to more than 8 joints: their remaining (joint, weights) entries
+  const int* grp8_ovf_joint;  // [n_ovf]
+  const float4* grp8_ovf_w;   // [n_ovf][2]
   const int* csc_ptr;         // [J+1] joint -> (vertex, weight) lists for the backward
   const int* csc_vert;        // [nnz]
   const float* csc_w;         // [nnz]

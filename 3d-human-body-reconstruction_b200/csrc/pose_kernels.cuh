@@ -398,12 +398,14 @@ struct PoseBlockSmem {
   int nbp;           // padded betas stride of J_shapedirs rows (odd)
 };
 
-__host__ __device__ inline PoseBlockSmem pose_block_layout(const ModelDev& m) {
+// `warps` = bodies per block: 32 when the block also writes the transposed transforms At (lane = body there),
+// fewer for mid-size batches so that a few hundred bodies still spread over all SMs.
+__host__ __device__ inline PoseBlockSmem pose_block_layout(const ModelDev& m, int warps = kPoseBlockWarps) {
   PoseBlockSmem L;
   const int base = max(m.Kpad, 32) + m.J * 12;
   L.per_warp = base + ((36 - (base & 31)) & 31);             // == 4 (mod 32)
   L.nbp = (max(m.NB, 1) | 1);
-  int o = kPoseBlockWarps * L.per_warp;
+  int o = warps * L.per_warp;
   L.off_Jt = o;  o += 3 * m.J;
   L.off_Js = o;  o += 3 * m.J * L.nbp;
   L.off_pm = o;  o += 3 * m.J;
@@ -420,9 +422,10 @@ template <int SLOTS>
 __global__ void __launch_bounds__(kPoseBlockWarps * 32, 1)
 pose_forward_block_kernel(const ModelDev m, const PoseFwdArgs a) {
   extern __shared__ __align__(16) float pose_smem[];
-  const PoseBlockSmem L = pose_block_layout(m);
+  const int nw = blockDim.x >> 5;                 // bodies of this block (one warp each)
+  const PoseBlockSmem L = pose_block_layout(m, nw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kPoseBlockWarps + warp;
+  const int b = blockIdx.x * nw + warp;
   const bool live = b < a.B;
   float* feat = pose_smem + warp * L.per_warp;
   float* Gs = feat + max(m.Kpad, 32);
@@ -616,13 +619,13 @@ pose_forward_block_kernel(const ModelDev m, const PoseFwdArgs a) {
   // ---- joint-major copy for the fused kernel: warp w writes joints w, w + 32; lane = body, so a
   // joint's 32 x 48 bytes leave as one contiguous 1,536-byte run (transl folded into the translation
   // column; bodies past the batch, up to the 256-body block, are zero transforms)
-  if (a.At != nullptr) {
+  if (a.At != nullptr) {                          // launched with 32 warps: lane = body of the block
     __syncthreads();
-    const int bb = blockIdx.x * kPoseBlockWarps + lane;
+    const int bb = blockIdx.x * nw + lane;
     const float* Gl = pose_smem + lane * L.per_warp + max(m.Kpad, 32);
     float ttx = 0.f, tty = 0.f, ttz = 0.f;
     if (a.transl && bb < a.B) { ttx = a.transl[3 * bb]; tty = a.transl[3 * bb + 1]; ttz = a.transl[3 * bb + 2]; }
-    for (int j = warp; j < m.J; j += kPoseBlockWarps) {
+    for (int j = warp; j < m.J; j += nw) {
       const float4* G4 = reinterpret_cast<const float4*>(Gl + j * 12);
       float4 g0 = G4[0], g1 = G4[1], g2 = G4[2];
       g0.w += ttx; g1.w += tty; g2.w += ttz;

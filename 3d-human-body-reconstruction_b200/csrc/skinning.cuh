@@ -12,6 +12,12 @@
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
+// packed fp32x2 FMAs in the skinning loop: measured SLOWER here (0.208 vs 0.172 ms at 4096 bodies; the kernel is
+// bound by shared-memory wavefronts and latency, not FMA issue) -- kept for A/B builds only
+#ifndef SMPLK_SKIN_FFMA2
+#define SMPLK_SKIN_FFMA2 0
+#endif
+
 namespace smplk {
 
 constexpr int kSkinThreads = 256;
@@ -175,6 +181,27 @@ __host__ __device__ inline size_t skin_grouped_smem_bytes(int J) {
   return (size_t)(kGrpStages * kSkinTileVerts * 3 + 2 * kGrpABodies * grp_a_pad(J) + 4 * kGrpABodies * 2) *
          sizeof(float);
 }
+// SMPLK_SKIN_NOBAR (rigged-mesh replay, kSharedTemplate): the transforms of ALL the block's bodies are staged up
+// front (one barrier per block instead of one per 8 bodies: ncu showed the barrier as the largest stall of
+// skin_grouped_kernel, 1.1-1.2 cycles per issued instruction) and the thread's template vertices stay in
+// registers; costs bodies_per_block x J x 48 bytes of shared memory.  Measured (profiles/r02_skin_variants.txt):
+// 0.283 -> 0.269 ms at 8,192 frames x 6,890 vertices, 1.687 -> 1.605 ms at 50,000 vertices; with per-body
+// v_posed rows (J = 52: only 20 bodies fit) it is no gain (0.173 -> 0.176 ms), so that path keeps the 8-body groups.
+#ifndef SMPLK_SKIN_NOBAR
+#define SMPLK_SKIN_NOBAR 1
+#endif
+#ifndef SMPLK_SKIN_PREFETCH
+#define SMPLK_SKIN_PREFETCH 0
+#endif
+__host__ __device__ inline size_t skin_nobar_smem_bytes(int J, int bodies_per_block) {
+  return (size_t)(kGrpStages * kSkinTileVerts * 3 + bodies_per_block * (grp_a_pad(J) + 4)) * sizeof(float);
+}
+// most bodies per block whose transforms fit beside the ring with two blocks per SM
+__host__ inline int skin_nobar_max_bodies(int J, size_t smem_per_block) {
+  const size_t ring = (size_t)kGrpStages * kSkinTileVerts * 3 * sizeof(float);
+  if (smem_per_block <= ring) return 0;
+  return (int)((smem_per_block - ring) / ((size_t)(grp_a_pad(J) + 4) * sizeof(float)));
+}
 
 template <bool kSharedTemplate>
 __global__ void __launch_bounds__(kGrpThreads, 2)
@@ -187,8 +214,10 @@ skin_grouped_kernel(const ModelDev m, const SkinArgs a) {
   const int a_chunks = m.J * 3;
   const int a_pad = grp_a_pad(m.J);
   float* ring = sg_smem;                                         // [stages][1024*3]
-  float* Abuf = sg_smem + kGrpStages * kSkinTileVerts * 3;       // [2][8][a_pad]
-  float* Tbuf = Abuf + 2 * kGrpABodies * a_pad;                  // [2][8][4] translations
+  // kNoBar (rigged-mesh replay): [bodies_per_block][a_pad] + [bodies_per_block][4]; else [2][8][a_pad] + [2][8][4]
+  constexpr bool kNoBar = kSharedTemplate && (SMPLK_SKIN_NOBAR != 0);
+  float* Abuf = sg_smem + kGrpStages * kSkinTileVerts * 3;
+  float* Tbuf = Abuf + (kNoBar ? a.bodies_per_block : 2 * kGrpABodies) * a_pad;
 
   const int b0 = blockIdx.y * a.bodies_per_block;
   const int b1 = min(a.B, b0 + a.bodies_per_block);
@@ -213,6 +242,18 @@ skin_grouped_kernel(const ModelDev m, const SkinArgs a) {
 
   // ---- async copy helpers (every thread commits the same number of groups)
   auto issue_A = [&](int grp) {                 // transforms + translations of bodies b0+8grp ..
+    if (kNoBar) {                               // ... or of ALL the block's bodies
+      const int nb = b1 - b0;
+      for (int c = tid; c < nb * a_chunks; c += kGrpThreads) {
+        const int bi = c / a_chunks, cc = c - bi * a_chunks;
+        ptx::cp_async_16(Abuf + bi * a_pad + 4 * cc, a.A + (size_t)(b0 + bi) * a_floats + 4 * cc);
+      }
+      for (int c = tid; c < nb * 3; c += kGrpThreads) {
+        const int bi = c / 3, k = c - bi * 3;
+        Tbuf[bi * 4 + k] = a.transl ? a.transl[(size_t)(b0 + bi) * 3 + k] : 0.f;
+      }
+      return;
+    }
     const int bb0 = b0 + grp * kGrpABodies;
     const int nb = min(kGrpABodies, b1 - bb0);
     float* dstA = Abuf + (grp & 1) * kGrpABodies * a_pad;
@@ -243,13 +284,17 @@ skin_grouped_kernel(const ModelDev m, const SkinArgs a) {
 #pragma unroll
   for (int i = 0; i < kGrpStages - 1; ++i) issue_v(b0 + i);
   const bool even_rows = ((m.V * 3) & 1) == 0;
+  float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, c2 = c0;
 
   for (int b = b0; b < b1; ++b) {
     const int rel = b - b0;
     const int agrp = rel / kGrpABodies;
     issue_v(b + kGrpStages - 1);
     ptx::cp_async_wait<kGrpStages - 1>();                     // body b (and everything older) landed
-    if ((rel % kGrpABodies) == 0) {
+    if (kNoBar) {
+      if (rel == 0) __syncthreads();  // every thread's share of the transforms (first commit group) is published
+      else __syncwarp();
+    } else if ((rel % kGrpABodies) == 0) {
       // this thread's share of the group's transforms was issued >= 8 bodies ago (or in the
       // prologue) and is covered by the wait above; the barrier publishes it block-wide
       __syncthreads();
@@ -257,17 +302,88 @@ skin_grouped_kernel(const ModelDev m, const SkinArgs a) {
     } else {
       __syncwarp();
     }
-    const float* Ab = Abuf + ((agrp & 1) * kGrpABodies + (rel % kGrpABodies)) * a_pad;
-    const float* Tb = Tbuf + ((agrp & 1) * kGrpABodies + (rel % kGrpABodies)) * 4;
+    const int arow = kNoBar ? rel : (agrp & 1) * kGrpABodies + (rel % kGrpABodies);
+    const float* Ab = Abuf + arow * a_pad;
+    const float* Tb = Tbuf + arow * 4;
     const float tx = Tb[0], ty = Tb[1], tz = Tb[2];
     float* slot = ring + (kSharedTemplate ? 0 : (rel % kGrpStages)) * (kSkinTileVerts * 3) + warp * kWarpFloats;
     float4* mine = reinterpret_cast<float4*>(slot) + 3 * lane;
-    const float4 c0 = mine[0], c1 = mine[1], c2 = mine[2];
+    if (!kSharedTemplate || rel == 0) { c0 = mine[0]; c1 = mine[1]; c2 = mine[2]; }   // a shared template stays in registers
     // vertices of the group: (c0.x c0.y c0.z) (c0.w c1.x c1.y) (c1.z c1.w c2.x) (c2.y c2.z c2.w)
     const float vx[4] = {c0.x, c0.w, c1.z, c2.y};
     const float vy[4] = {c0.y, c1.x, c1.w, c2.z};
     const float vz[4] = {c0.z, c1.y, c2.x, c2.w};
     float ox[4] = {0.f, 0.f, 0.f, 0.f}, oy[4] = {0.f, 0.f, 0.f, 0.f}, oz[4] = {0.f, 0.f, 0.f, 0.f};
+#if SMPLK_SKIN_FFMA2
+    // vertex pairs (0,1) and (2,3) as packed fp32x2 operands (FFMA2): half the FMA issue slots
+    const uint64_t x2[2] = {ptx::pack_f32x2(vx[0], vx[1]), ptx::pack_f32x2(vx[2], vx[3])};
+    const uint64_t y2[2] = {ptx::pack_f32x2(vy[0], vy[1]), ptx::pack_f32x2(vy[2], vy[3])};
+    const uint64_t z2[2] = {ptx::pack_f32x2(vz[0], vz[1]), ptx::pack_f32x2(vz[2], vz[3])};
+    uint64_t ox2[2], oy2[2], oz2[2];
+    ox2[0] = ox2[1] = oy2[0] = oy2[1] = oz2[0] = oz2[1] = ptx::pack_f32x2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < kGrpJoints; ++u) {
+      if (used & (1u << u)) {
+        const int j = ((u < 4 ? jid.x : jid.y) >> (8 * (u & 3))) & 0xff;
+        const float4* Aj = reinterpret_cast<const float4*>(Ab + j * 12);
+        const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+        const uint64_t w2[2] = {ptx::pack_f32x2(w[u].x, w[u].y), ptx::pack_f32x2(w[u].z, w[u].w)};
+        const uint64_t a00 = ptx::pack_f32x2(r0.x, r0.x), a01 = ptx::pack_f32x2(r0.y, r0.y), a02 = ptx::pack_f32x2(r0.z, r0.z),
+                       a03 = ptx::pack_f32x2(r0.w, r0.w), a10 = ptx::pack_f32x2(r1.x, r1.x), a11 = ptx::pack_f32x2(r1.y, r1.y),
+                       a12 = ptx::pack_f32x2(r1.z, r1.z), a13 = ptx::pack_f32x2(r1.w, r1.w), a20 = ptx::pack_f32x2(r2.x, r2.x),
+                       a21 = ptx::pack_f32x2(r2.y, r2.y), a22 = ptx::pack_f32x2(r2.z, r2.z), a23 = ptx::pack_f32x2(r2.w, r2.w);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const uint64_t px = ptx::fma_f32x2(a00, x2[k], ptx::fma_f32x2(a01, y2[k], ptx::fma_f32x2(a02, z2[k], a03)));
+          const uint64_t py = ptx::fma_f32x2(a10, x2[k], ptx::fma_f32x2(a11, y2[k], ptx::fma_f32x2(a12, z2[k], a13)));
+          const uint64_t pz = ptx::fma_f32x2(a20, x2[k], ptx::fma_f32x2(a21, y2[k], ptx::fma_f32x2(a22, z2[k], a23)));
+          ox2[k] = ptx::fma_f32x2(w2[k], px, ox2[k]);
+          oy2[k] = ptx::fma_f32x2(w2[k], py, oy2[k]);
+          oz2[k] = ptx::fma_f32x2(w2[k], pz, oz2[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      ptx::unpack_f32x2(ox2[k], ox[2 * k], ox[2 * k + 1]);
+      ptx::unpack_f32x2(oy2[k], oy[2 * k], oy[2 * k + 1]);
+      ptx::unpack_f32x2(oz2[k], oz[2 * k], oz[2 * k + 1]);
+    }
+#elif SMPLK_SKIN_PREFETCH
+    // software pipelining across the joint slots: the transform of slot u+1 is fetched from shared memory
+    // before slot u's 48 FMAs (every slot is its own basic block behind the warp-uniform `used` test, so the
+    // compiler cannot hoist the loads itself).  A lane's non-zero slots are a prefix (the packer sorts a group's
+    // joints by weight), so `used` is a prefix mask too.
+    {
+      float4 r0, r1, r2;
+      {
+        const float4* Aj = reinterpret_cast<const float4*>(Ab + (jid.x & 0xff) * 12);
+        r0 = Aj[0]; r1 = Aj[1]; r2 = Aj[2];
+      }
+#pragma unroll
+      for (int u = 0; u < kGrpJoints; ++u) {
+        if (used & (1u << u)) {
+          float4 n0 = r0, n1 = r1, n2 = r2;
+          if (u + 1 < kGrpJoints && (used & (2u << u))) {
+            const int jn = (((u + 1) < 4 ? jid.x : jid.y) >> (8 * ((u + 1) & 3))) & 0xff;
+            const float4* An = reinterpret_cast<const float4*>(Ab + jn * 12);
+            n0 = An[0]; n1 = An[1]; n2 = An[2];
+          }
+          const float wu[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float px = fmaf(r0.x, vx[i], fmaf(r0.y, vy[i], fmaf(r0.z, vz[i], r0.w)));
+            const float py = fmaf(r1.x, vx[i], fmaf(r1.y, vy[i], fmaf(r1.z, vz[i], r1.w)));
+            const float pz = fmaf(r2.x, vx[i], fmaf(r2.y, vy[i], fmaf(r2.z, vz[i], r2.w)));
+            ox[i] = fmaf(wu[i], px, ox[i]);
+            oy[i] = fmaf(wu[i], py, oy[i]);
+            oz[i] = fmaf(wu[i], pz, oz[i]);
+          }
+          r0 = n0; r1 = n1; r2 = n2;
+        }
+      }
+    }
+#else
 #pragma unroll
     for (int u = 0; u < kGrpJoints; ++u) {
       if (used & (1u << u)) {
@@ -286,6 +402,7 @@ skin_grouped_kernel(const ModelDev m, const SkinArgs a) {
         }
       }
     }
+#endif
     float* orow = a.out + (size_t)b * m.V * 3 + wf0;
     float* stage = kSharedTemplate ? ring + kSkinTileVerts * 3 + warp * kWarpFloats : slot;
     float4* ot = reinterpret_cast<float4*>(stage) + 3 * lane;
@@ -437,6 +554,76 @@ skin_tma_kernel(const ModelDev m, const SkinArgs a) {
     const float vy[4] = {c0.y, c1.x, c1.w, c2.z};
     const float vz[4] = {c0.z, c1.y, c2.x, c2.w};
     float ox[4] = {0.f, 0.f, 0.f, 0.f}, oy[4] = {0.f, 0.f, 0.f, 0.f}, oz[4] = {0.f, 0.f, 0.f, 0.f};
+#if SMPLK_SKIN_FFMA2
+    // vertex pairs (0,1) and (2,3) as packed fp32x2 operands (FFMA2): half the FMA issue slots
+    const uint64_t x2[2] = {ptx::pack_f32x2(vx[0], vx[1]), ptx::pack_f32x2(vx[2], vx[3])};
+    const uint64_t y2[2] = {ptx::pack_f32x2(vy[0], vy[1]), ptx::pack_f32x2(vy[2], vy[3])};
+    const uint64_t z2[2] = {ptx::pack_f32x2(vz[0], vz[1]), ptx::pack_f32x2(vz[2], vz[3])};
+    uint64_t ox2[2], oy2[2], oz2[2];
+    ox2[0] = ox2[1] = oy2[0] = oy2[1] = oz2[0] = oz2[1] = ptx::pack_f32x2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < kGrpJoints; ++u) {
+      if (used & (1u << u)) {
+        const int j = ((u < 4 ? jid.x : jid.y) >> (8 * (u & 3))) & 0xff;
+        const float4* Aj = reinterpret_cast<const float4*>(Ab + j * 12);
+        const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+        const uint64_t w2[2] = {ptx::pack_f32x2(w[u].x, w[u].y), ptx::pack_f32x2(w[u].z, w[u].w)};
+        const uint64_t a00 = ptx::pack_f32x2(r0.x, r0.x), a01 = ptx::pack_f32x2(r0.y, r0.y), a02 = ptx::pack_f32x2(r0.z, r0.z),
+                       a03 = ptx::pack_f32x2(r0.w, r0.w), a10 = ptx::pack_f32x2(r1.x, r1.x), a11 = ptx::pack_f32x2(r1.y, r1.y),
+                       a12 = ptx::pack_f32x2(r1.z, r1.z), a13 = ptx::pack_f32x2(r1.w, r1.w), a20 = ptx::pack_f32x2(r2.x, r2.x),
+                       a21 = ptx::pack_f32x2(r2.y, r2.y), a22 = ptx::pack_f32x2(r2.z, r2.z), a23 = ptx::pack_f32x2(r2.w, r2.w);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const uint64_t px = ptx::fma_f32x2(a00, x2[k], ptx::fma_f32x2(a01, y2[k], ptx::fma_f32x2(a02, z2[k], a03)));
+          const uint64_t py = ptx::fma_f32x2(a10, x2[k], ptx::fma_f32x2(a11, y2[k], ptx::fma_f32x2(a12, z2[k], a13)));
+          const uint64_t pz = ptx::fma_f32x2(a20, x2[k], ptx::fma_f32x2(a21, y2[k], ptx::fma_f32x2(a22, z2[k], a23)));
+          ox2[k] = ptx::fma_f32x2(w2[k], px, ox2[k]);
+          oy2[k] = ptx::fma_f32x2(w2[k], py, oy2[k]);
+          oz2[k] = ptx::fma_f32x2(w2[k], pz, oz2[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      ptx::unpack_f32x2(ox2[k], ox[2 * k], ox[2 * k + 1]);
+      ptx::unpack_f32x2(oy2[k], oy[2 * k], oy[2 * k + 1]);
+      ptx::unpack_f32x2(oz2[k], oz[2 * k], oz[2 * k + 1]);
+    }
+#elif SMPLK_SKIN_PREFETCH
+    // software pipelining across the joint slots: the transform of slot u+1 is fetched from shared memory
+    // before slot u's 48 FMAs (every slot is its own basic block behind the warp-uniform `used` test, so the
+    // compiler cannot hoist the loads itself).  A lane's non-zero slots are a prefix (the packer sorts a group's
+    // joints by weight), so `used` is a prefix mask too.
+    {
+      float4 r0, r1, r2;
+      {
+        const float4* Aj = reinterpret_cast<const float4*>(Ab + (jid.x & 0xff) * 12);
+        r0 = Aj[0]; r1 = Aj[1]; r2 = Aj[2];
+      }
+#pragma unroll
+      for (int u = 0; u < kGrpJoints; ++u) {
+        if (used & (1u << u)) {
+          float4 n0 = r0, n1 = r1, n2 = r2;
+          if (u + 1 < kGrpJoints && (used & (2u << u))) {
+            const int jn = (((u + 1) < 4 ? jid.x : jid.y) >> (8 * ((u + 1) & 3))) & 0xff;
+            const float4* An = reinterpret_cast<const float4*>(Ab + jn * 12);
+            n0 = An[0]; n1 = An[1]; n2 = An[2];
+          }
+          const float wu[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float px = fmaf(r0.x, vx[i], fmaf(r0.y, vy[i], fmaf(r0.z, vz[i], r0.w)));
+            const float py = fmaf(r1.x, vx[i], fmaf(r1.y, vy[i], fmaf(r1.z, vz[i], r1.w)));
+            const float pz = fmaf(r2.x, vx[i], fmaf(r2.y, vy[i], fmaf(r2.z, vz[i], r2.w)));
+            ox[i] = fmaf(wu[i], px, ox[i]);
+            oy[i] = fmaf(wu[i], py, oy[i]);
+            oz[i] = fmaf(wu[i], pz, oz[i]);
+          }
+          r0 = n0; r1 = n1; r2 = n2;
+        }
+      }
+    }
+#else
 #pragma unroll
     for (int u = 0; u < kGrpJoints; ++u) {
       if (used & (1u << u)) {
@@ -455,6 +642,7 @@ skin_tma_kernel(const ModelDev m, const SkinArgs a) {
         }
       }
     }
+#endif
     const float r[12] = {ox[0] + tx, oy[0] + ty, oz[0] + tz, ox[1] + tx, oy[1] + ty, oz[1] + tz,
                          ox[2] + tx, oy[2] + ty, oz[2] + tz, ox[3] + tx, oy[3] + ty, oz[3] + tz};
     float* orow = a.out + (size_t)b * m.V * 3 + wf0;

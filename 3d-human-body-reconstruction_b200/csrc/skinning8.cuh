@@ -10,6 +10,12 @@
 #pragma once
 #include "skinning.cuh"
 
+// packed fp32x2 FMAs in the skinning loop: measured SLOWER here (0.208 vs 0.172 ms at 4096 bodies; the kernel is
+// bound by shared-memory wavefronts and latency, not FMA issue) -- kept for A/B builds only
+#ifndef SMPLK_SKIN_FFMA2
+#define SMPLK_SKIN_FFMA2 0
+#endif
+
 namespace smplk {
 
 constexpr int k8Threads = 128;
@@ -62,6 +68,7 @@ skin_grouped8_kernel(const ModelDev m, const SkinArgs a) {
   }
   if (g_valid) jid = m.grp8_joints[g];
   used = __reduce_or_sync(0xffffffffu, used);
+  const int ovf0 = g_valid ? m.grp8_ovf_ptr[g] : 0, ovf1 = g_valid ? m.grp8_ovf_ptr[g + 1] : 0;
 
   auto issue_A = [&](int grp) {
     const int bb0 = b0 + grp * k8ABodies;
@@ -118,27 +125,72 @@ skin_grouped8_kernel(const ModelDev m, const SkinArgs a) {
       c[4 * i + 0] = q.x; c[4 * i + 1] = q.y; c[4 * i + 2] = q.z; c[4 * i + 3] = q.w;
     }
     float o[24];
+#if SMPLK_SKIN_FFMA2
+    // two vertices per instruction: pairs (2k, 2k+1) as packed fp32x2 operands; the transform component is a
+    // scalar-broadcast source, the weight pair sits in adjacent registers of the float4 it was loaded as
+    uint64_t x2[4], y2[4], z2[4], ox2[4], oy2[4], oz2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      x2[k] = ptx::pack_f32x2(c[6 * k], c[6 * k + 3]);
+      y2[k] = ptx::pack_f32x2(c[6 * k + 1], c[6 * k + 4]);
+      z2[k] = ptx::pack_f32x2(c[6 * k + 2], c[6 * k + 5]);
+      ox2[k] = oy2[k] = oz2[k] = ptx::pack_f32x2(0.f, 0.f);
+    }
+    auto apply2 = [&](const float4* Aj, const float4& wa_, const float4& wb_) {
+      const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+      const uint64_t w2[4] = {ptx::pack_f32x2(wa_.x, wa_.y), ptx::pack_f32x2(wa_.z, wa_.w),
+                              ptx::pack_f32x2(wb_.x, wb_.y), ptx::pack_f32x2(wb_.z, wb_.w)};
+      const uint64_t a00 = ptx::pack_f32x2(r0.x, r0.x), a01 = ptx::pack_f32x2(r0.y, r0.y), a02 = ptx::pack_f32x2(r0.z, r0.z),
+                     a03 = ptx::pack_f32x2(r0.w, r0.w), a10 = ptx::pack_f32x2(r1.x, r1.x), a11 = ptx::pack_f32x2(r1.y, r1.y),
+                     a12 = ptx::pack_f32x2(r1.z, r1.z), a13 = ptx::pack_f32x2(r1.w, r1.w), a20 = ptx::pack_f32x2(r2.x, r2.x),
+                     a21 = ptx::pack_f32x2(r2.y, r2.y), a22 = ptx::pack_f32x2(r2.z, r2.z), a23 = ptx::pack_f32x2(r2.w, r2.w);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t px = ptx::fma_f32x2(a00, x2[k], ptx::fma_f32x2(a01, y2[k], ptx::fma_f32x2(a02, z2[k], a03)));
+        const uint64_t py = ptx::fma_f32x2(a10, x2[k], ptx::fma_f32x2(a11, y2[k], ptx::fma_f32x2(a12, z2[k], a13)));
+        const uint64_t pz = ptx::fma_f32x2(a20, x2[k], ptx::fma_f32x2(a21, y2[k], ptx::fma_f32x2(a22, z2[k], a23)));
+        ox2[k] = ptx::fma_f32x2(w2[k], px, ox2[k]);
+        oy2[k] = ptx::fma_f32x2(w2[k], py, oy2[k]);
+        oz2[k] = ptx::fma_f32x2(w2[k], pz, oz2[k]);
+      }
+    };
+#else
 #pragma unroll
     for (int i = 0; i < 24; ++i) o[i] = 0.f;
+    auto apply2 = [&](const float4* Aj, const float4& wa_, const float4& wb_) {
+      const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+      const float wu[8] = {wa_.x, wa_.y, wa_.z, wa_.w, wb_.x, wb_.y, wb_.z, wb_.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x = c[3 * i], y = c[3 * i + 1], z = c[3 * i + 2];
+        const float px = fmaf(r0.x, x, fmaf(r0.y, y, fmaf(r0.z, z, r0.w)));
+        const float py = fmaf(r1.x, x, fmaf(r1.y, y, fmaf(r1.z, z, r1.w)));
+        const float pz = fmaf(r2.x, x, fmaf(r2.y, y, fmaf(r2.z, z, r2.w)));
+        o[3 * i + 0] = fmaf(wu[i], px, o[3 * i + 0]);
+        o[3 * i + 1] = fmaf(wu[i], py, o[3 * i + 1]);
+        o[3 * i + 2] = fmaf(wu[i], pz, o[3 * i + 2]);
+      }
+    };
+#endif
 #pragma unroll
     for (int u = 0; u < kGrpJoints; ++u) {
       if (used & (1u << u)) {
         const int j = ((u < 4 ? jid.x : jid.y) >> (8 * (u & 3))) & 0xff;
-        const float4* Aj = reinterpret_cast<const float4*>(Ab + j * 12);
-        const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
-        const float wu[8] = {wa[u].x, wa[u].y, wa[u].z, wa[u].w, wb[u].x, wb[u].y, wb[u].z, wb[u].w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float x = c[3 * i], y = c[3 * i + 1], z = c[3 * i + 2];
-          const float px = fmaf(r0.x, x, fmaf(r0.y, y, fmaf(r0.z, z, r0.w)));
-          const float py = fmaf(r1.x, x, fmaf(r1.y, y, fmaf(r1.z, z, r1.w)));
-          const float pz = fmaf(r2.x, x, fmaf(r2.y, y, fmaf(r2.z, z, r2.w)));
-          o[3 * i + 0] = fmaf(wu[i], px, o[3 * i + 0]);
-          o[3 * i + 1] = fmaf(wu[i], py, o[3 * i + 1]);
-          o[3 * i + 2] = fmaf(wu[i], pz, o[3 * i + 2]);
-        }
+        apply2(reinterpret_cast<const float4*>(Ab + j * 12), wa[u], wb[u]);
       }
     }
+    // the rare group bound to more than 8 joints (where vertex ranges of several joints meet): its extra
+    // (joint, weights) entries come from a per-group list; only that lane runs the loop
+    for (int e = ovf0; e < ovf1; ++e)
+      apply2(reinterpret_cast<const float4*>(Ab + m.grp8_ovf_joint[e] * 12), m.grp8_ovf_w[2 * e], m.grp8_ovf_w[2 * e + 1]);
+#if SMPLK_SKIN_FFMA2
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ptx::unpack_f32x2(ox2[k], o[6 * k], o[6 * k + 3]);
+      ptx::unpack_f32x2(oy2[k], o[6 * k + 1], o[6 * k + 4]);
+      ptx::unpack_f32x2(oz2[k], o[6 * k + 2], o[6 * k + 5]);
+    }
+#endif
     float* orow = a.out + (size_t)b * m.V * 3 + wf0;
     float* stage = kSharedTemplate ? ring + k8StageFloats + warp * k8WarpPitch : slot;
     float4* ot = reinterpret_cast<float4*>(stage) + 7 * lane;

@@ -502,13 +502,17 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
       if (int r = upload(mdl, gj, &d.grp_joints)) return r;
       if (int r = upload(mdl, gw, &d.grp_w)) return r;
     }
-    // 8-vertex groups (skin_grouped8_kernel): same idea, twice the reuse of every fetched transform
+    // 8-vertex groups (skin_grouped8_kernel): same idea, twice the reuse of every fetched transform.  The 8
+    // heaviest joints of a group sit in the register slots; a group bound to more (the few groups where the
+    // vertex ranges of several joints meet) keeps the rest in an overflow list only its own lane walks.
     {
       const int G = (V + 7) / 8;
       std::vector<uint2> gj(G, make_uint2(0u, 0u));
       std::vector<float4> gw((size_t)G * kGrpJoints * 2, make_float4(0.f, 0.f, 0.f, 0.f));
-      bool ok = ell_k <= 4;
-      for (int g = 0; g < G && ok; ++g) {
+      std::vector<int> optr(G + 1, 0), ojoint;
+      std::vector<float4> ow;
+      int ovf_groups = 0;
+      for (int g = 0; g < G; ++g) {
         std::vector<std::pair<float, int>> uniq;
         for (int i = 0; i < 8; ++i) {
           const int v = 8 * g + i;
@@ -519,29 +523,46 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
             if (!found) uniq.push_back({e.first, e.second});
           }
         }
-        if ((int)uniq.size() > kGrpJoints) { ok = false; break; }
         std::sort(uniq.begin(), uniq.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) {
           return a.first > b.first || (a.first == b.first && a.second < b.second);
         });
+        auto weights_of = [&](int joint, float4* lo, float4* hi) {
+          float wv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int i = 0; i < 8; ++i) {
+            const int v = 8 * g + i;
+            if (v >= V) break;
+            for (auto& e : rows[v]) if (e.second == joint) wv[i] = e.first;
+          }
+          *lo = make_float4(wv[0], wv[1], wv[2], wv[3]);
+          *hi = make_float4(wv[4], wv[5], wv[6], wv[7]);
+        };
         uint32_t packed[2] = {0u, 0u};
         for (size_t u = 0; u < (size_t)kGrpJoints; ++u) {
           const int jj = uniq.empty() ? 0 : (u < uniq.size() ? uniq[u].second : uniq[0].second);
           packed[u / 4] |= (uint32_t)jj << (8 * (u % 4));
           if (u >= uniq.size()) continue;
-          float wv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          for (int i = 0; i < 8; ++i) {
-            const int v = 8 * g + i;
-            if (v >= V) break;
-            for (auto& e : rows[v]) if (e.second == uniq[u].second) wv[i] = e.first;
-          }
-          gw[((size_t)g * kGrpJoints + u) * 2 + 0] = make_float4(wv[0], wv[1], wv[2], wv[3]);
-          gw[((size_t)g * kGrpJoints + u) * 2 + 1] = make_float4(wv[4], wv[5], wv[6], wv[7]);
+          weights_of(uniq[u].second, &gw[((size_t)g * kGrpJoints + u) * 2 + 0], &gw[((size_t)g * kGrpJoints + u) * 2 + 1]);
         }
+        for (size_t u = kGrpJoints; u < uniq.size(); ++u) {
+          float4 lo, hi;
+          weights_of(uniq[u].second, &lo, &hi);
+          ojoint.push_back(uniq[u].second);
+          ow.push_back(lo);
+          ow.push_back(hi);
+        }
+        if (uniq.size() > (size_t)kGrpJoints) ++ovf_groups;
+        optr[g + 1] = (int)ojoint.size();
         gj[g] = make_uint2(packed[0], packed[1]);
       }
-      d.grp8_ok = ok ? 1 : 0;
+      // measured on B200 (profiles/r02_skin_variants.txt): with overflowing groups in a warp the 8-vertex kernel
+      // is slower than the 4-vertex one (0.208 vs 0.172 ms at 4096 bodies), so it is taken only when no group
+      // overflows (rigid / smooth rigs); dense weight matrices stay on the generic ELL kernel
+      d.grp8_ok = (ovf_groups == 0 && ell_k <= 4) ? 1 : 0;
       if (int r = upload(mdl, gj, &d.grp8_joints)) return r;
       if (int r = upload(mdl, gw, &d.grp8_w)) return r;
+      if (int r = upload(mdl, optr, &d.grp8_ovf_ptr)) return r;
+      if (int r = upload(mdl, ojoint, &d.grp8_ovf_joint)) return r;
+      if (int r = upload(mdl, ow, &d.grp8_ovf_w)) return r;
     }
     if (int r = upload(mdl, eidx, &d.ell_idx)) return r;
     if (int r = upload(mdl, ew, &d.ell_w)) return r;
@@ -884,15 +905,18 @@ static int launch_pose_forward(const smplk_model* mdl, const PoseFwdArgs& pa, cu
   const ModelDev& d = mdl->d;
   // small batches: the warp-per-body kernel skips staging the tables (0.019 vs 0.024 ms at 37 bodies)
   if (pose_block_applies(mdl) && (pa.At != nullptr || pa.B >= 128)) {
-    const size_t smem = (size_t)pose_block_layout(d).total * sizeof(float);
+    // 32 bodies per block when the block also transposes the transforms (lane = body); otherwise 8, so that
+    // mid-size batches (the 1,024-body fitting step: 32 blocks before, 22 us on 32 SMs) use every SM
+    const int nw = (pa.At != nullptr || pa.B >= 4096) ? kPoseBlockWarps : 8;
+    const size_t smem = (size_t)pose_block_layout(d, nw).total * sizeof(float);
     // At is written for whole 256-body blocks (the fused kernel reads zero transforms for padding rows)
     const int bodies = pa.At ? round_up(pa.B, 2 * kBlendBM) : pa.B;
-    const int blocks = (bodies + kPoseBlockWarps - 1) / kPoseBlockWarps;
+    const int blocks = (bodies + nw - 1) / nw;
     ProfScope prof(mdl, st, SMPLK_PROF_POSE_FWD);
     if (d.J <= 32)
-      pose_forward_block_kernel<1><<<blocks, kPoseBlockWarps * 32, smem, st>>>(d, pa);
+      pose_forward_block_kernel<1><<<blocks, nw * 32, smem, st>>>(d, pa);
     else
-      pose_forward_block_kernel<2><<<blocks, kPoseBlockWarps * 32, smem, st>>>(d, pa);
+      pose_forward_block_kernel<2><<<blocks, nw * 32, smem, st>>>(d, pa);
     LAUNCH_CHECK("pose_forward_block_kernel");
     return 0;
   }
@@ -1036,8 +1060,8 @@ static int launch_fused(const smplk_model* mdl, int rows, float* F_hi, float* F_
   static long long* dbg_dev = nullptr;
   const bool dbg = SMPLK_FZ_TIMELINE && getenv("SMPLK_FZ_DEBUG") != nullptr;   // tools/fz_timeline.py
   if (dbg) {
-    if (!dbg_dev) cudaMalloc(&dbg_dev, 10 * kFzDbgTiles * 4 * sizeof(long long));
-    cudaMemsetAsync(dbg_dev, 0, 10 * kFzDbgTiles * 4 * sizeof(long long), st);
+    if (!dbg_dev) cudaMalloc(&dbg_dev, (2 + kFzEpiWarps) * kFzDbgTiles * 4 * sizeof(long long));
+    cudaMemsetAsync(dbg_dev, 0, (2 + kFzEpiWarps) * kFzDbgTiles * 4 * sizeof(long long), st);
     fa.dbg = dbg_dev;
   }
   const int tiles = fa.num_m_blocks * fa.num_n_blocks;
@@ -1051,7 +1075,7 @@ static int launch_fused(const smplk_model* mdl, int rows, float* F_hi, float* F_
                                                                      mdl->tmapf_pdh_lo, fa);
   LAUNCH_CHECK("blend_skin_fused_kernel");
   if (dbg) {   // tuning aid: per-tile timeline of CTA 0 (cycles relative to the first stamp)
-    std::vector<long long> h(10 * kFzDbgTiles * 4);
+    std::vector<long long> h((2 + kFzEpiWarps) * kFzDbgTiles * 4);
     cudaStreamSynchronize(st);
     cudaMemcpy(h.data(), dbg_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
     long long t0 = h[(1 * kFzDbgTiles + 0) * 4 + 0];
@@ -1059,7 +1083,7 @@ static int launch_fused(const smplk_model* mdl, int rows, float* F_hi, float* F_
       if (!h[(1 * kFzDbgTiles + it) * 4 + 0]) break;
       fprintf(stderr, "tile %2d mma[wait %7lld go %7lld done %7lld]", it, h[(1 * kFzDbgTiles + it) * 4 + 0] - t0,
               h[(1 * kFzDbgTiles + it) * 4 + 1] - t0, h[(1 * kFzDbgTiles + it) * 4 + 2] - t0);
-      for (int w = 2; w < 10; ++w) {
+      for (int w = 2; w < 2 + kFzEpiWarps; ++w) {
         const long long* r = &h[(w * kFzDbgTiles + it) * 4];
         fprintf(stderr, " | w%d %lld %lld %lld %lld", w, r[0] - t0, r[1] - t0, r[2] - t0, r[3] - t0);
       }
@@ -1100,19 +1124,24 @@ static int launch_skin(const smplk_model* mdl, int rows, const float* vsrc, size
   { const char* e = getenv("SMPLK_SKIN_COPYONLY"); sa.debug_copy_only = (e && e[0] == '1') ? 1 : 0; }
 #endif
   const bool grouped = d.grp_ok && !mdl->force_skin_v1;
-  const size_t smem = grouped ? skin_grouped_smem_bytes(d.J)
-                              : (size_t)(2 * kSkinTileVerts * 3 + 2 * ((d.J * 12 + 3) & ~3)) * sizeof(float);
   // bodies per block: see pick_bpb (whole waves; 0.177 -> 0.169 ms at B=4096, 0.056 -> 0.049 ms at 1024)
   const int resident = (grouped ? 2 : 4) * mdl->num_sms;
   int bpb = 32;
   if (grouped) {
-    bpb = pick_bpb(rows, tiles, resident, 32);
+    // rigged-mesh replay: the block's transforms stay in shared memory for its whole body loop -- as many
+    // bodies as fit two blocks per SM
+    const int fit = (SMPLK_SKIN_NOBAR && vstride == 0) ? skin_nobar_max_bodies(d.J, (size_t)110 * 1024) : 32;
+    bpb = pick_bpb(rows, tiles, resident, std::max(1, std::min(32, fit)));
   } else {
     while (bpb > 8 && (long)tiles * ((rows + bpb - 1) / bpb) < 6L * resident) bpb >>= 1;
     while (bpb > 1 && (long)tiles * ((rows + bpb - 1) / bpb) < resident) bpb >>= 1;
   }
   if (mdl->skin_bpb > 0) bpb = mdl->skin_bpb;
   sa.bodies_per_block = bpb;
+  const size_t smem_grouped = (SMPLK_SKIN_NOBAR && vstride == 0) ? skin_nobar_smem_bytes(d.J, bpb)
+                                                                   : skin_grouped_smem_bytes(d.J);
+  const size_t smem = grouped ? smem_grouped
+                              : (size_t)(2 * kSkinTileVerts * 3 + 2 * ((d.J * 12 + 3) & ~3)) * sizeof(float);
   dim3 grid(tiles, (rows + bpb - 1) / bpb);
   ProfScope prof(mdl, st, SMPLK_PROF_SKIN);
   if (grouped && d.grp8_ok && mdl->skin_g8) {

@@ -101,20 +101,28 @@ def _oracle_fit_grads(m, betas, pose, transl, target, d_loss, chunk=128):
 @pytest.mark.parametrize("B", [1024, 129])
 def test_fit_vertex_l2_matches_float64_oracle_at_config3_size(dev, smplh_model, B):
     """BASELINE config 3 at its own batch (1024) and at a ragged one: loss and gradients of the one-node
-    fitting step against float64 autograd.  Residual magnitudes span 6 decades across the bodies
-    (1e-2 .. 1e4 m) and the upstream d_loss 16 decades; one body has d_loss = 0.  The d_v_posed rows of
+    fitting step against float64 autograd.  Residual magnitudes span 5 decades across the bodies
+    (0.05 .. 1e4 m) and the upstream d_loss 16 decades; one body has d_loss = 0.  The d_v_posed rows of
     this path are bf16 two-term splits (16 mantissa bits): the bound is 1e-4 relative per body."""
     m = smplh_model
     dm = smplk.DeviceModel(m, device=0)
     betas, pose, transl = synthetic.make_inputs(m, B, seed=300 + B)
     rng = np.random.default_rng(B)
-    om32 = O.TorchOracleModel(m, dtype=torch.float64)
+    # V* = the forward of perturbed parameters (SURVEY 8d config 3): a coherent residual of 0.05 .. 1 m,
+    # plus per-body noise of 1e-3 .. 1e4 m.  (Pure noise residuals of ~1e-2 m are NOT a fair fp32 test:
+    # their true parameter gradient cancels like sqrt(V) while the 2e-7 m fp32 error of a limb's
+    # transform is coherent over its vertices -- 4e-4 relative on such a body for ANY fp32 path.)
+    om64 = O.TorchOracleModel(m, dtype=torch.float64)
+    s_b = 10.0 ** rng.uniform(-0.5, 0.0, size=(B, 1))
+    pb = betas + rng.standard_normal(betas.shape) * s_b
+    pp = pose + rng.standard_normal(pose.shape) * 0.3 * s_b
+    pt = transl + rng.standard_normal(transl.shape) * 10.0 ** rng.uniform(-1, 0.5, size=(B, 1))
     with torch.no_grad():
-        parts = [om32.forward_full_pose(*[torch.tensor(np.asarray(x[c:c + 256], np.float64)) for x in (betas, pose, transl)]).vertices
+        parts = [om64.forward_full_pose(*[torch.tensor(np.asarray(x[c:c + 256], np.float64)) for x in (pb, pp, pt)]).vertices
                  for c in range(0, B, 256)]
-    v_ref = torch.cat(parts).numpy()
-    res_scale = 10.0 ** rng.uniform(-2, 4, size=B)
-    target = (v_ref + rng.standard_normal(v_ref.shape) * res_scale[:, None, None]).astype(np.float32)
+    v_tgt = torch.cat(parts).numpy()
+    res_scale = 10.0 ** rng.uniform(-3, 4, size=B)
+    target = (v_tgt + rng.standard_normal(v_tgt.shape) * res_scale[:, None, None]).astype(np.float32)
     d_loss = 10.0 ** rng.uniform(-8, 8, size=B)
     d_loss[5] = 0.0
     tb, tp, tt = (_t(x, dev, True) for x in (betas, pose, transl))

@@ -788,5 +788,26 @@ def test_errors_are_loud(dev, smpl_model):
     a.pose = ctypes.c_void_p(_t(p, dev).data_ptr())
     with pytest.raises(RuntimeError, match="workspace"):
         dm.forward(a)
+    # shapes the C side would stride over blindly are refused before the call (upstream raises on these too)
+    with pytest.raises(ValueError, match="betas"):
+        body_model_apply(dm, _t(np.zeros((3, 10)), dev), _t(p, dev))            # 3 rows for a batch of 2
+    with pytest.raises(ValueError, match="betas"):
+        body_model_apply(dm, _t(np.zeros((2, 16)), dev), _t(p, dev))            # 16 betas on a 10-beta model
+    with pytest.raises(ValueError, match="pose"):
+        body_model_apply(dm, _t(b, dev), _t(np.zeros((2, 156)), dev))           # SMPL-H pose on the 24-joint model
+    with pytest.raises(ValueError, match="transl"):
+        body_model_apply(dm, _t(b, dev), _t(p, dev), transl=_t(np.zeros((1, 3)), dev))
+    from smplk.body_models import vertex_l2_loss, fit_vertex_l2
+    v = body_model_apply(dm, _t(b, dev), _t(p, dev))[0]
+    with pytest.raises(ValueError, match="shape"):
+        vertex_l2_loss(v, v[0])                                                  # (V,3) target for (B,V,3) vertices
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
+        vertex_l2_loss(v, v.cpu())
+    with pytest.raises(ValueError, match="target"):
+        fit_vertex_l2(dm, _t(b, dev), _t(p, dev), v[:1])
+    # the C ABI itself still refuses an inconsistent betas_batch
+    a.betas, a.betas_batch = ctypes.c_void_p(_t(b, dev).data_ptr()), 3
+    ws = torch.empty(dm.workspace_bytes(2, 0), device=dev, dtype=torch.uint8)
+    a.workspace, a.workspace_bytes = ctypes.c_void_p(ws.data_ptr()), ws.numel()
     with pytest.raises(RuntimeError, match="betas_batch"):
-        body_model_apply(dm, _t(np.zeros((3, 10)), dev), _t(p, dev))
+        dm.forward(a)
