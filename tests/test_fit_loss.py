@@ -145,3 +145,55 @@ def test_batched_fitting_step_through_body_model_and_loss():
     for name in ("betas", "body_pose", "global_orient", "left_hand_pose", "transl"):
         assert _rel(getattr(mod, name).grad, t[name].grad) <= 1e-4, name
     assert _rel(cam.translation.grad, ct.grad) <= 1e-4
+
+
+@pytest.mark.gpu
+def test_smplify_loss_with_shared_betas_row():
+    """the body modules allow ONE betas row for B poses (upstream lbs batch = max(...)); the prior
+    kernel must then see B rows (broadcast) and the betas gradient is the sum over the bodies."""
+    import smplk
+    from smplk import synthetic
+    from smplk.body_models import SMPLH
+    from smplk.fitting import PerspectiveCamera, SMPLifyLoss
+    from oracle import smpl_oracle as O
+    B = 5
+    dev = "cuda:0"
+    m = synthetic.make_model("smplh", seed=3)
+    mod = SMPLH(model=m, use_pca=True, num_pca_comps=12, batch_size=1, create_transl=False,
+                create_global_orient=False, create_body_pose=False, create_left_hand_pose=False,
+                create_right_hand_pose=False).to(dev)
+    rng = np.random.default_rng(9)
+    with torch.no_grad():
+        mod.betas.copy_(torch.tensor(rng.standard_normal((1, 16)) * 0.5, dtype=torch.float32))
+    vals = dict(global_orient=rng.standard_normal((B, 3)) * 0.2, body_pose=rng.standard_normal((B, 63)) * 0.3,
+                left_hand_pose=rng.standard_normal((B, 12)) * 0.5, right_hand_pose=rng.standard_normal((B, 12)) * 0.5,
+                transl=rng.standard_normal((B, 3)) * 0.1)
+    g = {k: torch.tensor(v, dtype=torch.float32, device=dev, requires_grad=True) for k, v in vals.items()}
+    out = mod(return_verts=True, return_full_pose=True, **g)
+    assert out.betas.shape == (1, 16) and out.joints.shape[0] == B
+    cam = PerspectiveCamera(translation=np.tile([[0.0, 0.0, 8.0]], (B, 1)), batch_size=B,
+                            center=np.tile([[256.0, 256.0]], (B, 1)))
+    Jn = out.joints.shape[1]
+    gt = torch.tensor(rng.standard_normal((B, Jn, 2)) * 30 + 256, dtype=torch.float32, device=dev)
+    conf = torch.tensor(rng.random((B, Jn)), dtype=torch.float32, device=dev)
+    jw = torch.ones(B, Jn, device=dev)
+    loss_fn = SMPLifyLoss(rho=100.0, data_weight=1.0, shape_weight=5.0, bending_prior_weight=3.17, hand_prior_weight=4.0)
+    loss = loss_fn(out, cam, gt, conf, joint_weights=jw)
+    loss.backward()
+    om = O.TorchOracleModel(m, dtype=torch.float64, num_pca_comps=12)
+    ob = mod.betas.detach().double().cpu().requires_grad_(True)
+    t = {k: torch.tensor(v, requires_grad=True) for k, v in vals.items()}
+    ro = om.forward(ob.expand(B, -1), t["global_orient"], t["body_pose"], t["left_hand_pose"], t["right_hand_pose"],
+                    transl=t["transl"])
+    ct = torch.tensor(np.tile([[0.0, 0.0, 8.0]], (B, 1)), requires_grad=True)
+    eye = torch.eye(3, dtype=torch.float64).repeat(B, 1, 1)
+    data = FO.data_term(ro.joints, eye, ct, torch.full((B, 2), 5000.0, dtype=torch.float64),
+                        torch.full((B, 2), 256.0, dtype=torch.float64), gt.double().cpu(), (jw * conf).double().cpu(), 100.0, 1.0)
+    pri = FO.prior_term(betas=ob.expand(B, -1), body_pose=ro.full_pose[:, 3:66], lhand=ro.left_hand_pose,
+                        rhand=ro.right_hand_pose, shape_weight=5.0, bending_prior_weight=3.17, hand_prior_weight=4.0)
+    ref = data.sum() + pri.sum()
+    ref.backward()
+    assert abs(float(loss) / float(ref) - 1) <= 1e-5
+    assert mod.betas.grad.shape == (1, 16) and _rel(mod.betas.grad, ob.grad) <= 1e-4
+    for name in ("body_pose", "global_orient", "left_hand_pose", "transl"):
+        assert _rel(g[name].grad, t[name].grad) <= 1e-4, name

@@ -172,3 +172,47 @@ def test_graphed_closure_refuses_cpu_parameters():
         GraphedClosure(lambda: (p ** 2).sum(), [p])
     with pytest.raises(ValueError):
         GraphedClosure(lambda: None, [torch.zeros(3)])
+
+
+def test_create_resolves_model_folders(tmp_path):
+    """`smplx.create(model_path=<folder>, model_type=..., gender=...)` as lib/gen_smplh.py:75-90 calls it:
+    <folder>/<type>/<TYPE>_<GENDER>.pkl (or the file directly inside <folder>, or an .npz)."""
+    import pickle
+    import numpy as np
+    from smplk import synthetic
+    from smplk.body_models import SMPL, SMPLH, create, resolve_model_path
+    keys = ("J_regressor", "weights", "v_template", "shapedirs", "posedirs", "f", "kintree_table",
+            "hands_componentsl", "hands_componentsr", "hands_meanl", "hands_meanr")
+    mh = synthetic.make_model("smplh", seed=1)
+    ms = synthetic.make_model("smpl", seed=2)
+    (tmp_path / "smplh").mkdir()
+    (tmp_path / "smpl").mkdir()
+    with open(tmp_path / "smplh" / "SMPLH_MALE.pkl", "wb") as f:
+        pickle.dump({k: mh[k] for k in keys}, f)
+    np.savez(tmp_path / "smpl" / "SMPL_NEUTRAL.npz", **{k: ms[k] for k in keys[:7]})
+    m = create(model_path=str(tmp_path), model_type="smplh", gender="male", use_pca=True, num_pca_comps=12,
+               create_transl=False, batch_size=2)
+    assert isinstance(m, SMPLH) and m.num_joints == 52 and m.betas.shape == (2, 16)
+    assert np.array_equal(np.asarray(m._model_dict["v_template"]), mh["v_template"])
+    s = create(model_path=str(tmp_path), model_type="smpl", gender="neutral")          # .npz next to a missing .pkl
+    assert isinstance(s, SMPL) and s.num_joints == 24
+    assert resolve_model_path(str(tmp_path / "smplh"), "smplh", "male").endswith("SMPLH_MALE.pkl")
+    direct = SMPLH(model_path=str(tmp_path / "smplh" / "SMPLH_MALE.pkl"), num_pca_comps=6)   # a file path is taken as is
+    assert direct.left_hand_pose.shape == (1, 6)
+    with pytest.raises(FileNotFoundError):
+        create(model_path=str(tmp_path), model_type="smplh", gender="female")
+    with pytest.raises(ValueError):
+        create(model_path=str(tmp_path), model_type="flame")
+
+
+def test_prior_inputs_broadcast_or_raise():
+    """shared betas (1,NB) with B > 1 poses must not leave rows 1..B-1 unwritten."""
+    import torch
+    from smplk.fitting import _prior_rows
+    b, p = torch.zeros(1, 10), torch.zeros(4, 63)
+    B, ts, bc = _prior_rows([b, None, p, None, None])
+    assert B == 4 and ts[0].shape == (4, 10) and ts[0].is_contiguous() and bc == [True, False, False, False, False]
+    B, ts, bc = _prior_rows([b, None, None, None, None], 3)
+    assert ts[0].shape == (3, 10) and bc[0]
+    with pytest.raises(ValueError):
+        _prior_rows([torch.zeros(2, 10), None, p, None, None])
