@@ -558,6 +558,124 @@ __global__ void __launch_bounds__(kDAThreads) dA_kernel(const ModelDev m, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// dA_seg_kernel -- the transform gradient of the fitting step, joint-major like dA_kernel but with the
+// list traversal turned inside out: a warp owns ONE segment (<= 128 entries) of one joint's vertex
+// list for a RUN of bodies.  Its 4 entries per lane (vertex offset, weight) are loaded once and stay in
+// registers, so a body costs no dependent index hop (dA_kernel: index list, then gathers -- two global
+// round trips per 128 entries, long-scoreboard stall 8.5 per issued instruction), and the gathers of
+// body b+1 are in flight while body b is reduced.  The 12 sums of a body are reduced with a halving
+// butterfly over 16 values (16 shuffles instead of 60) and written as per-segment partials
+// dAp[b][s][12]; dA_seg_reduce_kernel adds a joint's segments in fixed order (bit-reproducible) and forms
+// d_transl = sum_j dA[j][:,3] (valid because every vertex's weights sum to 1: checked at model create).
+// ------------------------------------------------------------------------------------------
+constexpr int kDASeg = 128;          // list entries per segment: 4 per lane
+constexpr int kDASegWarps = 4;
+
+struct DASegArgs {
+  int B;
+  int bodies_per_warp;
+  const float* dverts;    // (B,V,3)
+  const float* vsrc;      // v_posed rows
+  size_t vsrc_stride;
+  float* dAp;             // (B, S, 12) per-segment partial sums
+};
+
+__device__ __forceinline__ float halve_exchange(bool upper, float lo, float hi, int mask) {
+  // lanes of the upper half keep `hi` and hand out `lo`; the lower half the other way round
+  const float send = upper ? lo : hi;
+  const float keep = upper ? hi : lo;
+  return keep + __shfl_xor_sync(0xffffffffu, send, mask);
+}
+
+__global__ void __launch_bounds__(kDASegWarps * 32) dA_seg_kernel(const ModelDev m, const DASegArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * kDASegWarps + warp;
+  if (s >= m.seg_count) return;
+  const int beg = m.seg_beg[s], len = m.seg_len[s];
+  int off[4];
+  float w[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = 32 * u + lane;
+    const bool ok = i < len;
+    off[u] = ok ? 3 * m.csc_vert[beg + i] : 0;
+    w[u] = ok ? m.csc_w[beg + i] : 0.f;
+  }
+  const int b0 = blockIdx.y * a.bodies_per_warp;
+  const int b1 = min(a.B, b0 + a.bodies_per_warp);
+  if (b0 >= b1) return;
+  float gq[4][3], xq[4][3];
+  auto load = [&](int b, float (&g)[4][3], float (&x)[4][3]) {
+    const float* gp = a.dverts + (size_t)b * m.V * 3;
+    const float* vp = a.vsrc + (size_t)b * a.vsrc_stride;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        g[u][c] = gp[off[u] + c];
+        x[u][c] = vp[off[u] + c];
+      }
+    }
+  };
+  load(b0, gq, xq);
+  for (int b = b0; b < b1; ++b) {
+    float gn[4][3], xn[4][3];
+    load(min(b + 1, b1 - 1), gn, xn);              // next body's gathers fly during this body's reduction
+    float acc[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q] = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float gx = w[u] * gq[u][0], gy = w[u] * gq[u][1], gz = w[u] * gq[u][2];
+      const float x = xq[u][0], y = xq[u][1], z = xq[u][2];
+      acc[0] = fmaf(gx, x, acc[0]); acc[1] = fmaf(gx, y, acc[1]); acc[2] = fmaf(gx, z, acc[2]); acc[3] += gx;
+      acc[4] = fmaf(gy, x, acc[4]); acc[5] = fmaf(gy, y, acc[5]); acc[6] = fmaf(gy, z, acc[6]); acc[7] += gy;
+      acc[8] = fmaf(gz, x, acc[8]); acc[9] = fmaf(gz, y, acc[9]); acc[10] = fmaf(gz, z, acc[10]); acc[11] += gz;
+    }
+    // halving butterfly: 16 -> 8 -> 4 -> 2 -> 1 values per lane, then the pair (lane, lane ^ 1)
+    float r8[8], r4[4], r2[2];
+    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r8[i] = halve_exchange(u16, acc[i], acc[i + 8], 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r4[i] = halve_exchange(u8, r8[i], r8[i + 4], 8);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) r2[i] = halve_exchange(u4, r4[i], r4[i + 2], 4);
+    float r1 = halve_exchange(u2, r2[0], r2[1], 2);
+    r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+    // this lane now holds component  8 [lane&16] + 4 [lane&8] + 2 [lane&4] + [lane&2]
+    const int comp = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    if (!(lane & 1) && comp < 12) a.dAp[((size_t)b * m.seg_count + s) * 12 + comp] = r1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { gq[u][c] = gn[u][c]; xq[u][c] = xn[u][c]; }
+    }
+  }
+}
+
+// dA[b][j] = sum of the joint's segment partials (fixed order); dtr[b] = sum_j dA[b][j][:,3].  Block per body.
+__global__ void __launch_bounds__(256) dA_seg_reduce_kernel(const ModelDev m, int B, const float* __restrict__ dAp,
+                                                            float* __restrict__ dA, float* __restrict__ dtr) {
+  __shared__ float sA[kMaxJoints * 12];
+  const int b = blockIdx.x;
+  const float* p = dAp + (size_t)b * m.seg_count * 12;
+  for (int i = threadIdx.x; i < m.J * 12; i += blockDim.x) {
+    const int j = i / 12, c = i - 12 * j;
+    float acc = 0.f;
+    for (int s = m.joint_seg_ptr[j]; s < m.joint_seg_ptr[j + 1]; ++s) acc += p[s * 12 + c];
+    sA[i] = acc;
+    dA[(size_t)b * m.J * 12 + i] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int j = 0; j < m.J; ++j) t += sA[j * 12 + 4 * threadIdx.x + 3];
+    dtr[3 * b + threadIdx.x] = t;
+  }
+}
+
 // d r  from  dL/dR for R = rodrigues(r)  (same parametrisation as the forward).
 __device__ __forceinline__ void rodrigues_backward(const float* r, const float* dR, float* dr) {
   const float ex = r[0] + 1e-8f, ey = r[1] + 1e-8f, ez = r[2] + 1e-8f;

@@ -3,7 +3,7 @@
 struct BwdLayout {
   int m_blocks, n_blocks, k_blocks, splits, kbps, mpad;
   bool f16;           // backward GEMM on fp16 two-term-split operands (else 3xTF32)
-  size_t off_dverts, off_dvp_hi, off_dvp_lo, off_dA, off_dtr, off_scale, off_dfeat, total;
+  size_t off_dverts, off_dvp_hi, off_dvp_lo, off_dA, off_dtr, off_scale, off_dfeat, off_dAp, total;
 };
 
 // fp16 operands need the grouped skinning-backward kernel (it writes the scaled half rows)
@@ -25,6 +25,7 @@ static BwdLayout bwd_layout(const smplk_model* mdl, int batch) {
   L.off_dA = off;     off += align_up((size_t)batch * d.J * 12 * sizeof(float), 1024);
   L.off_dtr = off;    off += align_up((size_t)batch * 3 * sizeof(float), 1024);
   L.off_scale = off;  off += align_up((size_t)batch * 2 * sizeof(float), 1024);
+  L.off_dAp = off;    off += align_up((size_t)batch * d.seg_count * 12 * sizeof(float), 1024);   // dA_seg_kernel partials
   L.f16 = bwd_uses_f16(mdl);
   if (!d.lbs_only) {
     L.n_blocks = (d.Kpad + kBlendBN - 1) / kBlendBN;
@@ -115,6 +116,18 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
   const bool have_dv = dverts != nullptr;
   if (picks_only) {
     // dA, dtr and d_feat are already there
+  } else if (have_dv && dvp_ready && d.w_rows_normalised && d.seg_count > 0 && !model->da_v1) {
+    // fitting step: segment kernel + fixed-order reduction (d_transl from the translation columns)
+    DASegArgs ds;
+    ds.B = B; ds.dverts = dverts; ds.vsrc = v_posed; ds.vsrc_stride = (size_t)d.Npad;
+    ds.dAp = reinterpret_cast<float*>(sc + L.off_dAp);
+    ds.bodies_per_warp = std::max(1, std::min(16, B / 8));
+    { ProfScope prof(model, st, SMPLK_PROF_DA);
+    dim3 grid((d.seg_count + kDASegWarps - 1) / kDASegWarps, (B + ds.bodies_per_warp - 1) / ds.bodies_per_warp);
+    dA_seg_kernel<<<grid, kDASegWarps * 32, 0, st>>>(d, ds);
+    LAUNCH_CHECK("dA_seg_kernel");
+    dA_seg_reduce_kernel<<<B, 256, 0, st>>>(d, B, ds.dAp, dA, dtr); }
+    LAUNCH_CHECK("dA_seg_reduce_kernel");
   } else if (have_dv) {
     DAArgs da;
     da.B = B; da.dverts = dverts;

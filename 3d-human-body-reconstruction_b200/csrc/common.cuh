@@ -60,6 +60,13 @@ struct ModelDev {
   const int* csc_ptr;         // [J+1] joint -> (vertex, weight) lists for the backward
   const int* csc_vert;        // [nnz]
   const float* csc_w;         // [nnz]
+  // joint -> vertex lists cut into segments of <= 128 entries (dA_seg_kernel): one warp owns one segment for a
+  // run of bodies, its 4 entries per lane stay in registers
+  int seg_count;              // S
+  int w_rows_normalised;      // 1 when every vertex's weights sum to 1 (d_transl = sum_j dA[j][:,3] then)
+  const int* seg_beg;         // [S] first entry in csc_vert / csc_w
+  const int* seg_len;         // [S] 1..128
+  const int* joint_seg_ptr;   // [J+1] segments of joint j: joint_seg_ptr[j] .. joint_seg_ptr[j+1]
   const float* comp_l;        // [C][45]
   const float* comp_r;        // [C][45]
   const float* pose_mean;     // [3J]

@@ -129,6 +129,7 @@ struct smplk_model {
   bool force_skin_v1;   // SMPLK_SKIN_V1=1 in the environment: per-vertex gather kernel (A/B testing)
   bool sparse_picks;    // SMPLK_SPARSE_PICKS=0: keypoint-only gradients take the dense backward (A/B testing)
   bool fit_fused;       // fused skinning + loss + skinning-backward kernel of smplk_fit_vertex_l2 (SMPLK_FIT_FUSED=0: off)
+  bool da_v1;           // SMPLK_DA_V1=1 (A/B builds): the fitting step's dA through dA_kernel instead of dA_seg_kernel
   mutable bool prof_on;
   mutable std::vector<ProfRec> prof_pending;
   mutable double prof_ms[SMPLK_PROF_SLOTS];
@@ -571,6 +572,27 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     if (int r = upload(mdl, cptr, &d.csc_ptr)) return r;
     if (int r = upload(mdl, cvert, &d.csc_vert)) return r;
     if (int r = upload(mdl, cw, &d.csc_w)) return r;
+    {   // segments of the joint -> vertex lists (dA_seg_kernel)
+      std::vector<int> sbeg, slen, jptr(J + 1, 0);
+      for (int j = 0; j < J; ++j) {
+        for (int n = cptr[j]; n < cptr[j + 1]; n += kDASeg) {
+          sbeg.push_back(n);
+          slen.push_back(std::min(kDASeg, cptr[j + 1] - n));
+        }
+        jptr[j + 1] = (int)sbeg.size();
+      }
+      d.seg_count = (int)sbeg.size();
+      double worst = 0.0;
+      for (int v = 0; v < V; ++v) {
+        double sum = 0.0;
+        for (auto& e : rows[v]) sum += (double)e.first;
+        worst = std::max(worst, std::fabs(sum - 1.0));
+      }
+      d.w_rows_normalised = worst <= 1e-6 ? 1 : 0;
+      if (int r = upload(mdl, sbeg, &d.seg_beg)) return r;
+      if (int r = upload(mdl, slen, &d.seg_len)) return r;
+      if (int r = upload(mdl, jptr, &d.joint_seg_ptr)) return r;
+    }
     // fused epilogue tables: for every 12-vertex chunk of every 84-vertex tile, the distinct joints
     // its vertices are bound to and, per joint, the chunk's weights (0 where a vertex does not use it)
     if (!lbs_only) {
@@ -809,8 +831,9 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   mdl->copy_stream = nullptr;
   mdl->encode = nullptr;
   mdl->prof_on = false;
-  mdl->skin_bpb = 0; mdl->skin_g8 = true; mdl->skin_tma = false; mdl->force_skin_v1 = false;
+  mdl->skin_bpb = 0; mdl->skin_g8 = true; mdl->skin_tma = false; mdl->force_skin_v1 = false; mdl->da_v1 = false;
 #ifdef SMPLK_AB   // tuning switches of kernels that are not on a default path
+  { const char* e = getenv("SMPLK_DA_V1"); mdl->da_v1 = e && e[0] == '1'; }
   { const char* e = getenv("SMPLK_SKIN_BPB"); mdl->skin_bpb = e ? atoi(e) : 0; }
   { const char* e = getenv("SMPLK_SKIN_G8"); mdl->skin_g8 = !(e && e[0] == '0'); }
   { const char* e = getenv("SMPLK_SKIN_TMA"); mdl->skin_tma = (e && e[0] == '1'); }
