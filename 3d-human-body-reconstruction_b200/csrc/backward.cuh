@@ -566,8 +566,9 @@ __global__ void __launch_bounds__(kDAThreads) dA_kernel(const ModelDev m, const 
 // round trips per 128 entries, long-scoreboard stall 8.5 per issued instruction), and the gathers of
 // body b+1 are in flight while body b is reduced.  The 12 sums of a body are reduced with a halving
 // butterfly over 16 values (16 shuffles instead of 60) and written as per-segment partials
-// dAp[b][s][12]; dA_seg_reduce_kernel adds a joint's segments in fixed order (bit-reproducible) and forms
-// d_transl = sum_j dA[j][:,3] (valid because every vertex's weights sum to 1: checked at model create).
+// dAp[b][s][12]; the pose backward kernel adds a joint's (adjacent) segments in fixed order (bit-reproducible)
+// and forms d_transl = sum_j dA[j][:,3] (valid because every vertex's weights sum to 1: checked at model
+// create).  A separate reduction launch cost 9 us for this tiny sum.
 // ------------------------------------------------------------------------------------------
 constexpr int kDASeg = 128;          // list entries per segment: 4 per lane
 constexpr int kDASegWarps = 4;
@@ -655,27 +656,6 @@ __global__ void __launch_bounds__(kDASegWarps * 32) dA_seg_kernel(const ModelDev
   }
 }
 
-// dA[b][j] = sum of the joint's segment partials (fixed order); dtr[b] = sum_j dA[b][j][:,3].  Block per body.
-__global__ void __launch_bounds__(256) dA_seg_reduce_kernel(const ModelDev m, int B, const float* __restrict__ dAp,
-                                                            float* __restrict__ dA, float* __restrict__ dtr) {
-  __shared__ float sA[kMaxJoints * 12];
-  const int b = blockIdx.x;
-  const float* p = dAp + (size_t)b * m.seg_count * 12;
-  for (int i = threadIdx.x; i < m.J * 12; i += blockDim.x) {
-    const int j = i / 12, c = i - 12 * j;
-    float acc = 0.f;
-    for (int s = m.joint_seg_ptr[j]; s < m.joint_seg_ptr[j + 1]; ++s) acc += p[s * 12 + c];
-    sA[i] = acc;
-    dA[(size_t)b * m.J * 12 + i] = acc;
-  }
-  __syncthreads();
-  if (threadIdx.x < 3) {
-    float t = 0.f;
-    for (int j = 0; j < m.J; ++j) t += sA[j * 12 + 4 * threadIdx.x + 3];
-    dtr[3 * b + threadIdx.x] = t;
-  }
-}
-
 // d r  from  dL/dR for R = rodrigues(r)  (same parametrisation as the forward).
 __device__ __forceinline__ void rodrigues_backward(const float* r, const float* dR, float* dr) {
   const float ex = r[0] + 1e-8f, ey = r[1] + 1e-8f, ez = r[2] + 1e-8f;
@@ -718,6 +698,8 @@ struct PoseBwdArgs {
   int feat_splits;
   size_t feat_split_stride;  // floats
   const float* dtr_verts;    // (B,3) or null
+  const float* dAp;          // (B,S,12) per-segment partials of dA_seg_kernel, or null (then dA is read);
+                             // with dAp the vertex part of d_transl is sum_j dA[j][:,3] and dtr_verts is null
   float* d_betas;            // (betas_B,NB) or null (atomic accumulate when betas_B == 1)
   float* d_pose;             // (B,3J) or null
   float* d_pca_l;            // (B,C) or null
@@ -836,11 +818,31 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
   }
 
   // ---- seed: A_j = [G_R | G_t - G_R J_j], joints_fk = G_t
+  float dtr_acc[3] = {0.f, 0.f, 0.f};     // with dAp: sum_j dA[j][:,3] = the vertex part of d_transl (weights sum to 1 per vertex)
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
     const int j = lane + 32 * s;
     if (j < m.J) {
-      const float* g = a.dA + ((size_t)b * m.J + j) * 12;
+      float gl[12];
+      if (a.dAp != nullptr) {     // per-segment partials of dA_seg_kernel: a joint's segments are adjacent, summed in order
+        const float4* p4 = reinterpret_cast<const float4*>(a.dAp + ((size_t)b * m.seg_count + m.joint_seg_ptr[j]) * 12);
+        const int ns = m.joint_seg_ptr[j + 1] - m.joint_seg_ptr[j];
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0;
+        for (int q = 0; q < ns; ++q) {
+          const float4 t0 = p4[3 * q], t1 = p4[3 * q + 1], t2 = p4[3 * q + 2];
+          s0.x += t0.x; s0.y += t0.y; s0.z += t0.z; s0.w += t0.w;
+          s1.x += t1.x; s1.y += t1.y; s1.z += t1.z; s1.w += t1.w;
+          s2.x += t2.x; s2.y += t2.y; s2.z += t2.z; s2.w += t2.w;
+        }
+        gl[0] = s0.x; gl[1] = s0.y; gl[2] = s0.z; gl[3] = s0.w; gl[4] = s1.x; gl[5] = s1.y; gl[6] = s1.z; gl[7] = s1.w;
+        gl[8] = s2.x; gl[9] = s2.y; gl[10] = s2.z; gl[11] = s2.w;
+        dtr_acc[0] += gl[3]; dtr_acc[1] += gl[7]; dtr_acc[2] += gl[11];
+      } else {
+        const float* gsrc = a.dA + ((size_t)b * m.J + j) * 12;
+#pragma unroll
+        for (int q = 0; q < 12; ++q) gl[q] = gsrc[q];
+      }
+      const float* g = gl;
       const float* G = Gw + j * 12;
       float gt[3] = {g[3], g[7], g[11]};
       float djr[3] = {0.f, 0.f, 0.f};
@@ -1010,8 +1012,16 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
       }
     }
   }
+  if (a.dAp != nullptr) {                 // lanes hold their joints' translation columns: sum over the warp
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dtr_acc[q] += __shfl_xor_sync(0xffffffffu, dtr_acc[q], o);
+    }
+  }
   if (a.d_transl && lane < 3) {
     float t = a.dtr_verts ? a.dtr_verts[3 * b + lane] : 0.f;
+    if (a.dAp != nullptr) t += lane == 0 ? dtr_acc[0] : (lane == 1 ? dtr_acc[1] : dtr_acc[2]);
     if (a.d_joints)
       for (int j = 0; j < m.J; ++j) t += a.d_joints[(size_t)b * a.joints_ld + 3 * j + lane];
     a.d_transl[3 * b + lane] = gs * t;

@@ -114,6 +114,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
   }
 
   const bool have_dv = dverts != nullptr;
+  const float* seg_partials = nullptr;     // set when dA_seg_kernel ran: the pose kernel sums its per-segment partials
   if (picks_only) {
     // dA, dtr and d_feat are already there
   } else if (have_dv && dvp_ready && d.w_rows_normalised && d.seg_count > 0 && !model->da_v1) {
@@ -124,10 +125,9 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     ds.bodies_per_warp = std::max(1, std::min(16, B / 8));
     { ProfScope prof(model, st, SMPLK_PROF_DA);
     dim3 grid((d.seg_count + kDASegWarps - 1) / kDASegWarps, (B + ds.bodies_per_warp - 1) / ds.bodies_per_warp);
-    dA_seg_kernel<<<grid, kDASegWarps * 32, 0, st>>>(d, ds);
+    dA_seg_kernel<<<grid, kDASegWarps * 32, 0, st>>>(d, ds); }
     LAUNCH_CHECK("dA_seg_kernel");
-    dA_seg_reduce_kernel<<<B, 256, 0, st>>>(d, B, ds.dAp, dA, dtr); }
-    LAUNCH_CHECK("dA_seg_reduce_kernel");
+    seg_partials = ds.dAp;
   } else if (have_dv) {
     DAArgs da;
     da.B = B; da.dverts = dverts;
@@ -245,7 +245,8 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     LAUNCH_CHECK("reduce_splits_kernel");
     pb.feat_splits = 1;
   }
-  pb.dtr_verts = dtr;
+  pb.dtr_verts = seg_partials ? nullptr : dtr;
+  pb.dAp = seg_partials;
   pb.d_betas = d.NB > 0 ? a->d_betas : nullptr;
   pb.d_pose = a->d_pose; pb.d_pca_l = a->d_hand_pca_l; pb.d_pca_r = a->d_hand_pca_r;
   pb.d_transl = a->d_transl;
