@@ -322,8 +322,10 @@ class _BodyModelBase(nn.Module):
                  dtype=torch.float32, batch_size=1, gender="neutral", J_regressor_extra=None,
                  joint_map=None, vertex_ids=None, device=None, ext="pkl", **kwargs):
         super().__init__()
-        if dtype != torch.float32:
-            raise ValueError("smplk computes in float32 (got dtype %s)" % dtype)
+        # float64 (lib/gen_smplh.py:66-67 float_dtype) is accepted at the interface: parameters, buffers and
+        # outputs carry it, the kernels compute in float32 (inputs are cast down, outputs cast up)
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError("Unknown float type %s, exiting!" % dtype)
         if model is None:
             if model_path is None:
                 raise ValueError("give `model` (dict) or `model_path`")
@@ -341,6 +343,8 @@ class _BodyModelBase(nn.Module):
         W = model["weights"]
         W = W.toarray() if hasattr(W, "toarray") else np.asarray(W)
         self.register_buffer("lbs_weights", torch.tensor(W, dtype=dtype))
+        self.weigths = np.asarray(W)          # models/smplh.py:20 (sic)
+        self.seg_index = {}                   # models/smplh.py:18
         sd = np.asarray(model["shapedirs"])
         self.num_betas = sd.shape[2] if num_betas is None else min(num_betas, sd.shape[2])
         self.parents = _lib.parents_from_model(model)
@@ -390,7 +394,9 @@ class _BodyModelBase(nn.Module):
     def verts_numpy(self):
         """models/smplh.py:38 caches vertices[0] on the host every forward (a device sync);
         here the copy happens only when the attribute is read."""
-        return None if self._verts_cache is None else self._verts_cache[0].detach().cpu().numpy()
+        if self._verts_cache is None:          # models/smplh.py:19: the template until the first forward
+            return self.v_template.detach().cpu().numpy()
+        return self._verts_cache[0].detach().cpu().numpy()
 
     @torch.no_grad()
     def reset_params(self, **params_dict):
@@ -405,8 +411,16 @@ class _BodyModelBase(nn.Module):
         if value is None:
             value = getattr(self, name, None)
         if value is None:
-            value = torch.zeros(batch, cols, dtype=torch.float32, device=device)
+            value = torch.zeros(batch, cols, dtype=self.dtype, device=device)
         return value
+
+    @staticmethod
+    def _f32(t):
+        """Kernel-side view of an interface tensor (float64 interface: cast down; autograd casts the gradient up)."""
+        return t if (t is None or t.dtype == torch.float32) else t.float()
+
+    def _out(self, t):
+        return t if (t is None or t.dtype == self.dtype) else t.to(self.dtype)
 
     @staticmethod
     def _expand(t, B):
@@ -438,15 +452,15 @@ class SMPL(_BodyModelBase):
         be = self._default(betas, "betas", self.batch_size, self.num_betas, dev)
         tr = transl if transl is not None else getattr(self, "transl", None)
         B = max(go.shape[0], bp.shape[0], be.shape[0])
-        pose = torch.cat([self._expand(go, B), self._expand(bp, B)], dim=1)
+        pose = self._f32(torch.cat([self._expand(go, B), self._expand(bp, B)], dim=1))
         if tr is not None:
-            tr = self._expand(tr, B)
+            tr = self._f32(self._expand(tr, B))
         return self.device_model(dev), go, bp, be, tr, pose
 
     def vertex_l2(self, target, scale=1.0, betas=None, body_pose=None, global_orient=None, transl=None, reduce="none"):
         """Per-body scale * sum ||vertices - target||^2 as one autograd node (see fit_vertex_l2)."""
         dm, go, bp, be, tr, pose = self._assemble(betas, body_pose, global_orient, transl)
-        return fit_vertex_l2(dm, be, pose, target, transl=tr, scale=scale, reduce=reduce)
+        return self._out(fit_vertex_l2(dm, self._f32(be), pose, self._f32(target), transl=tr, scale=scale, reduce=reduce))
 
     def forward(self, betas=None, body_pose=None, global_orient=None, transl=None,
                 return_verts=True, return_full_pose=False, pose2rot=True, **kwargs):
@@ -454,11 +468,11 @@ class SMPL(_BodyModelBase):
             raise NotImplementedError("pose2rot=False (rotation-matrix input) is not supported")
         dm, go, bp, be, tr, pose = self._assemble(betas, body_pose, global_orient, transl)
         verts, joints, jreg, full_pose = body_model_apply(
-            dm, be, pose, transl=tr, want_regressed=self._regressor_extra is not None, want_verts=return_verts)
+            dm, self._f32(be), pose, transl=tr, want_regressed=self._regressor_extra is not None, want_verts=return_verts)
         self._verts_cache = None if verts is None else verts.detach()   # never keeps the autograd graph alive
         joints = self._finish(verts, joints, jreg, tr)
-        return ModelOutput(vertices=verts if return_verts else None, joints=joints,
-                           full_pose=full_pose if return_full_pose else None, betas=be,
+        return ModelOutput(vertices=self._out(verts) if return_verts else None, joints=self._out(joints),
+                           full_pose=self._out(full_pose) if return_full_pose else None, betas=be,
                            global_orient=go, body_pose=bp)
 
 
@@ -518,16 +532,16 @@ class SMPLH(_BodyModelBase):
         go_e, bp_e = self._expand(go, B), self._expand(bp, B)
         lh_e, rh_e = self._expand(lh, B), self._expand(rh, B)
         if tr is not None:
-            tr = self._expand(tr, B)
+            tr = self._f32(self._expand(tr, B))
         dm = self.device_model(dev)
         if self.use_pca:
             pad = self._pad_cache.get((B, str(dev)))
             if pad is None:       # hand slots of the axis-angle row (filled from the PCA coefficients in the kernel)
                 pad = self._pad_cache[(B, str(dev))] = torch.zeros(B, 90, dtype=torch.float32, device=dev)
-            pose = torch.cat([go_e, bp_e, pad], dim=1)
-            pca_l, pca_r = lh_e, rh_e
+            pose = torch.cat([self._f32(go_e), self._f32(bp_e), pad], dim=1)
+            pca_l, pca_r = self._f32(lh_e), self._f32(rh_e)
         else:
-            pose = torch.cat([go_e, bp_e, lh_e, rh_e], dim=1)
+            pose = self._f32(torch.cat([go_e, bp_e, lh_e, rh_e], dim=1))
             pca_l = pca_r = None
         return dm, go, bp, be, lh, rh, tr, pose, pca_l, pca_r, (go_e, bp_e, lh_e, rh_e)
 
@@ -536,8 +550,8 @@ class SMPLH(_BodyModelBase):
         """Per-body scale * sum ||vertices - target||^2 as one autograd node (see fit_vertex_l2)."""
         dm, _, _, be, _, _, tr, pose, pca_l, pca_r, _ = self._assemble(
             betas, global_orient, body_pose, left_hand_pose, right_hand_pose, transl)
-        return fit_vertex_l2(dm, be, pose, target, pca_l=pca_l, pca_r=pca_r, transl=tr, add_pose_mean=True,
-                             scale=scale, reduce=reduce)
+        return self._out(fit_vertex_l2(dm, self._f32(be), pose, self._f32(target), pca_l=pca_l, pca_r=pca_r, transl=tr,
+                                       add_pose_mean=True, scale=scale, reduce=reduce))
 
     def forward(self, betas=None, global_orient=None, body_pose=None, left_hand_pose=None,
                 right_hand_pose=None, transl=None, return_verts=True, return_full_pose=False,
@@ -547,7 +561,7 @@ class SMPLH(_BodyModelBase):
         dm, go, bp, be, lh, rh, tr, pose, pca_l, pca_r, (go_e, bp_e, lh_e, rh_e) = self._assemble(
             betas, global_orient, body_pose, left_hand_pose, right_hand_pose, transl)
         verts, joints, jreg, full_pose = body_model_apply(
-            dm, be, pose, pca_l=pca_l, pca_r=pca_r, transl=tr, add_pose_mean=True,
+            dm, self._f32(be), pose, pca_l=pca_l, pca_r=pca_r, transl=tr, add_pose_mean=True,
             want_regressed=self._regressor_extra is not None, want_verts=return_verts)
         self._verts_cache = None if verts is None else verts.detach()   # never keeps the autograd graph alive
         joints = self._finish(verts, joints, jreg, tr)
@@ -556,10 +570,10 @@ class SMPLH(_BodyModelBase):
         if self.use_pca:
             # upstream returns the PROJECTED 45-D hand poses (einsum with the components, before the mean
             # is added); here they are the hand slots of full_pose minus the mean, one kernel for both hands
-            hands = full_pose[:, 66:156] - self.pose_mean[66:156]
+            hands = self._out(full_pose[:, 66:156]) - self.pose_mean[66:156]
             lh, rh = hands[:, :45], hands[:, 45:]
-        return ModelOutput(vertices=verts if return_verts else None, joints=joints,
-                           full_pose=full_pose if return_full_pose else None, betas=be,
+        return ModelOutput(vertices=self._out(verts) if return_verts else None, joints=self._out(joints),
+                           full_pose=self._out(full_pose) if return_full_pose else None, betas=be,
                            global_orient=go, body_pose=bp, left_hand_pose=lh, right_hand_pose=rh)
 
 

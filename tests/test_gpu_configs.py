@@ -187,3 +187,36 @@ def test_config5_full_100k_frame_amass_sequence(dev, golden_dir):
     last = (N // n0 - 1) * n0
     for off in (n0, 57 * n0, last):
         assert float((v[off:off + n0] - v[:n0]).abs().max()) <= 1e-6
+
+
+def test_float64_interface_and_wrapper_attributes(dev, smplh_model):
+    """lib/gen_smplh.py:66-67 may ask for float64: parameters, buffers, outputs and gradients carry it, the
+    kernels compute in float32 (error bar unchanged: 1e-5 m / 1e-4 relative).  models/smplh.py:18-20 attributes:
+    verts_numpy (template until the first forward), weigths, seg_index."""
+    m = smplh_model
+    B = 130
+    mod = SMPLH(model=m, use_pca=True, num_pca_comps=12, batch_size=B, create_transl=True, dtype=torch.float64).to(dev)
+    assert mod.betas.dtype == torch.float64 and mod.v_template.dtype == torch.float64
+    assert np.array_equal(mod.verts_numpy, np.asarray(m["v_template"])) and mod.weigths.shape == (6890, 52)
+    assert mod.seg_index == {}
+    rng = np.random.default_rng(8)
+    vals = dict(betas=rng.standard_normal((B, 16)), global_orient=rng.standard_normal((B, 3)) * 0.3,
+                body_pose=rng.standard_normal((B, 63)) * 0.3, left_hand_pose=rng.standard_normal((B, 12)),
+                right_hand_pose=rng.standard_normal((B, 12)), transl=rng.standard_normal((B, 3)))
+    mod.reset_params(**vals)
+    out = mod(return_verts=True, return_full_pose=True)
+    assert out.vertices.dtype == torch.float64 and out.joints.dtype == torch.float64 and out.full_pose.dtype == torch.float64
+    ((out.vertices ** 2).sum() + (out.joints ** 2).sum()).backward()
+    assert mod.body_pose.grad.dtype == torch.float64
+    assert mod.verts_numpy.shape == (6890, 3) and np.allclose(mod.verts_numpy, out.vertices[0].detach().cpu().numpy())
+    om = O.TorchOracleModel(m, dtype=torch.float64, num_pca_comps=12)
+    t = {k: torch.tensor(v, requires_grad=True) for k, v in vals.items()}
+    ref = om.forward(t["betas"], t["global_orient"], t["body_pose"], t["left_hand_pose"], t["right_hand_pose"],
+                     transl=t["transl"])
+    ((ref.vertices ** 2).sum() + (ref.joints ** 2).sum()).backward()
+    assert float((out.vertices.detach().cpu() - ref.vertices.detach()).abs().max()) <= TOL
+    for name in ("betas", "body_pose", "left_hand_pose", "transl"):
+        g, r = getattr(mod, name).grad.cpu(), t[name].grad
+        assert float((g - r).abs().max() / r.abs().max()) <= GRAD_RTOL, name
+    loss = mod.vertex_l2(torch.zeros(B, 6890, 3, dtype=torch.float64, device=dev), reduce="sum")
+    assert loss.dtype == torch.float64 and abs(float(loss) / float((ref.vertices.detach() ** 2).sum()) - 1) <= 1e-5
