@@ -169,3 +169,26 @@ def test_twin_rejects_wrong_widths():
         tw.forward_batch(np.zeros((4, 156)), trans=np.zeros((3, 3)))
     with pytest.raises(ValueError):
         tw.set_params(pose=np.zeros((24, 3)))
+
+
+def test_recover_model_twin_exposes_compute_R_G_and_do_skinning():
+    """lib/model2video.py:55-81: the rigged-mesh twin's two halves of update() and the attributes they leave."""
+    rig = synthetic.make_rigged_mesh(3001, seed=9)
+    rm = smplk.RecoverModel(rig)
+    rng = np.random.default_rng(3)
+    pose = rng.standard_normal((24, 3)) * 0.4
+    trans = rng.standard_normal(3)
+    v = rm.set_params(pose=pose.copy(), trans=trans.copy()).copy()
+    pose[[13, 14, 22, 23]] = 0.0                                   # set_params zeroes these joints (:44-45)
+    ref = O.np_lbs_only(rig, pose, trans, ignore_joints=())
+    assert np.abs(v - ref["verts"]).max() <= 1e-5
+    G = rm.compute_R_G()
+    assert G.shape == (24, 4, 4) and np.abs(G - ref["G"]).max() <= 1e-5
+    assert np.abs(rm.R - O.np_rodrigues(pose)).max() <= 2e-6
+    assert np.array_equal(rm.J, np.asarray(rig["J"]))              # fixed rest joints of the rig
+    rm.do_skinning(G)
+    assert np.abs(rm.verts - ref["verts"]).max() <= 1e-5
+    G2 = G.copy()
+    G2[:, :3, 3] += 0.25                                           # an edited G moves every vertex by the same offset
+    rm.do_skinning(G2)
+    assert np.abs(rm.verts - (ref["verts"] + 0.25)).max() <= 1e-5

@@ -1,0 +1,30 @@
+#!/bin/bash
+# Reproduces the round-2 evidence under profiles/ on a B200 box (run through gpurun; everything lands in gpurun_out/):
+#   gpurun --timeout 1800 -- 'bash tools/gpu_evidence.sh'
+# then, here:  python tools/ncu_summary.py gpurun_out/r02_fused.ncu-rep   (etc.; see profiles/README.md)
+set -x
+python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log
+python tools/hbm_probe.py 4 > gpurun_out/r02_hbm_probe.json
+python bench.py --steps 30 --warmup 5 > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err
+python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r02_bench_ref.json 2> gpurun_out/r02_bench_ref.err
+# launch lists (cold-cache, serialised: compare shares) -- each only after the plain run exited 0
+python bench.py --steps 30 --warmup 5 --no-extras > gpurun_out/plain_bench.log 2>&1 && \
+  ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_bench.csv \
+      python bench.py --steps 30 --warmup 5 --no-extras > gpurun_out/ncu_bench.log 2>&1
+for t in fused twokernel fit lbs; do
+  python tools/ncu_targets.py $t > gpurun_out/plain_$t.log 2>&1 && \
+  ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_$t.csv \
+      python tools/ncu_targets.py $t > gpurun_out/ncu_l_$t.log 2>&1
+done
+# one --set full capture per kernel family
+cap() {  # name, target args, kernel regex, skip, count
+  python tools/ncu_targets.py $2 > gpurun_out/plain_cap_$1.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:"$3" -s $4 -c $5 -o gpurun_out/r02_$1 \
+      python tools/ncu_targets.py $2 > gpurun_out/ncu_f_$1.log 2>&1
+}
+cap fused fused blend_skin_fused 1 1
+cap twokernel twokernel 'skin_grouped|blend_tcgen05' 2 2
+cap fit fit 'dA_seg|skin_fit_l2|pose_' 4 4
+cap lbs lbs skin_ 1 1
+cap lbs200k "lbs 200000" skin_ 1 1
