@@ -89,7 +89,8 @@ class ClockSampler:
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "sm_mhz_min": float(min(self.samples)),
+                "note": "sampled through NVML during the timed steps and an untimed continuation of the same steps"}
 
 
 def _host_threads():
@@ -357,8 +358,16 @@ def main():
             step(i)
         e1.record(stream)
         barrier()
+        launches = _lib.launch_count() - launches0
+        n_timed = len(clocks.samples)
+        # the timed region lasts a few milliseconds, an NVML query about one: keep the same step running (untimed)
+        # until the sampler has seen the clocks UNDER THIS LOAD at least 20 times
+        t_probe = time.perf_counter()
+        while len(clocks.samples) < n_timed + 20 and time.perf_counter() - t_probe < 2.0:
+            for i in range(20):
+                step(i)
+            torch.cuda.synchronize(dev)
     ms_local = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - launches0
     ms = ms_local
     if world > 1:
         t = torch.tensor([ms_local], device=dev, dtype=torch.float64)
