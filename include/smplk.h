@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SMPLK_VERSION 1
+#define SMPLK_VERSION 2   /* 2: + smplk_skin_transforms, smplk_remove_rest (round 2) */
 
 #define SMPLK_OK 0
 #define SMPLK_E_ARG (-1)       /* null / inconsistent argument */

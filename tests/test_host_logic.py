@@ -21,7 +21,7 @@ def test_library_builds_and_exports_every_header_symbol():
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.smplk_version() == 1
+    assert lib.smplk_version() == 2
 
 
 def test_header_is_plain_c():
