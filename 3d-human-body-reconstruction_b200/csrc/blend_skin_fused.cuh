@@ -52,6 +52,9 @@ namespace smplk {
 #ifndef SMPLK_FZ_EPI_BACKOFF_NS
 #define SMPLK_FZ_EPI_BACKOFF_NS 20
 #endif
+#ifndef SMPLK_FZ_PROBE_NO_EPILOGUE
+#define SMPLK_FZ_PROBE_NO_EPILOGUE 0
+#endif
 #ifndef SMPLK_FZ_ROW_BYTES
 #define SMPLK_FZ_ROW_BYTES 64
 #endif
@@ -417,6 +420,14 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
       ptx::mbar_wait_backoff(&tmem_full[acc], acc_phase, SMPLK_FZ_EPI_BACKOFF_NS);
       ptx::tcgen05_fence_after();
       FZ_STAMP(dbg_on, &args.dbg[(warp * kFzDbgTiles + it) * 4 + 1]);
+#if SMPLK_FZ_PROBE_NO_EPILOGUE
+      // measurement probe (never in the product build): hand the accumulator straight back, so the kernel's time is
+      // the TMA + MMA pipeline of THIS configuration alone (64-byte operand rows x 4 stages); the output is garbage
+      ptx::cp_async_wait<0>();
+      ptx::tcgen05_fence_before();
+      ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);
+      continue;
+#endif
 
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; ++c) {
