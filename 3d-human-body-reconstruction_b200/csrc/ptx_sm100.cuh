@@ -358,9 +358,11 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
 }
 
 // ------------------------------------------------------------------ packed fp32x2 (FFMA2)
-// sm_100 executes fma.rn.f32x2 as one FFMA2: two fp32 FMAs per lane per instruction (a 3-register
-// FFMA issues every other cycle per scheduler, so this doubles the FP32 FMA rate); a {x, x} operand
-// becomes a scalar-broadcast source, no extra move.
+// sm_100 executes fma.rn.f32x2 as one FFMA2: two fp32 FMAs per lane per instruction.  Measured on B200
+// (tools/micro/ffma2_probe.cu, profiles/r02_ffma2_microbench.txt): an FFMA2 holds the FP32 pipe for 2 cycles, an FFMA
+// for 1 -- the same 32 FMA lanes per cycle per scheduler -- so it halves the instruction count (the freed issue slots
+// go to the loads around it), not the pipe time; dependent latency ~4.2 cycles for both.  A {x, x} operand becomes a
+// scalar-broadcast source, no extra move.
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
