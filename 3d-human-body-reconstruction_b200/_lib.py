@@ -116,7 +116,7 @@ EXPORTED_SYMBOLS = [
     "smplk_batch_rodrigues", "smplk_forward_host", "smplk_last_error_string", "smplk_version",
     "smplk_launch_count", "smplk_workspace_layout", "smplk_profile_enable", "smplk_profile_read", "smplk_vertex_l2",
     "smplk_inverse_lbs", "smplk_inverse_joints", "smplk_vertex_normals", "smplk_divide_faces",
-    "smplk_reprojection_loss", "smplk_fit_priors", "smplk_fit_vertex_l2", "smplk_skin_transforms", "smplk_remove_rest",
+    "smplk_reprojection_loss", "smplk_fit_priors", "smplk_fit_vertex_l2", "smplk_skin_transforms", "smplk_remove_rest", "smplk_model_set_option",
 ]
 PROF_SLOTS = ["pose_fwd", "blend_tcgen05", "blend_simt", "skin", "dA", "skin_bwd", "blend_bwd",
               "pose_bwd", "blend_skin_fused", "transpose"]
@@ -209,6 +209,8 @@ def load():
     lib.smplk_fit_vertex_l2.restype = ctypes.c_int
     lib.smplk_skin_transforms.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]
     lib.smplk_skin_transforms.restype = ctypes.c_int
+    lib.smplk_model_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int]
+    lib.smplk_model_set_option.restype = ctypes.c_int
     lib.smplk_remove_rest.argtypes = [i32, i32, vp, vp, vp, ctypes.c_int, vp]
     lib.smplk_remove_rest.restype = ctypes.c_int
     lib.smplk_profile_enable.argtypes = [ctypes.c_void_p, ctypes.c_int]
@@ -256,7 +258,7 @@ class DeviceModel:
     """Owns one `smplk_model*` (packed constants on one GPU)."""
 
     def __init__(self, model, device=0, num_betas=None, num_pca_comps=0, flat_hand_mean=False,
-                 regressor_posed=None, extra_vertex_ids=None, lbs_only=False):
+                 regressor_posed=None, extra_vertex_ids=None, lbs_only=False, options=None):
         lib = load()
         self._lib = lib
         self.handle = ctypes.c_void_p()
@@ -318,6 +320,13 @@ class DeviceModel:
         self.E, self.R, self.C = info.num_extra_verts, info.num_regressors, info.num_pca
         self.device = int(device)
         self.parents = parents
+        for name, value in (options or {}).items():
+            self.set_option(name, value)
+
+    def set_option(self, name, value):
+        """Kernel choice of this handle (smplk_model_set_option): 'fused', 'pose_block', 'blend_tf32',
+        'backward_tf32', 'gemm_2cta', 'fit_fused', 'sparse_picks'."""
+        check(self._lib.smplk_model_set_option(self.handle, name.encode(), int(value)))
 
     def __del__(self):
         try:

@@ -110,25 +110,25 @@ struct smplk_model {
   CUtensorMap tmap2_pd_hi, tmap2_pd_lo, tmap2_pdh_hi, tmap2_pdh_lo, tmap2_pdkn_hi, tmap2_pdkn_lo;
   bool use_2cta;
   CUtensorMap tmapf_pdh_hi, tmapf_pdh_lo;  // fused blend+skinning kernel: 84-vertex column tiles
-  bool use_fused;       // SMPLK_FUSED=0 in the environment selects the two-kernel forward (A/B runs)
-  bool use_pose_block;  // SMPLK_POSE_V1=1 selects the warp-per-body pose kernel + transposition pass
+  bool use_fused;       // option fused = 0 selects the two-kernel forward (cross-checks, stand-alone kernel timings)
+  bool use_pose_block;  // option pose_block = 0 selects the warp-per-body pose kernel + transposition pass
   CUtensorMap tmap_pdkn_hi, tmap_pdkn_lo;  // backward: B operand rows = blend features
   CUtensorMap tmap_pdknh_hi, tmap_pdknh_lo, tmap2_pdknh_hi, tmap2_pdknh_lo;   // same, fp16 two-term split
   CUtensorMap tmap_pdknb_hi, tmap_pdknb_lo, tmap2_pdknb_hi, tmap2_pdknb_lo;   // same, bf16 two-term split
-  bool bwd_f16;         // backward GEMM on fp16-split operands (SMPLK_BWD_TF32=1 keeps 3xTF32)
+  bool bwd_f16;         // backward GEMM on fp16-split operands (option backward_tf32 keeps 3xTF32)
   // host staging for smplk_forward_host
   void* stage_dev;
   size_t stage_bytes;
   cudaStream_t copy_stream;                 // device->host copies of smplk_forward_host
   std::vector<cudaEvent_t> chunk_events;    // one per chunk of that call
   // optional per-kernel device timing (smplk_profile_*)
-  BlendPath default_tc;  // BLEND_F16 unless SMPLK_BLEND=tf32 in the environment
+  BlendPath default_tc;  // BLEND_F16 unless the option blend_tf32 is set
   int skin_bpb;         // SMPLK_SKIN_BPB: override bodies per block (tuning)
   bool skin_g8;         // 8 vertices per thread (default; SMPLK_SKIN_G8=0 selects the 4-vertex kernel)
   bool skin_tma;        // SMPLK_SKIN_TMA=1: per-warp cp.async.bulk pipeline (measured slower: 0.210 vs 0.182 ms)
   bool force_skin_v1;   // SMPLK_SKIN_V1=1 in the environment: per-vertex gather kernel (A/B testing)
-  bool sparse_picks;    // SMPLK_SPARSE_PICKS=0: keypoint-only gradients take the dense backward (A/B testing)
-  bool fit_fused;       // fused skinning + loss + skinning-backward kernel of smplk_fit_vertex_l2 (SMPLK_FIT_FUSED=0: off)
+  bool sparse_picks;    // option sparse_picks = 0: keypoint-only gradients take the dense backward (cross-check)
+  bool fit_fused;       // fused skinning + loss + skinning-backward kernel of smplk_fit_vertex_l2 (option fit_fused = 0: off)
   bool da_v1;           // SMPLK_DA_V1=1 (A/B builds): the fitting step's dA through dA_kernel instead of dA_seg_kernel
   mutable bool prof_on;
   mutable std::vector<ProfRec> prof_pending;
@@ -831,21 +831,18 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   mdl->copy_stream = nullptr;
   mdl->encode = nullptr;
   mdl->prof_on = false;
+  // kernel choices: defaults are the product path; smplk_model_set_option changes them per handle (cross-checks of the
+  // parity tests, stand-alone kernel timings of the bench).  The product library reads NO environment variable.
   mdl->skin_bpb = 0; mdl->skin_g8 = true; mdl->skin_tma = false; mdl->force_skin_v1 = false; mdl->da_v1 = false;
-#ifdef SMPLK_AB   // tuning switches of kernels that are not on a default path
+  mdl->fit_fused = true; mdl->sparse_picks = true; mdl->use_2cta = true; mdl->use_fused = true;
+  mdl->use_pose_block = true; mdl->bwd_f16 = true; mdl->default_tc = BLEND_F16;
+#ifdef SMPLK_AB   // A/B builds (tools/): tuning switches of kernels that are on no default path
   { const char* e = getenv("SMPLK_DA_V1"); mdl->da_v1 = e && e[0] == '1'; }
   { const char* e = getenv("SMPLK_SKIN_BPB"); mdl->skin_bpb = e ? atoi(e) : 0; }
   { const char* e = getenv("SMPLK_SKIN_G8"); mdl->skin_g8 = !(e && e[0] == '0'); }
   { const char* e = getenv("SMPLK_SKIN_TMA"); mdl->skin_tma = (e && e[0] == '1'); }
   { const char* e = getenv("SMPLK_SKIN_V1"); mdl->force_skin_v1 = e && e[0] == '1'; }
 #endif
-  { const char* e = getenv("SMPLK_FIT_FUSED"); mdl->fit_fused = !(e && e[0] == '0'); }
-  { const char* e = getenv("SMPLK_SPARSE_PICKS"); mdl->sparse_picks = !(e && e[0] == '0'); }
-  { const char* e = getenv("SMPLK_GEMM_1CTA"); mdl->use_2cta = !(e && e[0] == '1'); }
-  { const char* e = getenv("SMPLK_FUSED"); mdl->use_fused = !(e && e[0] == '0'); }
-  { const char* e = getenv("SMPLK_POSE_V1"); mdl->use_pose_block = !(e && e[0] == '1'); }
-  { const char* e = getenv("SMPLK_BWD_TF32"); mdl->bwd_f16 = !(e && e[0] == '1'); }
-  { const char* e = getenv("SMPLK_BLEND"); mdl->default_tc = (e && strcmp(e, "tf32") == 0) ? BLEND_TF32 : BLEND_F16; }
   for (int i = 0; i < SMPLK_PROF_SLOTS; ++i) { mdl->prof_ms[i] = 0.0; mdl->prof_n[i] = 0; }
   if (prop.major != 10) {
     delete mdl;
@@ -858,6 +855,20 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
     return r;
   }
   *out = mdl;
+  return 0;
+}
+
+extern "C" int smplk_model_set_option(smplk_model* model, const char* name, int value) {
+  if (!model || !name) return fail(SMPLK_E_ARG, "null argument");
+  const bool on = value != 0;
+  if (!strcmp(name, "fused")) model->use_fused = on;                    // fused blend + skinning forward kernel
+  else if (!strcmp(name, "pose_block")) model->use_pose_block = on;     // block-level pose kernel (else warp per body)
+  else if (!strcmp(name, "blend_tf32")) model->default_tc = on ? BLEND_TF32 : BLEND_F16;   // 3xTF32 forward operands
+  else if (!strcmp(name, "backward_tf32")) model->bwd_f16 = !on;        // 3xTF32 backward GEMM
+  else if (!strcmp(name, "gemm_2cta")) model->use_2cta = on;            // CTA-pair GEMM kernels
+  else if (!strcmp(name, "fit_fused")) model->fit_fused = on;           // one-kernel skinning + loss + skinning backward
+  else if (!strcmp(name, "sparse_picks")) model->sparse_picks = on;     // sparse backward of joints-only losses
+  else return fail(SMPLK_E_ARG, "unknown option '%s'", name);
   return 0;
 }
 

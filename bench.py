@@ -318,7 +318,8 @@ def main():
 
     B = args.batch
     model = synthetic.make_model("smplh", seed=0)
-    dm = smplk.DeviceModel(model, device=local)
+    # SMPLK_BLEND=tf32 in the bench's environment runs the whole line on 3xTF32 operands (handle option blend_tf32)
+    dm = smplk.DeviceModel(model, device=local, options={"blend_tf32": 1} if os.environ.get("SMPLK_BLEND") == "tf32" else None)
     # NSETS rotating input sets; the per-step output (339 MB of vertices) already exceeds the 126 MB L2
     sets = []
     for s in range(NSETS):
@@ -448,11 +449,9 @@ def main():
             extras["roofline"] = tensor_roofline("blend_tcgen05_2cta_kernel<%s>" % ("f16" if fmt != "tf32" else "tf32"),
                                                  kern["blend_tcgen05"], 20736)
         # the stand-alone kernels (forward with SAVE_FOR_BACKWARD, LBS-only models, dense weights):
-        # timed through a second handle created with SMPLK_FUSED=0
+        # timed through a second handle created with the option fused=0
         if "blend_skin_fused" in kern and rank == 0:
-            os.environ["SMPLK_FUSED"] = "0"
-            dm_u = smplk.DeviceModel(model, device=local)
-            del os.environ["SMPLK_FUSED"]
+            dm_u = smplk.DeviceModel(model, device=local, options={"fused": 0})
             dm_u.profile_enable(True)
             for i in range(20):
                 b_, p_, t_ = sets[i % NSETS]
@@ -477,7 +476,7 @@ def main():
         if "skin" in kern:
             s_ms = kern["skin"]
             gbs = FWD_BYTES_SKIN * B / (s_ms * 1e-3) / 1e9
-            extras["roofline_skinning"] = {"kernel": "skin_grouped_kernel (two-kernel forward: SAVE_FOR_BACKWARD / SMPLK_FUSED=0)",
+            extras["roofline_skinning"] = {"kernel": "skin_grouped_kernel (two-kernel forward: SAVE_FOR_BACKWARD / handle option fused=0)",
                                            "bound": "hbm", "achieved": gbs,
                                            "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                                            "traffic": None, "ms_per_launch": s_ms,
@@ -667,9 +666,7 @@ def main():
         # ---- the operand format north_star names (3xTF32) next to the fp16 two-term default
         if rank == 0:
             try:
-                os.environ["SMPLK_BLEND"] = "tf32"
-                dm_t = smplk.DeviceModel(model, device=local)
-                del os.environ["SMPLK_BLEND"]
+                dm_t = smplk.DeviceModel(model, device=local, options={"blend_tf32": 1})
                 wst = torch.empty(dm_t.workspace_bytes(B, 0), device=dev, dtype=torch.uint8)
                 dm_t.profile_enable(True)
                 for i in range(10):
@@ -682,11 +679,10 @@ def main():
                     "kernel_ms": pt, "forward_ms": sum(pt.values()),
                     "blend_gemm_tflops_fp32_equiv": (GEMM_FLOPS_PER_BODY * B / (g_ms * 1e-3) / 1e12) if g_ms else None,
                     "frac_of_tf32_ceiling": (GEMM_FLOPS_PER_BODY * B / (g_ms * 1e-3) / 1e12) / ((tf32_peak or peaks["bf16"] / 2) / 3.0) if g_ms else None,
-                    "note": "SMPLK_BLEND=tf32: 3xTF32 blend GEMM (tcgen05 kind::tf32) + skinning kernel, same batch; the default is "
+                    "note": "handle option blend_tf32: 3xTF32 blend GEMM (tcgen05 kind::tf32) + skinning kernel, same batch; the default is "
                             "the fp16 hi+lo split fused with the skinning epilogue (equal 11+11 mantissa bits, half the tensor time)"}
                 del dm_t, wst
             except Exception as e:
-                os.environ.pop("SMPLK_BLEND", None)
                 sys.stderr.write("tf32 variant skipped: %r\n" % (e,))
 
         # ---- BASELINE config 4: one point of the batch sweep, 64K bodies on this GPU (vertices of the whole

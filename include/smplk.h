@@ -85,6 +85,18 @@ typedef struct {
 } smplk_model_info;
 int smplk_model_get_info(const smplk_model* model, smplk_model_info* info);
 
+/* Kernel choices of one handle (the defaults are the product path; the library reads no environment variable).
+ * Used by the parity tests to cross-check alternative kernels and by the bench to time stand-alone kernels:
+ *   "fused" (1)          fused blend GEMM + skinning forward kernel; 0 = blend GEMM, then skinning kernel
+ *   "pose_block" (1)     block-level pose kernel; 0 = warp-per-body kernel + transposition pass
+ *   "blend_tf32" (0)     1 = 3xTF32 operands in the forward GEMM instead of the fp16 two-term split
+ *   "backward_tf32" (0)  1 = 3xTF32 backward GEMM
+ *   "gemm_2cta" (1)      CTA-pair GEMM kernels; 0 = 1-CTA kernels
+ *   "fit_fused" (1)      smplk_fit_vertex_l2 as one skinning + loss + skinning-backward kernel
+ *   "sparse_picks" (1)   joints-only gradients through the sparse pick kernels; 0 = dense vertex backward
+ * Set options before the first forward that they affect; unknown names return SMPLK_E_ARG. */
+int smplk_model_set_option(smplk_model* model, const char* name, int value);
+
 #define SMPLK_FLAG_SAVE_FOR_BACKWARD 1u /* keep v_posed & transforms of ALL bodies in the workspace */
 #define SMPLK_FLAG_ADD_POSE_MEAN 2u     /* full_pose += pose_mean (flat_hand_mean=False upstream)   */
 #define SMPLK_FLAG_BLEND_SIMT 4u        /* force the exact-fp32 SIMT blend kernel (small batch / bring-up) */

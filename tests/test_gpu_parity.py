@@ -107,16 +107,14 @@ def test_blend_operand_formats_agree(dev, smplh_model):
 @pytest.mark.parametrize("B", [129, 257, 300, 1000, 2049])
 def test_fused_blend_skinning_matches_two_kernel_path_and_oracle(dev, smplh_model, B, monkeypatch):
     """The forward without SAVE_FOR_BACKWARD runs the fused kernel (blend GEMM whose epilogue skins
-    straight from TMEM); SMPLK_FUSED=0 selects blend GEMM -> v_posed -> skinning kernel.  Ragged
+    straight from TMEM); the handle option fused=0 selects blend GEMM -> v_posed -> skinning kernel.  Ragged
     batches exercise partial 256-body blocks and the last 85-vertex tile (5 vertices)."""
     m = smplh_model
     betas, pose, transl = synthetic.make_inputs(m, B, seed=100 + B)
     pose[0] = 0.0
     pose[B - 1] = pose[B - 1] / np.abs(pose[B - 1]).max() * 4.8
     dm_f = smplk.DeviceModel(m, device=0, extra_vertex_ids=m["extra_vertex_ids"])
-    monkeypatch.setenv("SMPLK_FUSED", "0")
-    dm_u = smplk.DeviceModel(m, device=0, extra_vertex_ids=m["extra_vertex_ids"])
-    monkeypatch.delenv("SMPLK_FUSED")
+    dm_u = smplk.DeviceModel(m, device=0, extra_vertex_ids=m["extra_vertex_ids"], options={"fused": 0})
     args = (_t(betas, dev), _t(pose, dev))
     dm_f.profile_enable(True)
     vf, jf, _, _ = body_model_apply(dm_f, *args, transl=_t(transl, dev))
@@ -160,9 +158,7 @@ def test_fused_forward_is_deterministic_and_agrees_with_two_kernel_path_on_rando
     8192-body chunks; outputs are pre-filled with NaN to expose unwritten elements."""
     m = smplh_model
     dm_f = smplk.DeviceModel(m, device=0)
-    monkeypatch.setenv("SMPLK_FUSED", "0")
-    dm_u = smplk.DeviceModel(m, device=0)
-    monkeypatch.delenv("SMPLK_FUSED")
+    dm_u = smplk.DeviceModel(m, device=0, options={"fused": 0})
     rng = np.random.default_rng(77)
     sizes = [129, 255, 256, 288, 1023, 4097, 8192 + 130] + [int(x) for x in rng.integers(130, 3000, size=4)]
     for B in sizes:
@@ -448,7 +444,7 @@ def test_backward_matches_autograd_oracle(dev, kind, B, pca, joint_w):
 def test_keypoint_only_backward_takes_the_sparse_path_and_matches_oracle(dev, kind, B, pca, monkeypatch):
     """A loss on joints alone (FK joints + vertex picks: the data term of lib/Gen_SMPLH/fitting.py:369-381)
     runs the sparse pick kernel instead of the dense vertex backward: same gradients as the float64
-    autograd oracle and as the dense path (SMPLK_SPARSE_PICKS=0), fewer launches."""
+    autograd oracle and as the dense path (handle option sparse_picks=0), fewer launches."""
     from smplk import _lib
     m = synthetic.make_model(kind, seed=17)
     J = 52 if kind == "smplh" else 24
@@ -476,9 +472,8 @@ def test_keypoint_only_backward_takes_the_sparse_path_and_matches_oracle(dev, ki
 
     results = {}
     for mode in ("sparse", "dense"):
-        if mode == "dense":
-            monkeypatch.setenv("SMPLK_SPARSE_PICKS", "0")
-        dm = smplk.DeviceModel(m, device=0, num_pca_comps=12 if pca else 0, extra_vertex_ids=m["extra_vertex_ids"])
+        dm = smplk.DeviceModel(m, device=0, num_pca_comps=12 if pca else 0, extra_vertex_ids=m["extra_vertex_ids"],
+                               options={"sparse_picks": 0} if mode == "dense" else None)
         gb, gp, gt = (_t(x, dev, True) for x in (betas, pose, transl))
         gl, gr = (_t(x, dev, True) for x in (lh, rh))
         v, j, _, _ = body_model_apply(dm, gb, gp, pca_l=gl if pca else None, pca_r=gr if pca else None, transl=gt,

@@ -14,6 +14,8 @@ dev = "cuda:0"
 m = synthetic.make_model("smplh", seed=0)
 for B in [int(x) for x in sys.argv[1:]] or [1, 64, 1024]:
     mod = SMPLH(model=m, use_pca=True, num_pca_comps=12, batch_size=B).to(dev)
+    if os.environ.get("SMPLK_SPARSE_PICKS") == "0":      # dense vertex backward for joints-only losses (handle option)
+        mod._dm_kwargs["options"] = {"sparse_picks": 0}
     cam = PerspectiveCamera(translation=np.tile([[0.0, 0.0, 10.0]], (B, 1)), batch_size=B,
                             center=np.tile([[512.0, 512.0]], (B, 1)))
     cam.translation.requires_grad_(False)
