@@ -708,11 +708,15 @@ struct PoseBwdArgs {
   const float* d_loss;       // (B) or null: scale of body b's parameter gradients
   int d_loss_stride;         // 1, or 0 when d_loss is one float for all bodies
   const float* d_full_pose;  // (B,3J) or null: gradient w.r.t. the assembled pose output
+  int staged_segs;           // seg_count when dAp is staged in shared memory (the launch sized it), else 0
 };
 
 // smem floats per warp of pose_backward_kernel: world G, local L, dG (12 each), dR (9), dJ, dfull (3 each)
 // + the summed blend-GEMM gradient row (Kpad)
-__host__ __device__ inline int pose_bwd_smem_floats(int J, int Kpad) { return J * 51 + Kpad; }
+// + (segs > 0) the body's per-segment partials of dA_seg_kernel, staged by cp.async while the forward is recomputed
+__host__ __device__ inline int pose_bwd_smem_floats(int J, int Kpad, int segs) {
+  return ((J * 51 + 3) & ~3) + Kpad + segs * 12;
+}
 
 // Split-K partials of the backward blend GEMM, d_feat[sp][row][k], summed into split 0 (in place).
 // One thread per (row, k): the loads of a thread are independent and coalesced across the warp, so
@@ -751,13 +755,27 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kPoseWarps + warp;
   if (b >= a.B) return;
-  float* Gw = pb_smem + warp * pose_bwd_smem_floats(m.J, m.Kpad);   // [J][12] world transforms
+  float* Gw = pb_smem + warp * pose_bwd_smem_floats(m.J, m.Kpad, a.staged_segs);   // [J][12] world transforms
   float* Lc = Gw + m.J * 12;                                // [J][12] local [R | Jrel]
   float* dG = Lc + m.J * 12;                                // [J][12]
   float* dRs = dG + m.J * 12;                               // [J][9]
   float* dJ = dRs + m.J * 9;                                // [J][3]
   float* dfull = dJ + m.J * 3;                              // [3J]
   const float* betas_row = a.betas ? a.betas + (size_t)(a.betas_B == 1 ? 0 : b) * m.NB : nullptr;
+  // this body's gradient inputs -> smem by cp.async, in flight while the forward is recomputed: the blend GEMM's row
+  // and the per-segment partials of dA (read straight from L2 the latter were up to ~10 dependent round trips per lane)
+  float* dfeat_sum = Gw + ((m.J * 51 + 3) & ~3);
+  float* sdA = dfeat_sum + m.Kpad;
+  const bool feat_staged = a.d_feat != nullptr && a.feat_splits == 1;
+  if (feat_staged) {
+    const float* f = a.d_feat + (size_t)b * m.Kpad;
+    for (int k = 4 * lane; k < m.Kpad; k += 128) ptx::cp_async_16(dfeat_sum + k, f + k);
+  }
+  if (a.staged_segs > 0) {
+    const float* src = a.dAp + (size_t)b * m.seg_count * 12;
+    for (int i = 4 * lane; i < a.staged_segs * 12; i += 128) ptx::cp_async_16(sdA + i, src + i);
+  }
+  ptx::cp_async_commit();
 
   // ---- forward recompute (same walk as pose_forward_kernel; cheaper than saving it)
   float rv[SLOTS][3], Jr[SLOTS][3];
@@ -819,13 +837,17 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
 
   // ---- seed: A_j = [G_R | G_t - G_R J_j], joints_fk = G_t
   float dtr_acc[3] = {0.f, 0.f, 0.f};     // with dAp: sum_j dA[j][:,3] = the vertex part of d_transl (weights sum to 1 per vertex)
+  ptx::cp_async_wait<0>();
+  __syncwarp();
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
     const int j = lane + 32 * s;
     if (j < m.J) {
       float gl[12];
       if (a.dAp != nullptr) {     // per-segment partials of dA_seg_kernel: a joint's segments are adjacent, summed in order
-        const float4* p4 = reinterpret_cast<const float4*>(a.dAp + ((size_t)b * m.seg_count + m.joint_seg_ptr[j]) * 12);
+        const float4* p4 = a.staged_segs > 0
+            ? reinterpret_cast<const float4*>(sdA + m.joint_seg_ptr[j] * 12)
+            : reinterpret_cast<const float4*>(a.dAp + ((size_t)b * m.seg_count + m.joint_seg_ptr[j]) * 12);
         const int ns = m.joint_seg_ptr[j + 1] - m.joint_seg_ptr[j];
         float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0;
         for (int q = 0; q < ns; ++q) {
@@ -932,8 +954,7 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
 
   // ---- pose-feature gradient from the blend GEMM (split-K partials already summed into the first
   // split's rows by reduce_splits_kernel): stage the body's row in smem with coalesced loads
-  float* dfeat_sum = dfull + 3 * m.J;
-  if (a.d_feat != nullptr) {
+  if (a.d_feat != nullptr && !feat_staged) {
     __syncwarp();
     const float* f = a.d_feat + (size_t)b * m.Kpad;
     for (int k = lane; k < m.P + m.NB; k += 32) {

@@ -256,7 +256,10 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
   if (pb.d_betas && pb.betas_B == 1)
     CUDA_TRY(cudaMemsetAsync(a->d_betas, 0, (size_t)d.NB * sizeof(float), st));
   const int blocks = (B + kPoseWarps - 1) / kPoseWarps;
-  const size_t smem = (size_t)kPoseWarps * pose_bwd_smem_floats(d.J, d.Kpad) * sizeof(float);
+  pb.staged_segs = 0;
+  if (seg_partials && (size_t)kPoseWarps * pose_bwd_smem_floats(d.J, d.Kpad, d.seg_count) * sizeof(float) <= 96 * 1024)
+    pb.staged_segs = d.seg_count;           // two blocks per SM still fit
+  const size_t smem = (size_t)kPoseWarps * pose_bwd_smem_floats(d.J, d.Kpad, pb.staged_segs) * sizeof(float);
   { ProfScope prof(model, st, SMPLK_PROF_POSE_BWD);
   if (d.J <= 32) pose_backward_kernel<1><<<blocks, kPoseWarps * 32, smem, st>>>(d, pb);
   else pose_backward_kernel<2><<<blocks, kPoseWarps * 32, smem, st>>>(d, pb); }

@@ -438,15 +438,26 @@ pose_forward_block_kernel(const ModelDev m, const PoseFwdArgs a) {
   int* sord = reinterpret_cast<int*>(pose_smem + L.off_ord);
   int* slvl = reinterpret_cast<int*>(pose_smem + L.off_lvl);
 
-  // ---- stage the model tables
-  for (int i = threadIdx.x; i < 3 * m.J; i += blockDim.x) {
-    sJt[i] = m.J_template[i];
-    spm[i] = (a.add_mean && m.pose_mean) ? m.pose_mean[i] : 0.f;
+  // ---- stage the model tables: 4-byte cp.async, everything in flight at once (as register loads the copies were
+  // ~10 dependent L2 round trips per thread: a quarter of the kernel at 1,024 bodies)
+  {
+    const uint32_t s0 = ptx::smem_u32(pose_smem);
+    auto stage = [&](const void* dst, const void* src) {
+      ptx::cp_async_4(s0 + static_cast<uint32_t>(reinterpret_cast<const char*>(dst) - reinterpret_cast<const char*>(pose_smem)), src);
+    };
+    const bool mean = a.add_mean && m.pose_mean;
+    for (int i = threadIdx.x; i < 3 * m.J; i += blockDim.x) {
+      stage(sJt + i, m.J_template + i);
+      if (mean) stage(spm + i, m.pose_mean + i);
+      else spm[i] = 0.f;
+    }
+    for (int i = threadIdx.x; i < 3 * m.J * m.NB; i += blockDim.x) stage(sJs + (i / m.NB) * L.nbp + (i % m.NB), m.J_shapedirs + i);
+    if (a.pca_l != nullptr || a.pca_r != nullptr)
+      for (int i = threadIdx.x; i < m.C * 45; i += blockDim.x) { stage(scl + i, m.comp_l + i); stage(scr + i, m.comp_r + i); }
+    for (int i = threadIdx.x; i < m.J; i += blockDim.x) { stage(spar + i, m.parents + i); stage(sord + i, m.order + i); }
+    for (int i = threadIdx.x; i < m.max_depth + 2; i += blockDim.x) stage(slvl + i, m.level_start + i);
+    ptx::cp_async_commit();
   }
-  for (int i = threadIdx.x; i < 3 * m.J * m.NB; i += blockDim.x) sJs[(i / m.NB) * L.nbp + (i % m.NB)] = m.J_shapedirs[i];
-  for (int i = threadIdx.x; i < m.C * 45; i += blockDim.x) { scl[i] = m.comp_l[i]; scr[i] = m.comp_r[i]; }
-  for (int i = threadIdx.x; i < m.J; i += blockDim.x) { spar[i] = m.parents[i]; sord[i] = m.order[i]; }
-  for (int i = threadIdx.x; i < m.max_depth + 2; i += blockDim.x) slvl[i] = m.level_start[i];
   // ---- this body's small inputs into the warp's feature row: betas at feat[P..], PCA coefficients
   // parked at feat[0..2C) until the features overwrite them
   const float* betas_row = (a.betas && live) ? a.betas + (size_t)(a.betas_B == 1 ? 0 : b) * m.NB : nullptr;
@@ -454,6 +465,7 @@ pose_forward_block_kernel(const ModelDev m, const PoseFwdArgs a) {
   float pca_c = 0.f;                      // lane i < C: left coefficient i; lane 16 + i: right coefficient i
   if (live && a.pca_l && lane < m.C) pca_c = a.pca_l[(size_t)b * m.C + lane];
   if (live && a.pca_r && lane >= 16 && lane - 16 < m.C) pca_c = a.pca_r[(size_t)b * m.C + lane - 16];
+  ptx::cp_async_wait<0>();
   __syncthreads();
 
   const int hand0 = m.J - 30;
