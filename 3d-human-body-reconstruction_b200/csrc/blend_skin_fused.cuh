@@ -107,6 +107,7 @@ struct FusedArgs {
   float* out;              // (rows, N) posed vertices
   int rows;
   int N;                   // 3 V
+  int out_odd_shift;       // TMA output: 2 when the odd bodies' rows start 8 bytes off a 16-byte boundary (V = 2 mod 4), else 0
   long long* dbg;          // tuning aid (SMPLK_FZ_TIMELINE builds): per-tile clock64 stamps of CTA 0
 };
 constexpr int kFzDbgTiles = 32;
@@ -148,12 +149,21 @@ transpose_transforms_kernel(int rows, int rows_pad, int J, const float* __restri
 #else
 #define SMPLK_FZ_BOUNDS __launch_bounds__(kFzThreads, 1)
 #endif
-template <int kN>
+// kTmaOut: results leave as TMA tensor stores, one 16-row x 36-column box per chunk for the even and one
+// for the odd bodies of the warp.  A (B, V, 3) fp32 row is 12 V bytes -- 82,680 = 8 mod 16 for V = 6,890 -- so
+// no tensor map can have ONE body per row (strides must be multiples of 16 bytes); TWO bodies per row (24 V
+// bytes, V even) can: `tmap_out_even` sees the even bodies (inner extent 3 V, so nothing spills into the odd
+// body), `tmap_out_odd` / `tmap_out_odd32` the same rows with inner extent 6 V, addressed at column 3 V + c.
+// Chunks cut by the end of the row take the per-lane store path.
+template <int kN, bool kTmaOut>
 __global__ void __cluster_dims__(2, 1, 1) SMPLK_FZ_BOUNDS
 blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
                         const __grid_constant__ CUtensorMap tmap_f_lo,
                         const __grid_constant__ CUtensorMap tmap_pd_hi,
-                        const __grid_constant__ CUtensorMap tmap_pd_lo, const FusedArgs args) {
+                        const __grid_constant__ CUtensorMap tmap_pd_lo,
+                        const __grid_constant__ CUtensorMap tmap_out_even,
+                        const __grid_constant__ CUtensorMap tmap_out_odd,
+                        const __grid_constant__ CUtensorMap tmap_out_odd32, const FusedArgs args) {
   extern __shared__ uint8_t fz_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(fz_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -183,6 +193,11 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
     ptx::prefetch_tmap(&tmap_f_lo);
     ptx::prefetch_tmap(&tmap_pd_hi);
     ptx::prefetch_tmap(&tmap_pd_lo);
+    if (kTmaOut) {
+      ptx::prefetch_tmap(&tmap_out_even);
+      ptx::prefetch_tmap(&tmap_out_odd);
+      ptx::prefetch_tmap(&tmap_out_odd32);
+    }
     for (int s = 0; s < kFzStages; ++s) {
       ptx::mbar_init(&full_bar[s], 2);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -273,7 +288,10 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
     const int part = (warp - 2) >> 2;         // which part of every tile's chunk range this warp takes
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
     const uint32_t stage_u32 = ptx::smem_u32(epi_base + (warp - 2) * kFzStageWords);
-    const uint32_t stage_row = stage_u32 + lane * (kFzStageStride * 4);   // this body's staged row
+    // this body's staged row; TMA output: even bodies in rows 0..15, odd bodies in rows 16..31 (one box each)
+    const uint32_t stage_row = stage_u32 + (kTmaOut ? ((lane & 1) * 16 + (lane >> 1)) : lane) * (kFzStageStride * 4);
+    [[maybe_unused]] const uint32_t stage_odd = stage_u32 + 16 * kFzStageStride * 4;    // TMA output: the odd bodies' rows
+    [[maybe_unused]] float cy0 = 0.f, cy1 = 0.f;                                        // ... and their two carried columns
     const uint32_t stage_col = stage_u32 + lane * 4;                      // this lane's staged column
     const uint32_t ring_warp = ptx::smem_u32(ring_base) + (warp - 2) * (kFzRing * kFzRingEntryBytes);
     const uint32_t ring_piece = ring_warp + lane * 16;    // this lane's 16-byte piece of lines l/8 + 4k
@@ -473,29 +491,93 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
         for (int k = 0; k < kFzChunkVerts / 2; ++k)
 #pragma unroll
           for (int d = 0; d < 3; ++d) ptx::unpack_f32x2(o2[3 * k + d], o[6 * k + d], o[6 * k + 3 + d]);
-        const int w0 = (c * kFzChunkCols) & 31;
-        const int g0 = w0 >> 2;                  // window position of the chunk's first 4-column group
-        __syncwarp();
+        if constexpr (kTmaOut) {
+          const int cbeg = c * kFzChunkCols;
+          // odd: this lane's body starts 8 bytes off a 16-byte boundary (V = 2 mod 4; for V = 0 mod 4 every row is aligned)
+          const bool odd = (lane & 1) != 0 && args.out_odd_shift != 0;
+          if (cbeg + kFzChunkCols <= cols_left) {
+            // Whole chunk inside the row.  A TMA store must START on a 16-byte boundary (measured:
+            // tools/micro/tma_store_probe.cu, illegal instruction otherwise) and an odd body's row starts 8 bytes
+            // off one, so the odd bodies' boxes sit two columns to the left of the chunk: [36 c - 2, 36 c + 34),
+            // the two leading columns carried over from the previous chunk.  The first chunk of a warp's range has
+            // no predecessor: its columns 0, 1 are stored by the lanes, columns 2..33 as a 32-column box
+            // (128-byte rows, 128B swizzle); the last carry of the range is stored by the lanes as well.
+            if (lane == 0) ptx::tma_store_wait_read<0>();     // the buffer's previous boxes were issued a chunk ago
+            __syncwarp();
+            const bool first = c == c_lo && args.out_odd_shift != 0;
+            if (first) {
+              if (!odd) {
 #pragma unroll
-        for (int g = 0; g < kFzChunkCols / 4; ++g)
-          if (g0 + g < 8) ptx::st_shared_v4(stage_row + (g0 + g) * 16, o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
-        __syncwarp();
-        FZ_STAMP(dbg_c, &dbg_p[2]);
-        store_window((c * kFzChunkCols) >> 5, c == c_lo ? w0 : 0, 32);   // columns below w0 of the range's first window are the other warp's
-        FZ_STAMP(dbg_c, &dbg_p[3]);
-        __syncwarp();
+                for (int g = 0; g < kFzChunkCols / 4; ++g)
+                  ptx::st_shared_v4(stage_row + g * 16, o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+              } else {
+                if (lane < nrows) *reinterpret_cast<float2*>(out_t + (size_t)lane * outN + cbeg) = make_float2(o[0], o[1]);
+                const uint32_t row32 = stage_odd + (lane >> 1) * 128;
+                const uint32_t sw = (row32 >> 7) & 7;
 #pragma unroll
-        for (int g = 1; g < kFzChunkCols / 4; ++g)
-          if (g0 + g >= 8) ptx::st_shared_v4(stage_row + (g0 + g - 8) * 16, o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
-        if (c == c_hi - 1) {                     // the last window of this warp's range is partial
+                for (int g = 0; g < 8; ++g)
+                  ptx::st_shared_v4(row32 + ((g ^ sw) << 4), o[4 * g + 2], o[4 * g + 3], o[4 * g + 4], o[4 * g + 5]);
+              }
+            } else {
+              float s0 = odd ? cy0 : o[0], s1 = odd ? cy1 : o[1], s2 = odd ? o[0] : o[2], s3 = odd ? o[1] : o[3];
+              ptx::st_shared_v4(stage_row, s0, s1, s2, s3);
+#pragma unroll
+              for (int g = 1; g < kFzChunkCols / 4; ++g) {
+                s0 = odd ? o[4 * g - 2] : o[4 * g]; s1 = odd ? o[4 * g - 1] : o[4 * g + 1];
+                s2 = odd ? o[4 * g] : o[4 * g + 2]; s3 = odd ? o[4 * g + 1] : o[4 * g + 3];
+                ptx::st_shared_v4(stage_row + g * 16, s0, s1, s2, s3);
+              }
+            }
+            cy0 = o[kFzChunkCols - 2]; cy1 = o[kFzChunkCols - 1];
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int col = nb * kFzTileCols + cbeg;
+              ptx::tma_store_2d(&tmap_out_even, epi_base + (warp - 2) * kFzStageWords, col, row0 >> 1);
+              if (first) ptx::tma_store_2d(&tmap_out_odd32, epi_base + (warp - 2) * kFzStageWords + 16 * kFzStageStride,
+                                           outN + col + 2, row0 >> 1);
+              else ptx::tma_store_2d(&tmap_out_odd, epi_base + (warp - 2) * kFzStageWords + 16 * kFzStageStride,
+                                     outN + col - args.out_odd_shift, row0 >> 1);
+              ptx::tma_store_commit();
+            }
+            // the range's (or the row's) last full chunk: its two trailing columns have no box to ride in
+            if ((c == c_hi - 1 || cbeg + 2 * kFzChunkCols > cols_left) && odd && lane < nrows)
+              *reinterpret_cast<float2*>(out_t + (size_t)lane * outN + cbeg + kFzChunkCols - 2) = make_float2(cy0, cy1);
+          } else if (cbeg < cols_left && lane < nrows) {
+            // the row's last vertices (one chunk of the last tile): straight from the registers
+            float* dst = out_t + (size_t)lane * outN + cbeg;
+#pragma unroll
+            for (int i = 0; i < kFzChunkCols; ++i)
+              if (cbeg + i < cols_left) dst[i] = o[i];
+          }
+          FZ_STAMP(dbg_c, &dbg_p[2]);
+          FZ_STAMP(dbg_c, &dbg_p[3]);
+        } else {
+          const int w0 = (c * kFzChunkCols) & 31;
+          const int g0 = w0 >> 2;                  // window position of the chunk's first 4-column group
           __syncwarp();
-          store_window(((c + 1) * kFzChunkCols) >> 5, 0, ((c + 1) * kFzChunkCols) & 31);
+#pragma unroll
+          for (int g = 0; g < kFzChunkCols / 4; ++g)
+            if (g0 + g < 8) ptx::st_shared_v4(stage_row + (g0 + g) * 16, o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+          __syncwarp();
+          FZ_STAMP(dbg_c, &dbg_p[2]);
+          store_window((c * kFzChunkCols) >> 5, c == c_lo ? w0 : 0, 32);   // columns below w0 of the range's first window are the other warp's
+          FZ_STAMP(dbg_c, &dbg_p[3]);
+          __syncwarp();
+#pragma unroll
+          for (int g = 1; g < kFzChunkCols / 4; ++g)
+            if (g0 + g >= 8) ptx::st_shared_v4(stage_row + (g0 + g - 8) * 16, o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+          if (c == c_hi - 1) {                     // the last window of this warp's range is partial
+            __syncwarp();
+            store_window(((c + 1) * kFzChunkCols) >> 5, 0, ((c + 1) * kFzChunkCols) & 31);
+          }
         }
       }
       FZ_STAMP(dbg_on, &args.dbg[(warp * kFzDbgTiles + it) * 4 + 3]);
     }
   }
 
+  if (kTmaOut && warp >= 2 && lane == 0) ptx::tma_store_wait<0>();
   ptx::tcgen05_fence_before();
   ptx::cluster_sync();
   if (warp == 1) {

@@ -16,6 +16,7 @@
 #include "blend_gemm.cuh"
 #include "blend_gemm_2cta.cuh"
 #include "blend_skin_fused.cuh"
+#include "lbs_replay_gemm.cuh"
 #include "common.cuh"
 #include "pose_kernels.cuh"
 #include "skinning.cuh"
@@ -110,6 +111,14 @@ struct smplk_model {
   CUtensorMap tmap2_pd_hi, tmap2_pd_lo, tmap2_pdh_hi, tmap2_pdh_lo, tmap2_pdkn_hi, tmap2_pdkn_lo;
   bool use_2cta;
   CUtensorMap tmapf_pdh_hi, tmapf_pdh_lo;  // fused blend+skinning kernel: 84-vertex column tiles
+  // rigged-mesh replay as a GEMM (lbs_replay_gemm.cuh): P = w (x) [v_template; 1], fp16 two-term split
+  CUtensorMap tmap_rp_hi, tmap_rp_lo;
+  const __half* rp_hi; const __half* rp_lo;   // [V][rp_kp]
+  int rp_kp;                                  // round_up(4 J, 32)
+  float rp_scale;                             // power of two applied to P
+  bool replay_gemm_ok;                        // LBS-only handle on sm_100 with the operand built
+  bool use_replay_gemm;                       // option replay_gemm = 0 selects the streaming skinning kernel
+  bool fused_tma_out;   // option fused_tma_out = 0: the fused kernel stores its result per lane instead of through TMA
   bool use_fused;       // option fused = 0 selects the two-kernel forward (cross-checks, stand-alone kernel timings)
   bool use_pose_block;  // option pose_block = 0 selects the warp-per-body pose kernel + transposition pass
   CUtensorMap tmap_pdkn_hi, tmap_pdkn_lo;  // backward: B operand rows = blend features
@@ -184,9 +193,9 @@ static int upload(smplk_model* mdl, const std::vector<T>& h, const T** out) {
 static int make_tmap_2d(const smplk_model* mdl, CUtensorMap* map, const void* ptr, uint64_t inner,
                         uint64_t outer, uint32_t box_inner, uint32_t box_outer,
                         CUtensorMapL2promotion promo, bool f16 = false,
-                        CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                        CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, uint64_t pitch_elems = 0) {
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {inner * (f16 ? sizeof(__half) : sizeof(float))};
+  cuuint64_t strides[1] = {(pitch_elems ? pitch_elems : inner) * (f16 ? sizeof(__half) : sizeof(float))};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = mdl->encode(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
@@ -715,6 +724,48 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     }
   }
 
+  // ---- rigged-mesh replay operand P[v][4 j + k] = w[v][j] [v_template[v]; 1]_k, scaled by a power of two
+  mdl->replay_gemm_ok = false;
+  if (lbs_only && mdl->cc_major == 10) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || fn == nullptr)
+      return fail(SMPLK_E_DEVICE, "cuTensorMapEncodeTiled not available from the driver");
+    mdl->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    const int Kp = round_up(4 * J, kRpKB);
+    double maxabs = 0.0;
+    for (int v = 0; v < V; ++v)
+      for (int j = 0; j < J; ++j) {
+        const double w = desc->weights[(size_t)v * J + j];
+        if (w == 0.0) continue;
+        maxabs = std::max(maxabs, std::fabs(w));
+        for (int k = 0; k < 3; ++k) maxabs = std::max(maxabs, std::fabs(w * desc->v_template[3 * v + k]));
+      }
+    float scale = 1.f;
+    if (maxabs > 0.0 && std::isfinite(maxabs)) scale = std::ldexp(1.f, (int)std::floor(std::log2(1024.0 / maxabs)));
+    std::vector<__half> ph((size_t)V * Kp, __float2half(0.f)), pl((size_t)V * Kp, __float2half(0.f));
+    for (int v = 0; v < V; ++v)
+      for (int j = 0; j < J; ++j) {
+        const double w = desc->weights[(size_t)v * J + j];
+        if (w == 0.0) continue;
+        for (int k = 0; k < 4; ++k) {
+          const float x = (float)(w * (k < 3 ? desc->v_template[3 * v + k] : 1.0)) * scale;
+          const __half h = __float2half_rn(x);
+          ph[(size_t)v * Kp + 4 * j + k] = h;
+          pl[(size_t)v * Kp + 4 * j + k] = __float2half_rn(x - __half2float(h));
+        }
+      }
+    if (int r = upload(mdl, ph, &mdl->rp_hi)) return r;
+    if (int r = upload(mdl, pl, &mdl->rp_lo)) return r;
+    mdl->rp_kp = Kp; mdl->rp_scale = scale;
+    const CUtensorMapL2promotion p256 = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    if (int r = make_tmap_2d(mdl, &mdl->tmap_rp_hi, mdl->rp_hi, Kp, V, kRpKB, kBlendBM, p256, true, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
+    if (int r = make_tmap_2d(mdl, &mdl->tmap_rp_lo, mdl->rp_lo, Kp, V, kRpKB, kBlendBM, p256, true, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
+    CUDA_TRY(cudaFuncSetAttribute(lbs_replay_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRpSmemAlloc));
+    mdl->replay_gemm_ok = true;
+  }
+
   // ---- TMA descriptors of the constant GEMM operand
   mdl->has_tma = false;
   if (!lbs_only && mdl->cc_major == 10) {
@@ -753,8 +804,9 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     if (int r = make_operand_tmap(mdl, &mdl->tmap_pdknb_lo, d.pd_kn_b_lo, d.Npad, d.Kpad, kBlendBN, p256, true)) return r;
     if (int r = make_operand_tmap_fused(mdl, &mdl->tmapf_pdh_hi, d.pdf_h_hi, d.Kpad, (uint64_t)d.fz_tiles * kBlendBN, p256)) return r;
     if (int r = make_operand_tmap_fused(mdl, &mdl->tmapf_pdh_lo, d.pdf_h_lo, d.Kpad, (uint64_t)d.fz_tiles * kBlendBN, p256)) return r;
-    CUDA_TRY(cudaFuncSetAttribute(blend_skin_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFzSmemAlloc));
-    CUDA_TRY(cudaFuncSetAttribute(blend_skin_fused_kernel<3 * 6890>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFzSmemAlloc));
+    CUDA_TRY(cudaFuncSetAttribute(blend_skin_fused_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFzSmemAlloc));
+    CUDA_TRY(cudaFuncSetAttribute(blend_skin_fused_kernel<3 * 6890, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFzSmemAlloc));
+    CUDA_TRY(cudaFuncSetAttribute(blend_skin_fused_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFzSmemAlloc));
     CUDA_TRY(cudaFuncSetAttribute(blend_tcgen05_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   k2SmemAlloc));
     CUDA_TRY(cudaFuncSetAttribute(blend_tcgen05_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -834,7 +886,7 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   // kernel choices: defaults are the product path; smplk_model_set_option changes them per handle (cross-checks of the
   // parity tests, stand-alone kernel timings of the bench).  The product library reads NO environment variable.
   mdl->skin_bpb = 0; mdl->skin_g8 = true; mdl->skin_tma = false; mdl->force_skin_v1 = false; mdl->da_v1 = false;
-  mdl->fit_fused = true; mdl->sparse_picks = true; mdl->use_2cta = true; mdl->use_fused = true;
+  mdl->fit_fused = true; mdl->sparse_picks = true; mdl->use_2cta = true; mdl->use_fused = true; mdl->fused_tma_out = true; mdl->use_replay_gemm = true;
   mdl->use_pose_block = true; mdl->bwd_f16 = true; mdl->default_tc = BLEND_F16;
 #ifdef SMPLK_AB   // A/B builds (tools/): tuning switches of kernels that are on no default path
   { const char* e = getenv("SMPLK_DA_V1"); mdl->da_v1 = e && e[0] == '1'; }
@@ -861,7 +913,9 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
 extern "C" int smplk_model_set_option(smplk_model* model, const char* name, int value) {
   if (!model || !name) return fail(SMPLK_E_ARG, "null argument");
   const bool on = value != 0;
-  if (!strcmp(name, "fused")) model->use_fused = on;                    // fused blend + skinning forward kernel
+  if (!strcmp(name, "fused_tma_out")) model->fused_tma_out = on;
+  else if (!strcmp(name, "replay_gemm")) model->use_replay_gemm = on;   // rigged-mesh replay on the tensor cores
+  else if (!strcmp(name, "fused")) model->use_fused = on;                    // fused blend + skinning forward kernel
   else if (!strcmp(name, "pose_block")) model->use_pose_block = on;     // block-level pose kernel (else warp per body)
   else if (!strcmp(name, "blend_tf32")) model->default_tc = on ? BLEND_TF32 : BLEND_F16;   // 3xTF32 forward operands
   else if (!strcmp(name, "backward_tf32")) model->bwd_f16 = !on;        // 3xTF32 backward GEMM
@@ -904,6 +958,8 @@ static WsLayout ws_layout(const ModelDev& d, int batch, uint32_t flags) {
   w.off_A = off;   off += align_up((size_t)w.chunk * d.J * 12 * sizeof(float), 1024);
   // transposed transforms of the fused blend+skinning kernel (256-body blocks)
   w.off_At = off;  if (!d.lbs_only) off += align_up((size_t)round_up(w.chunk, 2 * kBlendBM) * d.J * 12 * sizeof(float), 1024);
+  // rigged-mesh replay: the frames' transforms as the GEMM's second operand, fp16 hi rows then lo rows (3 per frame)
+  else off += align_up((size_t)2 * 3 * w.chunk * round_up(4 * d.J, kRpKB) * sizeof(__half), 1024);
   w.off_vposed = off;
   if (!d.lbs_only) off += align_up((size_t)w.chunk * d.Npad * sizeof(float), 1024);
   // d_v_posed of the fused fitting step: bf16 hi rows, then bf16 lo rows
@@ -1090,6 +1146,7 @@ static int launch_fused(const smplk_model* mdl, int rows, float* F_hi, float* F_
   fa.ch_off = d.fz_off; fa.ch_joint = d.fz_joint; fa.ch_w = d.fz_w;
   fa.At = At; fa.J = d.J;
   fa.out = out; fa.rows = rows; fa.N = d.N;
+  fa.out_odd_shift = (d.V % 4 == 2) ? 2 : 0;
   fa.dbg = nullptr;
   static long long* dbg_dev = nullptr;
   const bool dbg = SMPLK_FZ_TIMELINE && getenv("SMPLK_FZ_DEBUG") != nullptr;   // tools/fz_timeline.py
@@ -1100,13 +1157,32 @@ static int launch_fused(const smplk_model* mdl, int rows, float* F_hi, float* F_
   }
   const int tiles = fa.num_m_blocks * fa.num_n_blocks;
   const int grid = 2 * std::min(tiles, mdl->num_sms / 2);
+  // Output as TMA tensor stores when two (B, V, 3) rows make a 16-byte multiple (V even) and the caller's
+  // buffer is 16-byte aligned: see the kernel's kTmaOut note.  Otherwise the per-lane store path.
+  const bool tma_out = mdl->fused_tma_out && (d.V % 2 == 0) && rows >= 2 &&
+                       (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+  CUtensorMap tm_oe, tm_oo, tm_oo32;
+  if (tma_out) {
+    const auto promo = CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    if (int r = make_tmap_2d(mdl, &tm_oe, out, (uint64_t)d.N, (uint64_t)(rows + 1) / 2, kFzChunkCols, 16, promo,
+                             false, CU_TENSOR_MAP_SWIZZLE_NONE, 2 * (uint64_t)d.N)) return r;
+    if (int r = make_tmap_2d(mdl, &tm_oo, out, 2 * (uint64_t)d.N, (uint64_t)rows / 2, kFzChunkCols, 16, promo,
+                             false, CU_TENSOR_MAP_SWIZZLE_NONE, 2 * (uint64_t)d.N)) return r;
+    if (int r = make_tmap_2d(mdl, &tm_oo32, out, 2 * (uint64_t)d.N, (uint64_t)rows / 2, 32, 16, promo,
+                             false, CU_TENSOR_MAP_SWIZZLE_128B, 2 * (uint64_t)d.N)) return r;
+  } else {
+    tm_oe = tm_fhi; tm_oo = tm_fhi; tm_oo32 = tm_fhi;          // never dereferenced
+  }
   ProfScope prof(mdl, st, SMPLK_PROF_BLEND_SKIN_FUSED);
-  if (d.N == 3 * 6890)   // canonical SMPL-family vertex count: row pitch folded into the store addresses
-    blend_skin_fused_kernel<3 * 6890><<<grid, kFzThreads, kFzSmemAlloc, st>>>(tm_fhi, tm_flo, mdl->tmapf_pdh_hi,
-                                                                            mdl->tmapf_pdh_lo, fa);
+  if (tma_out)
+    blend_skin_fused_kernel<0, true><<<grid, kFzThreads, kFzSmemAlloc, st>>>(tm_fhi, tm_flo, mdl->tmapf_pdh_hi,
+                                                                           mdl->tmapf_pdh_lo, tm_oe, tm_oo, tm_oo32, fa);
+  else if (d.N == 3 * 6890)   // canonical SMPL-family vertex count: row pitch folded into the store addresses
+    blend_skin_fused_kernel<3 * 6890, false><<<grid, kFzThreads, kFzSmemAlloc, st>>>(tm_fhi, tm_flo, mdl->tmapf_pdh_hi,
+                                                                                   mdl->tmapf_pdh_lo, tm_oe, tm_oo, tm_oo32, fa);
   else
-    blend_skin_fused_kernel<0><<<grid, kFzThreads, kFzSmemAlloc, st>>>(tm_fhi, tm_flo, mdl->tmapf_pdh_hi,
-                                                                     mdl->tmapf_pdh_lo, fa);
+    blend_skin_fused_kernel<0, false><<<grid, kFzThreads, kFzSmemAlloc, st>>>(tm_fhi, tm_flo, mdl->tmapf_pdh_hi,
+                                                                            mdl->tmapf_pdh_lo, tm_oe, tm_oo, tm_oo32, fa);
   LAUNCH_CHECK("blend_skin_fused_kernel");
   if (dbg) {   // tuning aid: per-tile timeline of CTA 0 (cycles relative to the first stamp)
     std::vector<long long> h((2 + kFzEpiWarps) * kFzDbgTiles * 4);
@@ -1146,9 +1222,49 @@ static int pick_bpb(int rows, int tiles, int resident, int max_bpb) {
   return max_bpb;
 }
 
-static int launch_skin(const smplk_model* mdl, int rows, const float* vsrc, size_t vstride,
-                       const float* A, const float* transl, float* out, cudaStream_t st) {
+// Rigged-mesh replay of `rows` frames on the tensor cores: transforms -> fp16 operand rows, then one GEMM whose
+// epilogue writes the (rows, V, 3) vertices (lbs_replay_gemm.cuh).
+static int launch_replay_gemm(const smplk_model* mdl, int rows, const float* A, const float* transl, float* out,
+                              __half* T, cudaStream_t st) {
   const ModelDev& d = mdl->d;
+  const int Kp = mdl->rp_kp;
+  __half* T_hi = T;
+  __half* T_lo = T + (size_t)3 * rows * Kp;
+  {
+    ProfScope prof(mdl, st, SMPLK_PROF_TRANSPOSE);      // the transforms' re-layout pass, as for the fused forward
+    const long n = (long)3 * rows * (Kp / 4);
+    replay_operand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows, d.J, Kp, A, T_hi, T_lo);
+    LAUNCH_CHECK("replay_operand_kernel");
+  }
+  CUtensorMap tm_hi, tm_lo;
+  const CUtensorMapL2promotion p128 = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  if (int r = make_tmap_2d(mdl, &tm_hi, T_hi, Kp, (uint64_t)3 * rows, kRpKB, kRpBN / 2, p128, true, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
+  if (int r = make_tmap_2d(mdl, &tm_lo, T_lo, Kp, (uint64_t)3 * rows, kRpKB, kRpBN / 2, p128, true, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
+  ReplayArgs ra;
+  ra.V = d.V; ra.F = rows;
+  ra.num_m_blocks = (d.V + 2 * kBlendBM - 1) / (2 * kBlendBM);
+  ra.num_n_blocks = (rows + kRpTileFrames - 1) / kRpTileFrames;
+  ra.num_k_blocks = Kp / kRpKB;
+  ra.out_scale = 1.0f / mdl->rp_scale;
+  ra.transl = transl; ra.out = out;
+  const int tiles = ra.num_m_blocks * ra.num_n_blocks;
+  const int grid = 2 * std::min(tiles, mdl->num_sms / 2);
+  ProfScope prof(mdl, st, SMPLK_PROF_SKIN);
+  lbs_replay_gemm_kernel<<<grid, kRpThreads, kRpSmemAlloc, st>>>(mdl->tmap_rp_hi, mdl->tmap_rp_lo, tm_hi, tm_lo, ra);
+  LAUNCH_CHECK("lbs_replay_gemm_kernel");
+  return 0;
+}
+
+// frames from which the replay GEMM is used: below, its fixed costs (operand pass, 80-frame tiles) outweigh the
+// streaming kernel's
+constexpr int kReplayGemmMinRows = 64;
+
+static int launch_skin(const smplk_model* mdl, int rows, const float* vsrc, size_t vstride,
+                       const float* A, const float* transl, float* out, cudaStream_t st, __half* replay_T = nullptr) {
+  const ModelDev& d = mdl->d;
+  if (replay_T != nullptr && d.lbs_only && vstride == 0 && mdl->replay_gemm_ok && mdl->use_replay_gemm &&
+      rows >= kReplayGemmMinRows)
+    return launch_replay_gemm(mdl, rows, A, transl, out, replay_T, st);
   SkinArgs sa;
   sa.B = rows;
   const int tiles = (d.V + kSkinTileVerts - 1) / kSkinTileVerts;
@@ -1345,7 +1461,8 @@ static int forward_impl(const smplk_model* model, const smplk_forward_args* a, c
           LAUNCH_CHECK("skin_fit_l2_kernel");
         } else {
           if (int r = launch_skin(model, rows, d.lbs_only ? d.bias : v_posed,
-                                  d.lbs_only ? 0 : (size_t)d.Npad, A, pa.transl, vout, st)) return r;
+                                  d.lbs_only ? 0 : (size_t)d.Npad, A, pa.transl, vout, st,
+                                  d.lbs_only ? reinterpret_cast<__half*>(At) : nullptr)) return r;
           if (fit != nullptr) {   // generic weights: stand-alone loss kernel, gradient in place
             const int ls = (flags & SMPLK_FLAG_LOSS_SUM) ? 0 : 1;
             if (int r = vertex_l2_impl(rows, d.V * 3, vout, fit->target + (size_t)c0 * d.V * 3, fit->scale, vout,

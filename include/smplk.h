@@ -94,6 +94,10 @@ int smplk_model_get_info(const smplk_model* model, smplk_model_info* info);
  *   "gemm_2cta" (1)      CTA-pair GEMM kernels; 0 = 1-CTA kernels
  *   "fit_fused" (1)      smplk_fit_vertex_l2 as one skinning + loss + skinning-backward kernel
  *   "sparse_picks" (1)   joints-only gradients through the sparse pick kernels; 0 = dense vertex backward
+ *   "fused_tma_out" (1)  the fused forward kernel writes its result as TMA tensor stores (V even, 16-byte aligned
+ *                        verts); 0 = per-lane stores
+ *   "replay_gemm" (1)    rigged-mesh (LBS-only) handles replay >= 64 frames as one tensor-core GEMM
+ *                        (lib/model2video.py:55-85); 0 = streaming skinning kernel
  * Set options before the first forward that they affect; unknown names return SMPLK_E_ARG. */
 int smplk_model_set_option(smplk_model* model, const char* name, int value);
 
@@ -332,7 +336,8 @@ int smplk_fit_priors(const smplk_prior_args* args);
 #define SMPLK_PROF_BLEND_BWD 6
 #define SMPLK_PROF_POSE_BWD 7
 #define SMPLK_PROF_BLEND_SKIN_FUSED 8 /* fused blend GEMM + skinning epilogue (forward without SAVE_FOR_BACKWARD) */
-#define SMPLK_PROF_TRANSPOSE 9        /* transform transposition feeding the fused kernel */
+#define SMPLK_PROF_TRANSPOSE 9        /* transform re-layout pass feeding a tensor-core kernel (fused forward without the block
+                                        pose kernel; operand rows of the rigged-mesh replay GEMM) */
 #define SMPLK_PROF_SLOTS 10
 int smplk_profile_enable(smplk_model* model, int enable);
 int smplk_profile_read(smplk_model* model, double ms[SMPLK_PROF_SLOTS],

@@ -220,3 +220,99 @@ def test_float64_interface_and_wrapper_attributes(dev, smplh_model):
         assert float((g - r).abs().max() / r.abs().max()) <= GRAD_RTOL, name
     loss = mod.vertex_l2(torch.zeros(B, 6890, 3, dtype=torch.float64, device=dev), reduce="sum")
     assert loss.dtype == torch.float64 and abs(float(loss) / float((ref.vertices.detach() ** 2).sum()) - 1) <= 1e-5
+
+
+def _err(a, b):
+    return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
+
+
+def _lbs_forward(dm, pose, transl, dev):
+    """LBS-only forward through the C ABI (smplk_forward) with device buffers."""
+    import ctypes
+    n = pose.shape[0]
+    verts = torch.full((n, dm.V, 3), float("nan"), device=dev)
+    ws = torch.empty(dm.workspace_bytes(n, 0), device=dev, dtype=torch.uint8)
+    a = _lib.ForwardArgs()
+    a.batch, a.flags = n, 0
+    a.betas, a.betas_batch = None, 1
+    a.pose = ctypes.c_void_p(pose.data_ptr())
+    a.transl = ctypes.c_void_p(transl.data_ptr()) if transl is not None else None
+    a.verts = ctypes.c_void_p(verts.data_ptr())
+    a.workspace, a.workspace_bytes = ctypes.c_void_p(ws.data_ptr()), ws.numel()
+    a.stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    dm.forward(a)
+    torch.cuda.synchronize()
+    return verts
+
+
+@pytest.mark.parametrize("nv,frames", [(6890, 333), (50001, 97), (1000, 8192 + 77), (300, 64), (2 * 6890 + 1, 161)])
+def test_rigged_mesh_replay_gemm_matches_oracle_and_streaming_kernel(dev, nv, frames):
+    """config 5, rigged-mesh variant (lib/model2video.py:55-85): from 64 frames on, an LBS-only handle replays a clip as
+    one tensor-core GEMM verts = P . T^T (lbs_replay_gemm.cuh; fp16 two-term operands, three passes).  Checked
+    against the float64 oracle on frames at the 80-frame tile edges, the 8192-frame chunk edge and the clip's ends,
+    and against the streaming skinning kernel (handle option replay_gemm = 0) on every frame; ragged vertex blocks
+    (nv not a multiple of 256), odd vertex counts (4-byte aligned rows), with and without a translation."""
+    rig = synthetic.make_rigged_mesh(nv, seed=nv)
+    dm_g = smplk.DeviceModel(rig, device=0, lbs_only=True)
+    dm_s = smplk.DeviceModel(rig, device=0, lbs_only=True, options={"replay_gemm": 0})
+    rng = np.random.default_rng(frames)
+    pose = rng.standard_normal((frames, 72)).astype(np.float32) * 0.4
+    pose[0] = 0.0
+    pose[-1] = pose[-1] / np.abs(pose[-1]).max() * 3.0
+    trans = (rng.standard_normal((frames, 3)) * 3.0).astype(np.float32)
+    dm_g.profile_enable(True)
+    dm_s.profile_enable(True)
+    vg = _lbs_forward(dm_g, _t(pose, dev), _t(trans, dev), dev)
+    vs = _lbs_forward(dm_s, _t(pose, dev), _t(trans, dev), dev)
+    chunks = (frames + 8191) // 8192
+    full_chunks = sum(1 for c in range(chunks) if min(8192, frames - 8192 * c) >= 64)
+    pg, ps = dm_g.profile_read(), dm_s.profile_read()
+    assert pg["transpose"][1] == full_chunks and ps["transpose"][1] == 0, (pg, ps)     # the GEMM's operand pass ran
+    assert torch.isfinite(vg).all() and torch.isfinite(vs).all()
+    assert _err(vg, vs) <= 4e-6
+    idx = sorted(i for i in {0, 1, 79, 80, frames // 2, frames - 2, frames - 1, 8191, 8192, 8193} if i < frames)
+    for i in idx:
+        ref = O.np_lbs_only(rig, pose[i].astype(np.float64), trans[i].astype(np.float64), ignore_joints=())["verts"]
+        assert np.abs(vg[i].double().cpu().numpy() - ref).max() <= TOL, i
+    v0 = _lbs_forward(dm_g, _t(pose, dev), None, dev)                # no translation
+    assert _err(v0 + _t(trans, dev)[:, None, :], vg) <= 4e-6
+
+
+def test_rigged_mesh_replay_gemm_holds_accuracy_on_large_coordinates(dev):
+    """The GEMM's fp16 two-term operands carry a power-of-two scale chosen from the mesh: a rig in centimetres
+    (coordinates ~ 100) keeps fp32-level RELATIVE accuracy."""
+    rig = synthetic.make_rigged_mesh(4000, seed=5)
+    rig = dict(rig)
+    rig["v_template"] = np.asarray(rig["v_template"]) * 100.0
+    rig["J"] = np.asarray(rig["J"]) * 100.0
+    dm = smplk.DeviceModel(rig, device=0, lbs_only=True)
+    rng = np.random.default_rng(0)
+    pose = rng.standard_normal((128, 72)).astype(np.float32) * 0.5
+    trans = (rng.standard_normal((128, 3)) * 100.0).astype(np.float32)
+    v = _lbs_forward(dm, _t(pose, dev), _t(trans, dev), dev)
+    for i in (0, 64, 127):
+        ref = O.np_lbs_only(rig, pose[i].astype(np.float64), trans[i].astype(np.float64), ignore_joints=())["verts"]
+        assert np.abs(v[i].double().cpu().numpy() - ref).max() <= 1e-5 * 100.0 * 3
+
+
+@pytest.mark.parametrize("V,B", [(6890, 4097), (5002, 259), (84 * 5, 300), (1000, 300), (4001, 300)])
+def test_fused_forward_tma_stores_are_bitwise_the_lane_stores(dev, V, B):
+    """The fused kernel writes its result as TMA tensor stores when V is even and the buffer 16-byte aligned (even
+    bodies one box, odd bodies a box shifted by two carried columns; tools/micro/tma_store_probe.cu shows why);
+    handle option fused_tma_out = 0 keeps the per-lane stores.  Same arithmetic, so the outputs are bit-identical;
+    odd batch sizes end on a half super-row, V = 420 ends exactly on a tile and, like V = 1000, has 16-byte aligned rows
+    for every body (no shift); an odd V (4-byte aligned rows) takes the lane stores in both handles."""
+    m = synthetic.make_model("smplh", seed=3, num_verts=V)
+    dm_t = smplk.DeviceModel(m, device=0)
+    dm_l = smplk.DeviceModel(m, device=0, options={"fused_tma_out": 0})
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=B)
+    args = (_t(betas, dev), _t(pose, dev))
+    dm_t.profile_enable(True)
+    vt = body_model_apply(dm_t, *args, transl=_t(transl, dev))[0]
+    vl = body_model_apply(dm_l, *args, transl=_t(transl, dev))[0]
+    torch.cuda.synchronize()
+    assert dm_t.profile_read()["blend_skin_fused"][1] == 1
+    assert torch.isfinite(vt).all() and torch.equal(vt, vl)
+    ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(
+        *[torch.tensor(x, dtype=torch.float64) for x in (betas[:64], pose[:64], transl[:64])])
+    assert _err(vt[:64], ref.vertices) <= TOL
