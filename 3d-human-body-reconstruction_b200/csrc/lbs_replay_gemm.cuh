@@ -21,6 +21,12 @@
 // operands in 64-byte K rows (32 fp16, 64B swizzle) through a 6-stage TMA ring that runs across tiles; one
 // MMA-issuing thread in the leader; 8 epilogue warps (TMEM lane quarter x half of the tile's frames).
 // Tile order: replay_tile_coords below.
+//
+// kSkin = true: the SAME kernel as the skinning pass of the two-kernel forward (blend GEMM -> v_posed -> skinning;
+// every forward that keeps v_posed for a backward).  v_posed differs per body, so only the BLEND of the transforms
+// is a GEMM: Tm[v, (b, 4 c + k)] = sum_j w[v, j] A[b, j, c, k] (K = J, 12 accumulator columns per body, 20 bodies
+// per tile); the epilogue thread -- still one vertex -- reads its 12 bytes of v_posed[b], applies Tm (12 FMAs
+// instead of the streaming kernel's 60 and no shared-memory transform gathers) and stores its 12 bytes.
 #pragma once
 #include "blend_gemm_2cta.cuh"
 
@@ -42,16 +48,51 @@ static_assert(kRpStageBytes % 1024 == 0, "stage alignment");
 static_assert(kRpSmemAlloc <= 232448, "replay kernel shared memory exceeds the sm_100 limit");
 static_assert(kRpBN % 16 == 0 && kRpBN <= 256, "UMMA N of a CTA pair");
 static_assert((kRpBN / 2) % 16 == 8, "the epilogue reads its 120 columns as 7 x 16 + 8");
+static_assert(kRpBN / 2 == 120 && (kRpBN / 12) % 4 == 0, "kSkin: two rounds of 5 bodies per warp");
+
+constexpr int kRpTileBodies = kRpBN / 12;             // kSkin: 20 bodies per tile
 
 struct ReplayArgs {
-  int V, F;                // vertices, frames of this launch
+  int V, F;                // vertices, frames (kSkin: bodies) of this launch
   int num_m_blocks;        // 256-vertex blocks
   int num_n_blocks;        // 80-frame tiles
   int num_k_blocks;        // ceil(4 J / 32)
   float out_scale;         // 1 / (power-of-two scale of P)
   const float* transl;     // (F, 3) or null
   float* out;              // (F, V, 3)
+  const float* vsrc;       // kSkin: v_posed rows (F, vsrc_stride), 8-byte aligned, even stride
+  size_t vsrc_stride;
 };
+
+// kSkin operand: A (B, J, 12) fp32 -> T_hi / T_lo (12 B, Kp) fp16, row 12 b + r = [A[b, j, r] for j] (zero padded).
+// One block per body: its J x 12 floats are read coalesced into shared memory and leave as 8-byte pieces of four j.
+constexpr int kSkinOpThreads = 192;
+__global__ void __launch_bounds__(kSkinOpThreads)
+skin_operand_kernel(int B, int J, int Kp, const float* __restrict__ A, __half* __restrict__ T_hi,
+                    __half* __restrict__ T_lo) {
+  __shared__ float sa[kMaxJoints * 12 + 48];
+  const int b = blockIdx.x;
+  const float* src = A + (size_t)b * J * 12;
+  for (int i = threadIdx.x; i < Kp * 12; i += kSkinOpThreads) sa[i] = i < J * 12 ? src[i] : 0.f;
+  __syncthreads();
+  const int q4 = Kp / 4;
+  for (int i = threadIdx.x; i < 12 * q4; i += kSkinOpThreads) {
+    const int r = i / q4, j = 4 * (i % q4);
+    float x[4];
+    __half h[4], l[4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      x[n] = sa[(j + n) * 12 + r];
+      h[n] = __float2half_rn(x[n]);
+      l[n] = __float2half_rn(x[n] - __half2float(h[n]));
+    }
+    const size_t o = ((size_t)b * 12 + r) * Kp + j;
+    __half2* ph = reinterpret_cast<__half2*>(T_hi + o);
+    __half2* pl = reinterpret_cast<__half2*>(T_lo + o);
+    ph[0] = __halves2half2(h[0], h[1]); ph[1] = __halves2half2(h[2], h[3]);
+    pl[0] = __halves2half2(l[0], l[1]); pl[1] = __halves2half2(l[2], l[3]);
+  }
+}
 
 // Tile order.  Vertex blocks are taken in groups of `group` (= the number of clusters): within a group the vertex
 // block runs fastest, then the frame tile.  The clusters running at one time therefore write a few whole frames'
@@ -98,6 +139,7 @@ __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t* r) {
                : "memory");
 }
 
+template <bool kSkin>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kRpThreads, 1)
 lbs_replay_gemm_kernel(const __grid_constant__ CUtensorMap tmap_p_hi, const __grid_constant__ CUtensorMap tmap_p_lo,
                        const __grid_constant__ CUtensorMap tmap_t_hi, const __grid_constant__ CUtensorMap tmap_t_lo,
@@ -212,6 +254,8 @@ lbs_replay_gemm_kernel(const __grid_constant__ CUtensorMap tmap_p_hi, const __gr
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
     const float oscale = args.out_scale;
     const int V = args.V;
+    [[maybe_unused]] float2 na[kRpTileBodies / 2];      // kSkin: the next tile's v_posed, in flight
+    [[maybe_unused]] float nbv[kRpTileBodies / 2];
     for (int it = 0;; ++it) {
       const int tile = cluster_id + it * num_clusters;
       if (tile >= num_tiles) break;
@@ -220,48 +264,132 @@ lbs_replay_gemm_kernel(const __grid_constant__ CUtensorMap tmap_p_hi, const __gr
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int v = mb * 2 * kBlendBM + (int)rank * kBlendBM + q * 32 + lane;
-      const int f_base = nb * kRpTileFrames + half * (kRpTileFrames / 2);
       const bool v_ok = v < V;
-      ptx::mbar_wait_backoff(&tmem_full[acc], acc_phase, 20);
-      ptx::tcgen05_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                               static_cast<uint32_t>(acc * kBlendBN + half * (kRpBN / 2));
-      // the warp's whole share of the accumulator (40 frames x 3 = 120 columns) in one go: the loads fly together,
-      // the accumulator goes back to the MMA thread at once, and the stores below depend on nothing but registers
-      uint32_t r[kRpBN / 2];
+      // the warp's whole share of the accumulator (120 columns) in one go: the loads fly together, the accumulator
+      // goes back to the MMA thread at once, and the stores below depend on nothing but registers
+      if constexpr (!kSkin) {
+        uint32_t r[kRpBN / 2];
+        const int f_base = nb * kRpTileFrames + half * (kRpTileFrames / 2);
+        ptx::mbar_wait_backoff(&tmem_full[acc], acc_phase, 20);
+        ptx::tcgen05_fence_after();
 #pragma unroll
-      for (int i = 0; i < (kRpBN / 2) / 16; ++i) ptx::tmem_ld_32x32b_x16(taddr0 + 16 * i, r + 16 * i);
-      tmem_ld_32x32b_x8(taddr0 + 16 * ((kRpBN / 2) / 16), r + 16 * ((kRpBN / 2) / 16));
-      // the frames' translations: lane l of load i holds transl[3 f_base + 32 i + l] (broadcast by shuffle below)
-      float tv[(kRpBN / 2 + 31) / 32];
+        for (int i = 0; i < (kRpBN / 2) / 16; ++i) ptx::tmem_ld_32x32b_x16(taddr0 + 16 * i, r + 16 * i);
+        tmem_ld_32x32b_x8(taddr0 + 16 * ((kRpBN / 2) / 16), r + 16 * ((kRpBN / 2) / 16));
+        // the frames' translations: lane l of load i holds transl[3 f_base + 32 i + l] (broadcast by shuffle below)
+        float tv[(kRpBN / 2 + 31) / 32];
 #pragma unroll
-      for (int i = 0; i < (kRpBN / 2 + 31) / 32; ++i) {
-        const long idx = 3 * (long)f_base + 32 * i + lane;
-        tv[i] = (args.transl != nullptr && 32 * i + lane < kRpBN / 2 && idx < 3 * (long)args.F) ? __ldg(args.transl + idx) : 0.f;
-      }
-      ptx::tmem_ld_wait();
-      ptx::tcgen05_fence_before();
-      ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);
-      // 12 bytes per lane and frame as one 8-byte and one 4-byte store, whichever order is aligned: element index
-      // e = 3 (f V + v); e even -> (x, y) | z, e odd -> x | (y, z).  Branch-free: the lanes of a warp alternate.
-      const int nf = min(kRpTileFrames / 2, args.F - f_base);
-      size_t e = ((size_t)f_base * V + (v_ok ? v : 0)) * 3;
-      const size_t e_step = (size_t)V * 3;
-#pragma unroll
-      for (int k = 0; k < kRpTileFrames / 2; ++k) {
-        const float tx = __shfl_sync(0xffffffffu, tv[(3 * k) >> 5], (3 * k) & 31);
-        const float ty = __shfl_sync(0xffffffffu, tv[(3 * k + 1) >> 5], (3 * k + 1) & 31);
-        const float tz = __shfl_sync(0xffffffffu, tv[(3 * k + 2) >> 5], (3 * k + 2) & 31);
-        if (k < nf && v_ok) {
-          const float x = fmaf(__uint_as_float(r[3 * k]), oscale, tx);
-          const float y = fmaf(__uint_as_float(r[3 * k + 1]), oscale, ty);
-          const float z = fmaf(__uint_as_float(r[3 * k + 2]), oscale, tz);
-          const bool al = (e & 1) == 0;
-          float* p = args.out + e;
-          *reinterpret_cast<float2*>(p + (al ? 0 : 1)) = make_float2(al ? x : y, al ? y : z);
-          p[al ? 2 : 0] = al ? z : x;
+        for (int i = 0; i < (kRpBN / 2 + 31) / 32; ++i) {
+          const long idx = 3 * (long)f_base + 32 * i + lane;
+          tv[i] = (args.transl != nullptr && 32 * i + lane < kRpBN / 2 && idx < 3 * (long)args.F) ? __ldg(args.transl + idx) : 0.f;
         }
-        e += e_step;
+        ptx::tmem_ld_wait();
+        ptx::tcgen05_fence_before();
+        ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);
+        // 12 bytes per lane and frame as one 8-byte and one 4-byte store, whichever order is aligned: element index
+        // e = 3 (f V + v); e even -> (x, y) | z, e odd -> x | (y, z).  Branch-free: the lanes of a warp alternate.
+        const int nf = min(kRpTileFrames / 2, args.F - f_base);
+        size_t e = ((size_t)f_base * V + (v_ok ? v : 0)) * 3;
+        const size_t e_step = (size_t)V * 3;
+#pragma unroll
+        for (int k = 0; k < kRpTileFrames / 2; ++k) {
+          const float tx = __shfl_sync(0xffffffffu, tv[(3 * k) >> 5], (3 * k) & 31);
+          const float ty = __shfl_sync(0xffffffffu, tv[(3 * k + 1) >> 5], (3 * k + 1) & 31);
+          const float tz = __shfl_sync(0xffffffffu, tv[(3 * k + 2) >> 5], (3 * k + 2) & 31);
+          if (k < nf && v_ok) {
+            const float x = fmaf(__uint_as_float(r[3 * k]), oscale, tx);
+            const float y = fmaf(__uint_as_float(r[3 * k + 1]), oscale, ty);
+            const float z = fmaf(__uint_as_float(r[3 * k + 2]), oscale, tz);
+            const bool al = (e & 1) == 0;
+            float* p = args.out + e;
+            *reinterpret_cast<float2*>(p + (al ? 0 : 1)) = make_float2(al ? x : y, al ? y : z);
+            p[al ? 2 : 0] = al ? z : x;
+          }
+          e += e_step;
+        }
+      } else {
+        constexpr int kHalfBodies = kRpTileBodies / 2;
+        const int b_base = nb * kRpTileBodies + half * kHalfBodies;
+        const int nbod = min(kHalfBodies, args.F - b_base);
+        // this vertex's v_posed of the warp's bodies: 12 bytes per lane as an 8-byte and a 4-byte load, whichever order
+        // is aligned (row strides are even, so the parity is the vertex's).  The loads of the NEXT tile are issued
+        // before this tile's accumulator is waited for, so their HBM latency hides behind a whole tile.  Lanes past
+        // the last vertex and bodies past the last body read a clamped (valid) address and store nothing.
+        const bool al = (v & 1) == 0;
+        float2 pa[kHalfBodies];
+        float pb[kHalfBodies];
+        auto load_vp = [&](int vv, int bb0) {
+          const int vc = min(vv, V - 1);
+          const bool a2 = (vc & 1) == 0;
+          const float* p = args.vsrc + (size_t)min(bb0, args.F - 1) * args.vsrc_stride + 3 * (size_t)vc;
+          const int o2 = a2 ? 0 : 1, o1 = a2 ? 2 : 0;
+          const size_t last = (size_t)max(0, min(kHalfBodies, args.F - bb0) - 1) * args.vsrc_stride;
+          size_t off = 0;
+#pragma unroll
+          for (int i = 0; i < kHalfBodies; ++i) {
+            na[i] = *reinterpret_cast<const float2*>(p + off + o2);
+            nbv[i] = p[off + o1];
+            off = min(off + args.vsrc_stride, last);
+          }
+        };
+        if (it == 0) load_vp(v, b_base);
+#pragma unroll
+        for (int i = 0; i < kHalfBodies; ++i) { pa[i] = na[i]; pb[i] = nbv[i]; }
+        {
+          const int tile2 = tile + num_clusters;
+          if (tile2 < num_tiles) {
+            int mb2, nb2;
+            replay_tile_coords(tile2, args.num_m_blocks, args.num_n_blocks, num_clusters, mb2, nb2);
+            load_vp(mb2 * 2 * kBlendBM + (int)rank * kBlendBM + q * 32 + lane, nb2 * kRpTileBodies + half * kHalfBodies);
+          }
+        }
+        const long tidx = 3 * (long)b_base + lane;
+        const float tv = (args.transl != nullptr && lane < 3 * kHalfBodies && tidx < 3 * (long)args.F) ? __ldg(args.transl + tidx) : 0.f;
+        // output: element index e = 3 (b V + v); the 8-byte store goes where e is even
+        const int vodd = V & 1;
+        int par = (int)(((size_t)b_base * vodd + (size_t)v) & 1);
+        float* po = args.out + ((size_t)b_base * V + (v_ok ? v : 0)) * 3;
+        const size_t po_step = (size_t)V * 3;
+        ptx::mbar_wait_backoff(&tmem_full[acc], acc_phase, 20);
+        ptx::tcgen05_fence_after();
+        // the warp's 120 columns in two rounds of 5 bodies (60 registers; the register file gives a 10-warp block 168)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[60];
+          const uint32_t ta = taddr0 + 60 * h;
+          ptx::tmem_ld_32x32b_x16(ta, r);
+          ptx::tmem_ld_32x32b_x16(ta + 16, r + 16);
+          ptx::tmem_ld_32x32b_x16(ta + 32, r + 32);
+          tmem_ld_32x32b_x8(ta + 48, r + 48);
+          ptx::tmem_ld_32x32b_x4(ta + 56, r + 56);
+          ptx::tmem_ld_wait();
+          if (h == 1) {
+            ptx::tcgen05_fence_before();
+            ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);
+          }
+#pragma unroll
+          for (int ii = 0; ii < kHalfBodies / 2; ++ii) {
+            const int i = h * (kHalfBodies / 2) + ii;
+            const float tx = __shfl_sync(0xffffffffu, tv, 3 * i);
+            const float ty = __shfl_sync(0xffffffffu, tv, 3 * i + 1);
+            const float tz = __shfl_sync(0xffffffffu, tv, 3 * i + 2);
+            const float px = al ? pa[i].x : pb[i], py = al ? pa[i].y : pa[i].x, pz = al ? pb[i] : pa[i].y;
+            float t[12];
+#pragma unroll
+            for (int n = 0; n < 12; ++n) t[n] = __uint_as_float(r[12 * ii + n]);
+            const float x = fmaf(fmaf(t[0], px, fmaf(t[1], py, fmaf(t[2], pz, t[3]))), oscale, tx);
+            const float y = fmaf(fmaf(t[4], px, fmaf(t[5], py, fmaf(t[6], pz, t[7]))), oscale, ty);
+            const float z = fmaf(fmaf(t[8], px, fmaf(t[9], py, fmaf(t[10], pz, t[11]))), oscale, tz);
+            if (i < nbod && v_ok) {
+              const bool sal = par == 0;
+              *reinterpret_cast<float2*>(po + (sal ? 0 : 1)) = make_float2(sal ? x : y, sal ? y : z);
+              po[sal ? 2 : 0] = sal ? z : x;
+            }
+            po += po_step;
+            par ^= vodd;
+          }
+        }
       }
     }
   }

@@ -116,6 +116,15 @@ struct smplk_model {
   const __half* rp_hi; const __half* rp_lo;   // [V][rp_kp]
   int rp_kp;                                  // round_up(4 J, 32)
   float rp_scale;                             // power of two applied to P
+  // skinning pass of the two-kernel forward with the transform blend on the tensor cores (kSkin instance of the
+  // replay kernel): W[v][j] as fp16 two-term split
+  CUtensorMap tmap_sw_hi, tmap_sw_lo;
+  const __half* sw_hi; const __half* sw_lo;   // [V][sw_kp]
+  int sw_kp;                                  // round_up(J, 32)
+  float sw_scale;
+  bool skin_gemm_ok;
+  bool use_skin_gemm;                         // option skin_gemm = 1 (default 0: measured 0.164 + 0.015 ms operand pass against
+                                              // 0.170 ms of the streaming kernel at 4,096 bodies, profiles/r02_skin_gemm_ab.txt)
   bool replay_gemm_ok;                        // LBS-only handle on sm_100 with the operand built
   bool use_replay_gemm;                       // option replay_gemm = 0 selects the streaming skinning kernel
   bool fused_tma_out;   // option fused_tma_out = 0: the fused kernel stores its result per lane instead of through TMA
@@ -726,6 +735,7 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
 
   // ---- rigged-mesh replay operand P[v][4 j + k] = w[v][j] [v_template[v]; 1]_k, scaled by a power of two
   mdl->replay_gemm_ok = false;
+  mdl->skin_gemm_ok = false;
   if (lbs_only && mdl->cc_major == 10) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -762,7 +772,7 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
     const CUtensorMapL2promotion p256 = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     if (int r = make_tmap_2d(mdl, &mdl->tmap_rp_hi, mdl->rp_hi, Kp, V, kRpKB, kBlendBM, p256, true, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
     if (int r = make_tmap_2d(mdl, &mdl->tmap_rp_lo, mdl->rp_lo, Kp, V, kRpKB, kBlendBM, p256, true, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
-    CUDA_TRY(cudaFuncSetAttribute(lbs_replay_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRpSmemAlloc));
+    CUDA_TRY(cudaFuncSetAttribute(lbs_replay_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRpSmemAlloc));
     mdl->replay_gemm_ok = true;
   }
 
@@ -815,6 +825,31 @@ static int build_model(const smplk_model_desc* desc, smplk_model* mdl) {
                                   kGemmSmemAlloc));
     CUDA_TRY(cudaFuncSetAttribute(blend_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kGemmSmemAlloc));
+    {
+      // skin weights as a GEMM operand (lbs_replay_gemm.cuh, kSkin): W[v][j], power-of-two scale, fp16 hi + lo
+      const int Kp = round_up(J, kRpKB);
+      double maxabs = 0.0;
+      for (size_t i = 0; i < (size_t)V * J; ++i) maxabs = std::max(maxabs, std::fabs(desc->weights[i]));
+      float scale = 1.f;
+      if (maxabs > 0.0 && std::isfinite(maxabs)) scale = std::ldexp(1.f, (int)std::floor(std::log2(1024.0 / maxabs)));
+      std::vector<__half> wh((size_t)V * Kp, __float2half(0.f)), wl((size_t)V * Kp, __float2half(0.f));
+      for (int v = 0; v < V; ++v)
+        for (int j = 0; j < J; ++j) {
+          const float x = (float)desc->weights[(size_t)v * J + j] * scale;
+          if (x == 0.f) continue;
+          const __half h = __float2half_rn(x);
+          wh[(size_t)v * Kp + j] = h;
+          wl[(size_t)v * Kp + j] = __float2half_rn(x - __half2float(h));
+        }
+      if (int r = upload(mdl, wh, &mdl->sw_hi)) return r;
+      if (int r = upload(mdl, wl, &mdl->sw_lo)) return r;
+      mdl->sw_kp = Kp; mdl->sw_scale = scale;
+      const CUtensorMapL2promotion p256 = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+      if (int r = make_tmap_2d(mdl, &mdl->tmap_sw_hi, mdl->sw_hi, Kp, V, kRpKB, kBlendBM, p256, true, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
+      if (int r = make_tmap_2d(mdl, &mdl->tmap_sw_lo, mdl->sw_lo, Kp, V, kRpKB, kBlendBM, p256, true, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
+      CUDA_TRY(cudaFuncSetAttribute(lbs_replay_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRpSmemAlloc));
+      mdl->skin_gemm_ok = true;
+    }
     mdl->has_tma = true;
   }
   {
@@ -886,7 +921,7 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   // kernel choices: defaults are the product path; smplk_model_set_option changes them per handle (cross-checks of the
   // parity tests, stand-alone kernel timings of the bench).  The product library reads NO environment variable.
   mdl->skin_bpb = 0; mdl->skin_g8 = true; mdl->skin_tma = false; mdl->force_skin_v1 = false; mdl->da_v1 = false;
-  mdl->fit_fused = true; mdl->sparse_picks = true; mdl->use_2cta = true; mdl->use_fused = true; mdl->fused_tma_out = true; mdl->use_replay_gemm = true;
+  mdl->fit_fused = true; mdl->sparse_picks = true; mdl->use_2cta = true; mdl->use_fused = true; mdl->fused_tma_out = true; mdl->use_replay_gemm = true; mdl->use_skin_gemm = false;
   mdl->use_pose_block = true; mdl->bwd_f16 = true; mdl->default_tc = BLEND_F16;
 #ifdef SMPLK_AB   // A/B builds (tools/): tuning switches of kernels that are on no default path
   { const char* e = getenv("SMPLK_DA_V1"); mdl->da_v1 = e && e[0] == '1'; }
@@ -915,6 +950,7 @@ extern "C" int smplk_model_set_option(smplk_model* model, const char* name, int 
   const bool on = value != 0;
   if (!strcmp(name, "fused_tma_out")) model->fused_tma_out = on;
   else if (!strcmp(name, "replay_gemm")) model->use_replay_gemm = on;   // rigged-mesh replay on the tensor cores
+  else if (!strcmp(name, "skin_gemm")) model->use_skin_gemm = on;       // two-kernel forward: transform blend on the tensor cores
   else if (!strcmp(name, "fused")) model->use_fused = on;                    // fused blend + skinning forward kernel
   else if (!strcmp(name, "pose_block")) model->use_pose_block = on;     // block-level pose kernel (else warp per body)
   else if (!strcmp(name, "blend_tf32")) model->default_tc = on ? BLEND_TF32 : BLEND_F16;   // 3xTF32 forward operands
@@ -957,7 +993,9 @@ static WsLayout ws_layout(const ModelDev& d, int batch, uint32_t flags) {
   w.off_flo = off; off += align_up(rows_pad * d.Kpad * sizeof(float), 1024);
   w.off_A = off;   off += align_up((size_t)w.chunk * d.J * 12 * sizeof(float), 1024);
   // transposed transforms of the fused blend+skinning kernel (256-body blocks)
-  w.off_At = off;  if (!d.lbs_only) off += align_up((size_t)round_up(w.chunk, 2 * kBlendBM) * d.J * 12 * sizeof(float), 1024);
+  // ... or, in the two-kernel forward, the transforms as the operand rows of the skinning GEMM (12 per body, hi + lo)
+  w.off_At = off;  if (!d.lbs_only) off += align_up(std::max((size_t)round_up(w.chunk, 2 * kBlendBM) * d.J * 12 * sizeof(float),
+                                                             (size_t)2 * 12 * w.chunk * round_up(d.J, kRpKB) * sizeof(__half)), 1024);
   // rigged-mesh replay: the frames' transforms as the GEMM's second operand, fp16 hi rows then lo rows (3 per frame)
   else off += align_up((size_t)2 * 3 * w.chunk * round_up(4 * d.J, kRpKB) * sizeof(__half), 1024);
   w.off_vposed = off;
@@ -1223,34 +1261,46 @@ static int pick_bpb(int rows, int tiles, int resident, int max_bpb) {
 }
 
 // Rigged-mesh replay of `rows` frames on the tensor cores: transforms -> fp16 operand rows, then one GEMM whose
-// epilogue writes the (rows, V, 3) vertices (lbs_replay_gemm.cuh).
+// epilogue writes the (rows, V, 3) vertices (lbs_replay_gemm.cuh).  With `vsrc` (per-body v_posed rows): the skinning
+// pass of the two-kernel forward, transform blend as the GEMM, applied to v_posed in the epilogue (kSkin).
 static int launch_replay_gemm(const smplk_model* mdl, int rows, const float* A, const float* transl, float* out,
-                              __half* T, cudaStream_t st) {
+                              __half* T, cudaStream_t st, const float* vsrc = nullptr, size_t vstride = 0) {
   const ModelDev& d = mdl->d;
-  const int Kp = mdl->rp_kp;
+  const bool skin = vsrc != nullptr;
+  const int Kp = skin ? mdl->sw_kp : mdl->rp_kp;
+  const int rows_per = skin ? 12 : 3;                  // operand rows (= accumulator columns) per body / frame
   __half* T_hi = T;
-  __half* T_lo = T + (size_t)3 * rows * Kp;
+  __half* T_lo = T + (size_t)rows_per * rows * Kp;
   {
     ProfScope prof(mdl, st, SMPLK_PROF_TRANSPOSE);      // the transforms' re-layout pass, as for the fused forward
-    const long n = (long)3 * rows * (Kp / 4);
-    replay_operand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows, d.J, Kp, A, T_hi, T_lo);
+    if (skin) {
+      skin_operand_kernel<<<rows, kSkinOpThreads, 0, st>>>(rows, d.J, Kp, A, T_hi, T_lo);
+    } else {
+      const long n = (long)3 * rows * (Kp / 4);
+      replay_operand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows, d.J, Kp, A, T_hi, T_lo);
+    }
     LAUNCH_CHECK("replay_operand_kernel");
   }
   CUtensorMap tm_hi, tm_lo;
   const CUtensorMapL2promotion p128 = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
-  if (int r = make_tmap_2d(mdl, &tm_hi, T_hi, Kp, (uint64_t)3 * rows, kRpKB, kRpBN / 2, p128, true, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
-  if (int r = make_tmap_2d(mdl, &tm_lo, T_lo, Kp, (uint64_t)3 * rows, kRpKB, kRpBN / 2, p128, true, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
+  if (int r = make_tmap_2d(mdl, &tm_hi, T_hi, Kp, (uint64_t)rows_per * rows, kRpKB, kRpBN / 2, p128, true, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
+  if (int r = make_tmap_2d(mdl, &tm_lo, T_lo, Kp, (uint64_t)rows_per * rows, kRpKB, kRpBN / 2, p128, true, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
   ReplayArgs ra;
   ra.V = d.V; ra.F = rows;
   ra.num_m_blocks = (d.V + 2 * kBlendBM - 1) / (2 * kBlendBM);
-  ra.num_n_blocks = (rows + kRpTileFrames - 1) / kRpTileFrames;
+  const int per_tile = skin ? kRpTileBodies : kRpTileFrames;
+  ra.num_n_blocks = (rows + per_tile - 1) / per_tile;
   ra.num_k_blocks = Kp / kRpKB;
-  ra.out_scale = 1.0f / mdl->rp_scale;
+  ra.out_scale = 1.0f / (skin ? mdl->sw_scale : mdl->rp_scale);
   ra.transl = transl; ra.out = out;
+  ra.vsrc = vsrc; ra.vsrc_stride = vstride;
   const int tiles = ra.num_m_blocks * ra.num_n_blocks;
   const int grid = 2 * std::min(tiles, mdl->num_sms / 2);
   ProfScope prof(mdl, st, SMPLK_PROF_SKIN);
-  lbs_replay_gemm_kernel<<<grid, kRpThreads, kRpSmemAlloc, st>>>(mdl->tmap_rp_hi, mdl->tmap_rp_lo, tm_hi, tm_lo, ra);
+  if (skin)
+    lbs_replay_gemm_kernel<true><<<grid, kRpThreads, kRpSmemAlloc, st>>>(mdl->tmap_sw_hi, mdl->tmap_sw_lo, tm_hi, tm_lo, ra);
+  else
+    lbs_replay_gemm_kernel<false><<<grid, kRpThreads, kRpSmemAlloc, st>>>(mdl->tmap_rp_hi, mdl->tmap_rp_lo, tm_hi, tm_lo, ra);
   LAUNCH_CHECK("lbs_replay_gemm_kernel");
   return 0;
 }
@@ -1265,6 +1315,9 @@ static int launch_skin(const smplk_model* mdl, int rows, const float* vsrc, size
   if (replay_T != nullptr && d.lbs_only && vstride == 0 && mdl->replay_gemm_ok && mdl->use_replay_gemm &&
       rows >= kReplayGemmMinRows)
     return launch_replay_gemm(mdl, rows, A, transl, out, replay_T, st);
+  if (replay_T != nullptr && !d.lbs_only && vstride != 0 && (vstride % 2) == 0 && mdl->skin_gemm_ok && mdl->use_skin_gemm &&
+      rows >= kReplayGemmMinRows && (reinterpret_cast<uintptr_t>(vsrc) % 8) == 0)
+    return launch_replay_gemm(mdl, rows, A, transl, out, replay_T, st, vsrc, vstride);
   SkinArgs sa;
   sa.B = rows;
   const int tiles = (d.V + kSkinTileVerts - 1) / kSkinTileVerts;
@@ -1462,7 +1515,7 @@ static int forward_impl(const smplk_model* model, const smplk_forward_args* a, c
         } else {
           if (int r = launch_skin(model, rows, d.lbs_only ? d.bias : v_posed,
                                   d.lbs_only ? 0 : (size_t)d.Npad, A, pa.transl, vout, st,
-                                  d.lbs_only ? reinterpret_cast<__half*>(At) : nullptr)) return r;
+                                  reinterpret_cast<__half*>(At))) return r;
           if (fit != nullptr) {   // generic weights: stand-alone loss kernel, gradient in place
             const int ls = (flags & SMPLK_FLAG_LOSS_SUM) ? 0 : 1;
             if (int r = vertex_l2_impl(rows, d.V * 3, vout, fit->target + (size_t)c0 * d.V * 3, fit->scale, vout,

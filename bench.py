@@ -751,8 +751,10 @@ def main():
                     wgbs = N5 * nv * 12 / (msr * 1e-3) / 1e9
                     c5["lbs_only"].append({"verts": nv, "ms": msr, "value": N5 / (msr * 1e-3), "unit": "frames/s",
                                            "hbm_write_gbs": wgbs, "frac_of_hbm_peak": wgbs / peaks["hbm"],
+                                           "kernel": "lbs_replay_gemm_kernel (tcgen05: verts = P . T^T, K = 4 J = 96, three fp16 two-term passes; "
+                                                     "lane = vertex, 12-byte stores straight from the TMEM registers) + replay_operand_kernel",
                                            "note": "rigged-mesh replay (RecoverModel, 24 joints): the only HBM stream is the vertex write "
-                                                   "(template + weights are L2-resident); %d frames per call" % ckr})
+                                                   "(the P operand and the frames' transform rows are L2-resident); %d frames per call" % ckr})
                     del vr, wsr, rdm
                     torch.cuda.empty_cache()
                 extras["config5_sequence_100k"] = c5

@@ -96,6 +96,9 @@ int smplk_model_get_info(const smplk_model* model, smplk_model_info* info);
  *   "sparse_picks" (1)   joints-only gradients through the sparse pick kernels; 0 = dense vertex backward
  *   "fused_tma_out" (1)  the fused forward kernel writes its result as TMA tensor stores (V even, 16-byte aligned
  *                        verts); 0 = per-lane stores
+ *   "skin_gemm" (0)      1 = the skinning pass of the two-kernel forward blends the transforms on the tensor cores
+ *                        (same kernel as the replay GEMM, 12 accumulator columns per body); measured on a par with the
+ *                        streaming kernel, kept for cross-checks
  *   "replay_gemm" (1)    rigged-mesh (LBS-only) handles replay >= 64 frames as one tensor-core GEMM
  *                        (lib/model2video.py:55-85); 0 = streaming skinning kernel
  * Set options before the first forward that they affect; unknown names return SMPLK_E_ARG. */

@@ -316,3 +316,28 @@ def test_fused_forward_tma_stores_are_bitwise_the_lane_stores(dev, V, B):
     ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(
         *[torch.tensor(x, dtype=torch.float64) for x in (betas[:64], pose[:64], transl[:64])])
     assert _err(vt[:64], ref.vertices) <= TOL
+
+
+@pytest.mark.parametrize("kind,V,B", [("smplh", 6890, 333), ("smpl", 5003, 130)])
+def test_two_kernel_forward_with_tensor_core_transform_blend(dev, kind, V, B):
+    """Handle option skin_gemm = 1: the skinning pass of the two-kernel forward (SAVE_FOR_BACKWARD) blends the
+    transforms as a GEMM (kSkin instance of lbs_replay_gemm_kernel) and applies them to v_posed in its epilogue.
+    Same result as the streaming skinning kernel (default) and as the float64 oracle; gradients flow as before."""
+    m = synthetic.make_model(kind, seed=4, num_verts=V)
+    dm_g = smplk.DeviceModel(m, device=0, options={"skin_gemm": 1})
+    dm_s = smplk.DeviceModel(m, device=0)
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=V + B)
+    outs = []
+    for dm in (dm_g, dm_s):
+        b, p, t = _t(betas, dev, True), _t(pose, dev, True), _t(transl, dev, True)
+        dm.profile_enable(True)
+        v = body_model_apply(dm, b, p, transl=t)[0]
+        (v ** 2).sum().backward()
+        torch.cuda.synchronize()
+        outs.append((v.detach(), p.grad.clone(), dm.profile_read()))
+    assert outs[0][2]["transpose"][1] == 1 and outs[1][2]["transpose"][1] == 0       # the GEMM's operand pass ran
+    assert _err(outs[0][0], outs[1][0]) <= 3e-6
+    assert float((outs[0][1] - outs[1][1]).abs().max() / outs[1][1].abs().max()) <= 1e-5
+    ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(
+        *[torch.tensor(x, dtype=torch.float64) for x in (betas, pose, transl)])
+    assert _err(outs[0][0], ref.vertices) <= TOL
