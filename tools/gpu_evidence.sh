@@ -26,5 +26,16 @@ cap() {  # name, target args, kernel regex, skip, count
 cap fused fused blend_skin_fused 1 1
 cap twokernel twokernel 'skin_grouped|blend_tcgen05' 2 2
 cap fit fit 'dA_seg|skin_fit_l2|pose_' 4 4
-cap lbs lbs skin_ 1 1
-cap lbs200k "lbs 200000" skin_ 1 1
+cap lbs lbs 'lbs_replay_gemm|skin_' 1 1
+cap lbs200k "lbs 200000" 'lbs_replay_gemm|skin_' 1 1
+# probes behind the round-2 store-path decisions (tools/micro/*.cu are built by the caller: see their headers)
+if [ -x tools/micro/tma_store_probe ]; then
+  for a in "4 0 36" "4 4 36" "4 2 36" "4 1 36" "4 20670 36" "8 1 18" "8 10335 18" "4 2 32" "4 20672 36"; do
+    timeout 30 tools/micro/tma_store_probe $a; done > gpurun_out/r02_tma_store_probe.txt 2>&1
+fi
+if [ -x tools/micro/store_pattern_probe ]; then
+  { timeout 60 tools/micro/store_pattern_probe 6890 16384; timeout 60 tools/micro/store_pattern_probe 50000 2048; } > gpurun_out/r02_store_pattern_probe.txt 2>&1
+fi
+python tools/replay_ab.py > gpurun_out/r02_replay_gemm_ab.txt 2>&1
+python tools/skin_gemm_ab.py > gpurun_out/r02_skin_gemm_ab.txt 2>&1
+python tools/fz_ab.py > gpurun_out/r02_fused_tma_out_ab.txt 2>&1
