@@ -590,6 +590,7 @@ __device__ __forceinline__ float halve_exchange(bool upper, float lo, float hi, 
 }
 
 __global__ void __launch_bounds__(kDASegWarps * 32) dA_seg_kernel(const ModelDev m, const DASegArgs a) {
+  ptx::pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * kDASegWarps + warp;
   if (s >= m.seg_count) return;
@@ -606,6 +607,7 @@ __global__ void __launch_bounds__(kDASegWarps * 32) dA_seg_kernel(const ModelDev
   const int b0 = blockIdx.y * a.bodies_per_warp;
   const int b1 = min(a.B, b0 + a.bodies_per_warp);
   if (b0 >= b1) return;
+  ptx::pdl_wait();             // the segment tables above are constants; gradients and v_posed come from earlier kernels
   float gq[4][3], xq[4][3];
   auto load = [&](int b, float (&g)[4][3], float (&x)[4][3]) {
     const float* gp = a.dverts + (size_t)b * m.V * 3;
@@ -724,6 +726,8 @@ __host__ __device__ inline int pose_bwd_smem_floats(int J, int Kpad, int segs) {
 // the pose kernel's single warp per body.
 __global__ void __launch_bounds__(256)
 reduce_splits_kernel(int n, int splits, size_t stride, float* __restrict__ d_feat) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -745,6 +749,7 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
   // the skeleton's index tables, staged once per block: the level walks otherwise chain three or
   // four dependent global loads per level (L2 latency each when a single body is fitted)
   __shared__ int s_par[kMaxJoints], s_ord[kMaxJoints], s_lvl[kMaxJoints + 2], s_cptr[kMaxJoints + 1], s_cidx[kMaxJoints];
+  ptx::pdl_launch_dependents();
   for (int i = threadIdx.x; i < m.J; i += blockDim.x) {
     s_par[i] = m.parents[i]; s_ord[i] = m.order[i]; s_cptr[i] = m.child_ptr[i];
     if (i < m.J - 1) s_cidx[i] = m.child_idx[i];
@@ -767,17 +772,10 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
   float* dfeat_sum = Gw + ((m.J * 51 + 3) & ~3);
   float* sdA = dfeat_sum + m.Kpad;
   const bool feat_staged = a.d_feat != nullptr && a.feat_splits == 1;
-  if (feat_staged) {
-    const float* f = a.d_feat + (size_t)b * m.Kpad;
-    for (int k = 4 * lane; k < m.Kpad; k += 128) ptx::cp_async_16(dfeat_sum + k, f + k);
-  }
-  if (a.staged_segs > 0) {
-    const float* src = a.dAp + (size_t)b * m.seg_count * 12;
-    for (int i = 4 * lane; i < a.staged_segs * 12; i += 128) ptx::cp_async_16(sdA + i, src + i);
-  }
-  ptx::cp_async_commit();
 
-  // ---- forward recompute (same walk as pose_forward_kernel; cheaper than saving it)
+  // ---- forward recompute (same walk as pose_forward_kernel; cheaper than saving it).  Its first half -- pose
+  // assembly, Rodrigues, rest joints: the caller's read-only inputs and constant tables only -- runs BEFORE the
+  // programmatic-launch wait, i.e. beside the split reduction and the tail of the backward GEMM.
   float rv[SLOTS][3], Jr[SLOTS][3];
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
@@ -795,6 +793,17 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
       l4[2] = make_float4(R[6], R[7], R[8], Jr[s][2]);
     }
   }
+  ptx::pdl_wait();
+  // this body's gradient inputs -> smem by cp.async, in flight while the chain is walked
+  if (feat_staged) {
+    const float* f = a.d_feat + (size_t)b * m.Kpad;
+    for (int k = 4 * lane; k < m.Kpad; k += 128) ptx::cp_async_16(dfeat_sum + k, f + k);
+  }
+  if (a.staged_segs > 0) {
+    const float* src = a.dAp + (size_t)b * m.seg_count * 12;
+    for (int i = 4 * lane; i < a.staged_segs * 12; i += 128) ptx::cp_async_16(sdA + i, src + i);
+  }
+  ptx::cp_async_commit();
   __syncwarp();
   float pj[SLOTS][3];
 #pragma unroll

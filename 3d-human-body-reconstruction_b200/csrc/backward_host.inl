@@ -70,6 +70,14 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
   DEVICE_GUARD(model->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(a->stream);
   const int B = a->batch;
+  // Programmatic dependent launch inside this call: the FIRST kernel is launched with plain stream ordering (everything
+  // the caller queued before is complete when it starts), the later ones of the fitting-step chain (dA_seg ->
+  // backward GEMM -> split reduction -> pose backward) with the attribute.  The pose backward kernel recomputes its
+  // forward half from the caller's read-only inputs before its wait, which that first plain launch makes safe.
+  bool chain_started = false;
+  auto pdl_next = [&]() { const bool p = model->use_pdl && chain_started; chain_started = true; return p; };
+  if (a->d_betas && model->d.NB > 0 && (!a->betas || a->betas_batch == 1))    // shared betas: atomic accumulation target
+    CUDA_TRY(cudaMemsetAsync(a->d_betas, 0, (size_t)model->d.NB * sizeof(float), st));
   uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
   const float* A = reinterpret_cast<const float*>(ws + w.off_A);
   const float* v_posed = reinterpret_cast<const float*>(ws + w.off_vposed);
@@ -96,6 +104,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     { ProfScope prof(model, st, SMPLK_PROF_DA);
     pick_backward_kernel<<<B, kPickThreads, pick_bwd_smem_bytes(d.J, d.E), st>>>(d, pk); }
     LAUNCH_CHECK("pick_backward_kernel");
+    chain_started = true;
   }
 
   // ---- effective vertex gradient (vertex picks and posed-vertex regressors fold into it)
@@ -110,6 +119,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
                                                      (d.R > 0) ? a->d_joints_regressed : nullptr,
                                                      dverts_eff);
     LAUNCH_CHECK("scatter_joint_grads_kernel");
+    chain_started = true;
     dverts = dverts_eff;
   }
 
@@ -125,7 +135,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     ds.bodies_per_warp = std::max(1, std::min(16, B / 8));
     { ProfScope prof(model, st, SMPLK_PROF_DA);
     dim3 grid((d.seg_count + kDASegWarps - 1) / kDASegWarps, (B + ds.bodies_per_warp - 1) / ds.bodies_per_warp);
-    dA_seg_kernel<<<grid, kDASegWarps * 32, 0, st>>>(d, ds); }
+    launch_k(pdl_next(), dA_seg_kernel, grid, kDASegWarps * 32, 0, st, d, ds); }
     LAUNCH_CHECK("dA_seg_kernel");
     seg_partials = ds.dAp;
   } else if (have_dv) {
@@ -140,6 +150,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     while (jsplit < 8 && (long)B * jsplit * 2 <= 4L * model->num_sms && jsplit * (kDAThreads / 32) < d.J) jsplit *= 2;
     dA_kernel<<<dim3(B, jsplit), kDAThreads, 0, st>>>(d, da); }
     LAUNCH_CHECK("dA_kernel");
+    chain_started = true;
   } else {
     CUDA_TRY(cudaMemsetAsync(dA, 0, (size_t)B * d.J * 12 * sizeof(float), st));
     CUDA_TRY(cudaMemsetAsync(dtr, 0, (size_t)B * 3 * sizeof(float), st));
@@ -169,6 +180,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
       if (f16) skin_backward_grouped_kernel<kS, true><<<grid, kGrpThreads, smem, st>>>(d, sb);
       else skin_backward_grouped_kernel<kS, false><<<grid, kGrpThreads, smem, st>>>(d, sb);
       LAUNCH_CHECK("skin_backward_grouped_kernel");
+      chain_started = true;
     } else {
       int bpb = 16;
       while (bpb > 1 && (long)tiles * ((B + bpb - 1) / bpb) < 4L * 4 * model->num_sms) bpb >>= 1;
@@ -179,6 +191,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
       if (d.ell_k <= 4) skin_backward_kernel<true><<<grid, kSkinThreads, smem, st>>>(d, sb);
       else skin_backward_kernel<false><<<grid, kSkinThreads, smem, st>>>(d, sb); }
       LAUNCH_CHECK("skin_backward_kernel");
+      chain_started = true;
     }
 
     CUtensorMap tm_ahi, tm_alo, tm_out;
@@ -198,13 +211,14 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
       ga.out = dfeat; ga.out_ld = d.Kpad; ga.out_rows = L.splits * L.mpad; ga.out_cols = d.Kpad;
       const int tiles_g = L.m_blocks * L.n_blocks * L.splits;
       ProfScope prof(model, st, SMPLK_PROF_BLEND_BWD);
+      const bool pdl = pdl_next();
       if (f16)
-        blend_tcgen05_2cta_kernel<true><<<2 * std::min(tiles_g, model->num_sms / 2), kGemmThreads, k2SmemAlloc, st>>>(
-            tm_ahi, tm_alo, dvp_ready ? model->tmap2_pdknb_hi : model->tmap2_pdknh_hi,
-            dvp_ready ? model->tmap2_pdknb_lo : model->tmap2_pdknh_lo, tm_out, ga);
+        launch_k(pdl, blend_tcgen05_2cta_kernel<true>, 2 * std::min(tiles_g, model->num_sms / 2), kGemmThreads, k2SmemAlloc, st,
+                 tm_ahi, tm_alo, dvp_ready ? model->tmap2_pdknb_hi : model->tmap2_pdknh_hi,
+                 dvp_ready ? model->tmap2_pdknb_lo : model->tmap2_pdknh_lo, tm_out, ga);
       else
-        blend_tcgen05_2cta_kernel<false><<<2 * std::min(tiles_g, model->num_sms / 2), kGemmThreads, k2SmemAlloc, st>>>(
-            tm_ahi, tm_alo, model->tmap2_pdkn_hi, model->tmap2_pdkn_lo, tm_out, ga);
+        launch_k(pdl, blend_tcgen05_2cta_kernel<false>, 2 * std::min(tiles_g, model->num_sms / 2), kGemmThreads, k2SmemAlloc, st,
+                 tm_ahi, tm_alo, model->tmap2_pdkn_hi, model->tmap2_pdkn_lo, tm_out, ga);
       LAUNCH_CHECK("blend_tcgen05_2cta_kernel(backward)");
     } else {
     if (int r = make_operand_tmap(model, &tm_ahi, dvp_hi, d.Npad, B, kBlendBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, f16)) return r;
@@ -229,6 +243,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
       blend_tcgen05_kernel<false><<<std::min(tiles_g, model->num_sms), kGemmThreads, kGemmSmemAlloc, st>>>(
           tm_ahi, tm_alo, model->tmap_pdkn_hi, model->tmap_pdkn_lo, tm_out, ga); }
     LAUNCH_CHECK("blend_tcgen05_kernel(backward)");
+    chain_started = true;
     }
   }
 
@@ -241,7 +256,7 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
   pb.feat_splits = picks_only ? 1 : L.splits; pb.feat_split_stride = (size_t)L.mpad * d.Kpad;
   if (pb.d_feat != nullptr && L.splits > 1 && !picks_only) {      // sum the split-K partials in parallel, in place
     const int n = B * d.Kpad;
-    reduce_splits_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, L.splits, pb.feat_split_stride, dfeat);
+    launch_k(pdl_next(), reduce_splits_kernel, (n + 255) / 256, 256, 0, st, n, L.splits, pb.feat_split_stride, dfeat);
     LAUNCH_CHECK("reduce_splits_kernel");
     pb.feat_splits = 1;
   }
@@ -253,16 +268,16 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
   pb.d_loss = a->d_loss;
   pb.d_loss_stride = (a->flags & SMPLK_FLAG_LOSS_SUM) ? 0 : 1;
   pb.d_full_pose = a->d_full_pose;
-  if (pb.d_betas && pb.betas_B == 1)
-    CUDA_TRY(cudaMemsetAsync(a->d_betas, 0, (size_t)d.NB * sizeof(float), st));
+  // (a shared-betas gradient was zeroed at the top of the call: no memset node between the chain's kernels)
   const int blocks = (B + kPoseWarps - 1) / kPoseWarps;
   pb.staged_segs = 0;
   if (seg_partials && (size_t)kPoseWarps * pose_bwd_smem_floats(d.J, d.Kpad, d.seg_count) * sizeof(float) <= 96 * 1024)
     pb.staged_segs = d.seg_count;           // two blocks per SM still fit
   const size_t smem = (size_t)kPoseWarps * pose_bwd_smem_floats(d.J, d.Kpad, pb.staged_segs) * sizeof(float);
   { ProfScope prof(model, st, SMPLK_PROF_POSE_BWD);
-  if (d.J <= 32) pose_backward_kernel<1><<<blocks, kPoseWarps * 32, smem, st>>>(d, pb);
-  else pose_backward_kernel<2><<<blocks, kPoseWarps * 32, smem, st>>>(d, pb); }
+  const bool pdl = pdl_next();
+  if (d.J <= 32) launch_k(pdl, pose_backward_kernel<1>, blocks, kPoseWarps * 32, smem, st, d, pb);
+  else launch_k(pdl, pose_backward_kernel<2>, blocks, kPoseWarps * 32, smem, st, d, pb); }
   LAUNCH_CHECK("pose_backward_kernel");
   return 0;
 }

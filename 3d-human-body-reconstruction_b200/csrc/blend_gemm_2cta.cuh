@@ -64,6 +64,7 @@ blend_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
   constexpr int kElemsPerBlock = 128 / (kF16 ? 2 : 4);
   constexpr int kUmmaK = kF16 ? 16 : 8;
 
+  ptx::pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_f_hi);
     ptx::prefetch_tmap(&tmap_f_lo);
@@ -88,6 +89,7 @@ blend_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
   ptx::cluster_sync();            // barrier inits + TMEM allocation visible in both CTAs
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  ptx::pdl_wait();                // the set-up above overlaps the previous kernel's tail; its output is read from here on
 
   auto coord = [&](int tile, int& m0, int& n0, int& kb0, int& kb1, int& out_row0) {
     const int mb = tile % args.num_m_blocks;

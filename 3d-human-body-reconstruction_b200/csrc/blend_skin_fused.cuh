@@ -188,6 +188,7 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
   const int num_tiles = args.num_m_blocks * args.num_n_blocks;
   constexpr int kUmmaK = 16;
 
+  ptx::pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_f_hi);
     ptx::prefetch_tmap(&tmap_f_lo);
@@ -216,6 +217,9 @@ blend_skin_fused_kernel(const __grid_constant__ CUtensorMap tmap_f_hi,
   ptx::cluster_sync();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // barriers, TMEM and the descriptor prefetches above overlap the pose kernel's tail (programmatic dependent launch);
+  // its feature rows and transforms are read from here on
+  ptx::pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================

@@ -240,9 +240,11 @@ pose_forward_kernel(const ModelDev m, const PoseFwdArgs a) {
   // the skeleton's index tables, staged once per block: the level walk otherwise chains three
   // dependent global loads per level (L2 latency each for a single body)
   __shared__ int s_par[kMaxJoints], s_ord[kMaxJoints], s_lvl[kMaxJoints + 2];
+  ptx::pdl_launch_dependents();
   for (int i = threadIdx.x; i < m.J; i += blockDim.x) { s_par[i] = m.parents[i]; s_ord[i] = m.order[i]; }
   for (int i = threadIdx.x; i < m.max_depth + 2; i += blockDim.x) s_lvl[i] = m.level_start[i];
   __syncthreads();
+  ptx::pdl_wait();               // the workspace rows written below may still be read by the previous call's kernels
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kPoseWarps + warp;
   if (b >= a.B) return;
@@ -439,7 +441,9 @@ pose_forward_block_kernel(const ModelDev m, const PoseFwdArgs a) {
   int* slvl = reinterpret_cast<int*>(pose_smem + L.off_lvl);
 
   // ---- stage the model tables: 4-byte cp.async, everything in flight at once (as register loads the copies were
-  // ~10 dependent L2 round trips per thread: a quarter of the kernel at 1,024 bodies)
+  // ~10 dependent L2 round trips per thread: a quarter of the kernel at 1,024 bodies).  Under a programmatic
+  // dependent launch this part runs beside the tail of the previous kernel in the stream (constant tables only).
+  ptx::pdl_launch_dependents();
   {
     const uint32_t s0 = ptx::smem_u32(pose_smem);
     auto stage = [&](const void* dst, const void* src) {
@@ -458,6 +462,7 @@ pose_forward_block_kernel(const ModelDev m, const PoseFwdArgs a) {
     for (int i = threadIdx.x; i < m.max_depth + 2; i += blockDim.x) stage(slvl + i, m.level_start + i);
     ptx::cp_async_commit();
   }
+  ptx::pdl_wait();
   // ---- this body's small inputs into the warp's feature row: betas at feat[P..], PCA coefficients
   // parked at feat[0..2C) until the features overwrite them
   const float* betas_row = (a.betas && live) ? a.betas + (size_t)(a.betas_B == 1 ? 0 : b) * m.NB : nullptr;

@@ -422,5 +422,17 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// become resident while its predecessor in the stream still runs; `pdl_wait` blocks until the predecessor grid has
+// completed and its memory operations are visible (a no-op for a normal launch).  `pdl_launch_dependents` lets the
+// successor's blocks be scheduled as soon as every block of this grid has issued it (they still stop at their own
+// `pdl_wait` until this grid is complete), so the successor's prologue overlaps this grid's tail.
+// Rule in this library: before `pdl_wait` a kernel touches only its own shared memory / TMEM / barriers and the
+// model's constant tables (plus, for the pose backward, the caller's read-only inputs: the first kernel of every
+// API call is launched WITHOUT the attribute, so those were complete before the chain began).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace ptx
 }  // namespace smplk

@@ -45,6 +45,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, float& ra, flo
 __global__ void __launch_bounds__(kGrpThreads, 2)
 skin_fit_l2_kernel(const ModelDev m, const SkinFitArgs a) {
   extern __shared__ __align__(16) float sf_smem[];
+  ptx::pdl_launch_dependents();
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int v0 = blockIdx.x * kSkinTileVerts;
@@ -104,6 +105,7 @@ skin_fit_l2_kernel(const ModelDev m, const SkinFitArgs a) {
   // never-copied tail floats of the ring must be finite (they meet zero weights)
   for (int i = tid; i < kGrpStages * kSkinTileVerts * 3; i += kGrpThreads) ring[i] = 0.f;
   __syncthreads();
+  ptx::pdl_wait();          // group tables and the ring set-up above overlap the blend GEMM's tail; v_posed / A from here on
   issue_A(0);
 #pragma unroll
   for (int i = 0; i < kGrpStages - 1; ++i) issue_v(b0 + i);

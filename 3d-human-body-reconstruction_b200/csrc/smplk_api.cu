@@ -58,6 +58,21 @@ static int fail(int code, const char* fmt, ...) {
       return fail((int)e_, "launch of %s failed: %s", name, cudaGetErrorString(e_));     \
   } while (0)
 
+// Kernel launch with (pdl = true) or without the programmatic-stream-serialization attribute: see ptx::pdl_wait.
+// Only kernels that execute `pdl_wait` before their first access to mutable global memory may be launched with it.
+// Errors are picked up by the LAUNCH_CHECK that follows (cudaGetLastError).
+template <typename... KArgs, typename... Args>
+static void launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
 // Every entry point works on its model's (or the named) device and leaves the caller's current device
 // as it found it (a single process may drive several GPUs).
 struct DeviceGuard {
@@ -130,6 +145,7 @@ struct smplk_model {
   bool fused_tma_out;   // option fused_tma_out = 0: the fused kernel stores its result per lane instead of through TMA
   bool use_fused;       // option fused = 0 selects the two-kernel forward (cross-checks, stand-alone kernel timings)
   bool use_pose_block;  // option pose_block = 0 selects the warp-per-body pose kernel + transposition pass
+  bool use_pdl;         // option pdl = 0: every kernel of a call is launched with plain stream ordering (no programmatic dependent launch)
   CUtensorMap tmap_pdkn_hi, tmap_pdkn_lo;  // backward: B operand rows = blend features
   CUtensorMap tmap_pdknh_hi, tmap_pdknh_lo, tmap2_pdknh_hi, tmap2_pdknh_lo;   // same, fp16 two-term split
   CUtensorMap tmap_pdknb_hi, tmap_pdknb_lo, tmap2_pdknb_hi, tmap2_pdknb_lo;   // same, bf16 two-term split
@@ -922,7 +938,7 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   // parity tests, stand-alone kernel timings of the bench).  The product library reads NO environment variable.
   mdl->skin_bpb = 0; mdl->skin_g8 = true; mdl->skin_tma = false; mdl->force_skin_v1 = false; mdl->da_v1 = false;
   mdl->fit_fused = true; mdl->sparse_picks = true; mdl->use_2cta = true; mdl->use_fused = true; mdl->fused_tma_out = true; mdl->use_replay_gemm = true; mdl->use_skin_gemm = false;
-  mdl->use_pose_block = true; mdl->bwd_f16 = true; mdl->default_tc = BLEND_F16;
+  mdl->use_pose_block = true; mdl->use_pdl = true; mdl->bwd_f16 = true; mdl->default_tc = BLEND_F16;
 #ifdef SMPLK_AB   // A/B builds (tools/): tuning switches of kernels that are on no default path
   { const char* e = getenv("SMPLK_DA_V1"); mdl->da_v1 = e && e[0] == '1'; }
   { const char* e = getenv("SMPLK_SKIN_BPB"); mdl->skin_bpb = e ? atoi(e) : 0; }
@@ -952,6 +968,7 @@ extern "C" int smplk_model_set_option(smplk_model* model, const char* name, int 
   else if (!strcmp(name, "replay_gemm")) model->use_replay_gemm = on;   // rigged-mesh replay on the tensor cores
   else if (!strcmp(name, "skin_gemm")) model->use_skin_gemm = on;       // two-kernel forward: transform blend on the tensor cores
   else if (!strcmp(name, "fused")) model->use_fused = on;                    // fused blend + skinning forward kernel
+  else if (!strcmp(name, "pdl")) model->use_pdl = on;                    // programmatic dependent launch between a call's kernels
   else if (!strcmp(name, "pose_block")) model->use_pose_block = on;     // block-level pose kernel (else warp per body)
   else if (!strcmp(name, "blend_tf32")) model->default_tc = on ? BLEND_TF32 : BLEND_F16;   // 3xTF32 forward operands
   else if (!strcmp(name, "backward_tf32")) model->bwd_f16 = !on;        // 3xTF32 backward GEMM
@@ -1042,9 +1059,9 @@ static int launch_pose_forward(const smplk_model* mdl, const PoseFwdArgs& pa, cu
     const int blocks = (bodies + nw - 1) / nw;
     ProfScope prof(mdl, st, SMPLK_PROF_POSE_FWD);
     if (d.J <= 32)
-      pose_forward_block_kernel<1><<<blocks, nw * 32, smem, st>>>(d, pa);
+      launch_k(mdl->use_pdl, pose_forward_block_kernel<1>, blocks, nw * 32, smem, st, d, pa);
     else
-      pose_forward_block_kernel<2><<<blocks, nw * 32, smem, st>>>(d, pa);
+      launch_k(mdl->use_pdl, pose_forward_block_kernel<2>, blocks, nw * 32, smem, st, d, pa);
     LAUNCH_CHECK("pose_forward_block_kernel");
     return 0;
   }
@@ -1052,9 +1069,9 @@ static int launch_pose_forward(const smplk_model* mdl, const PoseFwdArgs& pa, cu
   const size_t smem = (size_t)kPoseWarps * (std::max(d.Kpad, 32) + d.J * 12) * sizeof(float);
   ProfScope prof(mdl, st, SMPLK_PROF_POSE_FWD);
   if (d.J <= 32)
-    pose_forward_kernel<1><<<blocks, kPoseWarps * 32, smem, st>>>(d, pa);
+    launch_k(mdl->use_pdl, pose_forward_kernel<1>, blocks, kPoseWarps * 32, smem, st, d, pa);
   else
-    pose_forward_kernel<2><<<blocks, kPoseWarps * 32, smem, st>>>(d, pa);
+    launch_k(mdl->use_pdl, pose_forward_kernel<2>, blocks, kPoseWarps * 32, smem, st, d, pa);
   LAUNCH_CHECK("pose_forward_kernel");
   return 0;
 }
@@ -1100,11 +1117,11 @@ static int launch_blend(const smplk_model* mdl, int rows, BlendPath path, float*
       const int grid = 2 * std::min(tiles, mdl->num_sms / 2);
       ProfScope prof(mdl, st, SMPLK_PROF_BLEND_TCGEN05);
       if (f16)
-        blend_tcgen05_2cta_kernel<true><<<grid, kGemmThreads, k2SmemAlloc, st>>>(
-            tm_fhi, tm_flo, mdl->tmap2_pdh_hi, mdl->tmap2_pdh_lo, tm_out, ga);
+        launch_k(mdl->use_pdl, blend_tcgen05_2cta_kernel<true>, grid, kGemmThreads, k2SmemAlloc, st,
+                 tm_fhi, tm_flo, mdl->tmap2_pdh_hi, mdl->tmap2_pdh_lo, tm_out, ga);
       else
-        blend_tcgen05_2cta_kernel<false><<<grid, kGemmThreads, k2SmemAlloc, st>>>(
-            tm_fhi, tm_flo, mdl->tmap2_pd_hi, mdl->tmap2_pd_lo, tm_out, ga);
+        launch_k(mdl->use_pdl, blend_tcgen05_2cta_kernel<false>, grid, kGemmThreads, k2SmemAlloc, st,
+                 tm_fhi, tm_flo, mdl->tmap2_pd_hi, mdl->tmap2_pd_lo, tm_out, ga);
       LAUNCH_CHECK("blend_tcgen05_2cta_kernel");
       return 0;
     }
@@ -1212,15 +1229,18 @@ static int launch_fused(const smplk_model* mdl, int rows, float* F_hi, float* F_
     tm_oe = tm_fhi; tm_oo = tm_fhi; tm_oo32 = tm_fhi;          // never dereferenced
   }
   ProfScope prof(mdl, st, SMPLK_PROF_BLEND_SKIN_FUSED);
+  // programmatic dependent launch only straight after the block pose kernel (with `A` given, the transposition pass,
+  // which has no trigger, sits in between and the attribute would buy nothing)
+  const bool pdl = mdl->use_pdl && A == nullptr && !dbg;
   if (tma_out)
-    blend_skin_fused_kernel<0, true><<<grid, kFzThreads, kFzSmemAlloc, st>>>(tm_fhi, tm_flo, mdl->tmapf_pdh_hi,
-                                                                           mdl->tmapf_pdh_lo, tm_oe, tm_oo, tm_oo32, fa);
+    launch_k(pdl, blend_skin_fused_kernel<0, true>, grid, kFzThreads, kFzSmemAlloc, st, tm_fhi, tm_flo, mdl->tmapf_pdh_hi,
+             mdl->tmapf_pdh_lo, tm_oe, tm_oo, tm_oo32, fa);
   else if (d.N == 3 * 6890)   // canonical SMPL-family vertex count: row pitch folded into the store addresses
-    blend_skin_fused_kernel<3 * 6890, false><<<grid, kFzThreads, kFzSmemAlloc, st>>>(tm_fhi, tm_flo, mdl->tmapf_pdh_hi,
-                                                                                   mdl->tmapf_pdh_lo, tm_oe, tm_oo, tm_oo32, fa);
+    launch_k(pdl, blend_skin_fused_kernel<3 * 6890, false>, grid, kFzThreads, kFzSmemAlloc, st, tm_fhi, tm_flo,
+             mdl->tmapf_pdh_hi, mdl->tmapf_pdh_lo, tm_oe, tm_oo, tm_oo32, fa);
   else
-    blend_skin_fused_kernel<0, false><<<grid, kFzThreads, kFzSmemAlloc, st>>>(tm_fhi, tm_flo, mdl->tmapf_pdh_hi,
-                                                                            mdl->tmapf_pdh_lo, tm_oe, tm_oo, tm_oo32, fa);
+    launch_k(pdl, blend_skin_fused_kernel<0, false>, grid, kFzThreads, kFzSmemAlloc, st, tm_fhi, tm_flo,
+             mdl->tmapf_pdh_hi, mdl->tmapf_pdh_lo, tm_oe, tm_oo, tm_oo32, fa);
   LAUNCH_CHECK("blend_skin_fused_kernel");
   if (dbg) {   // tuning aid: per-tile timeline of CTA 0 (cycles relative to the first stamp)
     std::vector<long long> h((2 + kFzEpiWarps) * kFzDbgTiles * 4);
@@ -1473,6 +1493,12 @@ static int forward_impl(const smplk_model* model, const smplk_forward_args* a, c
     const bool fused = fused_applies(model, rows, path, flags, a->verts != nullptr);
     const bool at_from_pose = fused && pose_block_applies(model);
     if (at_from_pose) pa.At = At;            // the block pose kernel writes the transposed transforms itself
+    if (fit != nullptr && a->verts && !fused && fit_fused_applies(model)) {
+      // the loss accumulator of skin_fit_l2_kernel: zeroed here, ahead of the chunk's first kernel, so that no memset
+      // node sits between two kernels of the chain (it would end the programmatic dependent launch there)
+      const int loss_stride = (flags & SMPLK_FLAG_LOSS_SUM) ? 0 : 1;
+      CUDA_TRY(cudaMemsetAsync(fit->loss + (size_t)c0 * loss_stride, 0, (size_t)(loss_stride ? rows : 1) * sizeof(float), st));
+    }
     if (int r = launch_pose_forward(model, pa, st)) return r;
     if (flags & SMPLK_FLAG_TRANSFORMS_ONLY) continue;    // pose / FK kernel only: A, joints, full_pose
     if (picks_fwd) {
@@ -1496,8 +1522,7 @@ static int forward_impl(const smplk_model* model, const smplk_forward_args* a, c
       } else {
         if (fit != nullptr && fit_fused_applies(model)) {
           // skinning + loss + gradient + skinning backward in one kernel; vout receives the gradient
-          const int loss_stride = (flags & SMPLK_FLAG_LOSS_SUM) ? 0 : 1;
-          CUDA_TRY(cudaMemsetAsync(fit->loss + (size_t)c0 * loss_stride, 0, (size_t)(loss_stride ? rows : 1) * sizeof(float), st));
+          const int loss_stride = (flags & SMPLK_FLAG_LOSS_SUM) ? 0 : 1;      // (zeroed before the pose kernel, above)
           SkinFitArgs fa;
           fa.B = rows;
           fa.vposed = v_posed; fa.vposed_stride = (size_t)d.Npad; fa.A = A; fa.transl = pa.transl;
@@ -1510,7 +1535,8 @@ static int forward_impl(const smplk_model* model, const smplk_forward_args* a, c
           if (model->skin_bpb > 0) bpb = model->skin_bpb;
           fa.bodies_per_block = bpb;
           ProfScope prof(model, st, SMPLK_PROF_SKIN);
-          skin_fit_l2_kernel<<<dim3(tiles, (rows + bpb - 1) / bpb), kGrpThreads, skin_grouped_smem_bytes(d.J), st>>>(d, fa);
+          launch_k(model->use_pdl, skin_fit_l2_kernel, dim3(tiles, (rows + bpb - 1) / bpb), kGrpThreads,
+                   skin_grouped_smem_bytes(d.J), st, d, fa);
           LAUNCH_CHECK("skin_fit_l2_kernel");
         } else {
           if (int r = launch_skin(model, rows, d.lbs_only ? d.bias : v_posed,
