@@ -20,6 +20,7 @@ constexpr int kPoseWarps = 4;
 struct PoseFwdArgs {
   int B;
   float* At;             // [ceil(B/256)*2][J][128][12] joint-major transforms per 128-body block (+ transl), or null (block kernel only)
+  int At_rows;           // rows of At (B rounded up to whole 256-body blocks): bodies in [B, At_rows) get zero transforms
   const float* betas;
   int betas_B;
   const float* pose;     // (B,3J)
@@ -581,31 +582,40 @@ pose_forward_block_kernel(const ModelDev m, const PoseFwdArgs a) {
     }
   }
 
-  // ---- walk the tree level by level: G_j = G_parent(j) * L_j
-  for (int d = 1; d <= m.max_depth; ++d) {
-    const int l0 = slvl[d], l1 = slvl[d + 1];
-    for (int i = l0 + lane; i < l1; i += 32) {
-      const int j = sord[i];
-      const float4* P4 = reinterpret_cast<const float4*>(Gs + spar[j] * 12);
-      float4* L4 = reinterpret_cast<float4*>(Gs + j * 12);
-      const float4 p0 = P4[0], p1 = P4[1], p2 = P4[2];
-      const float4 q0 = L4[0], q1 = L4[1], q2 = L4[2];
-      float4 o0, o1, o2;
-      o0.x = fmaf(p0.x, q0.x, fmaf(p0.y, q1.x, p0.z * q2.x));
-      o0.y = fmaf(p0.x, q0.y, fmaf(p0.y, q1.y, p0.z * q2.y));
-      o0.z = fmaf(p0.x, q0.z, fmaf(p0.y, q1.z, p0.z * q2.z));
-      o0.w = fmaf(p0.x, q0.w, fmaf(p0.y, q1.w, fmaf(p0.z, q2.w, p0.w)));
-      o1.x = fmaf(p1.x, q0.x, fmaf(p1.y, q1.x, p1.z * q2.x));
-      o1.y = fmaf(p1.x, q0.y, fmaf(p1.y, q1.y, p1.z * q2.y));
-      o1.z = fmaf(p1.x, q0.z, fmaf(p1.y, q1.z, p1.z * q2.z));
-      o1.w = fmaf(p1.x, q0.w, fmaf(p1.y, q1.w, fmaf(p1.z, q2.w, p1.w)));
-      o2.x = fmaf(p2.x, q0.x, fmaf(p2.y, q1.x, p2.z * q2.x));
-      o2.y = fmaf(p2.x, q0.y, fmaf(p2.y, q1.y, p2.z * q2.y));
-      o2.z = fmaf(p2.x, q0.z, fmaf(p2.y, q1.z, p2.z * q2.z));
-      o2.w = fmaf(p2.x, q0.w, fmaf(p2.y, q1.w, fmaf(p2.z, q2.w, p2.w)));
-      L4[0] = o0; L4[1] = o1; L4[2] = o2;
+  // ---- walk the tree level by level: G_j = G_parent(j) * L_j, with LANE = BODY of the block and the level's joints
+  // dealt to the warps.  (Lane = joint, one warp per body, left most lanes idle: a level of SMPL-H holds 1-10 joints,
+  // and the walk was 31 % of the kernel's executed instructions -- ncu source view, 71 instructions x 10 levels per body.)
+  // A body's table is per_warp = 4 (mod 32) words from the next, so the 8 lanes of an LDS.128 phase hit 32 distinct banks.
+  __syncthreads();
+  {
+    float* Gb = pose_smem + min(lane, nw - 1) * L.per_warp + max(m.Kpad, 32);
+    for (int d = 1; d <= m.max_depth; ++d) {
+      const int l0 = slvl[d], l1 = slvl[d + 1];
+      if (lane < nw) {
+        for (int i = l0 + warp; i < l1; i += nw) {
+          const int j = sord[i];
+          const float4* P4 = reinterpret_cast<const float4*>(Gb + spar[j] * 12);
+          float4* L4 = reinterpret_cast<float4*>(Gb + j * 12);
+          const float4 p0 = P4[0], p1 = P4[1], p2 = P4[2];
+          const float4 q0 = L4[0], q1 = L4[1], q2 = L4[2];
+          float4 o0, o1, o2;
+          o0.x = fmaf(p0.x, q0.x, fmaf(p0.y, q1.x, p0.z * q2.x));
+          o0.y = fmaf(p0.x, q0.y, fmaf(p0.y, q1.y, p0.z * q2.y));
+          o0.z = fmaf(p0.x, q0.z, fmaf(p0.y, q1.z, p0.z * q2.z));
+          o0.w = fmaf(p0.x, q0.w, fmaf(p0.y, q1.w, fmaf(p0.z, q2.w, p0.w)));
+          o1.x = fmaf(p1.x, q0.x, fmaf(p1.y, q1.x, p1.z * q2.x));
+          o1.y = fmaf(p1.x, q0.y, fmaf(p1.y, q1.y, p1.z * q2.y));
+          o1.z = fmaf(p1.x, q0.z, fmaf(p1.y, q1.z, p1.z * q2.z));
+          o1.w = fmaf(p1.x, q0.w, fmaf(p1.y, q1.w, fmaf(p1.z, q2.w, p1.w)));
+          o2.x = fmaf(p2.x, q0.x, fmaf(p2.y, q1.x, p2.z * q2.x));
+          o2.y = fmaf(p2.x, q0.y, fmaf(p2.y, q1.y, p2.z * q2.y));
+          o2.z = fmaf(p2.x, q0.z, fmaf(p2.y, q1.z, p2.z * q2.z));
+          o2.w = fmaf(p2.x, q0.w, fmaf(p2.y, q1.w, fmaf(p2.z, q2.w, p2.w)));
+          L4[0] = o0; L4[1] = o1; L4[2] = o2;
+        }
+      }
+      __syncthreads();
     }
-    __syncwarp();
   }
 
   // ---- skinning transforms A_j = [G_R | G_t - G_R J_j] (kept in the table), FK joints
@@ -636,12 +646,13 @@ pose_forward_block_kernel(const ModelDev m, const PoseFwdArgs a) {
   // ---- joint-major copy for the fused kernel: warp w writes joints w, w + 32; lane = body, so a
   // joint's 32 x 48 bytes leave as one contiguous 1,536-byte run (transl folded into the translation
   // column; bodies past the batch, up to the 256-body block, are zero transforms)
-  if (a.At != nullptr) {                          // launched with 32 warps: lane = body of the block
+  if (a.At != nullptr) {                          // lane = body of the block (nw <= 32 bodies)
     __syncthreads();
     const int bb = blockIdx.x * nw + lane;
     const float* Gl = pose_smem + lane * L.per_warp + max(m.Kpad, 32);
     float ttx = 0.f, tty = 0.f, ttz = 0.f;
     if (a.transl && bb < a.B) { ttx = a.transl[3 * bb]; tty = a.transl[3 * bb + 1]; ttz = a.transl[3 * bb + 2]; }
+    if (lane < nw && bb < a.At_rows)
     for (int j = warp; j < m.J; j += nw) {
       const float4* G4 = reinterpret_cast<const float4*>(Gl + j * 12);
       float4 g0 = G4[0], g1 = G4[1], g2 = G4[2];

@@ -1052,11 +1052,19 @@ static int launch_pose_forward(const smplk_model* mdl, const PoseFwdArgs& pa, cu
   if (pose_block_applies(mdl) && (pa.At != nullptr || pa.B >= 128)) {
     // 32 bodies per block when the block also transposes the transforms (lane = body); otherwise 8, so that
     // mid-size batches (the 1,024-body fitting step: 32 blocks before, 22 us on 32 SMs) use every SM
-    const int nw = (pa.At != nullptr || pa.B >= 4096) ? kPoseBlockWarps : 8;
-    const size_t smem = (size_t)pose_block_layout(d, nw).total * sizeof(float);
     // At is written for whole 256-body blocks (the fused kernel reads zero transforms for padding rows)
-    const int bodies = pa.At ? round_up(pa.B, 2 * kBlendBM) : pa.B;
+    const int bodies = pa.At ? pa.At_rows : pa.B;
+    int nw = (pa.At != nullptr || pa.B >= 4096) ? kPoseBlockWarps : 8;
+    // one wave: spread the bodies over every SM instead of filling 32-body blocks (4,096 bodies: 147 blocks of 28
+    // instead of 128 of 32 -- the kernel's time follows the bodies per SM)
+    if (pa.At != nullptr && bodies <= kPoseBlockWarps * mdl->num_sms)
+      nw = std::max(8, std::min(kPoseBlockWarps, (bodies + mdl->num_sms - 1) / mdl->num_sms));
+    size_t smem = (size_t)pose_block_layout(d, nw).total * sizeof(float);
     const int blocks = (bodies + nw - 1) / nw;
+    // One block per SM when the grid is a single wave: under a programmatic dependent launch the blocks are placed while
+    // the previous kernel drains, and small blocks would otherwise pile up (4 deep) on the SMs that free up first
+    // (measured: 1,024-body forward 0.0767 ms without, 0.0810 ms with PDL before this request was padded).
+    if (mdl->use_pdl && blocks <= mdl->num_sms) smem = std::max(smem, (size_t)116 * 1024);
     ProfScope prof(mdl, st, SMPLK_PROF_POSE_FWD);
     if (d.J <= 32)
       launch_k(mdl->use_pdl, pose_forward_block_kernel<1>, blocks, nw * 32, smem, st, d, pa);
@@ -1492,6 +1500,7 @@ static int forward_impl(const smplk_model* model, const smplk_forward_args* a, c
     pa.full_pose = a->full_pose ? a->full_pose + (size_t)c0 * 3 * d.J : nullptr;
     const bool fused = fused_applies(model, rows, path, flags, a->verts != nullptr);
     const bool at_from_pose = fused && pose_block_applies(model);
+    pa.At_rows = round_up(rows, 2 * kBlendBM);
     if (at_from_pose) pa.At = At;            // the block pose kernel writes the transposed transforms itself
     if (fit != nullptr && a->verts && !fused && fit_fused_applies(model)) {
       // the loss accumulator of skin_fit_l2_kernel: zeroed here, ahead of the chunk's first kernel, so that no memset
