@@ -685,6 +685,15 @@ __device__ __forceinline__ void rodrigues_backward(const float* r, const float* 
   dr[2] = dnz * inv + da * ez * inv;
 }
 
+// 0 (product): the backward chain walk of pose_backward_kernel runs one lane per joint; 1: one lane per gradient element
+// (A/B build, bitwise-equal gradients).  Measured on B200 at 1,024 bodies (profiles/r02_pose_bwd_walk_ab.txt): the
+// element walk is SLOWER, 0.0376 against 0.0334 ms -- a third of the instructions, but two short LDS -> FMA -> STS phases
+// and two warp syncs per level instead of one long phase with 12 independent FMA chains per lane; the kernel is bound
+// by the latency of its dependent steps (issue-active 26 %, 7 warps per SM), not by instruction issue.
+#ifndef SMPLK_POSE_BWD_ELEMWALK
+#define SMPLK_POSE_BWD_ELEMWALK 0
+#endif
+
 struct PoseBwdArgs {
   int B;
   const float* betas;
@@ -899,6 +908,55 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
   // gathers what its children (one level down, already final) send up, then derives its own dR and
   // dJrel from the now-final dG_j (the shared-memory float atomics this replaces were CAS loops and
   // 45 % of the kernel's stall samples).
+#if SMPLK_POSE_BWD_ELEMWALK
+  // A/B variant (see the macro's note): one lane per ELEMENT (joint of the level, row r, column k) of the 3x4 gradient
+  // instead of one lane per joint; a level is ceil(12 n / 32) rounds.  Every element keeps the summation order of the
+  // lane-per-joint version (bitwise-equal gradients).
+  for (int d = m.max_depth; d >= 0; --d) {
+    const int l0 = s_lvl[d], n12 = (s_lvl[d + 1] - l0) * 12;
+    // phase A: what the children (one level down, final) send up -> dG_j, and their part of dJ_j
+    for (int it = lane; it < n12; it += 32) {
+      const int i = it / 12, e = it - 12 * i, r = e >> 2, k = e & 3;
+      const int j = s_ord[l0 + i];
+      const int c0 = s_cptr[j], c1 = s_cptr[j + 1];
+      if (c1 > c0) {
+        const float* G = Gw + j * 12;
+        float acc = dG[j * 12 + e];
+        float djr = (k == 3) ? dJ[j * 3 + r] : 0.f;
+        for (int n = c0; n < c1; ++n) {
+          const int c = s_cidx[n];
+          const float* cg = dG + c * 12;
+          if (k < 3) {
+            const float* L = Lc + c * 12 + k * 4;
+            acc += cg[r * 4 + 0] * L[0] + cg[r * 4 + 1] * L[1] + cg[r * 4 + 2] * L[2] + cg[r * 4 + 3] * L[3];
+          } else {
+            acc += cg[r * 4 + 3];
+            djr -= G[0 * 4 + r] * cg[3] + G[1 * 4 + r] * cg[7] + G[2 * 4 + r] * cg[11];   // Jrel_c = J_c - J_j
+          }
+        }
+        dG[j * 12 + e] = acc;
+        if (k == 3) dJ[j * 3 + r] = djr;
+      }
+    }
+    __syncwarp();
+    // phase B: dR_j and the rest of dJ_j from the now-final dG_j
+    for (int it = lane; it < n12; it += 32) {
+      const int i = it / 12, e = it - 12 * i, r = e >> 2, k = e & 3;
+      const int j = s_ord[l0 + i];
+      const float* dg = dG + j * 12;
+      if (d >= 1) {
+        const float* Pm = Gw + s_par[j] * 12;
+        const float v = Pm[0 * 4 + r] * dg[0 * 4 + k] + Pm[1 * 4 + r] * dg[1 * 4 + k] + Pm[2 * 4 + r] * dg[2 * 4 + k];
+        if (k < 3) dRs[j * 9 + r * 3 + k] = v;
+        else dJ[j * 3 + r] += v;
+      } else {          // root: L_0 = [R_0 | J_0]
+        if (k < 3) dRs[j * 9 + r * 3 + k] = dg[r * 4 + k];
+        else dJ[j * 3 + r] += dg[r * 4 + 3];
+      }
+    }
+    __syncwarp();
+  }
+#else
   for (int d = m.max_depth; d >= 0; --d) {
     const int l0 = s_lvl[d], l1 = s_lvl[d + 1];
     for (int i = l0 + lane; i < l1; i += 32) {
@@ -953,6 +1011,7 @@ pose_backward_kernel(const ModelDev m, const PoseBwdArgs a) {
     }
     __syncwarp();
   }
+#endif
   float dRl[SLOTS][9];
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {

@@ -61,3 +61,4 @@ for val in (1, 0, 1, 0):
     same = all(torch.equal(a, c) for a, c in zip(grads[val], ggrads))
     print("%s=%d B=%d eager %.4f ms  graph %.4f ms  graph grads == eager grads: %s" % (opt, val, B, eager, graph, same), flush=True)
 print("grads equal across option values:", all(torch.equal(a, c) for a, c in zip(grads[1], grads[0])))
+print("grad digests (sum, sum |.|) betas / pose / transl:", [(float(g.double().sum()), float(g.double().abs().sum())) for g in grads[1]])
