@@ -101,6 +101,8 @@ int smplk_model_get_info(const smplk_model* model, smplk_model_info* info);
  *                        streaming kernel, kept for cross-checks
  *   "replay_gemm" (1)    rigged-mesh (LBS-only) handles replay >= 64 frames as one tensor-core GEMM
  *                        (lib/model2video.py:55-85); 0 = streaming skinning kernel
+ *   "pdl" (1)            the kernels of a call are launched with programmatic stream serialization (each kernel's set-up
+ *                        overlaps its predecessor's tail; results are bit-identical); 0 = plain stream ordering
  * Set options before the first forward that they affect; unknown names return SMPLK_E_ARG. */
 int smplk_model_set_option(smplk_model* model, const char* name, int value);
 

@@ -341,3 +341,59 @@ def test_two_kernel_forward_with_tensor_core_transform_blend(dev, kind, V, B):
     ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(
         *[torch.tensor(x, dtype=torch.float64) for x in (betas, pose, transl)])
     assert _err(outs[0][0], ref.vertices) <= TOL
+
+
+@pytest.mark.parametrize("B", [37, 300, 1024, 4096 + 29])
+def test_programmatic_dependent_launch_changes_no_bit(dev, smplh_model, B):
+    """Handle option pdl (default 1): the kernels of a call are launched with programmatic stream serialization and
+    run their set-up before `griddepcontrol.wait` -- the pose backward even recomputes its forward half there.  Only
+    scheduling changes, so the forward, the gradients of back-to-back fitting steps and of a CUDA-graph replay must
+    equal the plainly ordered launches (pdl = 0) bit for bit (the loss itself is summed with float atomics: 1e-6);
+    with one shared betas row the beta gradient is an atomic sum too (memset moved to the head of the call): 1e-5.
+    The batch sizes cover the warp-per-body pose kernel, 8-body blocks, one-wave 28-body blocks and several waves."""
+    m = smplh_model
+    dms = {k: smplk.DeviceModel(m, device=0, options={"pdl": k}) for k in (1, 0)}
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=B)
+    res, shared = {}, {}
+    for k, dm in dms.items():
+        with torch.no_grad():
+            v, j = body_model_apply(dm, _t(betas, dev), _t(pose, dev), transl=_t(transl, dev))[:2]
+        tgt = (v + 0.01).contiguous()
+
+        def step(b, p, t):
+            for x in (b, p, t):
+                x.grad = None
+            loss = fit_vertex_l2(dm, b, p, tgt, transl=t)
+            loss.sum().backward()
+            return loss.detach().clone()
+
+        b, p, t = _t(betas, dev, True), _t(pose, dev, True), _t(transl, dev, True)
+        losses = [step(b, p, t) for _ in range(3)]    # back to back: the next call's pose kernel follows the pose backward
+        eager = [x.grad.clone() for x in (b, p, t)]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            step(b, p, t)
+        torch.cuda.current_stream().wait_stream(s)
+        for x in (b, p, t):
+            x.grad = None
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fit_vertex_l2(dm, b, p, tgt, transl=t).sum().backward()
+        g.replay()
+        torch.cuda.synchronize()
+        for e, x in zip(eager, (b, p, t)):
+            assert torch.equal(e, x.grad)
+        assert float((losses[0] - losses[-1]).abs().max() / losses[0].abs().max()) <= 1e-6
+        res[k] = [v, j] + eager
+        b1, p1 = _t(betas[:1], dev, True), _t(pose, dev, True)
+        fit_vertex_l2(dm, b1, p1, tgt, transl=_t(transl, dev)).sum().backward()
+        shared[k] = (losses[-1], b1.grad.clone(), p1.grad.clone())
+    for x, y in zip(res[1], res[0]):
+        assert torch.isfinite(x).all() and torch.equal(x, y)
+    assert float((shared[1][0] - shared[0][0]).abs().max() / shared[0][0].abs().max()) <= 1e-6
+    assert float((shared[1][1] - shared[0][1]).abs().max() / shared[0][1].abs().max()) <= 1e-5
+    assert torch.equal(shared[1][2], shared[0][2])
+    ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(
+        *[torch.tensor(x, dtype=torch.float64) for x in (betas[:40], pose[:40], transl[:40])])
+    assert _err(res[1][0][:40], ref.vertices) <= TOL
