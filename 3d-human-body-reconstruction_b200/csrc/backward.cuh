@@ -589,6 +589,7 @@ __device__ __forceinline__ float halve_exchange(bool upper, float lo, float hi, 
   return keep + __shfl_xor_sync(0xffffffffu, send, mask);
 }
 
+template <bool kPair>
 __global__ void __launch_bounds__(kDASegWarps * 32) dA_seg_kernel(const ModelDev m, const DASegArgs a) {
   ptx::pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -609,16 +610,26 @@ __global__ void __launch_bounds__(kDASegWarps * 32) dA_seg_kernel(const ModelDev
   if (b0 >= b1) return;
   ptx::pdl_wait();             // the segment tables above are constants; gradients and v_posed come from earlier kernels
   float gq[4][3], xq[4][3];
+  // A vertex's three floats sit at float offset 3v: an 8-byte load of the aligned pair (x, y for an even, y, z for an
+  // odd vertex) + a 4-byte load of the third, chosen branch-free -- 4 gathers per entry instead of 6 (the kernel is
+  // bound by L1 wavefronts of these 12-byte-stride gathers).  Needs 8-byte aligned rows (kPair; else three 4-byte loads).
+  auto load3 = [&](const float* row, int o, float (&v)[3]) {
+    if (kPair) {
+      const bool odd = o & 1;
+      const float2 pr = *reinterpret_cast<const float2*>(row + o + (odd ? 1 : 0));
+      const float s1 = row[o + (odd ? 0 : 2)];
+      v[0] = odd ? s1 : pr.x; v[1] = odd ? pr.x : pr.y; v[2] = odd ? pr.y : s1;
+    } else {
+      v[0] = row[o]; v[1] = row[o + 1]; v[2] = row[o + 2];
+    }
+  };
   auto load = [&](int b, float (&g)[4][3], float (&x)[4][3]) {
     const float* gp = a.dverts + (size_t)b * m.V * 3;
     const float* vp = a.vsrc + (size_t)b * a.vsrc_stride;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        g[u][c] = gp[off[u] + c];
-        x[u][c] = vp[off[u] + c];
-      }
+      load3(gp, off[u], g[u]);
+      load3(vp, off[u], x[u]);
     }
   };
   load(b0, gq, xq);

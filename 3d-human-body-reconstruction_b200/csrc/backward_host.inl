@@ -135,7 +135,12 @@ extern "C" int smplk_backward(const smplk_model* model, const smplk_backward_arg
     ds.bodies_per_warp = std::max(1, std::min(16, B / 8));
     { ProfScope prof(model, st, SMPLK_PROF_DA);
     dim3 grid((d.seg_count + kDASegWarps - 1) / kDASegWarps, (B + ds.bodies_per_warp - 1) / ds.bodies_per_warp);
-    launch_k(pdl_next(), dA_seg_kernel, grid, kDASegWarps * 32, 0, st, d, ds); }
+    // paired gathers need 8-byte aligned rows: (B, V, 3) gradient rows (V even + aligned base) and v_posed rows (Npad % 4 == 0)
+    const bool pair = (d.V % 2 == 0) && (reinterpret_cast<uintptr_t>(dverts) % 8 == 0) &&
+                      (reinterpret_cast<uintptr_t>(v_posed) % 8 == 0) && (d.Npad % 2 == 0);
+    const bool pdl = pdl_next();
+    if (pair) launch_k(pdl, dA_seg_kernel<true>, grid, kDASegWarps * 32, 0, st, d, ds);
+    else launch_k(pdl, dA_seg_kernel<false>, grid, kDASegWarps * 32, 0, st, d, ds); }
     LAUNCH_CHECK("dA_seg_kernel");
     seg_partials = ds.dAp;
   } else if (have_dv) {
