@@ -39,3 +39,5 @@ fi
 python tools/replay_ab.py > gpurun_out/r02_replay_gemm_ab.txt 2>&1
 python tools/skin_gemm_ab.py > gpurun_out/r02_skin_gemm_ab.txt 2>&1
 python tools/fz_ab.py > gpurun_out/r02_fused_tma_out_ab.txt 2>&1
+# programmatic dependent launch on / off (forward sizes, fitting step) and the fitting step's per-kernel times
+{ python tools/pdl_ab.py; python tools/fit_ab.py 1024 pdl; python tools/fit_profile.py 1024; } > gpurun_out/r02_pdl_ab.txt 2>&1
