@@ -70,7 +70,14 @@ static void launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, si
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-  (void)cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+  if (e != cudaSuccess && pdl && (e == cudaErrorNotSupported || e == cudaErrorInvalidValue)) {
+    // a driver / capture mode without programmatic launch: same kernel with plain stream ordering (its
+    // griddepcontrol instructions are no-ops then)
+    (void)cudaGetLastError();
+    cfg.numAttrs = 0;
+    (void)cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+  }
 }
 
 // Every entry point works on its model's (or the named) device and leaves the caller's current device
@@ -145,6 +152,8 @@ struct smplk_model {
   bool fused_tma_out;   // option fused_tma_out = 0: the fused kernel stores its result per lane instead of through TMA
   bool use_fused;       // option fused = 0 selects the two-kernel forward (cross-checks, stand-alone kernel timings)
   bool use_pose_block;  // option pose_block = 0 selects the warp-per-body pose kernel + transposition pass
+  bool skip_pose;       // option skip_pose = 1 (measurement aid): smplk_forward launches no pose kernel and reuses the workspace rows
+                        // (features, transforms) of the previous call -> back-to-back launches of the blend / skinning kernel alone
   bool use_pdl;         // option pdl = 0: every kernel of a call is launched with plain stream ordering (no programmatic dependent launch)
   CUtensorMap tmap_pdkn_hi, tmap_pdkn_lo;  // backward: B operand rows = blend features
   CUtensorMap tmap_pdknh_hi, tmap_pdknh_lo, tmap2_pdknh_hi, tmap2_pdknh_lo;   // same, fp16 two-term split
@@ -938,7 +947,7 @@ extern "C" int smplk_model_create(const smplk_model_desc* desc, int device, smpl
   // parity tests, stand-alone kernel timings of the bench).  The product library reads NO environment variable.
   mdl->skin_bpb = 0; mdl->skin_g8 = true; mdl->skin_tma = false; mdl->force_skin_v1 = false; mdl->da_v1 = false;
   mdl->fit_fused = true; mdl->sparse_picks = true; mdl->use_2cta = true; mdl->use_fused = true; mdl->fused_tma_out = true; mdl->use_replay_gemm = true; mdl->use_skin_gemm = false;
-  mdl->use_pose_block = true; mdl->use_pdl = true; mdl->bwd_f16 = true; mdl->default_tc = BLEND_F16;
+  mdl->use_pose_block = true; mdl->use_pdl = true; mdl->skip_pose = false; mdl->bwd_f16 = true; mdl->default_tc = BLEND_F16;
 #ifdef SMPLK_AB   // A/B builds (tools/): tuning switches of kernels that are on no default path
   { const char* e = getenv("SMPLK_DA_V1"); mdl->da_v1 = e && e[0] == '1'; }
   { const char* e = getenv("SMPLK_SKIN_BPB"); mdl->skin_bpb = e ? atoi(e) : 0; }
@@ -968,6 +977,7 @@ extern "C" int smplk_model_set_option(smplk_model* model, const char* name, int 
   else if (!strcmp(name, "replay_gemm")) model->use_replay_gemm = on;   // rigged-mesh replay on the tensor cores
   else if (!strcmp(name, "skin_gemm")) model->use_skin_gemm = on;       // two-kernel forward: transform blend on the tensor cores
   else if (!strcmp(name, "fused")) model->use_fused = on;                    // fused blend + skinning forward kernel
+  else if (!strcmp(name, "skip_pose")) model->skip_pose = on;           // measurement aid: reuse the previous call's pose-kernel output
   else if (!strcmp(name, "pdl")) model->use_pdl = on;                    // programmatic dependent launch between a call's kernels
   else if (!strcmp(name, "pose_block")) model->use_pose_block = on;     // block-level pose kernel (else warp per body)
   else if (!strcmp(name, "blend_tf32")) model->default_tc = on ? BLEND_TF32 : BLEND_F16;   // 3xTF32 forward operands
@@ -1508,7 +1518,9 @@ static int forward_impl(const smplk_model* model, const smplk_forward_args* a, c
       const int loss_stride = (flags & SMPLK_FLAG_LOSS_SUM) ? 0 : 1;
       CUDA_TRY(cudaMemsetAsync(fit->loss + (size_t)c0 * loss_stride, 0, (size_t)(loss_stride ? rows : 1) * sizeof(float), st));
     }
-    if (int r = launch_pose_forward(model, pa, st)) return r;
+    if (!model->skip_pose) {
+      if (int r = launch_pose_forward(model, pa, st)) return r;
+    }
     if (flags & SMPLK_FLAG_TRANSFORMS_ONLY) continue;    // pose / FK kernel only: A, joints, full_pose
     if (picks_fwd) {
       PickFwdArgs pf;

@@ -103,6 +103,9 @@ int smplk_model_get_info(const smplk_model* model, smplk_model_info* info);
  *                        (lib/model2video.py:55-85); 0 = streaming skinning kernel
  *   "pdl" (1)            the kernels of a call are launched with programmatic stream serialization (each kernel's set-up
  *                        overlaps its predecessor's tail; results are bit-identical); 0 = plain stream ordering
+ *   "skip_pose" (0)      measurement aid: 1 = smplk_forward launches no pose kernel and reuses the workspace rows (blend
+ *                        features, transforms, FK joints) the previous call left there, i.e. it repeats that call's result
+ *                        with the blend / skinning kernel alone (bench.py times back-to-back launches of it this way)
  * Set options before the first forward that they affect; unknown names return SMPLK_E_ARG. */
 int smplk_model_set_option(smplk_model* model, const char* name, int value);
 

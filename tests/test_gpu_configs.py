@@ -8,6 +8,7 @@
   * config 5: a 100,000-frame SMPL-H sequence tiled from a real AMASS clip (156-D with hands,
     trans - trans[0], one betas row), spot-checked on both sides of every 8192-frame chunk boundary.
 """
+import ctypes
 import os
 
 import numpy as np
@@ -397,3 +398,42 @@ def test_programmatic_dependent_launch_changes_no_bit(dev, smplh_model, B):
     ref = O.TorchOracleModel(m, dtype=torch.float64).forward_full_pose(
         *[torch.tensor(x, dtype=torch.float64) for x in (betas[:40], pose[:40], transl[:40])])
     assert _err(res[1][0][:40], ref.vertices) <= TOL
+
+
+def test_skip_pose_option_repeats_the_previous_call(dev, smplh_model):
+    """Measurement aid of bench.py's roofline (handle option skip_pose): no pose kernel is launched, the blend /
+    skinning kernel runs again on the workspace rows of the previous call -- whatever pose the call is given."""
+    m = smplh_model
+    B = 300
+    dm = smplk.DeviceModel(m, device=0)
+    betas, pose, transl = synthetic.make_inputs(m, B, seed=5)
+    b, p, t = _t(betas, dev), _t(pose, dev), _t(transl, dev)
+    verts = torch.empty(B, dm.V, 3, device=dev)
+    joints = torch.empty(B, dm.J + dm.E, 3, device=dev)
+    ws = torch.empty(dm.workspace_bytes(B, 0), device=dev, dtype=torch.uint8)
+    stream = torch.cuda.current_stream(dev)
+
+    def call(pose_t):
+        a = _lib.ForwardArgs()
+        a.batch, a.flags = B, 0
+        a.betas, a.betas_batch = ctypes.c_void_p(b.data_ptr()), B
+        a.pose, a.transl = ctypes.c_void_p(pose_t.data_ptr()), ctypes.c_void_p(t.data_ptr())
+        a.verts, a.joints = ctypes.c_void_p(verts.data_ptr()), ctypes.c_void_p(joints.data_ptr())
+        a.workspace, a.workspace_bytes = ctypes.c_void_p(ws.data_ptr()), ws.numel()
+        a.stream = ctypes.c_void_p(stream.cuda_stream)
+        dm.forward(a)
+        torch.cuda.synchronize()
+        return verts.clone()
+
+    n0 = _lib.launch_count()
+    v_ref = call(p)
+    per_call = _lib.launch_count() - n0
+    dm.set_option("skip_pose", 1)
+    verts.zero_()
+    n0 = _lib.launch_count()
+    v_again = call(torch.zeros_like(p))
+    assert _lib.launch_count() - n0 == per_call - 1
+    assert torch.equal(v_ref, v_again)
+    dm.set_option("skip_pose", 0)
+    v_zero = call(torch.zeros_like(p))
+    assert not torch.equal(v_ref, v_zero)
