@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(kSkinOpThreads)
 skin_operand_kernel(int B, int J, int Kp, const float* __restrict__ A, __half* __restrict__ T_hi,
                     __half* __restrict__ T_lo) {
   __shared__ float sa[kMaxJoints * 12 + 48];
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int b = blockIdx.x;
   const float* src = A + (size_t)b * J * 12;
   for (int i = threadIdx.x; i < Kp * 12; i += kSkinOpThreads) sa[i] = i < J * 12 ? src[i] : 0.f;
@@ -113,6 +115,8 @@ __device__ __forceinline__ void replay_tile_coords(int tile, int num_mb, int num
 __global__ void __launch_bounds__(256)
 replay_operand_kernel(int F, int J, int Kp, const float* __restrict__ A, __half* __restrict__ T_hi,
                       __half* __restrict__ T_lo) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int q4 = Kp / 4;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;       // one 4-element group of one row
   if (i >= (long)3 * F * q4) return;
@@ -165,6 +169,7 @@ lbs_replay_gemm_kernel(const __grid_constant__ CUtensorMap tmap_p_hi, const __gr
   constexpr int kUmmaK = 16;
   constexpr int kKSteps = kRpKB / kUmmaK;
 
+  ptx::pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_p_hi);
     ptx::prefetch_tmap(&tmap_p_lo);
@@ -188,6 +193,7 @@ lbs_replay_gemm_kernel(const __grid_constant__ CUtensorMap tmap_p_hi, const __gr
   ptx::cluster_sync();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  ptx::pdl_wait();         // set-up above under the operand kernel's tail; its rows (and kSkin: v_posed) are read from here on
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================

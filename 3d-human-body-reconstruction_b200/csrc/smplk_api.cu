@@ -1312,10 +1312,10 @@ static int launch_replay_gemm(const smplk_model* mdl, int rows, const float* A, 
   {
     ProfScope prof(mdl, st, SMPLK_PROF_TRANSPOSE);      // the transforms' re-layout pass, as for the fused forward
     if (skin) {
-      skin_operand_kernel<<<rows, kSkinOpThreads, 0, st>>>(rows, d.J, Kp, A, T_hi, T_lo);
+      launch_k(mdl->use_pdl, skin_operand_kernel, rows, kSkinOpThreads, 0, st, rows, d.J, Kp, A, T_hi, T_lo);
     } else {
       const long n = (long)3 * rows * (Kp / 4);
-      replay_operand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows, d.J, Kp, A, T_hi, T_lo);
+      launch_k(mdl->use_pdl, replay_operand_kernel, (unsigned)((n + 255) / 256), 256, 0, st, rows, d.J, Kp, A, T_hi, T_lo);
     }
     LAUNCH_CHECK("replay_operand_kernel");
   }
@@ -1336,9 +1336,9 @@ static int launch_replay_gemm(const smplk_model* mdl, int rows, const float* A, 
   const int grid = 2 * std::min(tiles, mdl->num_sms / 2);
   ProfScope prof(mdl, st, SMPLK_PROF_SKIN);
   if (skin)
-    lbs_replay_gemm_kernel<true><<<grid, kRpThreads, kRpSmemAlloc, st>>>(mdl->tmap_sw_hi, mdl->tmap_sw_lo, tm_hi, tm_lo, ra);
+    launch_k(mdl->use_pdl, lbs_replay_gemm_kernel<true>, grid, kRpThreads, kRpSmemAlloc, st, mdl->tmap_sw_hi, mdl->tmap_sw_lo, tm_hi, tm_lo, ra);
   else
-    lbs_replay_gemm_kernel<false><<<grid, kRpThreads, kRpSmemAlloc, st>>>(mdl->tmap_rp_hi, mdl->tmap_rp_lo, tm_hi, tm_lo, ra);
+    launch_k(mdl->use_pdl, lbs_replay_gemm_kernel<false>, grid, kRpThreads, kRpSmemAlloc, st, mdl->tmap_rp_hi, mdl->tmap_rp_lo, tm_hi, tm_lo, ra);
   LAUNCH_CHECK("lbs_replay_gemm_kernel");
   return 0;
 }
