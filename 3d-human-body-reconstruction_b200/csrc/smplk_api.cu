@@ -1065,10 +1065,14 @@ static int launch_pose_forward(const smplk_model* mdl, const PoseFwdArgs& pa, cu
     // At is written for whole 256-body blocks (the fused kernel reads zero transforms for padding rows)
     const int bodies = pa.At ? pa.At_rows : pa.B;
     int nw = (pa.At != nullptr || pa.B >= 4096) ? kPoseBlockWarps : 8;
-    // one wave: spread the bodies over every SM instead of filling 32-body blocks (4,096 bodies: 147 blocks of 28
-    // instead of 128 of 32 -- the kernel's time follows the bodies per SM)
-    if (pa.At != nullptr && bodies <= kPoseBlockWarps * mdl->num_sms)
-      nw = std::max(8, std::min(kPoseBlockWarps, (bodies + mdl->num_sms - 1) / mdl->num_sms));
+    // whole waves: spread the bodies evenly over every SM instead of filling 32-body blocks (4,096 bodies: 147 blocks of
+    // 28 instead of 128 of 32; an 8,192-body chunk: 293 blocks of 28 = two full waves instead of 256 of 32 = 1.73 --
+    // the kernel's time follows the bodies per SM and wave)
+    if (nw == kPoseBlockWarps) {
+      const int waves = (bodies + kPoseBlockWarps * mdl->num_sms - 1) / (kPoseBlockWarps * mdl->num_sms);
+      const int slots = waves * mdl->num_sms;
+      nw = std::max(8, std::min(kPoseBlockWarps, (bodies + slots - 1) / slots));
+    }
     size_t smem = (size_t)pose_block_layout(d, nw).total * sizeof(float);
     const int blocks = (bodies + nw - 1) / nw;
     // One block per SM when the grid is a single wave: under a programmatic dependent launch the blocks are placed while
