@@ -216,3 +216,56 @@ def test_prior_inputs_broadcast_or_raise():
     assert ts[0].shape == (3, 10) and bc[0]
     with pytest.raises(ValueError):
         _prior_rows([torch.zeros(2, 10), None, p, None, None])
+
+
+def _csrc_text():
+    d = os.path.join(ROOT, "3d-human-body-reconstruction_b200", "csrc")
+    return {f: open(os.path.join(d, f)).read() for f in sorted(os.listdir(d))}
+
+
+def _kernel_body(text, name):
+    """Source of the __global__ function `name` (brace matching from its definition)."""
+    for m in re.finditer(r"\b%s\s*\(" % re.escape(name), text):
+        head = text[max(0, m.start() - 400):m.start()]
+        if "__global__" not in head.split(";")[-1] and "__global__" not in head.split("}")[-1]:
+            continue
+        i = text.index("{", m.end())
+        depth, j = 1, i + 1
+        while depth:
+            depth += {"{": 1, "}": -1}.get(text[j], 0)
+            j += 1
+        return text[i:j]
+    return None
+
+
+def test_every_programmatically_launched_kernel_waits_for_its_predecessor():
+    """Static guard of the PDL rule (ptx_sm100.cuh): a kernel that can be launched with the programmatic-stream-
+    serialization attribute (launch_k with a pdl argument) must execute griddepcontrol.wait; and a kernel that
+    triggers its dependents early must also wait, since its successor's wait relies on the chain being transitive."""
+    src = _csrc_text()
+    everything = "\n".join(src.values())
+    launched = set(re.findall(r"launch_k\(\s*[^,()]+(?:\(\))?,\s*([A-Za-z_][A-Za-z0-9_]*_kernel)\b", everything))
+    assert {"blend_skin_fused_kernel", "pose_forward_block_kernel", "pose_backward_kernel", "skin_fit_l2_kernel",
+            "dA_seg_kernel", "blend_tcgen05_2cta_kernel", "reduce_splits_kernel", "lbs_replay_gemm_kernel"} <= launched
+    for name in sorted(launched):
+        body = next((b for b in (_kernel_body(t, name) for t in src.values()) if b), None)
+        assert body is not None, name
+        assert "pdl_wait()" in body, "%s is launched through launch_k but never waits" % name
+    for fname, text in src.items():
+        for m in re.finditer(r"__global__[^;{]*?\b([A-Za-z_][A-Za-z0-9_]*_kernel)\s*\(", text):
+            body = _kernel_body(text, m.group(1))
+            if body and "pdl_launch_dependents()" in body:
+                assert "pdl_wait()" in body, "%s:%s triggers dependents but never waits" % (fname, m.group(1))
+
+
+def test_header_documents_every_handle_option():
+    """include/smplk.h lists the names smplk_model_set_option accepts: the list and the implementation agree."""
+    api = _csrc_text()["smplk_api.cu"]
+    fn = api[api.index('extern "C" int smplk_model_set_option'):]
+    fn = fn[:fn.index("\n}\n")]
+    names = set(re.findall(r'strcmp\(name, "([a-z0-9_]+)"\)', fn))
+    header = open(os.path.join(ROOT, "include", "smplk.h")).read()
+    doc = header[header.index("Kernel choices of one handle"):header.index("int smplk_model_set_option")]
+    documented = set(re.findall(r'"([a-z0-9_]+)" \(\d\)', doc))
+    assert names == documented, (sorted(names - documented), sorted(documented - names))
+    assert {"pdl", "skip_pose", "fused", "replay_gemm"} <= names
