@@ -392,6 +392,11 @@ pose_forward_kernel(const ModelDev m, const PoseFwdArgs a) {
 // copy At[128-body block][J][128][12] that the fused blend+skinning kernel reads (a warp's 32 bodies
 // are 1,536 contiguous bytes per joint), so there is no separate re-blocking pass.
 // ------------------------------------------------------------------------------------------
+// 1 (product): the block kernel walks the chain with lane = body; 0: lane = joint, one warp per body (A/B builds,
+// bitwise-equal results; tools/gpu_posewalk_ab.sh)
+#ifndef SMPLK_POSE_FWD_LANE_BODY
+#define SMPLK_POSE_FWD_LANE_BODY 1
+#endif
 constexpr int kPoseBlockWarps = 32;
 
 struct PoseBlockSmem {
@@ -582,6 +587,7 @@ pose_forward_block_kernel(const ModelDev m, const PoseFwdArgs a) {
     }
   }
 
+#if SMPLK_POSE_FWD_LANE_BODY
   // ---- walk the tree level by level: G_j = G_parent(j) * L_j, with LANE = BODY of the block and the level's joints
   // dealt to the warps.  (Lane = joint, one warp per body, left most lanes idle: a level of SMPL-H holds 1-10 joints,
   // and the walk was 31 % of the kernel's executed instructions -- ncu source view, 71 instructions x 10 levels per body.)
@@ -617,6 +623,34 @@ pose_forward_block_kernel(const ModelDev m, const PoseFwdArgs a) {
       __syncthreads();
     }
   }
+#else   // A/B build: the lane = joint walk (one warp per body)
+  // ---- walk the tree level by level: G_j = G_parent(j) * L_j
+  for (int d = 1; d <= m.max_depth; ++d) {
+    const int l0 = slvl[d], l1 = slvl[d + 1];
+    for (int i = l0 + lane; i < l1; i += 32) {
+      const int j = sord[i];
+      const float4* P4 = reinterpret_cast<const float4*>(Gs + spar[j] * 12);
+      float4* L4 = reinterpret_cast<float4*>(Gs + j * 12);
+      const float4 p0 = P4[0], p1 = P4[1], p2 = P4[2];
+      const float4 q0 = L4[0], q1 = L4[1], q2 = L4[2];
+      float4 o0, o1, o2;
+      o0.x = fmaf(p0.x, q0.x, fmaf(p0.y, q1.x, p0.z * q2.x));
+      o0.y = fmaf(p0.x, q0.y, fmaf(p0.y, q1.y, p0.z * q2.y));
+      o0.z = fmaf(p0.x, q0.z, fmaf(p0.y, q1.z, p0.z * q2.z));
+      o0.w = fmaf(p0.x, q0.w, fmaf(p0.y, q1.w, fmaf(p0.z, q2.w, p0.w)));
+      o1.x = fmaf(p1.x, q0.x, fmaf(p1.y, q1.x, p1.z * q2.x));
+      o1.y = fmaf(p1.x, q0.y, fmaf(p1.y, q1.y, p1.z * q2.y));
+      o1.z = fmaf(p1.x, q0.z, fmaf(p1.y, q1.z, p1.z * q2.z));
+      o1.w = fmaf(p1.x, q0.w, fmaf(p1.y, q1.w, fmaf(p1.z, q2.w, p1.w)));
+      o2.x = fmaf(p2.x, q0.x, fmaf(p2.y, q1.x, p2.z * q2.x));
+      o2.y = fmaf(p2.x, q0.y, fmaf(p2.y, q1.y, p2.z * q2.y));
+      o2.z = fmaf(p2.x, q0.z, fmaf(p2.y, q1.z, p2.z * q2.z));
+      o2.w = fmaf(p2.x, q0.w, fmaf(p2.y, q1.w, fmaf(p2.z, q2.w, p2.w)));
+      L4[0] = o0; L4[1] = o1; L4[2] = o2;
+    }
+    __syncwarp();
+  }
+#endif
 
   // ---- skinning transforms A_j = [G_R | G_t - G_R J_j] (kept in the table), FK joints
   const float tx = (a.transl && live) ? a.transl[3 * b + 0] : 0.f;
